@@ -1,0 +1,127 @@
+"""Drive the UNMODIFIED live reference (/root/reference) in-process to produce golden vectors.
+
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (the reference is not present on
+the GPU box); its outputs are committed under tests/golden/ by tools/make_golden.py.
+
+Follows the recipe in SURVEY.md §8(c): import scripts_of with a stub ``Bio`` package, then call
+  gathering.GetSequenceLengths            (gathering.py:444-464)
+  WaterfallMethod.ProcessBlastHits        (gathering.py:177-196)
+  WaterfallMethod.ConnectCognates         (gathering.py:251-259)
+  gathering.WriteGraph_perSpecies         (gathering.py:23-49)
+and assemble header + parts exactly like WriteGraphParallel (gathering.py:273-291).
+The fp64 B / BH / connect pickles are read back before deletion so that weights can be compared
+at 1e-9 instead of the file's %.3f.
+"""
+import os
+import sys
+import io
+import pickle
+import shutil
+import tempfile
+import contextlib
+import warnings
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("OFG_REFERENCE_ROOT", "/root/reference")
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "scripts_of"))
+
+
+
+
+def _import_reference_real():
+    if not reference_available():
+        raise RuntimeError("live reference not present at %s" % REFERENCE_ROOT)
+    for p in (_STUBS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from scripts_of import gathering, util, files, matrices
+    return gathering, util, files, matrices
+
+
+def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True):
+    """Run the reference hot path on WorkingDirectory ``wd`` (must end with '/').
+
+    Returns dict with: graph (bytes), seqsInfo fields, lengths, per-pair CSR of B (normalised),
+    BH, connect, fit params per pair (None when the pair was zeroed), stdout text.
+    """
+    gathering, util, files, matrices = _import_reference_real()
+    if not wd.endswith("/"):
+        wd += "/"
+    out = tempfile.mkdtemp(prefix="ofg_ref_") + "/"
+    pic = out + "pickle/"
+    os.mkdir(pic)
+    fh = files.FileHandler
+    saved = (fh.wd_base, fh.wd_current)
+    fh.wd_base = [wd]
+    fh.wd_current = out
+    res = {}
+    buf = io.StringIO()
+    fits = {}
+    try:
+        sp, n_all, _ = util.GetSpeciesToUse(wd + "SpeciesIDs.txt")
+        si = util.GetSeqsInfo([wd], sp, n_all)
+        L = gathering.GetSequenceLengths(si)
+        orig_fit = gathering.scnorm.CalculateFittingParameters
+        cur = {}
+
+        def fit_probe(Lf, S):
+            pars = orig_fit(Lf, S)
+            cur["pars"] = np.array(pars, dtype=np.float64)
+            cur["m"] = len(S)
+            return pars
+
+        orig_norm = gathering.WaterfallMethod.NormaliseScores
+
+        def norm_probe(B, Lengths, i, j):
+            cur.clear()
+            r = orig_norm(B, Lengths, i, j)
+            fits[(norm_probe.p, j)] = (cur.get("pars"), cur.get("m", 0), B.nnz)
+            return r
+
+        if capture_fit:
+            gathering.scnorm.CalculateFittingParameters = staticmethod(fit_probe)
+            gathering.WaterfallMethod.NormaliseScores = staticmethod(norm_probe)
+        try:
+            with contextlib.redirect_stdout(buf):
+                for p in range(si.nSpecies):
+                    norm_probe.p = p
+                    gathering.WaterfallMethod.ProcessBlastHits(si, [wd], L, p, pic, q_double_blast, False)
+                for p in range(si.nSpecies):
+                    gathering.WaterfallMethod.ConnectCognates(si, p, pic)
+                mats = {}
+                if keep_matrices:
+                    for p in range(si.nSpecies):
+                        for j in range(si.nSpecies):
+                            for name in ("B", "BH", "connect"):
+                                with open(pic + "%s%d_%d.pic" % (name, p, j), "rb") as f:
+                                    mats[(name, p, j)] = pickle.load(f).tocsr()
+                graph_fn = out + "OrthoFinder_graph.txt"
+                with open(graph_fn, "w") as g:
+                    g.write("(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (si.nSeqs, si.nSeqs))
+                    g.write("\n(mclmatrix\nbegin\n\n")
+                for p in range(si.nSpecies):
+                    gathering.WriteGraph_perSpecies((si, graph_fn, p, pic))
+                with open(graph_fn, "ab") as g:
+                    for p in range(si.nSpecies):
+                        with open(graph_fn + "_%d" % p, "rb") as part:
+                            g.write(part.read())
+        finally:
+            gathering.scnorm.CalculateFittingParameters = staticmethod(orig_fit)
+            gathering.WaterfallMethod.NormaliseScores = staticmethod(orig_norm)
+        with open(graph_fn, "rb") as g:
+            res["graph"] = g.read()
+        res.update(nSeqs=si.nSeqs, nSpecies=si.nSpecies, speciesToUse=list(si.speciesToUse),
+                   seqStartingIndices=list(si.seqStartingIndices),
+                   nSeqsPerSpecies=dict(si.nSeqsPerSpecies), lengths=[np.asarray(x) for x in L],
+                   mats=mats, fits=fits, stdout=buf.getvalue())
+    finally:
+        fh.wd_base, fh.wd_current = saved
+        shutil.rmtree(out, ignore_errors=True)
+    return res
