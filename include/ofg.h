@@ -1,0 +1,155 @@
+/* libofg — B200-native orthogroup-graph builder: C-ABI of the WaterfallMethod hot path.
+ *
+ * The reference (davidemms/OrthoFinder, scripts_of/) has no FFI for this path; the seam is the Python
+ * call site gathering.py:476-512 inside DoOrthogroups.  Every entry point below cites
+ * the reference code whose work it replaces.  Conventions: plain pointers and sizes only, return 0 on
+ * success or a negative OFG_ERR_* code (message via ofg_last_error); the library never exits the
+ * process; buffers handed out stay owned by the context; one context per GPU, not thread-safe.
+ * Species are addressed by their position in seqsInfo.speciesToUse ("list position"), exactly as
+ * iSpecies/jSpecies in gathering.py:177-196.
+ */
+#ifndef OFG_H
+#define OFG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ofg_ctx ofg_ctx;
+
+enum {
+    OFG_OK = 0,
+    OFG_ERR_CUDA = -1,         /* CUDA runtime failure */
+    OFG_ERR_ARG = -2,          /* bad argument / call order */
+    OFG_ERR_PARSE = -3,        /* malformed hit line: blast_file_processor.py:74-82,99-103 */
+    OFG_ERR_INCONSISTENT = -4, /* sequence id >= nSeqs: blast_file_processor.py:89-98 */
+    OFG_ERR_FIT = -5,          /* curve_fit would raise "Optimal parameters not found" (gathering.py:120) */
+    OFG_ERR_CAPACITY = -6,     /* an internal capacity was exceeded; see message */
+    OFG_ERR_UNSUPPORTED = -7,  /* input outside the supported grammar / ranges; see message */
+    OFG_ERR_MISSING = -8       /* a hit file required by the partition was not provided */
+};
+
+/* kinds of offending line reported with OFG_ERR_PARSE / OFG_ERR_INCONSISTENT */
+enum {
+    OFG_LINE_OK = 0,
+    OFG_LINE_BAD_ID = 1,     /* "Query or hit sequence ID ... missing or incorrectly formatted" (:75) */
+    OFG_LINE_BAD_SCORE = 2,  /* "12th field ... should be the bit-score" (:81) */
+    OFG_LINE_QUOTE = 3,      /* csv quoting: not produced by BLAST/DIAMOND/MMseqs2, rejected */
+    OFG_LINE_RANGE_Q = 4,    /* query id >= nSeqs_i (:89-98) */
+    OFG_LINE_RANGE_S = 5,    /* hit id >= nSeqs_j (:89-98) */
+    OFG_LINE_SCORE_FORMAT = 6 /* float() would accept it but the device grammar does not (inf/nan/>19 digits) */
+};
+
+/* stages of ofg_build(stop_after) — each one ends where the reference writes a pickle or the graph */
+enum {
+    OFG_STAGE_RAW = 1,      /* GetBLAST6Scores for every pair (blast_file_processor.py:38-104) */
+    OFG_STAGE_NORM = 2,     /* NormaliseScores + GetBH_s -> "B", "BH" (gathering.py:140-155,213-248) */
+    OFG_STAGE_THRESH = 3,   /* RBH + GetMostDistant_s for owned species (gathering.py:251-259,294-310) */
+    OFG_STAGE_GRAPH = 4     /* ConnectAllBetterThanCutoff_s + WriteGraph_perSpecies (:391-408, :23-49) */
+};
+
+/* flag bits stored in the top of the column word returned by ofg_pair_csr */
+#define OFG_FLAG_BH 0x80000000u      /* entry of BH_pj   (gathering.py:213-248) */
+#define OFG_FLAG_CONNECT 0x40000000u /* entry of connect_pj (gathering.py:391-408) */
+#define OFG_FLAG_REVERSE 0x20000000u /* connect_jp[c,r] is set (gathering.py:30, m2tr) */
+#define OFG_COL_MASK 0x1fffffffu
+
+/* synthetic hit-file parameters (orthofinder_b200/csrc/synth_hits.h) */
+typedef struct {
+    uint64_t seed;
+    int32_t hq, integer_scores, ident_levels, p_dup_permille, p_missing_permille, p_nohit_permille,
+        p_selfonly_permille, p_twin_permille, single_i, single_j;
+} ofg_synth_params;
+
+/* Create / destroy a context bound to CUDA device `device`. */
+int ofg_create(ofg_ctx** out, int device);
+void ofg_destroy(ofg_ctx* ctx);
+const char* ofg_last_error(const ofg_ctx* ctx);
+
+/* Index space and sequence lengths: util.SequencesInfo (util.py:54-84) and
+ * gathering.GetSequenceLengths (gathering.py:444-464).  n_seqs[p] genes for list position p,
+ * lengths_concat holds the S length vectors back to back (fp64, integer valued). */
+int ofg_set_species(ofg_ctx* ctx, int n_species, const int64_t* n_seqs, const double* lengths_concat);
+
+/* Query species (rows of the S x S pair grid) owned by this context: the unit the reference
+ * parallelises over (gathering.py:484-485).  Default: all.  With with_columns != 0 the context
+ * also ingests Blast{j}_{p} for every owned p (the transposed direction the reference reads back
+ * from pickles at gathering.py:254 and :30), so that only per-gene thresholds need exchanging. */
+int ofg_set_partition(ofg_ctx* ctx, int n_owned, const int32_t* owned_rows, int with_columns);
+
+/* Hit text of Blast{p}_{j}.txt (already decompressed): replaces the open()/csv.reader loop of
+ * blast_file_processor.py:59-88.  `ptr` is a host pointer (copied H2D here) or, with is_device != 0,
+ * a device pointer that is copied device-to-device into the context's text arena.  swap_cols != 0
+ * reads query/hit from columns 1/0 (the -1 one-way mode, blast_file_processor.py:41-54).
+ * A pair that is never added is an empty file (q_allow_empty, :62-63) only if allow_empty was set
+ * with ofg_set_option; otherwise ofg_build fails with OFG_ERR_MISSING. */
+int ofg_add_hits_text(ofg_ctx* ctx, int p, int j, const void* ptr, size_t nbytes, int swap_cols, int is_device);
+
+/* Drop all hit text (keeps species / partition). */
+int ofg_clear_hits(ofg_ctx* ctx);
+
+/* Generate Blast{species_ids[p]}_{species_ids[j]}.txt for every pair this context needs directly in
+ * device memory (bench / tests); byte-identical to the host generator for the same parameters. */
+int ofg_synth_hits(ofg_ctx* ctx, const ofg_synth_params* params, const int32_t* species_ids);
+/* Size of / copy out one generated (or added) file, for tests and for the host-buffer e2e bench. */
+int ofg_hits_text_size(ofg_ctx* ctx, int p, int j, size_t* nbytes);
+int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
+
+/* Options: "allow_empty" (0/1), "max_bytes_per_line_inv" (capacity: records <= bytes/this, default 24),
+ * "sel_capacity_frac_inv" (fit scratch = records/this, default 4). */
+int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
+
+/* Run the path up to and including `stop_after` (OFG_STAGE_*).  OFG_STAGE_THRESH stops before the
+ * thresholds of other ranks are needed; call ofg_thresholds_get / _set around the exchange and then
+ * ofg_build(ctx, OFG_STAGE_GRAPH) to finish.  Single GPU: ofg_build(ctx, OFG_STAGE_GRAPH). */
+int ofg_build(ofg_ctx* ctx, int stop_after);
+
+/* Per-gene cut-off "mostDistant" (gathering.py:294-310), global gene indexing (seqStartingIndices).
+ * _dev returns the device array of nSeqs doubles (entries of species not owned hold +inf until set);
+ * _set_dev tells the library that every entry is now valid (after the all-gather). */
+int ofg_thresholds_dev(ofg_ctx* ctx, double** dev_ptr, int64_t* n);
+int ofg_thresholds_mark_complete(ofg_ctx* ctx);
+int ofg_thresholds_copy(ofg_ctx* ctx, double* host_dst, int64_t n);
+
+/* Totals after a build: lines = non-empty records seen, records = lines kept after the self-hit and
+ * score > 0 filters, nnz = stored (q,s) after max-dedup, edges = entries of the final graph. */
+int ofg_counts(ofg_ctx* ctx, int64_t* lines, int64_t* records, int64_t* nnz, int64_t* edges);
+
+/* Introspection for the parity gates: matrix of pair (p,j) as row lengths + packed
+ * (col | flags, value) entries in row-major / column-ascending order.  Values are raw bit scores
+ * after OFG_STAGE_RAW and normalised scores afterwards ("B" pickles).  Pass NULL to query sizes. */
+int ofg_pair_csr(ofg_ctx* ctx, int p, int j, int64_t* n_rows, int64_t* nnz, int32_t* row_len, uint32_t* cols,
+                 double* vals);
+/* out[0]=a, out[1]=b (curve_fit parameters, gathering.py:119-121), out[2]=number of selected hits,
+ * out[3]=MINPACK info, out[4]=nfev, out[5]=1 if normalised / 0 if the pair was zeroed (:152-155). */
+int ofg_pair_fit(ofg_ctx* ctx, int p, int j, double out[6]);
+
+/* Final graph W = (connect_pj + connect_jp^T) .* B_pj for the owned rows (gathering.py:23-49):
+ * CSR with global gene indices, rows [row0, row0 + n_rows) contiguous per owned species in list order. */
+int ofg_graph_csr_size(ofg_ctx* ctx, int64_t* n_rows, int64_t* nnz);
+int ofg_graph_csr_copy(ofg_ctx* ctx, int64_t* row_ids, int64_t* indptr, int32_t* indices, double* data);
+/* MCL text of the owned rows ("%d    " + "%d:%.3f " ... + "$\n", gathering.py:39-48), in device memory;
+ * header (:279-280) and the closing ")\n" (:48) are added by the host wrapper. */
+int ofg_graph_text_size(ofg_ctx* ctx, size_t* nbytes);
+int ofg_graph_text_copy(ofg_ctx* ctx, void* host_dst, size_t cap);
+
+/* Kernel timing of the last ofg_build (CUDA events on the library's stream), milliseconds per group:
+ * 0 parse, 1 rows (bucket + row sort), 2 length sort, 3 select, 4 fit, 5 scale+BH, 6 thresholds,
+ * 7 connect, 8 emit, 9 total.  n_launches = kernels launched by the last build. */
+int ofg_last_timing(ofg_ctx* ctx, float ms[10], int64_t* n_launches);
+/* Stream the library launches on (cudaStream_t), so callers can record their own events on it. */
+void* ofg_stream(ofg_ctx* ctx);
+
+/* Standalone device functions exposed for unit parity tests (each runs one small kernel). */
+int ofg_test_log10(ofg_ctx* ctx, const double* host_x, double* host_y, int64_t n);      /* np.log10 emulation */
+int ofg_test_format(ofg_ctx* ctx, const double* host_x, char* host_out, int64_t n);     /* "%.3f", 32 B slots */
+int ofg_test_parse_score(ofg_ctx* ctx, const char* host_text, int64_t nbytes, double* host_y, int32_t* host_ok,
+                         int64_t n_fields);                                             /* '\n'-separated */
+int ofg_test_lmfit(ofg_ctx* ctx, const double* host_lx, const double* host_ly, int64_t m, double out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+"""ctypes binding of libofg.so (include/ofg.h).  No fallback: a missing library is an error."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libofg.so")
+
+OFG_OK = 0
+ERR_NAMES = {-1: "OFG_ERR_CUDA", -2: "OFG_ERR_ARG", -3: "OFG_ERR_PARSE", -4: "OFG_ERR_INCONSISTENT", -5: "OFG_ERR_FIT",
+             -6: "OFG_ERR_CAPACITY", -7: "OFG_ERR_UNSUPPORTED", -8: "OFG_ERR_MISSING"}
+ERR_PARSE, ERR_INCONSISTENT, ERR_FIT, ERR_UNSUPPORTED, ERR_MISSING = -3, -4, -5, -7, -8
+STAGE_RAW, STAGE_NORM, STAGE_THRESH, STAGE_GRAPH = 1, 2, 3, 4
+FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, COL_MASK = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
+
+# every symbol include/ofg.h declares (tests/test_abi.py checks the library exports all of them)
+SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "ofg_set_partition", "ofg_add_hits_text",
+           "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_build",
+           "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_counts", "ofg_pair_csr",
+           "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
+           "ofg_last_timing", "ofg_stream", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
+
+_lib = None
+
+
+def load():
+    """Load libofg.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libofg.so is not built (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.ofg_last_error.restype = ctypes.c_char_p
+    lib.ofg_last_error.argtypes = [ctypes.c_void_p]
+    lib.ofg_stream.restype = ctypes.c_void_p
+    lib.ofg_stream.argtypes = [ctypes.c_void_p]
+    lib.ofg_destroy.restype = None
+    lib.ofg_destroy.argtypes = [ctypes.c_void_p]
+    vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
+    sigs = {
+        "ofg_create": [ctypes.POINTER(vp), i32],
+        "ofg_set_species": [vp, i32, vp, vp],
+        "ofg_set_partition": [vp, i32, vp, i32],
+        "ofg_add_hits_text": [vp, i32, i32, vp, sz, i32, i32],
+        "ofg_clear_hits": [vp],
+        "ofg_synth_hits": [vp, vp, vp],
+        "ofg_hits_text_size": [vp, i32, i32, ctypes.POINTER(sz)],
+        "ofg_hits_text_copy": [vp, i32, i32, vp, sz],
+        "ofg_set_option": [vp, ctypes.c_char_p, i64],
+        "ofg_build": [vp, i32],
+        "ofg_thresholds_dev": [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)],
+        "ofg_thresholds_mark_complete": [vp],
+        "ofg_thresholds_copy": [vp, vp, i64],
+        "ofg_counts": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
+        "ofg_pair_csr": [vp, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), vp, vp, vp],
+        "ofg_pair_fit": [vp, i32, i32, vp],
+        "ofg_graph_csr_size": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)],
+        "ofg_graph_csr_copy": [vp, vp, vp, vp, vp],
+        "ofg_graph_text_size": [vp, ctypes.POINTER(sz)],
+        "ofg_graph_text_copy": [vp, vp, sz],
+        "ofg_last_timing": [vp, vp, ctypes.POINTER(i64)],
+        "ofg_test_log10": [vp, vp, vp, i64],
+        "ofg_test_format": [vp, vp, vp, i64],
+        "ofg_test_parse_score": [vp, ctypes.c_char_p, i64, vp, vp, i64],
+        "ofg_test_lmfit": [vp, vp, vp, i64, vp],
+    }
+    for name, args in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,411 @@
+// Stages NORM (part 3), THRESH and GRAPH: everything after the fit.
+//
+//  fit_kernel      : one CTA per species pair, ofg_fit_core.h (curve_fit / MINPACK lmdif emulation)
+//  factors_kernel  : per-gene factors 10^-b * Lq^-a and Lh^-a   (gathering.py:124-131)
+//  scale_bh_kernel : B' = ((10^-b * Lq^-a) * B) * Lh^-a left to right, row maxima, best hits with the
+//                    1e-3 band for j != p, per-gene best hit in another species (gathering.py:213-234)
+//  bh_self_kernel  : best-hit flags of the within-species matrix (gathering.py:236-247)
+//  rbh_kernel      : RBH_pk = BH_pk AND BH_kp^T by binary search in the transposed pair, per-gene
+//                    "most distant" threshold with last-column-wins semantics (gathering.py:294-306)
+//  thresh_final    : genes without an RBH get bestHit + 1e-6 (gathering.py:308-309)
+//  connect_kernel  : connect_pj = B' >= threshold (gathering.py:391-408) and the reverse flag
+//                    connect_jp^T scattered into the transposed pair (gathering.py:27-31)
+//  emit_*          : W = (connect + connect^T) .* B' as CSR with global gene ids and as MCL text with
+//                    glibc-exact "%d:%.3f " formatting (gathering.py:39-48)
+#pragma once
+#include "ofg_common.cuh"
+#include "ofg_fit_core.h"
+
+// ---------------------------------------------------------------- fit
+constexpr int FIT_THREADS = 256;
+
+struct FitArgs {
+    int P;
+    const u64* pair_sel_off;  // [P+1] offsets of each pair's selected points in lx / ly
+    u64 sel_cap;
+    const double* lx;
+    const double* ly;
+    double* fvec;
+    double* wa4;
+    double* c0;
+    double* c1;
+    double* fit;      // [P][8]: a, b, m, info, nfev, iterative, ok, pad
+    u32* err_flags;   // bit 0: a fit failed (curve_fit would raise); bit 1: selection overflowed sel_cap
+};
+
+__global__ void __launch_bounds__(FIT_THREADS) fit_kernel(FitArgs a)
+{
+    __shared__ FitShared sh;
+    for (int pair = blockIdx.x; pair < a.P; pair += gridDim.x) {
+        const u64 o0 = a.pair_sel_off[pair], o1 = a.pair_sel_off[pair + 1];
+        const long m = (long)(o1 - o0);
+        double* out = a.fit + (size_t)pair * 8;
+        if (o1 > a.sel_cap) {
+            if (threadIdx.x == 0) { atomicOr(a.err_flags, 2u); out[6] = 0.0; out[2] = (double)m; out[3] = -1.0; }
+            continue;
+        }
+        if (m <= 1) {  // len(topScores) > 1 fails: the pair's hits are ignored (gathering.py:145,152-155)
+            if (threadIdx.x == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = (double)m; out[3] = 0.0; out[4] = 0.0; out[5] = 0.0; out[6] = 0.0; }
+            continue;
+        }
+        const int info = fit_loglinear(a.lx + o0, a.ly + o0, m, a.fvec + o0, a.wa4 + o0, a.c0 + o0, a.c1 + o0, &sh, out);
+        if (threadIdx.x == 0) {
+            const bool ok = info >= 1 && info <= 4;
+            out[6] = ok ? 1.0 : 0.0;
+            if (!ok) atomicOr(a.err_flags, 1u);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- normalisation factors
+struct FactorArgs {
+    const PairDesc* pairs;
+    int P;
+    const double* fit;
+    const double* lengths;
+    double* rowfac;   // [total rows]
+    double* colfac;   // [total cols]
+};
+
+__global__ void __launch_bounds__(256) factors_kernel(FactorArgs a)
+{
+    // grid.y = pair, grid.x strides over Gi + Gj genes
+    const int pair = blockIdx.y;
+    const PairDesc pd = a.pairs[pair];
+    const double* f = a.fit + (size_t)pair * 8;
+    if (f[6] == 0.0) return;
+    const double pa = f[0], pb = f[1];
+    const double ten_mb = pow(10.0, -pb);  // 10**(-params[1])
+    const int64_t n = (int64_t)pd.Gi + pd.Gj;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < pd.Gi) a.rowfac[pd.row_base + i] = __dmul_rn(ten_mb, pow(a.lengths[pd.li_off + i], -pa));
+        else a.colfac[pd.col_base + (i - pd.Gi)] = pow(a.lengths[pd.lj_off + (i - pd.Gi)], -pa);
+    }
+}
+
+// ---------------------------------------------------------------- scale + best hits
+struct ScaleArgs {
+    int64_t n_rows;
+    const u32* row_start;
+    u32* rowlen;
+    u32* cols;       // flags are OR-ed into the top bits
+    double* vals;    // raw scores in, normalised scores out
+    const PairDesc* pairs;
+    const int64_t* pair_row_base;
+    int P;
+    const double* fit;
+    const double* rowfac;
+    const double* colfac;
+    double* rowmax;  // [n_rows]
+    double* best;    // [nSeqs] bit patterns, 0 = no hit in another species
+};
+
+__global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const int n = (int)a.rowlen[row];
+        if (n == 0) continue;
+        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        const PairDesc& pd = a.pairs[pair];
+        if (a.fit[(size_t)pair * 8 + 6] == 0.0) {  // zeroed pair: sparse.lil_matrix(B.get_shape())
+            if (lane == 0) a.rowlen[row] = 0;
+            continue;
+        }
+        const u32 s0 = a.row_start[row];
+        const double rf = a.rowfac[row];
+        const double* cf = a.colfac + pd.col_base;
+        double m = 0.0;
+        for (int k = lane; k < n; k += 32) {
+            const u32 c = a.cols[s0 + k];
+            const double v = __dmul_rn(__dmul_rn(rf, a.vals[s0 + k]), cf[c]);
+            a.vals[s0 + k] = v;
+            m = fmax(m, v);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(OFG_FULL, m, d));
+        if (lane == 0) a.rowmax[row] = m;
+        if (!pd.same) {
+            const double thr = __dsub_rn(m, 1e-3);
+            for (int k = lane; k < n; k += 32)
+                if (a.vals[s0 + k] > thr) a.cols[s0 + k] |= OFG_FLAG_BH;
+            if (lane == 0 && pd.owned_row && m > 0.0) atomic_max_pos_double(&a.best[pd.gi_start + (row - pd.row_base)], m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bh_self_kernel(ScaleArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const int n = (int)a.rowlen[row];
+        if (n == 0) continue;
+        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        const PairDesc& pd = a.pairs[pair];
+        if (!pd.same) continue;
+        const u32 s0 = a.row_start[row];
+        const double b = a.best[pd.gi_start + (row - pd.row_base)];
+        const double bestv = (__double_as_longlong(b) == 0) ? -1.0 : b;  // bestHitForSequence starts at -1
+        const double thr = __dsub_rn(bestv, 1e-3);
+        for (int k = lane; k < n; k += 32)
+            if (a.vals[s0 + k] > thr) a.cols[s0 + k] |= OFG_FLAG_BH;
+    }
+}
+
+// ---------------------------------------------------------------- RBH + thresholds
+struct GraphArgs {
+    int64_t n_rows;
+    const u32* row_start;
+    const u32* rowlen;
+    u32* cols;
+    const double* vals;
+    const PairDesc* pairs;
+    const int64_t* pair_row_base;
+    int P;
+    const int32_t* pair_of;  // [S*S] pair index of (p, j) or -1
+    int S;
+    double* most;            // [nSeqs] thresholds (bit patterns while being reduced)
+    const double* best;
+};
+
+// index of column `want` in the row [s0, s0+n) of the slotted CSR, or -1
+__device__ __forceinline__ int64_t find_col(const u32* cols, u32 s0, int n, u32 want)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const u32 c = cols[s0 + mid] & OFG_COL_MASK;
+        if (c < want) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && (cols[s0 + lo] & OFG_COL_MASK) == want) return (int64_t)s0 + lo;
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const int n = (int)a.rowlen[row];
+        if (n == 0) continue;
+        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        const PairDesc& pd = a.pairs[pair];
+        if (pd.same || !pd.owned_row) continue;
+        const int tp = a.pair_of[pd.j * a.S + pd.p];
+        if (tp < 0) continue;
+        const PairDesc& td = a.pairs[tp];
+        const u32 s0 = a.row_start[row];
+        const u32 r = (u32)(row - pd.row_base);
+        int last = -1;  // largest k (column order) with an RBH
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            bool rbh = false;
+            if (k < n) {
+                const u32 cw = a.cols[s0 + k];
+                if (cw & OFG_FLAG_BH) {
+                    const int64_t trow = td.row_base + (cw & OFG_COL_MASK);
+                    const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
+                    rbh = e >= 0 && (a.cols[e] & OFG_FLAG_BH);
+                }
+            }
+            const u32 bal = __ballot_sync(OFG_FULL, rbh);
+            if (bal) last = k0 + (31 - __clz(bal));
+        }
+        if (last >= 0 && lane == 0) atomic_min_pos_double(&a.most[pd.gi_start + r], a.vals[s0 + last]);
+    }
+}
+
+__global__ void thresh_final_kernel(double* most, const double* best, const uint8_t* owned_gene, int64_t n)
+{
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+        if (!owned_gene[g]) continue;
+        const double md = most[g];
+        if (md > 1e8) most[g] = __dadd_rn(best[g], 1e-6);  // best bit pattern 0 == 0.0 == "no hit"
+    }
+}
+
+// ---------------------------------------------------------------- connect
+__global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const int n = (int)a.rowlen[row];
+        if (n == 0) continue;
+        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        const PairDesc& pd = a.pairs[pair];
+        const u32 s0 = a.row_start[row];
+        const u32 r = (u32)(row - pd.row_base);
+        const double md = a.most[pd.gi_start + r];
+        const int tp = a.pair_of[pd.j * a.S + pd.p];
+        for (int k = lane; k < n; k += 32) {
+            const u32 cw = a.cols[s0 + k];
+            const u32 c = cw & OFG_COL_MASK;
+            if (a.vals[s0 + k] >= md && !(pd.same && c == r)) {
+                atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
+                if (tp >= 0) {
+                    const PairDesc& td = a.pairs[tp];
+                    const int64_t trow = td.row_base + c;
+                    const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
+                    if (e >= 0) atomicOr(&a.cols[e], OFG_FLAG_REVERSE);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- emission
+// exact "%.3f" digits of a non-negative finite double: X = round-half-even(v * 1000) on the exact
+// binary value (what glibc printf does); returns false if it does not fit 64 bits.
+__host__ __device__ __forceinline__ bool ofg_fixed3(double v, unsigned long long* X)
+{
+    unsigned long long bits;
+#if defined(__CUDA_ARCH__)
+    bits = (unsigned long long)__double_as_longlong(v);
+#else
+    memcpy(&bits, &v, 8);
+#endif
+    const int eb = (int)((bits >> 52) & 0x7ff);
+    unsigned long long mant = bits & 0x000fffffffffffffULL;
+    int e;
+    if (eb == 0) e = -1074; else { mant |= 0x0010000000000000ULL; e = eb - 1075; }
+    const unsigned long long P = mant * 1000ULL;  // < 2^63
+    if (e >= 0) {
+        if (e > 0 && (P >> (64 - e)) != 0) return false;
+        *X = P << e;
+        return true;
+    }
+    const int sh = -e;
+    if (sh >= 64) { *X = 0; return true; }
+    unsigned long long q = P >> sh;
+    const unsigned long long rem = P & ((1ULL << sh) - 1ULL), half = 1ULL << (sh - 1);
+    if (rem > half || (rem == half && (q & 1ULL))) q++;
+    *X = q;
+    return true;
+}
+
+__host__ __device__ __forceinline__ int ofg_ndigits(unsigned long long v)
+{
+    int n = 1;
+    while (v >= 10ULL) { v /= 10ULL; n++; }
+    return n;
+}
+
+__host__ __device__ __forceinline__ int ofg_put_u64(char* out, unsigned long long v)
+{
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + (int)(v % 10ULL)); v /= 10ULL; } while (v);
+    for (int k = 0; k < n; k++) out[k] = tmp[n - 1 - k];
+    return n;
+}
+
+// "%d:%.3f " for (global column, weight); returns bytes (written only if out != nullptr)
+__host__ __device__ __forceinline__ int ofg_format_entry(unsigned long long gcol, double w, char* out, bool* ok)
+{
+    unsigned long long X = 0;
+    if (!ofg_fixed3(w, &X)) { *ok = false; X = 0; }
+    const unsigned long long ip = X / 1000ULL;
+    const int fr = (int)(X % 1000ULL);
+    if (!out) return ofg_ndigits(gcol) + 1 + ofg_ndigits(ip) + 1 + 3 + 1;
+    int n = ofg_put_u64(out, gcol);
+    out[n++] = ':';
+    n += ofg_put_u64(out + n, ip);
+    out[n++] = '.';
+    out[n++] = (char)('0' + fr / 100);
+    out[n++] = (char)('0' + (fr / 10) % 10);
+    out[n++] = (char)('0' + fr % 10);
+    out[n++] = ' ';
+    return n;
+}
+
+struct EmitArgs {
+    GraphArgs g;
+    int64_t n_units;          // owned genes x S : unit u = local_gene * S + j
+    const int64_t* gene_of_local;  // [owned genes] global gene id
+    const int32_t* species_of_local;  // [owned genes] list position p
+    const int64_t* seq_start; // [S] seqStartingIndices
+    u32* unit_cnt;            // [n_units] edges of the unit
+    u32* unit_bytes;          // [n_units] text bytes of the unit
+    const u64* cnt_off;       // [n_units + 1]
+    const u64* byte_off;      // [n_units + 1]
+    int32_t* out_indices;
+    double* out_data;
+    char* out_text;
+    u32* err_flags;           // bit 2: a weight could not be formatted
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(256) emit_kernel(EmitArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int S = a.g.S;
+    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < a.n_units; u += n_warps) {
+        const int64_t lg = u / S;
+        const int j = (int)(u - lg * S);
+        const int p = a.species_of_local[lg];
+        const int64_t gene = a.gene_of_local[lg];
+        const int pair = a.g.pair_of[p * S + j];
+        u32 cnt = 0, bytes = 0;
+        u64 ocnt = 0, obyte = 0;
+        if (WRITE) { ocnt = a.cnt_off[u]; obyte = a.byte_off[u]; }
+        // "%d    " before the first species, "$\n" after the last (gathering.py:42,47)
+        if (j == 0) {
+            const int nd = ofg_ndigits((unsigned long long)gene);
+            if (WRITE && lane == 0) {
+                char* o = a.out_text + obyte;
+                int n = ofg_put_u64(o, (unsigned long long)gene);
+                o[n] = ' '; o[n + 1] = ' '; o[n + 2] = ' '; o[n + 3] = ' ';
+            }
+            bytes += nd + 4;
+            obyte += nd + 4;
+        }
+        if (pair >= 0) {
+            const PairDesc& pd = a.g.pairs[pair];
+            const int64_t row = pd.row_base + (gene - pd.gi_start);
+            const int n = (int)a.g.rowlen[row];
+            const u32 s0 = a.g.row_start[row];
+            const unsigned long long goff = (unsigned long long)a.seq_start[j];
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                u32 cw = 0;
+                if (k < n) cw = a.g.cols[s0 + k];
+                const int mult = ((cw & OFG_FLAG_CONNECT) ? 1 : 0) + ((cw & OFG_FLAG_REVERSE) ? 1 : 0);
+                const bool on = k < n && mult > 0;
+                double w = 0.0;
+                int len = 0;
+                bool ok = true;
+                const unsigned long long gc = goff + (cw & OFG_COL_MASK);
+                if (on) {
+                    w = __dmul_rn((double)mult, a.g.vals[s0 + k]);  // (connect + connect^T) .* B
+                    len = ofg_format_entry(gc, w, nullptr, &ok);
+                    if (!ok) atomicOr(a.err_flags, 4u);
+                }
+                // warp exclusive scans of the edge count and the byte count
+                const u32 bal = __ballot_sync(OFG_FULL, on);
+                const u32 epos = __popc(bal & lanemask_lt());
+                u32 binc = warp_incl_scan((u32)len);
+                const u32 bpos = binc - (u32)len;
+                const u32 btot = __shfl_sync(OFG_FULL, binc, 31);
+                if (WRITE && on) {
+                    a.out_indices[ocnt + epos] = (int32_t)gc;
+                    a.out_data[ocnt + epos] = w;
+                    ofg_format_entry(gc, w, a.out_text + obyte + bpos, &ok);
+                }
+                cnt += __popc(bal);
+                bytes += btot;
+                ocnt += __popc(bal);
+                obyte += btot;
+            }
+        }
+        if (j == S - 1) {
+            if (WRITE && lane == 0) { a.out_text[obyte] = '$'; a.out_text[obyte + 1] = '\n'; }
+            bytes += 2;
+        }
+        if (!WRITE && lane == 0) { a.unit_cnt[u] = cnt; a.unit_bytes[u] = bytes; }
+    }
+}

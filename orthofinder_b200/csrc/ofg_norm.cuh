@@ -1,0 +1,285 @@
+// Stage NORM, parts 1-2: the per-pair length binning and top-5% selection of
+// scnorm.GetTopPercentileOfScores (gathering.py:93-116).
+//
+//  radix sort : STABLE segmented LSD radix sort of (Lf, score) records by Lf inside each pair.  The
+//               input order is the matrix order (row, col), so stability reproduces the reference's
+//               sorted(zip(L, range(n))) tie-break by original index (:96) without carrying an index.
+//               Unused slots carry a key one bit above the largest Lf and sink to the end of the pair.
+//  bin_cut    : one CTA per length bin: 95th percentile with numpy's linear interpolation via an
+//               8-pass radix select on the fp64 bit patterns; counts the hits >= cut-off.
+//  bin_select : order-preserving compaction of the selected hits, fused with the two np.log10 calls
+//               of gathering.py:82,120 (bit-exact SVML emulation, ofg_log10.cuh).
+#pragma once
+#include "ofg_common.cuh"
+#include "ofg_log10.cuh"
+
+// ---------------------------------------------------------------- segmented stable radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
+constexpr int RS_MAX_BITS = 9;
+constexpr int RS_MAX_DIGITS = 1 << RS_MAX_BITS;
+
+struct RadixArgs {
+    const u32* key_in;
+    const double* val_in;
+    u32* key_out;
+    double* val_out;
+    const int64_t* tile_prefix;    // [P+1] sort tiles before each pair
+    const int64_t* pair_slot;      // [P+1] first slot of each pair
+    int P;
+    int64_t n_tiles;
+    int shift, bits;               // digit = (key >> shift) & ((1 << bits) - 1)
+    u32* counters;                 // [n_tiles << bits], layout [pair][digit][tile in pair]
+};
+
+__device__ __forceinline__ void rs_tile_range(const RadixArgs& a, int64_t tile, int& pair, int64_t& e0, int& cnt,
+                                              int64_t& cidx0, int64_t& ntp)
+{
+    pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
+    const int64_t t = tile - a.tile_prefix[pair];
+    ntp = a.tile_prefix[pair + 1] - a.tile_prefix[pair];
+    e0 = a.pair_slot[pair] + t * RS_TILE;
+    const int64_t rem = a.pair_slot[pair + 1] - e0;
+    cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
+    cidx0 = (a.tile_prefix[pair] << a.bits) + t;  // + digit * ntp
+}
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(RadixArgs a)
+{
+    __shared__ u32 s_hist[RS_MAX_DIGITS];
+    const int nd = 1 << a.bits;
+    const u32 mask = (u32)nd - 1u;
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int pair, cnt;
+        int64_t e0, cidx0, ntp;
+        rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
+        for (int d = threadIdx.x; d < nd; d += RS_THREADS) s_hist[d] = 0;
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt; k += RS_THREADS) atomicAdd(&s_hist[(a.key_in[e0 + k] >> a.shift) & mask], 1u);
+        __syncthreads();
+        for (int d = threadIdx.x; d < nd; d += RS_THREADS) a.counters[cidx0 + (int64_t)d * ntp] = s_hist[d];
+        __syncthreads();
+    }
+}
+
+// counters must hold the exclusive scan (global destination of the first record of each
+// (pair, digit, tile) group) when this runs.
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
+{
+    __shared__ u32 s_cnt[RS_THREADS / 32][RS_MAX_DIGITS];  // per-warp digit counts -> per-warp bases
+    __shared__ u32 s_gbase[RS_MAX_DIGITS];
+    const int nd = 1 << a.bits;
+    const u32 mask = (u32)nd - 1u;
+    const int w = threadIdx.x >> 5, lane = lane_id();
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int pair, cnt;
+        int64_t e0, cidx0, ntp;
+        rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
+        for (int d = threadIdx.x; d < nd * (RS_THREADS / 32); d += RS_THREADS) (&s_cnt[0][0])[(d / nd) * RS_MAX_DIGITS + (d % nd)] = 0;
+        for (int d = threadIdx.x; d < nd; d += RS_THREADS) s_gbase[d] = a.counters[cidx0 + (int64_t)d * ntp];
+        __syncthreads();
+        u32 key[RS_ITEMS];
+        uint16_t loc[RS_ITEMS];
+        // warp w owns records [w*512, w*512+512) of the tile, iteration it covers 32 consecutive ones:
+        // order (warp, iteration, lane) == input order, which makes the ranking stable
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int k = w * (RS_ITEMS * 32) + it * 32 + lane;
+            const bool valid = k < cnt;
+            key[it] = valid ? a.key_in[e0 + k] : 0u;
+            const u32 d = valid ? ((key[it] >> a.shift) & mask) : 0xffffffffu;
+            const u32 peers = __match_any_sync(OFG_FULL, d);
+            const int leader = __ffs(peers) - 1;
+            u32 old = 0;
+            if (valid && lane == leader) {
+                old = s_cnt[w][d];
+                s_cnt[w][d] = old + (u32)__popc(peers);
+            }
+            old = __shfl_sync(OFG_FULL, old, leader);
+            loc[it] = (uint16_t)(old + (u32)__popc(peers & lanemask_lt()));
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive prefix over warps for every digit, plus the global base
+        for (int d = threadIdx.x; d < nd; d += RS_THREADS) {
+            u32 run = s_gbase[d];
+#pragma unroll
+            for (int ww = 0; ww < RS_THREADS / 32; ww++) {
+                const u32 c = s_cnt[ww][d];
+                s_cnt[ww][d] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int k = w * (RS_ITEMS * 32) + it * 32 + lane;
+            if (k < cnt) {
+                const u32 d = (key[it] >> a.shift) & mask;
+                const u32 dst = s_cnt[w][d] + loc[it];
+                a.key_out[dst] = key[it];
+                a.val_out[dst] = a.val_in[e0 + k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- bins: percentile cut-off + selection
+constexpr int BIN_THREADS = 128;
+constexpr int BIN_MAXN = 1024;
+
+struct BinTask {      // host-built, one per length bin (or one per pair with < 100 hits: "take all")
+    u32 first;        // first sorted slot of the bin
+    u32 n;            // records in the bin
+    int32_t pair;
+    int32_t take_all; // nScores < 100 (gathering.py:100-102)
+};
+
+struct BinArgs {
+    const BinTask* tasks;
+    int64_t n_tasks;
+    const u32* key;        // sorted Lf
+    const double* val;     // scores in the same order
+    // numpy percentile(…, 95) 'linear': k = floor((n-1)*0.95), g = (n-1)*0.95 - k, for n = 20, 200, 1000
+    int k20, k200, k1000;
+    double g20, g200, g1000;
+    double* cut;           // [n_tasks]
+    u32* cnt;              // [n_tasks] selected per bin
+    const u64* sel_off;    // [n_tasks + 1] exclusive scan of cnt (bin_select only)
+    double* lx;            // out: log10(Lf) of selected hits, reference order
+    double* ly;            // out: log10(score)
+    u64 sel_cap;
+};
+
+// k-th smallest (0-based) of n positive doubles held in shared memory as bit patterns; also returns
+// how many are <= it.  Whole CTA participates.
+__device__ u64 bin_kth(const u64* s_bits, int n, int k, u32* s_hist, u32* s_tmp, int* n_le)
+{
+    u64 prefix = 0;
+    int kk = k;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int d = threadIdx.x; d < 256; d += BIN_THREADS) s_hist[d] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += BIN_THREADS) {
+            const u64 b = s_bits[i];
+            const bool match = (shift == 56) || ((b >> (shift + 8)) == prefix);
+            if (match) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // lane l owns buckets [8l, 8l+8)
+            u32 h[8], s = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { h[t] = s_hist[threadIdx.x * 8 + t]; s += h[t]; }
+            const u32 inc = warp_incl_scan(s);
+            const u32 exc = inc - s;
+            const bool mine = (u32)kk >= exc && (u32)kk < inc;
+            if (mine) {
+                u32 run = exc;
+                int bsel = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if ((u32)kk >= run && (u32)kk < run + h[t]) bsel = t;
+                    run += h[t];
+                }
+                u32 below = exc;
+                for (int t = 0; t < bsel; t++) below += h[t];
+                s_tmp[0] = (u32)(threadIdx.x * 8 + bsel);
+                s_tmp[1] = below;
+            }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | (u64)s_tmp[0];
+        kk -= (int)s_tmp[1];
+        __syncthreads();
+    }
+    // count <= value
+    if (threadIdx.x == 0) s_tmp[2] = 0;
+    __syncthreads();
+    u32 c = 0;
+    for (int i = threadIdx.x; i < n; i += BIN_THREADS) c += (s_bits[i] <= prefix);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(OFG_FULL, c, d);
+    if (lane_id() == 0 && c) atomicAdd(&s_tmp[2], c);
+    __syncthreads();
+    *n_le = (int)s_tmp[2];
+    __syncthreads();
+    return prefix;
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
+{
+    __shared__ u64 s_bits[BIN_MAXN];
+    __shared__ u32 s_hist[256];
+    __shared__ u32 s_tmp[4];
+    __shared__ u64 s_min;
+    for (int64_t t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const BinTask bt = a.tasks[t];
+        if (bt.take_all) {
+            if (threadIdx.x == 0) { a.cut[t] = 0.0; a.cnt[t] = bt.n; }
+            continue;
+        }
+        const int n = (int)bt.n;
+        for (int i = threadIdx.x; i < n; i += BIN_THREADS) s_bits[i] = (u64)__double_as_longlong(a.val[bt.first + i]);
+        __syncthreads();
+        const int k = n == 1000 ? a.k1000 : (n == 200 ? a.k200 : a.k20);
+        const double g = n == 1000 ? a.g1000 : (n == 200 ? a.g200 : a.g20);
+        int n_le;
+        const u64 ak = bin_kth(s_bits, n, k, s_hist, s_tmp, &n_le);
+        u64 ak1 = ak;
+        if (n_le <= k + 1) {  // a[k+1] is the smallest value above a[k]
+            if (threadIdx.x == 0) s_min = ~0ULL;
+            __syncthreads();
+            u64 m = ~0ULL;
+            for (int i = threadIdx.x; i < n; i += BIN_THREADS) {
+                const u64 b = s_bits[i];
+                if (b > ak && b < m) m = b;
+            }
+            if (m != ~0ULL) atomicMin(&s_min, m);
+            __syncthreads();
+            ak1 = s_min;
+            if (ak1 == ~0ULL) ak1 = ak;
+        }
+        const double va = __longlong_as_double((long long)ak), vb = __longlong_as_double((long long)ak1);
+        // numpy _lerp for gamma < 0.5: a + (b - a) * gamma, separately rounded
+        const double cut = __dadd_rn(va, __dmul_rn(__dsub_rn(vb, va), g));
+        if (threadIdx.x == 0) s_tmp[3] = 0;
+        __syncthreads();
+        u32 c = 0;
+        for (int i = threadIdx.x; i < n; i += BIN_THREADS) c += (__longlong_as_double((long long)s_bits[i]) >= cut);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(OFG_FULL, c, d);
+        if (lane_id() == 0 && c) atomicAdd(&s_tmp[3], c);
+        __syncthreads();
+        if (threadIdx.x == 0) { a.cut[t] = cut; a.cnt[t] = s_tmp[3]; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) bin_select_kernel(BinArgs a)
+{
+    __shared__ u32 s_scan[BIN_THREADS / 32 + 1];
+    for (int64_t t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const BinTask bt = a.tasks[t];
+        const double cut = a.cut[t];
+        u64 out = a.sel_off[t];
+        for (u32 i0 = 0; i0 < bt.n; i0 += BIN_THREADS) {
+            const u32 i = i0 + threadIdx.x;
+            double sc = 0.0;
+            bool sel = false;
+            if (i < bt.n) {
+                sc = a.val[bt.first + i];
+                sel = bt.take_all || (sc >= cut);
+            }
+            u32 tot;
+            const u32 ex = block_excl_scan<BIN_THREADS>(sel ? 1u : 0u, s_scan, &tot);
+            if (sel && out + ex < a.sel_cap) {
+                a.lx[out + ex] = ofg_log10_svml((double)a.key[bt.first + i]);
+                a.ly[out + ex] = ofg_log10_svml(sc);
+            }
+            out += tot;
+        }
+    }
+}

@@ -1,0 +1,375 @@
+"""Host side of the B200 orthogroup-graph builder: a drop-in for the hot path of
+gathering.DoOrthogroups (reference scripts_of/gathering.py:476-512).
+
+Two layers:
+  * GraphBuilder      — thin object wrapper over the C-ABI context (include/ofg.h).
+  * WaterfallMethod / DoOrthogroupsGraph — the reference-facing interface: same names, argument
+    meaning and error behaviour as WaterfallMethod.ProcessBlastHits / ConnectCognates /
+    WriteGraphParallel, taking a util.SequencesInfo-shaped object and the blast directory list and
+    producing OrthoFinder_graph.txt.
+
+All numerics run in hand-written CUDA kernels inside libofg.so; this module only moves bytes
+(file -> pinned host -> device, device -> file) and translates error codes into the reference's
+messages.  There is no CPU fallback.
+"""
+import ctypes
+import gzip
+import os
+import sys
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+
+# util.py:54-61
+SequencesInfo = namedtuple("SequencesInfo", "nSeqs nSpecies speciesToUse seqStartingIndices nSeqsPerSpecies")
+
+
+class OfgError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("%s: %s" % (_lib.ERR_NAMES.get(code, str(code)), message))
+        self.code = code
+        self.message = message
+
+
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class GraphBuilder:
+    """One context per GPU (include/ofg.h).  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.ofg_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise OfgError(rc, "ofg_create failed on device %d (is a CUDA device visible?)" % device)
+        self.h = h
+        self.device = device
+        self.S = 0
+        self.n_seqs = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ofg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise OfgError(rc, self.lib.ofg_last_error(self.h).decode(errors="replace"))
+
+    # ---- inputs
+    def set_species(self, n_seqs, lengths):
+        """n_seqs[p], lengths[p] (fp64 vectors) per used species in list order
+        (util.SequencesInfo + gathering.GetSequenceLengths)."""
+        n = np.ascontiguousarray(n_seqs, dtype=np.int64)
+        L = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.float64) for x in lengths]) if len(lengths)
+                                 else np.zeros(0))
+        assert L.size == int(n.sum()), "lengths do not match n_seqs"
+        self._ck(self.lib.ofg_set_species(self.h, len(n), _vp(n), _vp(L)))
+        self.S = len(n)
+        self.n_seqs = [int(x) for x in n]
+
+    def set_partition(self, owned_rows, with_columns):
+        o = np.ascontiguousarray(owned_rows, dtype=np.int32)
+        self._ck(self.lib.ofg_set_partition(self.h, len(o), _vp(o), int(bool(with_columns))))
+
+    def set_option(self, name, value):
+        self._ck(self.lib.ofg_set_option(self.h, name.encode(), int(value)))
+
+    def add_hits(self, p, j, data, swap_cols=False):
+        """data: bytes-like / numpy uint8 host buffer, or (device_ptr, nbytes) tuple."""
+        if isinstance(data, tuple):
+            ptr, n = data
+            self._ck(self.lib.ofg_add_hits_text(self.h, p, j, ctypes.c_void_p(ptr), n, int(swap_cols), 1))
+            return
+        if isinstance(data, np.ndarray):
+            buf = np.ascontiguousarray(data, dtype=np.uint8)
+            self._ck(self.lib.ofg_add_hits_text(self.h, p, j, _vp(buf), buf.size, int(swap_cols), 0))
+            return
+        b = bytes(data)
+        self._ck(self.lib.ofg_add_hits_text(self.h, p, j, ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), len(b),
+                                            int(swap_cols), 0))
+
+    def add_hits_ptr(self, p, j, host_ptr, nbytes, swap_cols=False):
+        self._ck(self.lib.ofg_add_hits_text(self.h, p, j, ctypes.c_void_p(host_ptr), nbytes, int(swap_cols), 0))
+
+    def clear_hits(self):
+        self._ck(self.lib.ofg_clear_hits(self.h))
+
+    def synth_hits(self, params, species_ids):
+        ids = np.ascontiguousarray(species_ids, dtype=np.int32)
+        self._ck(self.lib.ofg_synth_hits(self.h, ctypes.byref(params), _vp(ids)))
+
+    def hits_text(self, p, j):
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.ofg_hits_text_size(self.h, p, j, ctypes.byref(n)))
+        buf = np.empty(max(n.value, 1), np.uint8)
+        self._ck(self.lib.ofg_hits_text_copy(self.h, p, j, _vp(buf), n.value))
+        return buf[:n.value].tobytes()
+
+    def hits_text_size(self, p, j):
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.ofg_hits_text_size(self.h, p, j, ctypes.byref(n)))
+        return n.value
+
+    def hits_text_into(self, p, j, host_ptr, cap):
+        self._ck(self.lib.ofg_hits_text_copy(self.h, p, j, ctypes.c_void_p(host_ptr), cap))
+
+    # ---- run
+    def build(self, stop_after=_lib.STAGE_GRAPH):
+        self._ck(self.lib.ofg_build(self.h, int(stop_after)))
+
+    # ---- outputs
+    def counts(self):
+        a, b, c, d = (ctypes.c_int64(0) for _ in range(4))
+        self._ck(self.lib.ofg_counts(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return dict(lines=a.value, records=b.value, nnz=c.value, edges=d.value)
+
+    def timing(self):
+        ms = np.zeros(10, np.float32)
+        n = ctypes.c_int64(0)
+        self._ck(self.lib.ofg_last_timing(self.h, _vp(ms), ctypes.byref(n)))
+        names = ["parse", "rows", "length_sort", "select", "fit", "scale_bh", "thresholds", "connect", "emit", "total"]
+        d = {k: float(v) for k, v in zip(names, ms)}
+        d["launches"] = n.value
+        return d
+
+    def pair_csr(self, p, j):
+        nr, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._ck(self.lib.ofg_pair_csr(self.h, p, j, ctypes.byref(nr), ctypes.byref(nnz), None, None, None))
+        rl = np.zeros(max(nr.value, 1), np.int32)
+        cols = np.zeros(max(nnz.value, 1), np.uint32)
+        vals = np.zeros(max(nnz.value, 1), np.float64)
+        self._ck(self.lib.ofg_pair_csr(self.h, p, j, ctypes.byref(nr), ctypes.byref(nnz), _vp(rl), _vp(cols), _vp(vals)))
+        rl = rl[:nr.value]
+        indptr = np.concatenate(([0], np.cumsum(rl, dtype=np.int64)))
+        return indptr, cols[:nnz.value], vals[:nnz.value]
+
+    def pair_fit(self, p, j):
+        out = np.zeros(6)
+        self._ck(self.lib.ofg_pair_fit(self.h, p, j, _vp(out)))
+        return dict(a=out[0], b=out[1], m=int(out[2]), info=int(out[3]), nfev=int(out[4]), normalised=bool(out[5]))
+
+    def thresholds(self):
+        n = int(sum(self.n_seqs))
+        out = np.zeros(max(n, 1))
+        self._ck(self.lib.ofg_thresholds_copy(self.h, _vp(out), n))
+        return out[:n]
+
+    def thresholds_dev(self):
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64(0)
+        self._ck(self.lib.ofg_thresholds_dev(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def thresholds_mark_complete(self):
+        self._ck(self.lib.ofg_thresholds_mark_complete(self.h))
+
+    def graph_csr(self):
+        nr, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._ck(self.lib.ofg_graph_csr_size(self.h, ctypes.byref(nr), ctypes.byref(nnz)))
+        rows = np.zeros(max(nr.value, 1), np.int64)
+        indptr = np.zeros(nr.value + 1, np.int64)
+        idx = np.zeros(max(nnz.value, 1), np.int32)
+        dat = np.zeros(max(nnz.value, 1), np.float64)
+        self._ck(self.lib.ofg_graph_csr_copy(self.h, _vp(rows), _vp(indptr), _vp(idx), _vp(dat)))
+        return rows[:nr.value], indptr, idx[:nnz.value], dat[:nnz.value]
+
+    def graph_text_size(self):
+        n = ctypes.c_size_t(0)
+        self._ck(self.lib.ofg_graph_text_size(self.h, ctypes.byref(n)))
+        return n.value
+
+    def graph_text_body(self, out=None):
+        n = self.graph_text_size()
+        buf = out if out is not None else np.empty(max(n, 1), np.uint8)
+        assert buf.size >= n
+        self._ck(self.lib.ofg_graph_text_copy(self.h, _vp(buf), n))
+        return buf[:n]
+
+
+def graph_header(n_seqs_total):
+    """gathering.py:279-280."""
+    return ("(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (n_seqs_total, n_seqs_total)).encode() + \
+        b"\n(mclmatrix\nbegin\n\n"
+
+
+GRAPH_FOOTER = b")\n"  # gathering.py:48, written after the last species
+
+
+# --------------------------------------------------------------------------------------------------
+# Reference-facing interface
+# --------------------------------------------------------------------------------------------------
+def GetSpeciesToUse(speciesIDsFN):
+    """util.py:178-192 (host; not part of the device path)."""
+    use, skipped = [], 0
+    with open(speciesIDsFN) as f:
+        for line in f:
+            line = line.rstrip()
+            if not line:
+                continue
+            if line.startswith("#"):
+                skipped += 1
+            else:
+                use.append(int(line.split(": ")[0]))
+    return use, len(use) + skipped
+
+
+def GetSeqsInfo(inputDirectory_list, speciesToUse, nSpAll):
+    """util.py:64-84."""
+    starts, n, per = [0], 0, {}
+    for k in range(nSpAll):
+        for d in inputDirectory_list:
+            fn = os.path.join(d, "Species%d.fa" % k)
+            if os.path.exists(fn):
+                break
+        c = 0
+        with open(fn) as f:
+            for line in f:
+                if len(line) > 1 and line[0] == ">":
+                    c += 1
+        per[k] = c
+        if k in speciesToUse:
+            n += c
+            starts.append(n)
+    return SequencesInfo(nSeqs=n, nSpecies=len(speciesToUse), speciesToUse=list(speciesToUse),
+                         seqStartingIndices=starts[:-1], nSeqsPerSpecies=per)
+
+
+def GetSequenceLengths(seqsInfo, fasta_dir_list):
+    """gathering.py:444-464: one fp64 vector per used species."""
+    out = []
+    for k in seqsInfo.speciesToUse:
+        L = np.zeros(seqsInfo.nSeqsPerSpecies[k])
+        for d in fasta_dir_list:
+            fn = os.path.join(d, "Species%d.fa" % k)
+            if os.path.exists(fn):
+                break
+        cur, idx, first = 0, -1, True
+        with open(fn) as f:
+            for row in f:
+                if len(row) > 1 and row[0] == ">":
+                    if first:
+                        first = False
+                    else:
+                        L[idx] = cur
+                        cur = 0
+                    idx = int(row[1:].split("_")[1])
+                else:
+                    cur += len(row.rstrip())
+        L[idx] = cur
+        out.append(L)
+    return out
+
+
+def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
+    """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted)."""
+    fn = None
+    for d in blastDir_list:
+        fn = os.path.join(d, "Blast%d_%d.txt" % (iSpecies, jSpecies))
+        if os.path.exists(fn) or os.path.exists(fn + ".gz"):
+            break
+    if not os.path.exists(fn) and not os.path.exists(fn + ".gz"):
+        if q_allow_empty:
+            return None, fn
+        raise FileNotFoundError(fn)
+    if os.path.exists(fn + ".gz"):
+        with gzip.open(fn + ".gz", "rb") as f:
+            return f.read(), fn
+    with open(fn, "rb") as f:
+        return f.read(), fn
+
+
+class WaterfallMethod:
+    """Mirror of gathering.WaterfallMethod for the graph hot path, backed by libofg."""
+
+    @staticmethod
+    def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
+                   builder=None):
+        """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
+        the device-resident graph.  Returns the GraphBuilder holding it."""
+        if v2_scores:
+            raise NotImplementedError("--scores-v2 (gathering.py:157-174,314-388) is not on the device path yet")
+        gb = builder or GraphBuilder(device)
+        sp = list(seqsInfo.speciesToUse)
+        n_seqs = [seqsInfo.nSeqsPerSpecies[k] for k in sp]
+        gb.set_species(n_seqs, Lengths)
+        gb.set_option("allow_empty", int(q_allow_empty))
+        for p, kp in enumerate(sp):
+            for j, kj in enumerate(sp):
+                swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54
+                data, fn = _read_hit_file(blastDir_list, kj if swap else kp, kp if swap else kj, q_allow_empty)
+                if data is not None:
+                    gb.add_hits(p, j, data, swap_cols=swap)
+        try:
+            gb.build(_lib.STAGE_GRAPH)
+        except OfgError as e:
+            WaterfallMethod._report(e, sp, blastDir_list)
+            raise
+        for p in range(len(sp)):
+            for j in range(len(sp)):
+                f = gb.pair_fit(p, j)
+                if not f["normalised"]:
+                    # gathering.py:146-155
+                    if p == j and f["m"] == 0:
+                        print("WARNING: THIS IS UNCOMMON, there are zero hits when searching the genes in species %d "
+                              "against itself. Check the input proteome contains all the genes from that species and "
+                              "check the search program is working (default is diamond)." % p)
+                    else:
+                        print("WARNING: Too few hits between species %d and species %d to normalise the scores, "
+                              "these hits will be ignored" % (p, j))
+        return gb
+
+    @staticmethod
+    def _report(e, sp, blastDir_list):
+        """Reproduce the reference's messages (blast_file_processor.py:74-103, gathering.py:209)."""
+        msg = e.message
+        if e.code in (_lib.ERR_PARSE, _lib.ERR_INCONSISTENT, _lib.ERR_UNSUPPORTED) and msg.startswith("pair="):
+            head, line = msg.split(" line=", 1)
+            p, j = [int(x) for x in head.split()[0][5:].split(",")]
+            kind = int(head.split("kind=")[1].split()[0])
+            i_sp, j_sp = sp[p], sp[j]
+            if e.code == _lib.ERR_INCONSISTENT:
+                sys.stderr.write("\nERROR: Inconsistent input files.\n")
+            elif kind == 1:
+                sys.stderr.write("\nERROR: Query or hit sequence ID in BLAST results file was missing or incorrectly formatted.\n")
+            elif kind in (2, 6):
+                sys.stderr.write("\nERROR: 12th field in BLAST results file line should be the bit-score for the hit\n")
+            print("ERROR: Blast%d_%d.txt is corrupted" % (i_sp, j_sp))
+            sys.stderr.write("Malformatted line in %sBlast%d_%d.txt\nOffending line was:\n" % (blastDir_list[0], i_sp, j_sp))
+            sys.stderr.write(line + "\n")
+            print("ERROR: Error processing files Blast%d_*" % i_sp)
+
+    @staticmethod
+    def WriteGraphParallel(gb, seqsInfo, graphFN):
+        """gathering.py:273-291: header, rows of every species, ')' — one file."""
+        with open(graphFN, "wb") as f:
+            f.write(graph_header(seqsInfo.nSeqs))
+            f.write(gb.graph_text_body().tobytes())
+            f.write(GRAPH_FOOTER)
+        return graphFN
+
+
+def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empty=False, device=0):
+    """The part of gathering.DoOrthogroups between :476 and :512 for a `-b <dir> -og` run: reads
+    SpeciesIDs.txt / Species*.fa / Blast*_*.txt from workingDir and writes OrthoFinder_graph.txt."""
+    if not workingDir.endswith(os.sep):
+        workingDir += os.sep
+    sp, n_all = GetSpeciesToUse(workingDir + "SpeciesIDs.txt")
+    si = GetSeqsInfo([workingDir], sp, n_all)
+    L = GetSequenceLengths(si, [workingDir])
+    gb = WaterfallMethod.BuildGraph(si, [workingDir], L, qDoubleBlast=qDoubleBlast, q_allow_empty=q_allow_empty,
+                                    device=device)
+    if graphFN is None:
+        graphFN = workingDir + "OrthoFinder_graph.txt"  # files.py:324-327 GetGraphFilename
+    WaterfallMethod.WriteGraphParallel(gb, si, graphFN)
+    return graphFN, gb, si
