@@ -213,8 +213,8 @@ def test_shuffled_lines_long_rows_and_long_lines(gb):
         rng.shuffle(lines)
         texts[k] = b"\n".join(lines) + b"\n"
     # one query of species 0 hits every gene of species 1 (400 > 256), each with a duplicate HSP
-    extra = b"".join(_mk(5, s, b"%d.5" % (40 + (s * 7) % 90)) + _mk(5, s, b"33") for s in range(g.n_seqs[1]))
-    texts[(0, 1)] = extra[:len(extra) // 2] + texts[(0, 1)] + extra[len(extra) // 2:]
+    extra = [_mk(5, s, b"%d.5" % (40 + (s * 7) % 90)) + _mk(5, s, b"33") for s in range(g.n_seqs[1])]
+    texts[(0, 1)] = b"".join(extra[:150]) + texts[(0, 1)] + b"".join(extra[150:])
     long_line = _mk(7, 3, b"88.8")[:-1] + b"\t" + b"x" * 3000 + b"\n"
     texts[(0, 1)] += long_line
     _oracle_vs_device(gb, g.n_seqs, g.lengths, texts)
