@@ -139,6 +139,9 @@ int ofg_graph_text_copy(ofg_ctx* ctx, void* host_dst, size_t cap);
  * 0 parse, 1 rows (bucket + row sort), 2 length sort, 3 select, 4 fit, 5 scale+BH, 6 thresholds,
  * 7 connect, 8 emit, 9 total.  n_launches = kernels launched by the last build. */
 int ofg_last_timing(ofg_ctx* ctx, float ms[10], int64_t* n_launches);
+/* Per-kernel device time of the last build: one text line "name launches total_ms" per kernel, measured
+ * with CUDA events recorded after every launch on the library's stream (host-sync gaps excluded). */
+int ofg_kernel_report(ofg_ctx* ctx, char* buf, size_t cap);
 /* Stream the library launches on (cudaStream_t), so callers can record their own events on it. */
 void* ofg_stream(ofg_ctx* ctx);
 

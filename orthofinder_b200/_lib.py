@@ -17,7 +17,7 @@ SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "of
            "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_build",
            "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_counts", "ofg_pair_csr",
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
-           "ofg_last_timing", "ofg_stream", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
+           "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
 _lib = None
 
@@ -60,6 +60,7 @@ def load():
         "ofg_graph_text_size": [vp, ctypes.POINTER(sz)],
         "ofg_graph_text_copy": [vp, vp, sz],
         "ofg_last_timing": [vp, vp, ctypes.POINTER(i64)],
+        "ofg_kernel_report": [vp, ctypes.c_char_p, sz],
         "ofg_test_log10": [vp, vp, vp, i64],
         "ofg_test_format": [vp, vp, vp, i64],
         "ofg_test_parse_score": [vp, ctypes.c_char_p, i64, vp, vp, i64],

@@ -97,6 +97,10 @@ struct ofg_ctx {
     float ms[10] = {0};
     int64_t launches = 0;
     cudaEvent_t ev[12] = {nullptr};
+    cudaEvent_t tl_ev[192] = {nullptr};
+    const char* tl_name[192] = {nullptr};
+    int tl_n = 0;
+    std::string kernel_report;
 };
 
 namespace {
@@ -118,12 +122,27 @@ int fail(ofg_ctx* c, int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(c, OFG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-#define CKL()                                                                                            \
+#define CKL(name)                                                                                        \
     do {                                                                                                 \
         c->launches++;                                                                                   \
+        note_launch(c, name);                                                                            \
         cudaError_t e_ = cudaGetLastError();                                                             \
         if (e_ != cudaSuccess) return fail(c, OFG_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// per-kernel timeline: one event after every launch (cheap), resolved after the build
+void note_launch(ofg_ctx* c, const char* name)
+{
+    if (c->tl_n >= (int)(sizeof(c->tl_ev) / sizeof(c->tl_ev[0]))) return;
+    if (!c->tl_ev[c->tl_n]) cudaEventCreate(&c->tl_ev[c->tl_n]);
+    cudaEventRecord(c->tl_ev[c->tl_n], c->stream);
+    c->tl_name[c->tl_n] = name;
+    c->tl_n++;
+}
+void mark_timeline(ofg_ctx* c)  // start-of-segment marker (after a host sync the previous event is stale)
+{
+    note_launch(c, nullptr);
+}
 
 int grid_for(ofg_ctx* c, int64_t work_items, int per_cta, int ctas_per_sm)
 {
@@ -164,7 +183,7 @@ __global__ void test_score_kernel(const uint8_t* text, int64_t nbytes, const int
 }
 __global__ void __launch_bounds__(FIT_THREADS) test_fit_kernel(const double* lx, const double* ly, long m, double* scratch, double* out)
 {
-    __shared__ FitShared sh;
+    __shared__ __align__(16) FitShared sh;
     fit_loglinear(lx, ly, m, scratch, scratch + m, scratch + 2 * m, scratch + 3 * m, &sh, out);
 }
 
@@ -180,11 +199,11 @@ int device_scan(ofg_ctx* c, const u32* in, int64_t n, TO* out, int write_total)
     TO* part = c->scan_partial.as<TO>();
     const int g = grid_for(c, n_chunks, 1, 8);
     scan_reduce_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part);
-    CKL();
+    CKL("scan_reduce_kernel<TO>");
     scan_partials_kernel<TO><<<1, 1024, 0, c->stream>>>(part, n_chunks, (TO*)nullptr);
-    CKL();
+    CKL("scan_partials_kernel<TO>");
     scan_apply_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part, out, write_total);
-    CKL();
+    CKL("scan_apply_kernel<TO>");
     return 0;
 }
 
@@ -289,6 +308,7 @@ void describe_line(ofg_ctx* c, int pair, u64 errword, std::string* out)
 // ------------------------------------------------------------------------------------------ stages
 int stage_raw(ofg_ctx* c)
 {
+    mark_timeline(c);
     const int P = (int)c->pairs.size();
     // text offsets into the descriptors
     int64_t total_padded = 0;
@@ -343,13 +363,14 @@ int stage_raw(ofg_ctx* c)
         a.cap = cap; a.coo_count = sm; a.rowcount = c->rowcount.as<u32>();
         a.pair_lines = d_pair_lines; a.pair_valid = d_pair_valid; a.pair_err = d_pair_err;
         parse_kernel<<<grid_for(c, n_tiles, 1, 8), PARSE_THREADS, 0, c->stream>>>(a);
-        CKL();
+        CKL("parse_kernel");
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
     // host sync 1: line counts, errors
     std::vector<u64> small(small_words);
     CK(cudaMemcpyAsync(small.data(), sm, small_words * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);
     c->pair_lines.assign(small.begin() + 8, small.begin() + 8 + P);
     c->pair_valid.assign(small.begin() + 8 + P, small.begin() + 8 + 2 * P);
     const u64 coo_count = small[0];
@@ -381,7 +402,7 @@ int stage_raw(ofg_ctx* c)
         scatter_rows_kernel<<<grid_for(c, (int64_t)coo_count, 256 * 8, 8), 256, 0, c->stream>>>(
             c->coo_row.as<u32>(), c->coo_col.as<u32>(), c->coo_val.as<double>(), coo_count, c->row_start.as<u32>(),
             c->rowlen.as<u32>(), c->cols.as<u32>(), c->vals.as<double>());
-        CKL();
+        CKL("scatter_rows_kernel");
     }
     // sentinel key: one bit above the largest possible length product
     double maxL = 1.0;
@@ -400,15 +421,16 @@ int stage_raw(ofg_ctx* c)
     r.scratch_cols = c->coo_col.as<u32>(); r.scratch_vals = c->coo_val.as<double>();
     if (c->n_rows > 0) {
         rowsort_kernel<<<grid_for(c, c->n_rows, ROWSORT_WARPS, 16), ROWSORT_WARPS * 32, 0, c->stream>>>(r);
-        CKL();
+        CKL("rowsort_kernel");
         rowsort_long_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(r);
-        CKL();
+        CKL("rowsort_long_kernel");
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
     // host sync 2: stored entries per pair
     std::vector<u64> nnz(P);
     CK(cudaMemcpyAsync(nnz.data(), d_pair_nnz, sizeof(u64) * P, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);
     c->pair_nnz = nnz;
     c->tot_nnz = 0;
     for (int i = 0; i < P; i++) c->tot_nnz += (int64_t)nnz[i];
@@ -421,6 +443,7 @@ int stage_raw(ofg_ctx* c)
 
 int stage_norm(ofg_ctx* c)
 {
+    mark_timeline(c);
     const int P = (int)c->pairs.size();
     u64* sm = c->d_small.as<u64>();
     u32* err_flags = (u32*)(sm + 2);
@@ -450,10 +473,10 @@ int stage_norm(ofg_ctx* c)
             a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
             const int g = grid_for(c, n_tiles, 1, 6);
             radix_hist_kernel<<<g, RS_THREADS, 0, c->stream>>>(a);
-            CKL();
+            CKL("radix_hist_kernel");
             if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
             radix_scatter_kernel<<<g, RS_THREADS, 0, c->stream>>>(a);
-            CKL();
+            CKL("radix_scatter_kernel");
             std::swap(kin, kout);
             std::swap(vin, vout);
         }
@@ -503,10 +526,10 @@ int stage_norm(ofg_ctx* c)
     if (n_tasks > 0) {
         const int g = grid_for(c, n_tasks, 1, 12);
         bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
-        CKL();
+        CKL("bin_cut_kernel");
         if (device_scan<u64>(c, b.cnt, n_tasks, c->sel_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         bin_select_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
-        CKL();
+        CKL("bin_select_kernel");
     } else {
         CK(cudaMemsetAsync(c->sel_off.p, 0, 16, c->stream));
     }
@@ -515,14 +538,14 @@ int stage_norm(ofg_ctx* c)
     CK(c->pair_sel_off.ensure((size_t)(P + 2) * 8));
     gather_u64_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(c->sel_off.as<u64>(), c->task_prefix.as<u64>(), P + 1,
                                                                    c->pair_sel_off.as<u64>());
-    CKL();
+    CKL("gather_u64_kernel");
     FitArgs f;
     f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
     f.fvec = c->fvec.as<double>(); f.wa4 = c->wa4.as<double>(); f.c0 = c->c0.as<double>(); f.c1 = c->c1.as<double>();
     f.fit = c->fit.as<double>(); f.err_flags = err_flags;
     if (P > 0) {
         fit_kernel<<<P, FIT_THREADS, 0, c->stream>>>(f);
-        CKL();
+        CKL("fit_kernel");
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
     // ---- factors, scale, best hits
@@ -540,7 +563,7 @@ int stage_norm(ofg_ctx* c)
         for (int i = 0; i < P; i++) maxg = std::max<int64_t>(maxg, (int64_t)c->pairs[i].Gi + c->pairs[i].Gj);
         dim3 g((unsigned)std::min<int64_t>((maxg + 255) / 256, 64), (unsigned)P);
         factors_kernel<<<g, 256, 0, c->stream>>>(fa);
-        CKL();
+        CKL("factors_kernel");
         ScaleArgs sa;
         sa.n_rows = c->n_rows; sa.row_start = c->row_start.as<u32>(); sa.rowlen = c->rowlen.as<u32>();
         sa.cols = c->cols.as<u32>(); sa.vals = c->vals.as<double>(); sa.pairs = c->d_pairs.as<PairDesc>();
@@ -549,9 +572,9 @@ int stage_norm(ofg_ctx* c)
         sa.best = c->best.as<double>();
         const int g2 = grid_for(c, c->n_rows, 8, 8);
         scale_bh_kernel<<<g2, 256, 0, c->stream>>>(sa);
-        CKL();
+        CKL("scale_bh_kernel");
         bh_self_kernel<<<g2, 256, 0, c->stream>>>(sa);
-        CKL();
+        CKL("bh_self_kernel");
     }
     CK(cudaEventRecord(c->ev[6], c->stream));
     // host sync 3: fit table, error flags
@@ -560,6 +583,7 @@ int stage_norm(ofg_ctx* c)
     if (P > 0) CK(cudaMemcpyAsync(c->fit_host.data(), c->fit.p, (size_t)P * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);
     if (flags & 2u)
         return fail(c, OFG_ERR_CAPACITY, "selection capacity exceeded (%llu points); lower option sel_capacity_frac_inv", (unsigned long long)c->sel_cap);
     if (flags & 1u) {
@@ -574,6 +598,7 @@ int stage_norm(ofg_ctx* c)
 
 int stage_thresh(ofg_ctx* c)
 {
+    mark_timeline(c);
     const int P = (int)c->pairs.size();
     // owned gene mask and initial thresholds: 1e9 for owned genes (gathering.py:296), +inf elsewhere
     std::vector<uint8_t> og((size_t)c->N + 1, 0);
@@ -582,17 +607,18 @@ int stage_thresh(ofg_ctx* c)
         for (int64_t g = c->seq_start[p]; g < c->seq_start[p] + c->n_seqs[p]; g++) { og[g] = 1; init[g] = 1e9; }
     if (upload(c, c->owned_gene, og.data(), og.size())) return OFG_ERR_CUDA;
     if (upload(c, c->most, init.data(), init.size() * 8)) return OFG_ERR_CUDA;
-    CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+    CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);  // host vectors go out of scope
     if (P > 0 && c->n_rows > 0) {
         GraphArgs g;
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
         g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
         g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
         rbh_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(g);
-        CKL();
+        CKL("rbh_kernel");
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
                                                                                c->owned_gene.as<uint8_t>(), c->N);
-        CKL();
+        CKL("thresh_final_kernel");
     }
     CK(cudaEventRecord(c->ev[7], c->stream));
     c->thresholds_complete = ((int)c->owned.size() == c->S);
@@ -602,6 +628,7 @@ int stage_thresh(ofg_ctx* c)
 
 int stage_graph(ofg_ctx* c)
 {
+    mark_timeline(c);
     const int P = (int)c->pairs.size();
     if (!c->thresholds_complete)
         return fail(c, OFG_ERR_ARG, "thresholds of species owned by other contexts are missing: exchange them and call ofg_thresholds_mark_complete");
@@ -613,7 +640,7 @@ int stage_graph(ofg_ctx* c)
     g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
     if (P > 0 && c->n_rows > 0) {
         connect_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(g);
-        CKL();
+        CKL("connect_kernel");
     }
     CK(cudaEventRecord(c->ev[8], c->stream));
     // emission units: owned genes (list order) x S
@@ -627,6 +654,7 @@ int stage_graph(ofg_ctx* c)
     if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
     if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
     CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);
     CK(c->unit_cnt.ensure((size_t)(n_units + 1) * 4));
     CK(c->unit_bytes.ensure((size_t)(n_units + 1) * 4));
     CK(c->cnt_off.ensure((size_t)(n_units + 2) * 8));
@@ -641,25 +669,27 @@ int stage_graph(ofg_ctx* c)
     if (n_units > 0) {
         const int ge = grid_for(c, n_units, 8, 8);
         emit_kernel<false><<<ge, 256, 0, c->stream>>>(e);
-        CKL();
+        CKL("emit_kernel<false>");
         if (device_scan<u64>(c, e.unit_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         if (device_scan<u64>(c, e.unit_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         u64 tots[2] = {0, 0};
         CK(cudaMemcpyAsync(&tots[0], c->cnt_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(&tots[1], c->byte_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));  // host sync 4: output sizes
+        CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);  // host sync 4: output sizes
         c->tot_edges = (int64_t)tots[0]; c->tot_text = (int64_t)tots[1];
         CK(c->out_indices.ensure((size_t)(tots[0] + 16) * 4));
         CK(c->out_data.ensure((size_t)(tots[0] + 16) * 8));
         CK(c->out_text.ensure((size_t)tots[1] + 64));
         e.out_indices = c->out_indices.as<int32_t>(); e.out_data = c->out_data.as<double>(); e.out_text = c->out_text.as<char>();
         emit_kernel<true><<<ge, 256, 0, c->stream>>>(e);
-        CKL();
+        CKL("emit_kernel<true>");
     }
     CK(cudaEventRecord(c->ev[9], c->stream));
     u32 flags = 0;
     CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    mark_timeline(c);
     if (flags & 4u) return fail(c, OFG_ERR_UNSUPPORTED, "a graph weight is too large for \"%%.3f\" formatting on the device");
     c->stage_done = OFG_STAGE_GRAPH;
     return 0;
@@ -815,7 +845,7 @@ int ofg_synth_hits(ofg_ctx* c, const ofg_synth_params* params, const int32_t* sp
     a.text = nullptr;
     const int g = grid_for(c, c->n_rows, 128, 16);
     synth_kernel<false><<<g, 128, 0, c->stream>>>(a);
-    CKL();
+    CKL("synth_kernel<false>");
     if (device_scan<u64>(c, a.row_bytes, c->n_rows, c->synth_off.as<u64>(), 1)) return OFG_ERR_CUDA;
     std::vector<u64> offs((size_t)c->n_rows + 1);
     CK(cudaMemcpyAsync(offs.data(), c->synth_off.p, offs.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -836,7 +866,7 @@ int ofg_synth_hits(ofg_ctx* c, const ofg_synth_params* params, const int32_t* sp
     if (upload(c, c->file_off, file_off.data(), sizeof(int64_t) * P)) return OFG_ERR_CUDA;
     a.text = c->text.as<uint8_t>();
     synth_kernel<true><<<g, 128, 0, c->stream>>>(a);
-    CKL();
+    CKL("synth_kernel<true>");
     CK(cudaStreamSynchronize(c->stream));
     c->text_used = used;
     c->stage_done = 0;
@@ -875,6 +905,7 @@ int ofg_build(ofg_ctx* c, int stop_after)
     if (c->stage_done >= stop_after) c->stage_done = 0;  // asked for a stage that is already built: rebuild from the text
     const bool fresh = c->stage_done == 0;
     if (fresh) {
+        c->tl_n = 0;
         c->launches = 0;
         for (int i = 0; i < 10; i++) c->ms[i] = 0.f;
     }
@@ -909,6 +940,29 @@ int ofg_build(ofg_ctx* c, int stop_after)
         for (int k = 0; k < 9; k++) tot += c->ms[k];
         c->ms[9] = tot;
     }
+    return OFG_OK;
+}
+
+int ofg_kernel_report(ofg_ctx* c, char* buf, size_t cap)
+{
+    if (!c || !buf || cap == 0) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    struct Agg { const char* name; int n; double ms; };
+    std::vector<Agg> agg;
+    for (int i = 1; i < c->tl_n; i++) {
+        if (!c->tl_name[i]) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->tl_ev[i - 1], c->tl_ev[i]) != cudaSuccess) continue;
+        bool found = false;
+        for (auto& a : agg) if (!strcmp(a.name, c->tl_name[i])) { a.n++; a.ms += t; found = true; break; }
+        if (!found) agg.push_back(Agg{c->tl_name[i], 1, (double)t});
+    }
+    std::string r;
+    char line[256];
+    for (auto& a : agg) { snprintf(line, sizeof line, "%s %d %.6f\n", a.name, a.n, a.ms); r += line; }
+    if (r.size() + 1 > cap) return fail(c, OFG_ERR_ARG, "report buffer too small");
+    memcpy(buf, r.c_str(), r.size() + 1);
     return OFG_OK;
 }
 
@@ -1067,7 +1121,7 @@ int ofg_test_log10(ofg_ctx* c, const double* host_x, double* host_y, int64_t n)
     CK(x.ensure((size_t)n * 8)); CK(y.ensure((size_t)n * 8));
     CK(cudaMemcpyAsync(x.p, host_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     test_log10_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(x.as<double>(), y.as<double>(), n);
-    CKL();
+    CKL("test_log10_kernel");
     CK(cudaMemcpyAsync(host_y, y.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     x.release(); y.release();
@@ -1083,7 +1137,7 @@ int ofg_test_format(ofg_ctx* c, const double* host_x, char* host_out, int64_t n)
     CK(cudaMemcpyAsync(x.p, host_x, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemsetAsync(o.p, 0, (size_t)n * 32, c->stream));
     test_format_kernel<<<grid_for(c, n, 256, 8), 256, 0, c->stream>>>(x.as<double>(), o.as<char>(), n);
-    CKL();
+    CKL("test_format_kernel");
     CK(cudaMemcpyAsync(host_out, o.p, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     x.release(); o.release();
@@ -1103,7 +1157,7 @@ int ofg_test_parse_score(ofg_ctx* c, const char* host_text, int64_t nbytes, doub
     CK(cudaMemcpyAsync(t.p, host_text, (size_t)nbytes, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(s.p, starts.data(), (size_t)n_fields * 8, cudaMemcpyHostToDevice, c->stream));
     test_score_kernel<<<grid_for(c, n_fields, 256, 8), 256, 0, c->stream>>>(t.as<uint8_t>(), nbytes, s.as<int64_t>(), n_fields, y.as<double>(), k.as<int32_t>());
-    CKL();
+    CKL("test_score_kernel");
     CK(cudaMemcpyAsync(host_y, y.p, (size_t)n_fields * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(host_ok, k.p, (size_t)n_fields * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1120,7 +1174,7 @@ int ofg_test_lmfit(ofg_ctx* c, const double* host_lx, const double* host_ly, int
     CK(cudaMemcpyAsync(x.p, host_lx, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(y.p, host_ly, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
     test_fit_kernel<<<1, FIT_THREADS, 0, c->stream>>>(x.as<double>(), y.as<double>(), (long)m, s.as<double>(), o.as<double>());
-    CKL();
+    CKL("test_fit_kernel");
     double h[8];
     CK(cudaMemcpyAsync(h, o.p, 48, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -40,13 +40,30 @@
 #define FSQRT(a) sqrt((a))
 #endif
 
-#define FIT_CH 1024  // doubles staged per chunk for the sequential chains
+#define FIT_CH 512   // doubles staged per chunk and buffer for the sequential chains
+#define FIT_MAXV 3   // chains that can run side by side (one per warp)
 
-struct FitShared {  // lives in shared memory on the device
-    double a[FIT_CH];
-    double b[FIT_CH];
-    double out;
+struct FitShared {  // lives in shared memory on the device (24.6 KB)
+    double buf[FIT_MAXV][2][FIT_CH];  // staged squares (enorm) / products (dot), double buffered
+    double out[FIT_MAXV];
+    int tag[FIT_MAXV][2];             // chunk tag set when a staged chunk holds a value outside MINPACK's mid range
 };
+
+// ordered sum of n staged terms (n even-aligned buffer), two per 16-byte shared-memory load
+FIT_FN double fit_ordered_sum(double s, const double* q, int len)
+{
+    int i = 0;
+#if defined(__CUDACC__)
+    const double2* q2 = reinterpret_cast<const double2*>(q);
+    for (; i + 8 <= len; i += 8) {
+        const double2 a = q2[(i >> 1)], b = q2[(i >> 1) + 1], c = q2[(i >> 1) + 2], d = q2[(i >> 1) + 3];
+        s = FADD(s, a.x); s = FADD(s, a.y); s = FADD(s, b.x); s = FADD(s, b.y);
+        s = FADD(s, c.x); s = FADD(s, c.y); s = FADD(s, d.x); s = FADD(s, d.y);
+    }
+#endif
+    for (; i < len; i++) s = FADD(s, q[i]);
+    return s;
+}
 
 struct FitEnormAcc {
     double s1, s2, s3, x1max, x3max, agiant;
@@ -63,6 +80,29 @@ struct FitEnormAcc {
             if (xabs > x1max) { double t = FDIV(x1max, xabs); s1 = FADD(1.0, FMUL(s1, FMUL(t, t))); x1max = xabs; }
             else { double t = FDIV(xabs, x1max); s1 = FADD(s1, FMUL(t, t)); }
         }
+    }
+    // same sequence of operations as add() applied to v[0..len), with the squares of a batch of 8
+    // computed ahead of the (strictly ordered) additions when all 8 are in MINPACK's mid range
+    FIT_MFN void add_run(const double* v, int len)
+    {
+        const double rdwarf = 3.834e-20;
+        int i = 0;
+        for (; i + 8 <= len; i += 8) {
+            double x[8];
+            bool mid = true;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { x[k] = fabs(v[i + k]); mid = mid && (x[k] > rdwarf && x[k] < agiant); }
+            if (mid) {
+                double q[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) q[k] = FMUL(x[k], x[k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) s2 = FADD(s2, q[k]);
+            } else {
+                for (int k = 0; k < 8; k++) add(v[i + k]);
+            }
+        }
+        for (; i < len; i++) add(v[i]);
     }
     FIT_MFN double result() const
     {
@@ -83,41 +123,129 @@ FIT_FN double fit_enorm_small(int n, const double* x)
     return acc.result();
 }
 
-// enorm of a long vector: staged through shared memory, accumulated by thread 0 in index order
-FIT_FN double fit_enorm_big(const double* x, long n, FitShared* sh)
+// enorm of up to FIT_MAXV long vectors side by side.  Vector v is accumulated in index order by lane 0
+// of warp v while the warps >= FIT_MAXV stage the next chunk of every vector (double buffering).  With
+// fewer than 128 threads (the host build) staging and accumulation simply alternate.
+FIT_FN void fit_enorm_multi(int nv, const double* const* x, const long* n, FitShared* sh, double* out)
 {
     FitEnormAcc acc;
-    acc.init((double)n);
-    for (long c0 = 0; c0 < n; c0 += FIT_CH) {
-        const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
-        for (int i = FIT_TID; i < len; i += FIT_NT) sh->a[i] = x[c0 + i];
-        FIT_SYNC();
-        if (FIT_TID == 0)
-            for (int i = 0; i < len; i++) acc.add(sh->a[i]);
-        FIT_SYNC();
+    acc.init(1.0);
+    const bool overlap = FIT_NT >= 128;
+    const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;  // chain this thread accumulates (device)
+    long nmax = 0;
+    for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
+    if (!overlap) {
+        for (int v = 0; v < nv; v++) {
+            acc.init((double)n[v]);
+            for (long c0 = 0; c0 < n[v]; c0 += FIT_CH) {
+                const int len = (int)((n[v] - c0) < FIT_CH ? (n[v] - c0) : FIT_CH);
+                for (int i = FIT_TID; i < len; i += FIT_NT) sh->buf[0][0][i] = x[v][c0 + i];
+                FIT_SYNC();
+                if (FIT_TID == 0) acc.add_run(sh->buf[0][0], len);
+                FIT_SYNC();
+            }
+            if (FIT_TID == 0) sh->out[v] = acc.result();
+        }
+    } else {
+        if (my_v >= 0 && my_v < nv) acc.init((double)n[my_v]);
+        const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
+        const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
+        // The loaders stage the SQUARES of chunk c+1 (independent, any order) while lane 0 of warp v adds the
+        // squares of chunk c in index order: same operations as FitEnormAcc::add for mid-range values.  A chunk
+        // holding a value outside the mid range is tagged and accumulated from the raw values instead.
+        const double rdwarf = 3.834e-20;
+        for (long c = -1; c < n_chunks; c++) {
+            if (FIT_TID >= first_loader) {
+                const long c1 = (c + 1) * FIT_CH;
+                for (int v = 0; v < nv; v++) {
+                    if (c1 >= n[v]) continue;
+                    const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
+                    const double agiant = FDIV(1.304e19, (double)n[v]);
+                    bool odd = false;
+                    for (int i = FIT_TID - first_loader; i < len; i += n_loaders) {
+                        const double xa = fabs(x[v][c1 + i]);
+                        odd = odd || !(xa > rdwarf && xa < agiant);
+                        sh->buf[v][(c + 1) & 1][i] = FMUL(xa, xa);
+                    }
+                    if (odd) sh->tag[v][(c + 1) & 1] = (int)(c + 2);
+                }
+            } else if (c >= 0 && my_v >= 0 && my_v < nv) {
+                const long c0 = c * FIT_CH;
+                if (c0 < n[my_v]) {
+                    const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
+                    if (sh->tag[my_v][c & 1] == (int)(c + 1)) {
+                        for (int i = 0; i < len; i++) acc.add(x[my_v][c0 + i]);
+                    } else {
+                        acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][c & 1], len);
+                    }
+                }
+            }
+            FIT_SYNC();
+        }
+        if (my_v >= 0 && my_v < nv) sh->out[my_v] = acc.result();
     }
-    if (FIT_TID == 0) sh->out = acc.result();
     FIT_SYNC();
-    const double r = sh->out;
+    for (int v = 0; v < nv; v++) out[v] = sh->out[v];
     FIT_SYNC();
-    return r;
 }
 
-// sum_{i} a[i]*b[i], index order, product rounded before the add
+FIT_FN double fit_enorm_big(const double* x, long n, FitShared* sh)
+{
+    const double* xs[1] = {x};
+    long ns[1] = {n};
+    double o[1];
+    fit_enorm_multi(1, xs, ns, sh, o);
+    return o[0];
+}
+
+// sum_{i} a[i]*b[i], index order, product rounded before the add (products of a batch are formed ahead
+// of the ordered additions); same double-buffered staging, a in buf[0], b in buf[1]
 FIT_FN double fit_dot_big(const double* a, const double* b, long n, FitShared* sh)
 {
     double sum = 0.0;
-    for (long c0 = 0; c0 < n; c0 += FIT_CH) {
-        const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
-        for (int i = FIT_TID; i < len; i += FIT_NT) { sh->a[i] = a[c0 + i]; sh->b[i] = b[c0 + i]; }
-        FIT_SYNC();
-        if (FIT_TID == 0)
-            for (int i = 0; i < len; i++) sum = FADD(sum, FMUL(sh->a[i], sh->b[i]));
+    const bool overlap = FIT_NT >= 128;
+    const int first_loader = 32, n_loaders = FIT_NT - 32;
+    const long n_chunks = (n + FIT_CH - 1) / FIT_CH;
+    if (overlap) {
+        if (FIT_TID >= first_loader) {
+            const int len = (int)(n < FIT_CH ? n : FIT_CH);
+            for (int i = FIT_TID - first_loader; i < len; i += n_loaders) sh->buf[0][0][i] = FMUL(a[i], b[i]);
+        }
         FIT_SYNC();
     }
-    if (FIT_TID == 0) sh->out = sum;
+    for (long c = 0; c < n_chunks; c++) {
+        const long c0 = c * FIT_CH;
+        const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
+        if (!overlap) {
+            for (int i = FIT_TID; i < len; i += FIT_NT) { sh->buf[0][c & 1][i] = a[c0 + i]; sh->buf[1][c & 1][i] = b[c0 + i]; }
+            FIT_SYNC();
+        }
+        if (overlap && FIT_TID >= first_loader) {
+            const long c1 = c0 + FIT_CH;
+            if (c1 < n) {
+                const int l1 = (int)((n - c1) < FIT_CH ? (n - c1) : FIT_CH);
+                for (int i = FIT_TID - first_loader; i < l1; i += n_loaders) sh->buf[0][(c + 1) & 1][i] = FMUL(a[c1 + i], b[c1 + i]);
+            }
+        } else if (overlap && FIT_TID == 0) {
+            sum = fit_ordered_sum(sum, sh->buf[0][c & 1], len);
+        } else if (FIT_TID == 0) {
+            const double* pa = sh->buf[0][c & 1];
+            const double* pb = sh->buf[1][c & 1];
+            int i = 0;
+            for (; i + 8 <= len; i += 8) {
+                double q[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) q[k] = FMUL(pa[i + k], pb[i + k]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) sum = FADD(sum, q[k]);
+            }
+            for (; i < len; i++) sum = FADD(sum, FMUL(pa[i], pb[i]));
+        }
+        FIT_SYNC();
+    }
+    if (FIT_TID == 0) sh->out[0] = sum;
     FIT_SYNC();
-    const double r = sh->out;
+    const double r = sh->out[0];
     FIT_SYNC();
     return r;
 }
@@ -271,7 +399,8 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
 
     fit_resid(lx, ly, m, x[0], x[1], fvec);
     nfev = 1;
-    double fnorm = fit_enorm_big(fvec, m, sh);
+    double fnorm = 0.0;
+    bool have_fnorm = false;
     for (;;) {
         // fdjac2
         for (int j = 0; j < 2; j++) {
@@ -286,9 +415,17 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             FIT_SYNC();
         }
         nfev += 2;
-        // qrfac with column pivoting
+        // qrfac with column pivoting; the initial |fvec| rides along with the two column norms
+        {
+            const double* xs[3] = {col[0], col[1], fvec};
+            long ns[3] = {m, m, m};
+            double o[3];
+            fit_enorm_multi(have_fnorm ? 2 : 3, xs, ns, sh, o);
+            acnorm[0] = o[0];
+            acnorm[1] = o[1];
+            if (!have_fnorm) { fnorm = o[2]; have_fnorm = true; }
+        }
         for (int j = 0; j < 2; j++) {
-            acnorm[j] = fit_enorm_big(col[j], m, sh);
             rdiag[j] = acnorm[j];
             wa[j] = rdiag[j];
             ipvt[j] = j;
@@ -304,7 +441,8 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
                 const int k = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = k;
             }
             double* cj = col[j];
-            double ajnorm = fit_enorm_big(cj + j, m - j, sh);
+            // enorm(a[j:, j]); for j = 0 this is the full (pivoted) column, already computed as acnorm
+            double ajnorm = (j == 0) ? acnorm[ipvt[0]] : fit_enorm_big(cj + j, m - j, sh);
             if (ajnorm != 0.0) {
                 if (cj[j] < 0.0) ajnorm = -ajnorm;
                 FIT_SYNC();

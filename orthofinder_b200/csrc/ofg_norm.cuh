@@ -76,18 +76,24 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
         int pair, cnt;
         int64_t e0, cidx0, ntp;
         rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
-        for (int d = threadIdx.x; d < nd * (RS_THREADS / 32); d += RS_THREADS) (&s_cnt[0][0])[(d / nd) * RS_MAX_DIGITS + (d % nd)] = 0;
+        for (int d = threadIdx.x; d < RS_MAX_DIGITS * (RS_THREADS / 32); d += RS_THREADS) (&s_cnt[0][0])[d] = 0;
         for (int d = threadIdx.x; d < nd; d += RS_THREADS) s_gbase[d] = a.counters[cidx0 + (int64_t)d * ntp];
-        __syncthreads();
         u32 key[RS_ITEMS];
         uint16_t loc[RS_ITEMS];
         // warp w owns records [w*512, w*512+512) of the tile, iteration it covers 32 consecutive ones:
-        // order (warp, iteration, lane) == input order, which makes the ranking stable
+        // order (warp, iteration, lane) == input order, which makes the ranking stable.
+        // All loads are issued before the (serialising) ranking loop.
+        const int kbase = w * (RS_ITEMS * 32) + lane;
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
-            const int k = w * (RS_ITEMS * 32) + it * 32 + lane;
+            const int k = kbase + it * 32;
+            key[it] = k < cnt ? a.key_in[e0 + k] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int k = kbase + it * 32;
             const bool valid = k < cnt;
-            key[it] = valid ? a.key_in[e0 + k] : 0u;
             const u32 d = valid ? ((key[it] >> a.shift) & mask) : 0xffffffffu;
             const u32 peers = __match_any_sync(OFG_FULL, d);
             const int leader = __ffs(peers) - 1;
@@ -112,14 +118,24 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
             }
         }
         __syncthreads();
+        // payload: 8 loads in flight, then 8 scattered stores, twice
 #pragma unroll
-        for (int it = 0; it < RS_ITEMS; it++) {
-            const int k = w * (RS_ITEMS * 32) + it * 32 + lane;
-            if (k < cnt) {
-                const u32 d = (key[it] >> a.shift) & mask;
-                const u32 dst = s_cnt[w][d] + loc[it];
-                a.key_out[dst] = key[it];
-                a.val_out[dst] = a.val_in[e0 + k];
+        for (int h = 0; h < RS_ITEMS; h += 8) {
+            double val[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int k = kbase + (h + t) * 32;
+                val[t] = k < cnt ? a.val_in[e0 + k] : 0.0;
+            }
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const int k = kbase + (h + t) * 32;
+                if (k < cnt) {
+                    const u32 d = (key[h + t] >> a.shift) & mask;
+                    const u32 dst = s_cnt[w][d] + loc[h + t];
+                    a.key_out[dst] = key[h + t];
+                    a.val_out[dst] = val[t];
+                }
             }
         }
         __syncthreads();

@@ -27,12 +27,20 @@ OFG_HD_INLINE bool ofg_is_term(int c) { return c == '\n' || c == '\r'; }
 // Python str.strip()/int()/float() whitespace that can occur inside a tab-separated field
 OFG_HD_INLINE bool ofg_is_space(int c) { return c == ' ' || c == '\v' || c == '\f' || c == 0x1c || c == 0x1d || c == 0x1e || c == 0x1f; }
 
+// 10^k for 0 <= k <= 22, all exactly representable
+#if defined(__CUDACC__)
+__device__ __constant__ double OFG_POW10_DEV[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                                                    1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+#endif
 OFG_HD_INLINE double ofg_pow10_exact(int k)
 {
-    // 10^k for 0 <= k <= 22, all exactly representable
-    const double t[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
-                          1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+#if defined(__CUDA_ARCH__)
+    return OFG_POW10_DEV[k];
+#else
+    static const double t[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                                 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
     return t[k];
+#endif
 }
 
 // Parses the id field starting at pos (ends at '\t' or a line terminator).  On success *id holds the

@@ -163,16 +163,17 @@ __device__ __forceinline__ bool rs_before(u32 cj, double vj, int j, u32 ck, doub
 
 __global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs a)
 {
-    __shared__ u32 s_c[ROWSORT_WARPS][ROWSORT_MAXN];
+    __shared__ __align__(16) u32 s_c[ROWSORT_WARPS][ROWSORT_MAXN + 4];
     __shared__ double s_v[ROWSORT_WARPS][ROWSORT_MAXN];
     __shared__ u32 s_oc[ROWSORT_WARPS][ROWSORT_MAXN];
-    __shared__ double s_ov[ROWSORT_WARPS][ROWSORT_MAXN];
+    __shared__ u64 s_ov[ROWSORT_WARPS][ROWSORT_MAXN];  // best score (bit pattern, > 0) per output slot
     const int w = threadIdx.x >> 5, lane = lane_id();
     u32* c = s_c[w];
     double* v = s_v[w];
     u32* oc = s_oc[w];
-    double* ov = s_ov[w];
+    u64* ov = s_ov[w];
     const int64_t n_warps = (int64_t)gridDim.x * ROWSORT_WARPS;
+    int pair = -1;
     for (int64_t row = (int64_t)blockIdx.x * ROWSORT_WARPS + w; row < a.n_rows; row += n_warps) {
         const u32 s0 = a.row_start[row];
         const int n = (int)(a.row_start[row + 1] - s0);
@@ -184,42 +185,46 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs
             if (lane == 0) a.long_rows[atomicAdd(a.n_long, 1u)] = (u32)row;
             continue;
         }
-        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        // rows are visited in increasing order: the pair index only moves forward
+        if (pair < 0) pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        while (row >= a.pair_row_base[pair + 1]) pair++;
         const PairDesc& pd = a.pairs[pair];
         const double Lq = a.lengths[pd.li_off + (row - pd.row_base)];
         const double* Lh = a.lengths + pd.lj_off;
         for (int k = lane; k < n; k += 32) {
             c[k] = a.cols[s0 + k];
             v[k] = a.vals[s0 + k];
+            ov[k] = 0ULL;
         }
+        if (lane < 4) c[n + lane] = 0xffffffffu;  // padding for the 4-wide compares (never < or == a real column)
         __syncwarp();
+        const uint4* c4 = reinterpret_cast<const uint4*>(c);
+        const int n4 = (n + 3) >> 2;
         for (int k = lane; k < n; k += 32) {
             const u32 ck = c[k];
             const double vk = v[k];
-            int rank = 0;
-            bool head = true;
-            for (int j = 0; j < n; j++) {
-                const u32 cj = c[j];
-                const bool b = rs_before(cj, v[j], j, ck, vk, k);
-                rank += b;
-                head = head && !(b && cj == ck);
+            int rank = 0;  // number of strictly smaller columns: duplicates of a column share the slot
+            for (int j4 = 0; j4 < n4; j4++) {
+                const uint4 q = c4[j4];
+                rank += (q.x < ck) + (q.y < ck) + (q.z < ck) + (q.w < ck);
             }
-            oc[rank] = ck | (head ? 0x80000000u : 0u);
-            ov[rank] = vk;
+            oc[rank] = ck;
+            atomicMax(&ov[rank], (u64)__double_as_longlong(vk));  // B[q,s] = max over duplicate HSP lines
         }
         __syncwarp();
         int outn = 0;
         for (int k0 = 0; k0 < n; k0 += 32) {
             const int k = k0 + lane;
-            const bool h = k < n && (oc[k] >> 31);
+            const bool h = k < n && ov[k] != 0ULL;
             const u32 bal = __ballot_sync(OFG_FULL, h);
             if (h) {
                 const u32 pos = s0 + outn + __popc(bal & lanemask_lt());
-                const u32 col = oc[k] & 0x7fffffffu;
+                const u32 col = oc[k];
+                const double val = __longlong_as_double((long long)ov[k]);
                 a.cols[pos] = col;
-                a.vals[pos] = ov[k];
+                a.vals[pos] = val;
                 a.key[pos] = (u32)(Lq * Lh[col]);
-                a.keyval[pos] = ov[k];
+                a.keyval[pos] = val;
             }
             outn += __popc(bal);
         }

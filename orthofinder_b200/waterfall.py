@@ -143,6 +143,16 @@ class GraphBuilder:
         d["launches"] = n.value
         return d
 
+    def kernel_report(self):
+        """{kernel name: (launches, total ms)} of the last build."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._ck(self.lib.ofg_kernel_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(" ", 2)
+            out[name] = (int(n), float(ms))
+        return out
+
     def pair_csr(self, p, j):
         nr, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
         self._ck(self.lib.ofg_pair_csr(self.h, p, j, ctypes.byref(nr), ctypes.byref(nnz), None, None, None))
