@@ -62,100 +62,104 @@ __device__ __forceinline__ u32 bytes_eq_hi(u32 w, u32 pattern)
 // gathers the four 0x80 flags into bits 0..3 (the partial products never collide below bit 32)
 __device__ __forceinline__ u32 hi_to_nibble(u32 t) { return (t * 0x00204081u) >> 28; }
 
-// Field boundaries of the record starting at byte st of the staged window, from the bitmaps: first and
-// second tab, the tab before field 11 and the line end.  False if the record leaves the window or has
-// fewer than 12 fields (the generic parser then handles it).
-__device__ __forceinline__ bool locate_fields(const u32* s_tab, const u32* s_term, int st, int* tab1, int* tab2, int* tab11,
-                                              int* score_end)
+// ---- warp-converged fast path --------------------------------------------------------------------------
+// Every lane of a warp holds one record (or none).  All loops below have warp-uniform trip counts and use
+// predication instead of early exits, so the 32 records are parsed in lock step; a record that does not fit
+// the plain shapes BLAST / DIAMOND / MMseqs2 write ("<species>_<digits>", "<digits>[.<digits>]", <= 9 digits,
+// 12+ fields within 128 bytes) is handed to the generic parser afterwards.
+
+// 128-bit window of a bitmap starting at byte st (bit i = byte st + i)
+__device__ __forceinline__ void rel_mask128(const u32* m, int st, u64* lo, u64* hi)
 {
-    const int w0 = st >> 5;
-    const u32 low = ~0u << (st & 31);
-    int ww = w0;
-    u32 m = s_term[ww] & low;
-    while (!m) {
-        if (++ww >= PARSE_WORDS) return false;
-        m = s_term[ww];
+    const int w0 = st >> 5, sh = st & 31;
+    const u32 a0 = m[w0], a1 = m[w0 + 1], a2 = m[w0 + 2], a3 = m[w0 + 3], a4 = m[w0 + 4];
+    const u32 r0 = __funnelshift_r(a0, a1, sh), r1 = __funnelshift_r(a1, a2, sh);
+    const u32 r2 = __funnelshift_r(a2, a3, sh), r3 = __funnelshift_r(a3, a4, sh);
+    *lo = (u64)r0 | ((u64)r1 << 32);
+    *hi = (u64)r2 | ((u64)r3 << 32);
+}
+__device__ __forceinline__ int ctz128(u64 lo, u64 hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
+
+// Field boundaries relative to the record start: first / second tab, tab before field 11, end of field 11.
+__device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* s_term, int st, bool act, int* tab1, int* tab2,
+                                                   int* tab11, int* score_end)
+{
+    u64 ea, eb, ta, tb;
+    rel_mask128(s_term, st, &ea, &eb);
+    rel_mask128(s_tab, st, &ta, &tb);
+    const int le = (ea | eb) ? ctz128(ea, eb) : 128;
+    bool ok = act && le < 128 && st + le < PARSE_TILE + PARSE_OVERLAP;
+    // tabs of this record only
+    if (le < 64) { ta &= (1ULL << le) - 1ULL; tb = 0; }
+    else if (le < 128) { tb &= (1ULL << (le - 64)) - 1ULL; }
+    ok = ok && (__popcll(ta) + __popcll(tb) >= 11);
+    const u64 t2m = ta & (ta - 1ULL);
+    ok = ok && t2m != 0;  // the two id fields end inside the first 64 bytes
+    *tab1 = __ffsll((long long)ta) - 1;
+    *tab2 = __ffsll((long long)t2m) - 1;
+    u64 a = ta, b = tb;
+#pragma unroll
+    for (int k = 0; k < 10; k++) {  // drop the ten lowest tabs
+        if (a) a &= a - 1ULL; else b &= b - 1ULL;
     }
-    const int le = ww * 32 + __ffs(m) - 1;
-    const int wend = le >> 5;
-    int cnt = 0, t1 = -1, t2 = -1;
-    ww = w0;
-    m = s_tab[ww] & low;
-    for (;;) {
-        const int c = __popc(m);
-        if (t1 < 0 && cnt + c >= 1) { u32 x = m; t1 = ww * 32 + __ffs(x) - 1; }
-        if (t2 < 0 && cnt + c >= 2) { u32 x = m; for (int k = cnt + 1; k < 2; k++) x &= x - 1; t2 = ww * 32 + __ffs(x) - 1; }
-        if (cnt + c >= 11) {
-            u32 x = m;
-            for (int k = cnt + 1; k < 11; k++) x &= x - 1;
-            *tab11 = ww * 32 + __ffs(x) - 1;
-            // field 11 ends at the next tab of the line, if any, else at the line end
-            x &= x - 1;
-            int se = le;
-            for (;;) {
-                if (x) { const int t12 = ww * 32 + __ffs(x) - 1; if (t12 < le) se = t12; break; }
-                if (++ww > wend) break;
-                x = s_tab[ww];
-            }
-            *score_end = se;
-            break;
-        }
-        cnt += c;
-        if (++ww > wend) return false;
-        m = s_tab[ww];
-    }
-    *tab1 = t1; *tab2 = t2;
-    return *tab11 < le;
+    *tab11 = ctz128(a, b);
+    if (a) a &= a - 1ULL; else b &= b - 1ULL;
+    *score_end = (a | b) ? ctz128(a, b) : le;
+    return ok;
 }
 
-// Plain fields, the only shapes BLAST / DIAMOND / MMseqs2 write: "<species>_<digits>" and
-// "<digits>[.<digits>]" with at most 9 digits.  Anything else returns false and takes the generic parser.
-__device__ __forceinline__ bool fast_id(const uint8_t* s, int p, int end, u32* out)
+__device__ __forceinline__ bool conv_id(const uint8_t* s, int p, int len, bool act, u32* out)
 {
-    while (p < end && s[p] != '_') p++;
-    p++;
-    const int nd = end - p;
-    if (nd < 1 || nd > 9) return false;
+    const int maxlen = __reduce_max_sync(OFG_FULL, act ? len : 0);
     u32 v = 0;
-    for (; p < end; p++) {
-        const u32 d = (u32)s[p] - (u32)'0';
-        if (d > 9u) return false;
-        v = v * 10u + d;
+    int nd = 0;
+    bool seen = false, bad = false;
+    for (int i = 0; i < maxlen; i++) {
+        if (act && i < len) {
+            const u32 c = s[p + i];
+            const u32 d = c - (u32)'0';
+            if (!seen) seen = (c == (u32)'_');
+            else if (d > 9u) bad = true;
+            else { v = v * 10u + d; nd++; }
+        }
     }
     *out = v;
-    return true;
+    return act && seen && !bad && nd >= 1 && nd <= 9;
 }
 
-__device__ __forceinline__ bool fast_score(const uint8_t* s, int p, int end, double* out)
+__device__ __forceinline__ bool conv_score(const uint8_t* s, int p, int len, bool act, double* out)
 {
-    const int len = end - p;
-    if (len < 1 || len > 10) return false;
+    act = act && len >= 1 && len <= 10;
+    const int maxlen = __reduce_max_sync(OFG_FULL, act ? len : 0);
     u32 m = 0;
     int frac = -1, nd = 0;
-    for (; p < end; p++) {
-        const u32 c = s[p];
-        const u32 d = c - (u32)'0';
-        if (d <= 9u) { m = m * 10u + d; nd++; if (frac >= 0) frac++; }
-        else if (c == (u32)'.' && frac < 0) frac = 0;
-        else return false;
+    bool bad = false;
+    for (int i = 0; i < maxlen; i++) {
+        if (act && i < len) {
+            const u32 c = s[p + i];
+            const u32 d = c - (u32)'0';
+            if (d <= 9u) { m = m * 10u + d; nd++; frac += (frac >= 0); }
+            else if (c == (u32)'.' && frac < 0) frac = 0;
+            else bad = true;
+        }
     }
-    if (nd < 1 || nd > 9) return false;
     const double v = (double)m;
-    *out = frac > 0 ? v / OFG_POW10_DEV[frac] : v;  // exact: m < 2^30, one correctly rounded division
-    return true;
+    *out = frac > 0 ? v / OFG_POW10_DEV[frac > 9 ? 9 : frac] : v;  // exact: m < 2^30, one correctly rounded division
+    return act && !bad && nd >= 1 && nd <= 9;
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
 {
     __shared__ __align__(16) uint8_t s_text[PARSE_TILE + PARSE_OVERLAP];
     __shared__ uint16_t s_lstart[PARSE_TILE / 2];
-    __shared__ u32 s_term[PARSE_WORDS];
-    __shared__ u32 s_tab[PARSE_WORDS];
+    __shared__ u32 s_term[PARSE_WORDS + 8];  // + padding read by the 128-bit windows: all terminators
+    __shared__ u32 s_tab[PARSE_WORDS + 8];
     __shared__ u32 s_scan[PARSE_THREADS / 32 + 1];
     __shared__ u64 s_base;
     __shared__ u32 s_valid;
     __shared__ int s_prev_term;
     const int tid = threadIdx.x;
+    if (tid < 8) { s_term[PARSE_WORDS + tid] = 0xffffffffu; s_tab[PARSE_WORDS + tid] = 0u; }
 
     int pair = -1;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -230,25 +234,24 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
             const u32 li = li0 + tid;
             u32 row = OFG_ROW_SENTINEL, col = 0;
             double score = 0.0;
-            if (li < nl_total) {
-                const int st = s_lstart[li];
-                u32 f0 = 0, f1 = 0;
-                SmemSrc ss{s_text, PARSE_TILE + PARSE_OVERLAP, false};
-                int rc = -1;
-                int tab1, tab2, tab11, send;
-                if (locate_fields(s_tab, s_term, st, &tab1, &tab2, &tab11, &send)) {
-                    // fast path: the bitmaps give the field boundaries, only ids and score are read bytewise
-                    if (fast_id(s_text, st, tab1, &f0) && fast_id(s_text, tab1 + 1, tab2, &f1) &&
-                        fast_score(s_text, tab11 + 1, send, &score))
-                        rc = OFG_PL_OK;
-                }
-                if (rc != OFG_PL_OK) {  // anything unusual: the generic record parser decides (and names the error)
-                    ss.truncated = false;
+            const bool act = li < nl_total;
+            const int st = act ? (int)s_lstart[li] : 0;
+            u32 f0 = 0, f1 = 0;
+            int tab1, tab2, tab11, send;
+            bool fast = locate_fields_conv(s_tab, s_term, st, act, &tab1, &tab2, &tab11, &send);
+            const bool ok0 = conv_id(s_text, st, tab1, fast, &f0);
+            const bool ok1 = conv_id(s_text, st + tab1 + 1, tab2 - tab1 - 1, fast, &f1);
+            const bool ok2 = conv_score(s_text, st + tab11 + 1, send - tab11 - 1, fast, &score);
+            fast = fast && ok0 && ok1 && ok2;
+            if (act) {
+                int rc = OFG_PL_OK;
+                if (!fast) {  // anything unusual: the generic record parser decides (and names the error)
+                    SmemSrc ss{s_text, PARSE_TILE + PARSE_OVERLAP, false};
                     rc = ofg_parse_record(ss, (int64_t)st, &f0, &f1, &score);
-                }
-                if (ss.truncated) {  // line longer than the staged window: re-parse from global memory
-                    GlobalSrc gs{gfile, pd.text_len};
-                    rc = ofg_parse_record(gs, t0 + st, &f0, &f1, &score);
+                    if (ss.truncated) {  // line longer than the staged window: re-parse from global memory
+                        GlobalSrc gs{gfile, pd.text_len};
+                        rc = ofg_parse_record(gs, t0 + st, &f0, &f1, &score);
+                    }
                 }
                 int kind = rc;
                 if (rc == OFG_PL_OK) {
