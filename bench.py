@@ -127,7 +127,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from orthofinder_b200 import waterfall, _lib
+    from orthofinder_b200 import waterfall, _lib, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -141,7 +141,7 @@ def run_ours(args):
     ids = list(range(S))
     gb = waterfall.GraphBuilder(local)
     gb.set_species([G] * S, L)
-    owned = [p for p in range(S) if p % world == rank]
+    owned = sharding.partition_rows(S, world)[rank]
     if world > 1:
         gb.set_partition(owned, True)
     t0 = time.time()
@@ -149,20 +149,12 @@ def run_ours(args):
     log("[rank %d] generated hit text on device in %.1fs" % (rank, time.time() - t0))
     stream = torch.cuda.ExternalStream(gb.lib.ofg_stream(gb.h), device=torch.device("cuda", local))
 
-    class _Dev:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-
     def step():
         if world == 1:
             gb.build(_lib.STAGE_GRAPH)
         else:
             gb.build(_lib.STAGE_THRESH)
-            ptr, n = gb.thresholds_dev()
-            t = torch.as_tensor(_Dev(ptr, n), device=torch.device("cuda", local))
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)  # owned entries are finite, the rest +inf: MIN == all-gather
-            torch.cuda.synchronize()
-            gb.thresholds_mark_complete()
+            sharding.exchange_thresholds(gb, local)  # one NCCL all-reduce(MIN): owned entries finite, the rest +inf
             gb.build(_lib.STAGE_GRAPH)
 
     def barrier():
@@ -178,7 +170,7 @@ def run_ours(args):
     text_bytes_all = 0
     pairs_here = [(p, j) for p in owned for j in range(S)]
     if world > 1:
-        pairs_here += [(j, p) for p in owned for j in range(S) if j % world != rank]
+        pairs_here += sharding.rank_pairs(owned, S)[1]
     for (p, j) in pairs_here:
         sizes[(p, j)] = gb.hits_text_size(p, j)
         text_bytes_all += sizes[(p, j)]

@@ -1,0 +1,61 @@
+"""Sharding of the pair grid by query species (design A).
+
+Rank r owns a set of query species p ("rows" of the S x S pair grid), exactly the unit the reference
+parallelises over (gathering.py:484-485).  Everything that is reduced per gene (row maxima, best hit in
+another species, the "most distant" threshold) stays local to the owner.  The two places where the
+reference reads the transposed direction from pickles (BH_jp at gathering.py:254, connect_jp at :30) are
+served by also ingesting the column pairs Blast{j}_{p}: their fit, normalisation and best hits depend
+only on that file and the two length vectors, so they are recomputed locally and bit-identically, and the
+only data exchanged is the per-gene threshold vector (8 bytes per gene): one all-reduce(MIN) over a
+vector that holds +inf for genes a rank does not own, which is an all-gather in one NCCL call.
+"""
+import numpy as np
+
+
+def partition_rows(n_species, world, weights=None):
+    """Greedy longest-first assignment of query species to ranks, balanced by `weights` (e.g. hit-file
+    bytes per query species; default: equal).  Returns a list of sorted species lists, one per rank."""
+    w = np.ones(n_species) if weights is None else np.asarray(weights, dtype=np.float64)
+    load = [0.0] * world
+    owned = [[] for _ in range(world)]
+    for p in sorted(range(n_species), key=lambda k: (-w[k], k)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        owned[r].append(p)
+        load[r] += w[p]
+    return [sorted(o) for o in owned]
+
+
+def rank_pairs(owned, n_species):
+    """(row pairs, column pairs) a rank ingests: (p, j) for owned p and every j, plus (j, p) for j it does
+    not own."""
+    own = set(owned)
+    rows = [(p, j) for p in owned for j in range(n_species)]
+    cols = [(j, p) for p in owned for j in range(n_species) if j not in own]
+    return rows, cols
+
+
+def merge_thresholds_host(parts):
+    """Element-wise minimum of per-rank threshold vectors (+inf where a rank owns nothing): what the
+    all-reduce computes."""
+    out = np.array(parts[0], dtype=np.float64, copy=True)
+    for p in parts[1:]:
+        np.minimum(out, p, out=out)
+    return out
+
+
+class _DeviceVector:
+    """Zero-copy view of a device fp64 vector for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def exchange_thresholds(gb, device_index):
+    """In-place NCCL all-reduce(MIN) of the library's threshold vector (one collective over NVLink)."""
+    import torch
+    import torch.distributed as dist
+    ptr, n = gb.thresholds_dev()
+    t = torch.as_tensor(_DeviceVector(ptr, n), device=torch.device("cuda", device_index))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()
+    gb.thresholds_mark_complete()

@@ -270,6 +270,64 @@ def test_error_paths(gb):
     gb.set_option("allow_empty", 0)
 
 
+def test_two_partitions_stitch_to_the_single_context_graph():
+    """Design A of SURVEY.md §8e on one GPU: two contexts, each owning half of the query species and
+    re-parsing its column pairs, exchange only the per-gene thresholds (element-wise min, what the NCCL
+    all-reduce does) and together reproduce the single-context graph byte for byte."""
+    from orthofinder_b200 import sharding
+    g = Golden("synth_C5_small")
+    S = len(g.n_seqs)
+    whole = waterfall.GraphBuilder(0)
+    _load(whole, g.n_seqs, g.lengths, g.hit_text)
+    whole.build()
+    w_rows, w_indptr, w_idx, w_dat = whole.graph_csr()
+    w_text = whole.graph_text_body().tobytes()
+    sizes = [sum(len(g.hit_text(p, j)) for j in range(S)) for p in range(S)]
+    parts = sharding.partition_rows(S, 2, sizes)
+    ctxs = []
+    for owned in parts:
+        c = waterfall.GraphBuilder(0)
+        c.set_species(g.n_seqs, g.lengths)
+        c.set_partition(owned, True)
+        rows_p, cols_p = sharding.rank_pairs(owned, S)
+        for (p, j) in rows_p + cols_p:
+            c.add_hits(p, j, g.hit_text(p, j))
+        c.build(_lib.STAGE_THRESH)
+        ctxs.append(c)
+    md = sharding.merge_thresholds_host([c.thresholds() for c in ctxs])
+    assert np.array_equal(md, whole.thresholds())
+    import torch
+    rows_all, text_all = [], {}
+    for owned, c in zip(parts, ctxs):
+        ptr, n = c.thresholds_dev()
+        t = torch.as_tensor(sharding._DeviceVector(ptr, n), device="cuda:0")
+        t.copy_(torch.from_numpy(md).cuda())
+        torch.cuda.synchronize()
+        c.thresholds_mark_complete()
+        c.build(_lib.STAGE_GRAPH)
+        rows, indptr, idx, dat = c.graph_csr()
+        for k, r in enumerate(rows):
+            a, b = w_indptr[r], w_indptr[r + 1]
+            assert np.array_equal(idx[indptr[k]:indptr[k + 1]], w_idx[a:b])
+            assert np.array_equal(dat[indptr[k]:indptr[k + 1]], w_dat[a:b])
+        rows_all += list(rows)
+        # text of each owned species is a contiguous block in list order
+        text_all[tuple(owned)] = c.graph_text_body().tobytes()
+        c.close()
+    assert sorted(rows_all) == list(range(sum(g.n_seqs)))
+    # stitch the text by species order
+    starts = np.concatenate(([0], np.cumsum(g.n_seqs)))
+    by_species = {}
+    for owned, txt in text_all.items():
+        lines = txt.split(b"\n")[:-1]
+        o = 0
+        for p in owned:
+            by_species[p] = b"\n".join(lines[o:o + g.n_seqs[p]]) + b"\n"
+            o += g.n_seqs[p]
+    assert b"".join(by_species[p] for p in range(S)) == w_text
+    whole.close()
+
+
 def test_rebuild_is_deterministic_and_sorted(gb):
     """Size-independent properties on a mid-size job (8 species x 2000 genes x 50 hits/query, 7 M lines):
     two builds give identical bytes; rows are strictly column-sorted; weights are positive and finite."""
