@@ -253,7 +253,7 @@ def run_ours(args):
             gb.hits_text_into(k[0], k[1], base + o, n)
             offs[k] = o
             o += n
-        gb.build()
+        step()
         out_pinned = torch.empty(gb.graph_text_size() + (1 << 20), dtype=torch.uint8).pin_memory()
         out_np = out_pinned.numpy()
         gb.set_option("reserve_text_bytes", total + 16 * len(sizes) + 4096)
