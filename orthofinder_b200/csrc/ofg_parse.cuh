@@ -4,7 +4,7 @@
 //
 // Layout: all files of the context live back to back in one text arena, each padded with '\n' to a
 // multiple of 16 bytes (blank lines are skipped by the reference, :68-69, so padding is neutral).
-// A CTA takes an 8 KB tile of one file, stages it (plus 1 KB of overlap for the line that crosses
+// A CTA takes a 16 KB tile of one file, stages it (plus 1 KB of overlap for the line that crosses
 // the tile end) in shared memory with 16-byte loads, marks line starts with SIMD-in-word byte
 // compares + a CTA scan, then parses one line per thread out of shared memory.  Records are written
 // at (tile base + line index), the tile base coming from one atomicAdd per tile; lines that are
@@ -14,10 +14,11 @@
 #include "ofg_common.cuh"
 #include "ofg_parse_line.h"
 
-constexpr int PARSE_TILE = 8192;
+constexpr int PARSE_TILE = 16384;
 constexpr int PARSE_OVERLAP = 1024;
 constexpr int PARSE_THREADS = 256;
-static_assert(PARSE_TILE / 32 == PARSE_THREADS, "one 32-byte chunk per thread");
+constexpr int PARSE_CPT = PARSE_TILE / 32 / PARSE_THREADS;  // 32-byte chunks of the tile body per thread (adjacent)
+static_assert(PARSE_CPT * 32 * PARSE_THREADS == PARSE_TILE, "tile must split evenly");
 constexpr int PARSE_WORDS = (PARSE_TILE + PARSE_OVERLAP) / 32;
 
 struct ParseArgs {
@@ -162,14 +163,23 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
     if (tid < 8) { s_term[PARSE_WORDS + tid] = 0xffffffffu; s_tab[PARSE_WORDS + tid] = 0u; }
 
     int pair = -1;
+    // per-pair constants, reloaded only when the tile loop crosses into another file
+    int64_t p_tile0 = 0, p_tile1 = 0, p_text_len = 0, p_row_base = 0;
+    const uint8_t* gfile = nullptr;
+    u32 p_Gi = 0, p_Gj = 0;
+    bool p_same = false, p_swap = false;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         // tiles are visited in increasing order: the pair index only moves forward
-        if (pair < 0) pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
-        while (tile >= a.tile_prefix[pair + 1]) pair++;
-        const PairDesc pd = a.pairs[pair];
-        const int64_t t0 = (tile - a.tile_prefix[pair]) * (int64_t)PARSE_TILE;
-        const uint8_t* gfile = a.text + pd.text_off;
-        const int64_t remain = pd.text_len - t0;
+        if (pair < 0 || tile >= p_tile1) {
+            if (pair < 0) pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
+            while (tile >= a.tile_prefix[pair + 1]) pair++;
+            const PairDesc& d = a.pairs[pair];
+            p_tile0 = a.tile_prefix[pair]; p_tile1 = a.tile_prefix[pair + 1];
+            p_text_len = d.text_len; p_row_base = d.row_base; gfile = a.text + d.text_off;
+            p_Gi = (u32)d.Gi; p_Gj = (u32)d.Gj; p_same = d.same != 0; p_swap = d.swap != 0;
+        }
+        const int64_t t0 = (tile - p_tile0) * (int64_t)PARSE_TILE;
+        const int64_t remain = p_text_len - t0;
         const int nload = (int)(remain < (int64_t)(PARSE_TILE + PARSE_OVERLAP) ? remain : (int64_t)(PARSE_TILE + PARSE_OVERLAP));
         const int body = (int)(remain < (int64_t)PARSE_TILE ? remain : (int64_t)PARSE_TILE);
         {
@@ -184,44 +194,55 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
             }
         }
         __syncthreads();
-        // structural bitmaps of the whole staged window (32 bytes per word): terminators and tabs
-        u32 starts = 0, quotes = 0;
-        for (int ch = tid; ch < PARSE_WORDS; ch += PARSE_THREADS) {
-            const u32* w = reinterpret_cast<const u32*>(s_text + ch * 32);
-            u32 term = 0, tabs = 0, qu = 0;
-            const uint4 lo4 = reinterpret_cast<const uint4*>(w)[0], hi4 = reinterpret_cast<const uint4*>(w)[1];
-            const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        // structural bitmaps of the whole staged window (32 bytes per word): terminators and tabs.
+        // Thread t owns the adjacent body words [t*CPT, (t+1)*CPT) (their line starts come out in order);
+        // the overlap words are shared out to the first threads.
+        u32 starts[PARSE_CPT];
+        u32 quotes = 0;
+        int n_starts = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const u32 x = xs[k];
-                term |= hi_to_nibble(bytes_eq_hi(x, 0x0a0a0a0au) | bytes_eq_hi(x, 0x0d0d0d0du)) << (4 * k);
-                tabs |= hi_to_nibble(bytes_eq_hi(x, 0x09090909u)) << (4 * k);
+        for (int k = 0; k < PARSE_CPT + 1; k++) {
+            int ch;
+            if (k < PARSE_CPT) ch = tid * PARSE_CPT + k;
+            else { ch = PARSE_TILE / 32 + tid; if (ch >= PARSE_WORDS) break; }
+            const uint4* w4 = reinterpret_cast<const uint4*>(s_text + ch * 32);
+            const uint4 lo4 = w4[0], hi4 = w4[1];
+            const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+            u32 term = 0, tabs = 0, qu = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const u32 x = xs[b];
+                term |= hi_to_nibble(bytes_eq_hi(x, 0x0a0a0a0au) | bytes_eq_hi(x, 0x0d0d0d0du)) << (4 * b);
+                tabs |= hi_to_nibble(bytes_eq_hi(x, 0x09090909u)) << (4 * b);
                 const u32 tq = bytes_eq_hi(x, 0x22222222u);
-                if (tq) qu |= hi_to_nibble(tq) << (4 * k);
+                if (tq) qu |= hi_to_nibble(tq) << (4 * b);
             }
             s_term[ch] = term;
             s_tab[ch] = tabs;
-            if (ch == tid) {  // body chunk of this thread: line starts
-                const int off = tid * 32;
-                const u32 prev = (tid == 0) ? (u32)s_prev_term : (u32)ofg_is_term(s_text[off - 1]);
-                starts = ~term & ((term << 1) | prev);
-                quotes = qu;
-                const int nvalid = body - off;  // bytes of this chunk inside the body
-                if (nvalid <= 0) { starts = 0; quotes = 0; }
-                else if (nvalid < 32) { starts &= (1u << nvalid) - 1u; quotes &= (1u << nvalid) - 1u; }
+            if (k < PARSE_CPT) {  // body word: line starts
+                const int off = ch * 32;
+                const u32 prev = (ch == 0) ? (u32)s_prev_term : (u32)ofg_is_term(s_text[off - 1]);
+                u32 st = ~term & ((term << 1) | prev);
+                const int nvalid = body - off;  // bytes of this word inside the body
+                if (nvalid <= 0) { st = 0; qu = 0; }
+                else if (nvalid < 32) { st &= (1u << nvalid) - 1u; qu &= (1u << nvalid) - 1u; }
+                starts[k] = st;
+                n_starts += __popc(st);
+                if (qu && !quotes) quotes = ((u32)off + (u32)__ffs(qu) - 1u) | 0x80000000u;
             }
         }
-        if (quotes) {
-            int b = __ffs(quotes) - 1;
-            // report the line holding the quote: approximate by the byte offset of the quote itself
-            atomicMin(&a.pair_err[pair], ((u64)(t0 + tid * 32 + b) << 4) | (u64)OFG_LINE_QUOTE);
-        }
+        if (quotes)  // csv quoting is not supported: report the byte offset of the quote
+            atomicMin(&a.pair_err[pair], ((u64)(t0 + (quotes & 0x7fffffffu)) << 4) | (u64)OFG_LINE_QUOTE);
         u32 nl_total;
-        u32 pos = block_excl_scan<PARSE_THREADS>(__popc(starts), s_scan, &nl_total);
-        while (starts) {
-            int b = __ffs(starts) - 1;
-            s_lstart[pos++] = (uint16_t)(tid * 32 + b);
-            starts &= starts - 1;
+        u32 pos = block_excl_scan<PARSE_THREADS>((u32)n_starts, s_scan, &nl_total);
+#pragma unroll
+        for (int k = 0; k < PARSE_CPT; k++) {
+            u32 st = starts[k];
+            while (st) {
+                const int b = __ffs(st) - 1;
+                s_lstart[pos++] = (uint16_t)((tid * PARSE_CPT + k) * 32 + b);
+                st &= st - 1;
+            }
         }
         if (tid == 0) {
             s_base = atomicAdd(a.coo_count, (u64)nl_total);
@@ -229,8 +250,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
         }
         __syncthreads();
         const u64 base = s_base;
-        const int64_t Gi = pd.Gi, Gj = pd.Gj;
         for (u32 li0 = 0; li0 < nl_total; li0 += PARSE_THREADS) {
+            if (li0 + (u32)(tid & ~31) >= nl_total) continue;  // warp without records (warp-uniform)
             const u32 li = li0 + tid;
             u32 row = OFG_ROW_SENTINEL, col = 0;
             double score = 0.0;
@@ -249,21 +270,21 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
                     SmemSrc ss{s_text, PARSE_TILE + PARSE_OVERLAP, false};
                     rc = ofg_parse_record(ss, (int64_t)st, &f0, &f1, &score);
                     if (ss.truncated) {  // line longer than the staged window: re-parse from global memory
-                        GlobalSrc gs{gfile, pd.text_len};
+                        GlobalSrc gs{gfile, p_text_len};
                         rc = ofg_parse_record(gs, t0 + st, &f0, &f1, &score);
                     }
                 }
                 int kind = rc;
                 if (rc == OFG_PL_OK) {
-                    const u32 q = pd.swap ? f1 : f0, s = pd.swap ? f0 : f1;
-                    if (pd.same && q == s) {
+                    const u32 q = p_swap ? f1 : f0, s = p_swap ? f0 : f1;
+                    if (p_same && q == s) {
                         // self hit: skipped before any range check (:83-84)
-                    } else if ((int64_t)q >= Gi) {
+                    } else if (q >= p_Gi) {
                         kind = OFG_LINE_RANGE_Q;
-                    } else if ((int64_t)s >= Gj) {
+                    } else if (s >= p_Gj) {
                         kind = OFG_LINE_RANGE_S;
                     } else if (score > 0.0) {  // stored only if score > current (initially 0) (:87)
-                        row = (u32)(pd.row_base + q);
+                        row = (u32)p_row_base + q;
                         col = s;
                     }
                 }
