@@ -471,11 +471,12 @@ int stage_norm(ofg_ctx* c)
             a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
             a.tile_prefix = c->sort_tile_prefix.as<int64_t>(); a.pair_slot = c->pair_slot.as<int64_t>();
             a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
-            const int g = grid_for(c, n_tiles, 1, 6);
+            const int g = grid_for(c, n_tiles, 1, 3);
             radix_hist_kernel<<<g, RS_THREADS, 0, c->stream>>>(a);
             CKL("radix_hist_kernel");
             if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
-            radix_scatter_kernel<<<g, RS_THREADS, 0, c->stream>>>(a);
+            CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
+            radix_scatter_kernel<<<g, RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);
             CKL("radix_scatter_kernel");
             std::swap(kin, kout);
             std::swap(vin, vout);
@@ -650,7 +651,7 @@ int stage_graph(ofg_ctx* c)
     sp_of.reserve((size_t)c->n_owned_genes);
     for (int p : c->owned)
         for (int64_t q = 0; q < c->n_seqs[p]; q++) { gene_of.push_back(c->seq_start[p] + q); sp_of.push_back(p); }
-    const int64_t n_units = (int64_t)gene_of.size() * c->S;
+    const int64_t n_units = (int64_t)gene_of.size();  // one unit per graph row (gene)
     if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
     if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
     CK(cudaStreamSynchronize(c->stream));
@@ -660,18 +661,18 @@ int stage_graph(ofg_ctx* c)
     CK(c->cnt_off.ensure((size_t)(n_units + 2) * 8));
     CK(c->byte_off.ensure((size_t)(n_units + 2) * 8));
     EmitArgs e;
-    e.g = g; e.n_units = n_units; e.gene_of_local = c->gene_of_local.as<int64_t>();
+    e.g = g; e.n_genes = n_units; e.gene_of_local = c->gene_of_local.as<int64_t>();
     e.species_of_local = c->species_of_local.as<int32_t>(); e.seq_start = c->d_seq_start.as<int64_t>();
-    e.unit_cnt = c->unit_cnt.as<u32>(); e.unit_bytes = c->unit_bytes.as<u32>();
+    e.gene_cnt = c->unit_cnt.as<u32>(); e.gene_bytes = c->unit_bytes.as<u32>();
     e.cnt_off = c->cnt_off.as<u64>(); e.byte_off = c->byte_off.as<u64>();
     e.out_indices = nullptr; e.out_data = nullptr; e.out_text = nullptr; e.err_flags = err_flags;
     c->tot_edges = 0; c->tot_text = 0;
     if (n_units > 0) {
-        const int ge = grid_for(c, n_units, 8, 8);
-        emit_kernel<false><<<ge, 256, 0, c->stream>>>(e);
+        const int ge = grid_for(c, n_units, EMIT_WARPS, 6);
+        emit_kernel<false><<<ge, EMIT_WARPS * 32, 0, c->stream>>>(e);
         CKL("emit_kernel<false>");
-        if (device_scan<u64>(c, e.unit_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
-        if (device_scan<u64>(c, e.unit_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
+        if (device_scan<u64>(c, e.gene_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
+        if (device_scan<u64>(c, e.gene_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         u64 tots[2] = {0, 0};
         CK(cudaMemcpyAsync(&tots[0], c->cnt_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(&tots[1], c->byte_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -682,7 +683,7 @@ int stage_graph(ofg_ctx* c)
         CK(c->out_data.ensure((size_t)(tots[0] + 16) * 8));
         CK(c->out_text.ensure((size_t)tots[1] + 64));
         e.out_indices = c->out_indices.as<int32_t>(); e.out_data = c->out_data.as<double>(); e.out_text = c->out_text.as<char>();
-        emit_kernel<true><<<ge, 256, 0, c->stream>>>(e);
+        emit_kernel<true><<<ge, EMIT_WARPS * 32, 0, c->stream>>>(e);
         CKL("emit_kernel<true>");
     }
     CK(cudaEventRecord(c->ev[9], c->stream));
@@ -1081,10 +1082,10 @@ int ofg_graph_csr_copy(ofg_ctx* c, int64_t* row_ids, int64_t* indptr, int32_t* i
         for (int p : c->owned) for (int64_t q = 0; q < c->n_seqs[p]; q++) row_ids[o++] = c->seq_start[p] + q;
     }
     if (indptr) {
-        std::vector<u64> off((size_t)n * c->S + 1);
+        std::vector<u64> off((size_t)n + 1);
         if (n > 0) CK(cudaMemcpyAsync(off.data(), c->cnt_off.p, off.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        for (int64_t g = 0; g < n; g++) indptr[g] = (int64_t)off[(size_t)g * c->S];
+        for (int64_t g = 0; g < n; g++) indptr[g] = (int64_t)off[(size_t)g];
         indptr[n] = c->tot_edges;
     }
     if (indices && c->tot_edges) CK(cudaMemcpyAsync(indices, c->out_indices.p, (size_t)c->tot_edges * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -324,88 +324,144 @@ __host__ __device__ __forceinline__ int ofg_format_entry(unsigned long long gcol
 
 struct EmitArgs {
     GraphArgs g;
-    int64_t n_units;          // owned genes x S : unit u = local_gene * S + j
-    const int64_t* gene_of_local;  // [owned genes] global gene id
+    int64_t n_genes;          // owned genes, list order
+    const int64_t* gene_of_local;     // [owned genes] global gene id
     const int32_t* species_of_local;  // [owned genes] list position p
     const int64_t* seq_start; // [S] seqStartingIndices
-    u32* unit_cnt;            // [n_units] edges of the unit
-    u32* unit_bytes;          // [n_units] text bytes of the unit
-    const u64* cnt_off;       // [n_units + 1]
-    const u64* byte_off;      // [n_units + 1]
+    u32* gene_cnt;            // [n_genes] edges of the graph row
+    u32* gene_bytes;          // [n_genes] text bytes of the graph row
+    const u64* cnt_off;       // [n_genes + 1]
+    const u64* byte_off;      // [n_genes + 1]
     int32_t* out_indices;
     double* out_data;
     char* out_text;
     u32* err_flags;           // bit 2: a weight could not be formatted
 };
 
+constexpr int EMIT_WARPS = 8;
+constexpr int EMIT_LIST = 64;  // edges buffered per warp before they are formatted
+
+// One warp per graph row (gene).  The row's entries live in S matrix rows (one per target species); the
+// lanes first fetch those S row descriptors in parallel, then sweep the concatenated entries 32 at a time
+// (independent loads), collect the flagged ones in order into a small shared list and format that list
+// densely (one edge per lane).  WRITE = false only counts edges and text bytes.
 template <bool WRITE>
-__global__ void __launch_bounds__(256) emit_kernel(EmitArgs a)
+__global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(EmitArgs a)
 {
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    __shared__ u32 s_s0[EMIT_WARPS][32];
+    __shared__ u32 s_pre[EMIT_WARPS][33];
+    __shared__ u64 s_goff[EMIT_WARPS][32];
+    __shared__ u64 s_gc[EMIT_WARPS][EMIT_LIST];
+    __shared__ double s_w[EMIT_WARPS][EMIT_LIST];
+    const int lane = lane_id(), w = threadIdx.x >> 5;
     const int S = a.g.S;
-    for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < a.n_units; u += n_warps) {
-        const int64_t lg = u / S;
-        const int j = (int)(u - lg * S);
+    const int64_t n_warps = (int64_t)gridDim.x * EMIT_WARPS;
+    for (int64_t lg = (int64_t)blockIdx.x * EMIT_WARPS + w; lg < a.n_genes; lg += n_warps) {
         const int p = a.species_of_local[lg];
         const int64_t gene = a.gene_of_local[lg];
-        const int pair = a.g.pair_of[p * S + j];
         u32 cnt = 0, bytes = 0;
         u64 ocnt = 0, obyte = 0;
-        if (WRITE) { ocnt = a.cnt_off[u]; obyte = a.byte_off[u]; }
-        // "%d    " before the first species, "$\n" after the last (gathering.py:42,47)
-        if (j == 0) {
+        if (WRITE) { ocnt = a.cnt_off[lg]; obyte = a.byte_off[lg]; }
+        {   // "%d    " (gathering.py:42)
             const int nd = ofg_ndigits((unsigned long long)gene);
             if (WRITE && lane == 0) {
                 char* o = a.out_text + obyte;
-                int n = ofg_put_u64(o, (unsigned long long)gene);
+                const int n = ofg_put_u64(o, (unsigned long long)gene);
                 o[n] = ' '; o[n + 1] = ' '; o[n + 2] = ' '; o[n + 3] = ' ';
             }
             bytes += nd + 4;
             obyte += nd + 4;
         }
-        if (pair >= 0) {
-            const PairDesc& pd = a.g.pairs[pair];
-            const int64_t row = pd.row_base + (gene - pd.gi_start);
-            const int n = (int)a.g.rowlen[row];
-            const u32 s0 = a.g.row_start[row];
-            const unsigned long long goff = (unsigned long long)a.seq_start[j];
-            for (int k0 = 0; k0 < n; k0 += 32) {
-                const int k = k0 + lane;
-                u32 cw = 0;
-                if (k < n) cw = a.g.cols[s0 + k];
-                const int mult = ((cw & OFG_FLAG_CONNECT) ? 1 : 0) + ((cw & OFG_FLAG_REVERSE) ? 1 : 0);
-                const bool on = k < n && mult > 0;
-                double w = 0.0;
+        int nlist = 0;
+        // flush the buffered edges: one edge per lane
+        auto flush = [&]() {
+            for (int b0 = 0; b0 < nlist; b0 += 32) {
+                const int i = b0 + lane;
+                const bool on = i < nlist;
                 int len = 0;
                 bool ok = true;
-                const unsigned long long gc = goff + (cw & OFG_COL_MASK);
+                u64 gc = 0;
+                double wt = 0.0;
                 if (on) {
-                    w = __dmul_rn((double)mult, a.g.vals[s0 + k]);  // (connect + connect^T) .* B
-                    len = ofg_format_entry(gc, w, nullptr, &ok);
+                    gc = s_gc[w][i];
+                    wt = s_w[w][i];
+                    len = ofg_format_entry(gc, wt, nullptr, &ok);
                     if (!ok) atomicOr(a.err_flags, 4u);
                 }
-                // warp exclusive scans of the edge count and the byte count
-                const u32 bal = __ballot_sync(OFG_FULL, on);
-                const u32 epos = __popc(bal & lanemask_lt());
-                u32 binc = warp_incl_scan((u32)len);
-                const u32 bpos = binc - (u32)len;
+                const u32 binc = warp_incl_scan((u32)len);
                 const u32 btot = __shfl_sync(OFG_FULL, binc, 31);
                 if (WRITE && on) {
-                    a.out_indices[ocnt + epos] = (int32_t)gc;
-                    a.out_data[ocnt + epos] = w;
-                    ofg_format_entry(gc, w, a.out_text + obyte + bpos, &ok);
+                    a.out_indices[ocnt + i - b0] = (int32_t)gc;
+                    a.out_data[ocnt + i - b0] = wt;
+                    ofg_format_entry(gc, wt, a.out_text + obyte + (binc - (u32)len), &ok);
                 }
-                cnt += __popc(bal);
-                bytes += btot;
-                ocnt += __popc(bal);
+                const int nb = nlist - b0 < 32 ? nlist - b0 : 32;
+                ocnt += nb;
                 obyte += btot;
+                bytes += btot;
+                cnt += nb;
             }
+            nlist = 0;
+            __syncwarp();
+        };
+        for (int j0 = 0; j0 < S; j0 += 32) {
+            // row descriptors of up to 32 target species
+            const int j = j0 + lane;
+            u32 n = 0, s0 = 0;
+            if (j < S) {
+                const int pair = a.g.pair_of[p * S + j];
+                if (pair >= 0) {
+                    const PairDesc& pd = a.g.pairs[pair];
+                    const int64_t row = pd.row_base + (gene - pd.gi_start);
+                    n = a.g.rowlen[row];
+                    s0 = a.g.row_start[row];
+                }
+                s_goff[w][lane] = (u64)a.seq_start[j];
+            }
+            const u32 inc = warp_incl_scan(n);
+            s_s0[w][lane] = s0;
+            s_pre[w][lane] = inc - n;
+            if (lane == 31) s_pre[w][32] = inc;
+            __syncwarp();
+            const u32 total = s_pre[w][32];
+            for (u32 e0 = 0; e0 < total; e0 += 32) {
+                const u32 e = e0 + lane;
+                bool on = false;
+                u64 gc = 0;
+                double wt = 0.0;
+                if (e < total) {
+                    // species slot holding entry e: last jj with pre[jj] <= e
+                    int lo = 0, hi = 32;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_pre[w][mid] <= e) lo = mid; else hi = mid;
+                    }
+                    const u32 slot = s_s0[w][lo] + (e - s_pre[w][lo]);
+                    const u32 cw = a.g.cols[slot];
+                    const int mult = ((cw & OFG_FLAG_CONNECT) ? 1 : 0) + ((cw & OFG_FLAG_REVERSE) ? 1 : 0);
+                    if (mult) {
+                        on = true;
+                        gc = s_goff[w][lo] + (cw & OFG_COL_MASK);
+                        wt = __dmul_rn((double)mult, a.g.vals[slot]);  // (connect + connect^T) .* B
+                    }
+                }
+                const u32 bal = __ballot_sync(OFG_FULL, on);
+                const int nb = __popc(bal);
+                if (nlist + nb > EMIT_LIST) flush();
+                if (on) {
+                    const int pos = nlist + __popc(bal & lanemask_lt());
+                    s_gc[w][pos] = gc;
+                    s_w[w][pos] = wt;
+                }
+                nlist += nb;
+                __syncwarp();
+            }
+            __syncwarp();
         }
-        if (j == S - 1) {
-            if (WRITE && lane == 0) { a.out_text[obyte] = '$'; a.out_text[obyte + 1] = '\n'; }
-            bytes += 2;
-        }
-        if (!WRITE && lane == 0) { a.unit_cnt[u] = cnt; a.unit_bytes[u] = bytes; }
+        flush();
+        // "$\n" (gathering.py:47)
+        if (WRITE && lane == 0) { a.out_text[obyte] = '$'; a.out_text[obyte + 1] = '\n'; }
+        bytes += 2;
+        if (!WRITE && lane == 0) { a.gene_cnt[lg] = cnt; a.gene_bytes[lg] = bytes; }
     }
 }

@@ -14,11 +14,13 @@
 #include "ofg_log10.cuh"
 
 // ---------------------------------------------------------------- segmented stable radix sort
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 8;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 records
 constexpr int RS_MAX_BITS = 9;
 constexpr int RS_MAX_DIGITS = 1 << RS_MAX_BITS;
+static_assert(RS_MAX_DIGITS == RS_THREADS, "one digit per thread in the offset phase");
 
 struct RadixArgs {
     const u32* key_in;
@@ -36,7 +38,9 @@ struct RadixArgs {
 __device__ __forceinline__ void rs_tile_range(const RadixArgs& a, int64_t tile, int& pair, int64_t& e0, int& cnt,
                                               int64_t& cidx0, int64_t& ntp)
 {
-    pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
+    // tiles are visited in increasing order: the pair index only moves forward
+    if (pair < 0) pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
+    while (tile >= a.tile_prefix[pair + 1]) pair++;
     const int64_t t = tile - a.tile_prefix[pair];
     ntp = a.tile_prefix[pair + 1] - a.tile_prefix[pair];
     e0 = a.pair_slot[pair] + t * RS_TILE;
@@ -50,44 +54,57 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(RadixArgs a)
     __shared__ u32 s_hist[RS_MAX_DIGITS];
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
+    int pair = -1;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        int pair, cnt;
+        int cnt;
         int64_t e0, cidx0, ntp;
         rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
-        for (int d = threadIdx.x; d < nd; d += RS_THREADS) s_hist[d] = 0;
+        s_hist[threadIdx.x] = 0;
         __syncthreads();
         for (int k = threadIdx.x; k < cnt; k += RS_THREADS) atomicAdd(&s_hist[(a.key_in[e0 + k] >> a.shift) & mask], 1u);
         __syncthreads();
-        for (int d = threadIdx.x; d < nd; d += RS_THREADS) a.counters[cidx0 + (int64_t)d * ntp] = s_hist[d];
+        if ((int)threadIdx.x < nd) a.counters[cidx0 + (int64_t)threadIdx.x * ntp] = s_hist[threadIdx.x];
         __syncthreads();
     }
 }
 
-// counters must hold the exclusive scan (global destination of the first record of each
-// (pair, digit, tile) group) when this runs.
+// Dynamic shared memory of radix_scatter_kernel
+struct RadixSmem {
+    double val[RS_TILE];                    // 32 KB  records in tile-sorted order
+    u32 key[RS_TILE];                       // 16 KB
+    unsigned short cnt[RS_WARPS][RS_MAX_DIGITS];  // 16 KB per-warp digit counts -> per-warp offsets inside a digit run
+    u32 gbase[RS_MAX_DIGITS];               // global destination of the first record of each digit run
+    u32 tbase[RS_MAX_DIGITS];               // tile-local start of each digit run
+    u32 scan[RS_WARPS + 1];
+};
+
+// counters must hold the exclusive scan (global destination of the first record of each (pair, digit, tile)
+// group) when this runs.  Stable: ranks follow (warp, iteration, lane) == input order.  Records are first
+// permuted into tile-sorted order in shared memory so that every digit run leaves as one coalesced write.
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
 {
-    __shared__ u32 s_cnt[RS_THREADS / 32][RS_MAX_DIGITS];  // per-warp digit counts -> per-warp bases
-    __shared__ u32 s_gbase[RS_MAX_DIGITS];
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    RadixSmem& sm = *reinterpret_cast<RadixSmem*>(rs_smem_raw);
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
     const int w = threadIdx.x >> 5, lane = lane_id();
+    int pair = -1;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        int pair, cnt;
+        int cnt;
         int64_t e0, cidx0, ntp;
         rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
-        for (int d = threadIdx.x; d < RS_MAX_DIGITS * (RS_THREADS / 32); d += RS_THREADS) (&s_cnt[0][0])[d] = 0;
-        for (int d = threadIdx.x; d < nd; d += RS_THREADS) s_gbase[d] = a.counters[cidx0 + (int64_t)d * ntp];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) sm.cnt[ww][threadIdx.x] = 0;
+        sm.gbase[threadIdx.x] = (int)threadIdx.x < nd ? a.counters[cidx0 + (int64_t)threadIdx.x * ntp] : 0u;
         u32 key[RS_ITEMS];
-        uint16_t loc[RS_ITEMS];
-        // warp w owns records [w*512, w*512+512) of the tile, iteration it covers 32 consecutive ones:
-        // order (warp, iteration, lane) == input order, which makes the ranking stable.
-        // All loads are issued before the (serialising) ranking loop.
-        const int kbase = w * (RS_ITEMS * 32) + lane;
+        double val[RS_ITEMS];
+        unsigned short loc[RS_ITEMS];
+        const int kbase = w * (RS_ITEMS * 32) + lane;  // warp w owns records [w*256, w*256+256) of the tile
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
             const int k = kbase + it * 32;
             key[it] = k < cnt ? a.key_in[e0 + k] : 0u;
+            val[it] = k < cnt ? a.val_in[e0 + k] : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -99,43 +116,49 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
             const int leader = __ffs(peers) - 1;
             u32 old = 0;
             if (valid && lane == leader) {
-                old = s_cnt[w][d];
-                s_cnt[w][d] = old + (u32)__popc(peers);
+                old = sm.cnt[w][d];
+                sm.cnt[w][d] = (unsigned short)(old + (u32)__popc(peers));
             }
             old = __shfl_sync(OFG_FULL, old, leader);
-            loc[it] = (uint16_t)(old + (u32)__popc(peers & lanemask_lt()));
+            loc[it] = (unsigned short)(old + (u32)__popc(peers & lanemask_lt()));
             __syncwarp();
         }
         __syncthreads();
-        // exclusive prefix over warps for every digit, plus the global base
-        for (int d = threadIdx.x; d < nd; d += RS_THREADS) {
-            u32 run = s_gbase[d];
+        // thread d: exclusive prefix over warps inside digit d, then tile-local start of the digit run
+        u32 total = 0;
+        {
+            const int d = threadIdx.x;
 #pragma unroll
-            for (int ww = 0; ww < RS_THREADS / 32; ww++) {
-                const u32 c = s_cnt[ww][d];
-                s_cnt[ww][d] = run;
-                run += c;
+            for (int ww = 0; ww < RS_WARPS; ww++) {
+                const u32 c = sm.cnt[ww][d];
+                sm.cnt[ww][d] = (unsigned short)total;
+                total += c;
+            }
+        }
+        u32 tile_total;
+        const u32 tb = block_excl_scan<RS_THREADS>(total, sm.scan, &tile_total);
+        sm.tbase[threadIdx.x] = tb;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int k = kbase + it * 32;
+            if (k < cnt) {
+                const u32 d = (key[it] >> a.shift) & mask;
+                const u32 tpos = sm.tbase[d] + sm.cnt[w][d] + loc[it];
+                sm.key[tpos] = key[it];
+                sm.val[tpos] = val[it];
             }
         }
         __syncthreads();
-        // payload: 8 loads in flight, then 8 scattered stores, twice
 #pragma unroll
-        for (int h = 0; h < RS_ITEMS; h += 8) {
-            double val[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int k = kbase + (h + t) * 32;
-                val[t] = k < cnt ? a.val_in[e0 + k] : 0.0;
-            }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const int k = kbase + (h + t) * 32;
-                if (k < cnt) {
-                    const u32 d = (key[h + t] >> a.shift) & mask;
-                    const u32 dst = s_cnt[w][d] + loc[h + t];
-                    a.key_out[dst] = key[h + t];
-                    a.val_out[dst] = val[t];
-                }
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int i = it * RS_THREADS + threadIdx.x;
+            if (i < cnt) {
+                const u32 kk = sm.key[i];
+                const u32 d = (kk >> a.shift) & mask;
+                const u32 dst = sm.gbase[d] + ((u32)i - sm.tbase[d]);
+                a.key_out[dst] = kk;
+                a.val_out[dst] = sm.val[i];
             }
         }
         __syncthreads();
