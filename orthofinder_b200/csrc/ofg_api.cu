@@ -525,11 +525,11 @@ int stage_norm(ofg_ctx* c)
     b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
     b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
     if (n_tasks > 0) {
-        const int g = grid_for(c, n_tasks, 1, 12);
+        const int g = grid_for(c, n_tasks, BIN_WARPS, 6);
         bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
         CKL("bin_cut_kernel");
         if (device_scan<u64>(c, b.cnt, n_tasks, c->sel_off.as<u64>(), 1)) return OFG_ERR_CUDA;
-        bin_select_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
+        bin_select_kernel<<<grid_for(c, n_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
         CKL("bin_select_kernel");
     } else {
         CK(cudaMemsetAsync(c->sel_off.p, 0, 16, c->stream));
@@ -574,8 +574,15 @@ int stage_norm(ofg_ctx* c)
         const int g2 = grid_for(c, c->n_rows, 8, 8);
         scale_bh_kernel<<<g2, 256, 0, c->stream>>>(sa);
         CKL("scale_bh_kernel");
-        bh_self_kernel<<<g2, 256, 0, c->stream>>>(sa);
-        CKL("bh_self_kernel");
+        std::vector<int32_t> diag;
+        int64_t max_gi = 1;
+        for (int i = 0; i < P; i++) if (c->pairs[i].same) { diag.push_back(i); max_gi = std::max<int64_t>(max_gi, c->pairs[i].Gi); }
+        if (!diag.empty()) {
+            if (upload(c, c->file_off, diag.data(), diag.size() * 4)) return OFG_ERR_CUDA;  // small scratch buffer
+            dim3 gd((unsigned)std::min<int64_t>((max_gi + 7) / 8, 256), (unsigned)diag.size());
+            bh_self_kernel<<<gd, 256, 0, c->stream>>>(sa, c->file_off.as<int32_t>());
+            CKL("bh_self_kernel");
+        }
     }
     CK(cudaEventRecord(c->ev[6], c->stream));
     // host sync 3: fit table, error flags

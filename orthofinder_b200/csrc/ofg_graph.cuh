@@ -84,6 +84,14 @@ __global__ void __launch_bounds__(256) factors_kernel(FactorArgs a)
     }
 }
 
+// rows are visited in increasing order by every warp: the pair index only moves forward
+__device__ __forceinline__ int advance_pair(const int64_t* pair_row_base, int P, int pair, int64_t row)
+{
+    if (pair < 0) pair = upper_bound_dev(pair_row_base, P + 1, row) - 1;
+    while (row >= pair_row_base[pair + 1]) pair++;
+    return pair;
+}
+
 // ---------------------------------------------------------------- scale + best hits
 struct ScaleArgs {
     int64_t n_rows;
@@ -105,10 +113,11 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
 {
     const int lane = lane_id();
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int pair = -1;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
         const int n = (int)a.rowlen[row];
         if (n == 0) continue;
-        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
         const PairDesc& pd = a.pairs[pair];
         if (a.fit[(size_t)pair * 8 + 6] == 0.0) {  // zeroed pair: sparse.lil_matrix(B.get_shape())
             if (lane == 0) a.rowlen[row] = 0;
@@ -136,18 +145,18 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
     }
 }
 
-__global__ void __launch_bounds__(256) bh_self_kernel(ScaleArgs a)
+__global__ void __launch_bounds__(256) bh_self_kernel(ScaleArgs a, const int32_t* diag_pairs)
 {
+    // grid.y = index into the list of within-species pairs; warps stride over that pair's rows
     const int lane = lane_id();
+    const PairDesc& pd = a.pairs[diag_pairs[blockIdx.y]];
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+    for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < pd.Gi; q += n_warps) {
+        const int64_t row = pd.row_base + q;
         const int n = (int)a.rowlen[row];
         if (n == 0) continue;
-        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
-        const PairDesc& pd = a.pairs[pair];
-        if (!pd.same) continue;
         const u32 s0 = a.row_start[row];
-        const double b = a.best[pd.gi_start + (row - pd.row_base)];
+        const double b = a.best[pd.gi_start + q];
         const double bestv = (__double_as_longlong(b) == 0) ? -1.0 : b;  // bestHitForSequence starts at -1
         const double thr = __dsub_rn(bestv, 1e-3);
         for (int k = lane; k < n; k += 32)
@@ -188,10 +197,11 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
 {
     const int lane = lane_id();
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int pair = -1;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
         const int n = (int)a.rowlen[row];
         if (n == 0) continue;
-        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
         const PairDesc& pd = a.pairs[pair];
         if (pd.same || !pd.owned_row) continue;
         const int tp = a.pair_of[pd.j * a.S + pd.p];
@@ -232,10 +242,11 @@ __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
 {
     const int lane = lane_id();
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int pair = -1;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
         const int n = (int)a.rowlen[row];
         if (n == 0) continue;
-        const int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
         const PairDesc& pd = a.pairs[pair];
         const u32 s0 = a.row_start[row];
         const u32 r = (u32)(row - pd.row_base);

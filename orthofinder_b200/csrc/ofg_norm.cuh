@@ -192,133 +192,135 @@ struct BinArgs {
     u64 sel_cap;
 };
 
-// k-th smallest (0-based) of n positive doubles held in shared memory as bit patterns; also returns
-// how many are <= it.  Whole CTA participates.
-__device__ u64 bin_kth(const u64* s_bits, int n, int k, u32* s_hist, u32* s_tmp, int* n_le)
+// One WARP per length bin (no CTA barriers).  k-th smallest (0-based) of n positive doubles held in this
+// warp's shared-memory slice as bit patterns, by an 8-pass radix select with a warp-private histogram;
+// also returns how many values are <= it.
+__device__ __forceinline__ u64 warp_kth(const u64* s_bits, int n, int k, u32* s_hist, int* n_le)
 {
+    const int lane = lane_id();
     u64 prefix = 0;
     int kk = k;
     for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int d = threadIdx.x; d < 256; d += BIN_THREADS) s_hist[d] = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += BIN_THREADS) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) s_hist[lane * 8 + t] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
             const u64 b = s_bits[i];
             const bool match = (shift == 56) || ((b >> (shift + 8)) == prefix);
             if (match) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // lane l owns buckets [8l, 8l+8)
-            u32 h[8], s = 0;
+        __syncwarp();
+        // lane l owns buckets [8l, 8l+8)
+        u32 h[8], sum = 0;
 #pragma unroll
-            for (int t = 0; t < 8; t++) { h[t] = s_hist[threadIdx.x * 8 + t]; s += h[t]; }
-            const u32 inc = warp_incl_scan(s);
-            const u32 exc = inc - s;
-            const bool mine = (u32)kk >= exc && (u32)kk < inc;
-            if (mine) {
-                u32 run = exc;
-                int bsel = 0;
+        for (int t = 0; t < 8; t++) { h[t] = s_hist[lane * 8 + t]; sum += h[t]; }
+        const u32 inc = warp_incl_scan(sum);
+        const u32 exc = inc - sum;
+        const bool mine = (u32)kk >= exc && (u32)kk < inc;
+        u32 bsel = 0, below = exc;
+        if (mine) {
+            u32 run = exc;
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    if ((u32)kk >= run && (u32)kk < run + h[t]) bsel = t;
-                    run += h[t];
-                }
-                u32 below = exc;
-                for (int t = 0; t < bsel; t++) below += h[t];
-                s_tmp[0] = (u32)(threadIdx.x * 8 + bsel);
-                s_tmp[1] = below;
+            for (int t = 0; t < 8; t++) {
+                if ((u32)kk >= run + h[t]) { below = run + h[t]; bsel = t + 1; }
+                run += h[t];
             }
         }
-        __syncthreads();
-        prefix = (prefix << 8) | (u64)s_tmp[0];
-        kk -= (int)s_tmp[1];
-        __syncthreads();
+        const u32 src = __ffs(__ballot_sync(OFG_FULL, mine)) - 1;
+        const u32 bucket = __shfl_sync(OFG_FULL, (u32)(lane * 8) + bsel, src);
+        const u32 blw = __shfl_sync(OFG_FULL, below, src);
+        prefix = (prefix << 8) | (u64)bucket;
+        kk -= (int)blw;
+        __syncwarp();
     }
-    // count <= value
-    if (threadIdx.x == 0) s_tmp[2] = 0;
-    __syncthreads();
     u32 c = 0;
-    for (int i = threadIdx.x; i < n; i += BIN_THREADS) c += (s_bits[i] <= prefix);
+    for (int i = lane; i < n; i += 32) c += (s_bits[i] <= prefix);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(OFG_FULL, c, d);
-    if (lane_id() == 0 && c) atomicAdd(&s_tmp[2], c);
-    __syncthreads();
-    *n_le = (int)s_tmp[2];
-    __syncthreads();
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(OFG_FULL, c, d);
+    *n_le = (int)c;
     return prefix;
 }
 
+constexpr int BIN_WARPS = 4;
+static_assert(BIN_WARPS * 32 == BIN_THREADS, "one warp per bin");
+
 __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
 {
-    __shared__ u64 s_bits[BIN_MAXN];
-    __shared__ u32 s_hist[256];
-    __shared__ u32 s_tmp[4];
-    __shared__ u64 s_min;
-    for (int64_t t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+    __shared__ u64 s_bits_all[BIN_WARPS][BIN_MAXN];
+    __shared__ u32 s_hist_all[BIN_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = lane_id();
+    u64* s_bits = s_bits_all[w];
+    u32* s_hist = s_hist_all[w];
+    const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
+    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
         const BinTask bt = a.tasks[t];
         if (bt.take_all) {
-            if (threadIdx.x == 0) { a.cut[t] = 0.0; a.cnt[t] = bt.n; }
+            if (lane == 0) { a.cut[t] = 0.0; a.cnt[t] = bt.n; }
             continue;
         }
         const int n = (int)bt.n;
-        for (int i = threadIdx.x; i < n; i += BIN_THREADS) s_bits[i] = (u64)__double_as_longlong(a.val[bt.first + i]);
-        __syncthreads();
+        for (int i = lane; i < n; i += 32) s_bits[i] = (u64)__double_as_longlong(a.val[bt.first + i]);
+        __syncwarp();
         const int k = n == 1000 ? a.k1000 : (n == 200 ? a.k200 : a.k20);
         const double g = n == 1000 ? a.g1000 : (n == 200 ? a.g200 : a.g20);
         int n_le;
-        const u64 ak = bin_kth(s_bits, n, k, s_hist, s_tmp, &n_le);
+        const u64 ak = warp_kth(s_bits, n, k, s_hist, &n_le);
         u64 ak1 = ak;
         if (n_le <= k + 1) {  // a[k+1] is the smallest value above a[k]
-            if (threadIdx.x == 0) s_min = ~0ULL;
-            __syncthreads();
             u64 m = ~0ULL;
-            for (int i = threadIdx.x; i < n; i += BIN_THREADS) {
+            for (int i = lane; i < n; i += 32) {
                 const u64 b = s_bits[i];
                 if (b > ak && b < m) m = b;
             }
-            if (m != ~0ULL) atomicMin(&s_min, m);
-            __syncthreads();
-            ak1 = s_min;
-            if (ak1 == ~0ULL) ak1 = ak;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const u64 o = __shfl_xor_sync(OFG_FULL, m, d);
+                m = o < m ? o : m;
+            }
+            ak1 = (m == ~0ULL) ? ak : m;
         }
         const double va = __longlong_as_double((long long)ak), vb = __longlong_as_double((long long)ak1);
         // numpy _lerp for gamma < 0.5: a + (b - a) * gamma, separately rounded
         const double cut = __dadd_rn(va, __dmul_rn(__dsub_rn(vb, va), g));
-        if (threadIdx.x == 0) s_tmp[3] = 0;
-        __syncthreads();
         u32 c = 0;
-        for (int i = threadIdx.x; i < n; i += BIN_THREADS) c += (__longlong_as_double((long long)s_bits[i]) >= cut);
+        for (int i = lane; i < n; i += 32) c += (__longlong_as_double((long long)s_bits[i]) >= cut);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(OFG_FULL, c, d);
-        if (lane_id() == 0 && c) atomicAdd(&s_tmp[3], c);
-        __syncthreads();
-        if (threadIdx.x == 0) { a.cut[t] = cut; a.cnt[t] = s_tmp[3]; }
-        __syncthreads();
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(OFG_FULL, c, d);
+        if (lane == 0) { a.cut[t] = cut; a.cnt[t] = c; }
+        __syncwarp();
     }
 }
 
 __global__ void __launch_bounds__(BIN_THREADS) bin_select_kernel(BinArgs a)
 {
-    __shared__ u32 s_scan[BIN_THREADS / 32 + 1];
-    for (int64_t t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+    const int w = threadIdx.x >> 5, lane = lane_id();
+    const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
+    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
         const BinTask bt = a.tasks[t];
         const double cut = a.cut[t];
         u64 out = a.sel_off[t];
-        for (u32 i0 = 0; i0 < bt.n; i0 += BIN_THREADS) {
-            const u32 i = i0 + threadIdx.x;
-            double sc = 0.0;
-            bool sel = false;
-            if (i < bt.n) {
-                sc = a.val[bt.first + i];
-                sel = bt.take_all || (sc >= cut);
+        for (u32 i0 = 0; i0 < bt.n; i0 += 128) {
+            double sc[4];
+            bool sel[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {  // four independent loads in flight
+                const u32 i = i0 + u * 32 + lane;
+                sc[u] = i < bt.n ? a.val[bt.first + i] : 0.0;
             }
-            u32 tot;
-            const u32 ex = block_excl_scan<BIN_THREADS>(sel ? 1u : 0u, s_scan, &tot);
-            if (sel && out + ex < a.sel_cap) {
-                a.lx[out + ex] = ofg_log10_svml((double)a.key[bt.first + i]);
-                a.ly[out + ex] = ofg_log10_svml(sc);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const u32 i = i0 + u * 32 + lane;
+                sel[u] = i < bt.n && (bt.take_all || sc[u] >= cut);
+                const u32 bal = __ballot_sync(OFG_FULL, sel[u]);
+                if (sel[u]) {
+                    const u64 o = out + __popc(bal & lanemask_lt());
+                    if (o < a.sel_cap) {
+                        a.lx[o] = ofg_log10_svml((double)a.key[bt.first + i]);
+                        a.ly[o] = ofg_log10_svml(sc[u]);
+                    }
+                }
+                out += __popc(bal);
             }
-            out += tot;
         }
     }
 }
