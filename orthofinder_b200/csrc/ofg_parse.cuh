@@ -81,9 +81,11 @@ __device__ __forceinline__ void rel_mask128(const u32* m, int st, u64* lo, u64* 
 }
 __device__ __forceinline__ int ctz128(u64 lo, u64 hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
 
-// Field boundaries relative to the record start: first / second tab, tab before field 11, end of field 11.
+// Field boundaries relative to the record start for a record with EXACTLY 12 fields inside a 128-byte
+// window: first and second tab, the last (11th) tab and the line end.  Anything else is left to the
+// generic parser.
 __device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* s_term, int st, bool act, int* tab1, int* tab2,
-                                                   int* tab11, int* score_end)
+                                                   int* tab11, int* line_end)
 {
     u64 ea, eb, ta, tb;
     rel_mask128(s_term, st, &ea, &eb);
@@ -93,65 +95,99 @@ __device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* 
     // tabs of this record only
     if (le < 64) { ta &= (1ULL << le) - 1ULL; tb = 0; }
     else if (le < 128) { tb &= (1ULL << (le - 64)) - 1ULL; }
-    ok = ok && (__popcll(ta) + __popcll(tb) >= 11);
+    ok = ok && (__popcll(ta) + __popcll(tb) == 11);
     const u64 t2m = ta & (ta - 1ULL);
     ok = ok && t2m != 0;  // the two id fields end inside the first 64 bytes
     *tab1 = __ffsll((long long)ta) - 1;
     *tab2 = __ffsll((long long)t2m) - 1;
-    u64 a = ta, b = tb;
-#pragma unroll
-    for (int k = 0; k < 10; k++) {  // drop the ten lowest tabs
-        if (a) a &= a - 1ULL; else b &= b - 1ULL;
-    }
-    *tab11 = ctz128(a, b);
-    if (a) a &= a - 1ULL; else b &= b - 1ULL;
-    *score_end = (a | b) ? ctz128(a, b) : le;
+    *tab11 = tb ? 127 - __clzll((long long)tb) : 63 - __clzll((long long)ta);
+    *line_end = le;
     return ok;
 }
 
-__device__ __forceinline__ bool conv_id(const uint8_t* s, int p, int len, bool act, u32* out)
+// 8 bytes [end - 8, end) of the staged text as a little-endian u64 (byte end-1 is the most significant).
+// The buffer has a 16-byte front pad, so end >= 0 is enough.
+__device__ __forceinline__ u64 load8_ending_at(const uint8_t* s_text, int end)
 {
-    const int maxlen = __reduce_max_sync(OFG_FULL, act ? len : 0);
-    u32 v = 0;
-    int nd = 0;
-    bool seen = false, bad = false;
-    for (int i = 0; i < maxlen; i++) {
-        if (act && i < len) {
-            const u32 c = s[p + i];
-            const u32 d = c - (u32)'0';
-            if (!seen) seen = (c == (u32)'_');
-            else if (d > 9u) bad = true;
-            else { v = v * 10u + d; nd++; }
-        }
-    }
-    *out = v;
-    return act && seen && !bad && nd >= 1 && nd <= 9;
+    const int a = end - 8;
+    const u32* wp = reinterpret_cast<const u32*>(s_text + (a & ~3));  // (a & ~3) >= -16: inside the pad
+    const u32 a0 = wp[0], a1 = wp[1], a2 = wp[2];
+    const int sh = (a & 3) * 8;
+    return (u64)__funnelshift_r(a0, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
 }
 
-__device__ __forceinline__ bool conv_score(const uint8_t* s, int p, int len, bool act, double* out)
+// 0x80 in every byte of y that is zero (exact)
+__device__ __forceinline__ u64 zero_bytes64(u64 y)
 {
-    act = act && len >= 1 && len <= 10;
-    const int maxlen = __reduce_max_sync(OFG_FULL, act ? len : 0);
-    u32 m = 0;
-    int frac = -1, nd = 0;
-    bool bad = false;
-    for (int i = 0; i < maxlen; i++) {
-        if (act && i < len) {
-            const u32 c = s[p + i];
-            const u32 d = c - (u32)'0';
-            if (d <= 9u) { m = m * 10u + d; nd++; frac += (frac >= 0); }
-            else if (c == (u32)'.' && frac < 0) frac = 0;
-            else bad = true;
-        }
-    }
+    const u64 m = 0x7f7f7f7f7f7f7f7fULL;
+    return ~(((y & m) + m) | y | m);
+}
+
+// X holds 8 ASCII characters, first character in the lowest byte.  Returns false unless all are digits;
+// *out = their decimal value (SWAR, three multiplies).
+__device__ __forceinline__ bool swar_digits8(u64 X, u32* out)
+{
+    const bool ok = (((X + 0x4646464646464646ULL) | (X - 0x3030303030303030ULL)) & 0x8080808080808080ULL) == 0;
+    u64 v = X & 0x0F0F0F0F0F0F0F0FULL;
+    v = (v * 2561ULL) >> 8;
+    v = ((v & 0x00FF00FF00FF00FFULL) * 6553601ULL) >> 16;
+    v = ((v & 0x0000FFFF0000FFFFULL) * 42949672960001ULL) >> 32;
+    *out = (u32)v;
+    return ok;
+}
+
+// "<anything>_<1..7 digits>" of length 2..8 with exactly one underscore, ending at byte `end` (the tab).
+__device__ __forceinline__ bool swar_id(const uint8_t* s_text, int end, int len, bool act, u32* out)
+{
+    act = act && len >= 2 && len <= 8;
+    const int l = act ? len : 8, e = act ? end : 8;
+    const u64 w = load8_ending_at(s_text, e);
+    const u64 vm = ~0ULL << (8 * (8 - l));
+    const u64 us = zero_bytes64(w ^ 0x5f5f5f5f5f5f5f5fULL) & vm;
+    const bool one = us != 0 && (us & (us - 1ULL)) == 0;
+    const int u = one ? (__ffsll((long long)us) - 1) >> 3 : 0;  // byte index of the underscore
+    const int nd = 7 - u;
+    const bool shape = one && nd >= 1;
+    const int ndc = shape ? nd : 1;
+    const u64 D = w >> (8 * (8 - ndc));                       // digits, first digit in the lowest byte
+    const u64 X = (D << (8 * (8 - ndc))) | (0x3030303030303030ULL >> (8 * ndc));
+    u32 v;
+    const bool dig = swar_digits8(X, &v);
+    *out = v;
+    return act && shape && dig;
+}
+
+// "<digits>[.<digits>]" of length 1..8 ending at byte `end`, at most 8 digits: exact fp64 value.
+__device__ __forceinline__ bool swar_score(const uint8_t* s_text, int end, int len, bool act, double* out)
+{
+    act = act && len >= 1 && len <= 8;
+    const int l = act ? len : 8, e = act ? end : 8;
+    const u64 w = load8_ending_at(s_text, e);
+    const u64 vm = ~0ULL << (8 * (8 - l));
+    const u64 dots = zero_bytes64(w ^ 0x2e2e2e2e2e2e2e2eULL) & vm;
+    const bool has_dot = dots != 0;
+    const bool one = (dots & (dots - 1ULL)) == 0;  // zero or one dot
+    const int u = has_dot ? (__ffsll((long long)dots) - 1) >> 3 : 7;
+    const int frac = has_dot ? 7 - u : 0;
+    // remove the dot: everything below it moves up one byte
+    const u64 lower = w & ((1ULL << (8 * u)) - 1ULL);
+    const u64 upper = (u == 7) ? 0ULL : ((w >> (8 * (u + 1))) << (8 * (u + 1)));
+    const u64 Y = has_dot ? (upper | (lower << 8)) : w;
+    const int ndig = has_dot ? l - 1 : l;
+    const bool shape = one && ndig >= 1;
+    const int nc = shape ? ndig : 1;
+    const u64 X = (nc == 8) ? Y : ((Y & (~0ULL << (8 * (8 - nc)))) | (0x3030303030303030ULL >> (8 * nc)));
+    u32 m;
+    const bool dig = swar_digits8(X, &m);
     const double v = (double)m;
-    *out = frac > 0 ? v / OFG_POW10_DEV[frac > 9 ? 9 : frac] : v;  // exact: m < 2^30, one correctly rounded division
-    return act && !bad && nd >= 1 && nd <= 9;
+    *out = frac > 0 ? v / OFG_POW10_DEV[frac] : v;  // exact: m < 10^8, one correctly rounded division
+    return act && shape && dig;
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
 {
-    __shared__ __align__(16) uint8_t s_text[PARSE_TILE + PARSE_OVERLAP];
+    __shared__ __align__(16) uint8_t s_text_raw[16 + PARSE_TILE + PARSE_OVERLAP];  // 16-byte front pad for load8_ending_at
+    uint8_t* const s_text = s_text_raw + 16;
     __shared__ uint16_t s_lstart[PARSE_TILE / 2];
     __shared__ u32 s_term[PARSE_WORDS + 8];  // + padding read by the 128-bit windows: all terminators
     __shared__ u32 s_tab[PARSE_WORDS + 8];
@@ -258,11 +294,11 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
             const bool act = li < nl_total;
             const int st = act ? (int)s_lstart[li] : 0;
             u32 f0 = 0, f1 = 0;
-            int tab1, tab2, tab11, send;
-            bool fast = locate_fields_conv(s_tab, s_term, st, act, &tab1, &tab2, &tab11, &send);
-            const bool ok0 = conv_id(s_text, st, tab1, fast, &f0);
-            const bool ok1 = conv_id(s_text, st + tab1 + 1, tab2 - tab1 - 1, fast, &f1);
-            const bool ok2 = conv_score(s_text, st + tab11 + 1, send - tab11 - 1, fast, &score);
+            int tab1, tab2, tab11, lend;
+            bool fast = locate_fields_conv(s_tab, s_term, st, act, &tab1, &tab2, &tab11, &lend);
+            const bool ok0 = swar_id(s_text, st + tab1, tab1, fast, &f0);
+            const bool ok1 = swar_id(s_text, st + tab2, tab2 - tab1 - 1, fast, &f1);
+            const bool ok2 = swar_score(s_text, st + lend, lend - tab11 - 1, fast, &score);
             fast = fast && ok0 && ok1 && ok2;
             if (act) {
                 int rc = OFG_PL_OK;
