@@ -198,56 +198,64 @@ FIT_FN double fit_enorm_big(const double* x, long n, FitShared* sh)
     return o[0];
 }
 
-// sum_{i} a[i]*b[i], index order, product rounded before the add (products of a batch are formed ahead
-// of the ordered additions); same double-buffered staging, a in buf[0], b in buf[1]
-FIT_FN double fit_dot_big(const double* a, const double* b, long n, FitShared* sh)
+// Up to FIT_MAXV dot products side by side: out[v] = sum_i a[v][i]*b[v][i], index order, product rounded
+// before the add.  Chain v is accumulated by lane 0 of warp v from products staged (double buffered) by the
+// warps >= FIT_MAXV; the host build alternates staging and accumulation.
+FIT_FN void fit_dot_multi(int nv, const double* const* a, const double* const* b, const long* n, FitShared* sh, double* out)
 {
-    double sum = 0.0;
     const bool overlap = FIT_NT >= 128;
-    const int first_loader = 32, n_loaders = FIT_NT - 32;
-    const long n_chunks = (n + FIT_CH - 1) / FIT_CH;
-    if (overlap) {
-        if (FIT_TID >= first_loader) {
-            const int len = (int)(n < FIT_CH ? n : FIT_CH);
-            for (int i = FIT_TID - first_loader; i < len; i += n_loaders) sh->buf[0][0][i] = FMUL(a[i], b[i]);
+    double sum = 0.0;
+    if (!overlap) {
+        for (int v = 0; v < nv; v++) {
+            sum = 0.0;
+            for (long c0 = 0; c0 < n[v]; c0 += FIT_CH) {
+                const int len = (int)((n[v] - c0) < FIT_CH ? (n[v] - c0) : FIT_CH);
+                for (int i = FIT_TID; i < len; i += FIT_NT) sh->buf[0][0][i] = FMUL(a[v][c0 + i], b[v][c0 + i]);
+                FIT_SYNC();
+                if (FIT_TID == 0) sum = fit_ordered_sum(sum, sh->buf[0][0], len);
+                FIT_SYNC();
+            }
+            if (FIT_TID == 0) sh->out[v] = sum;
         }
-        FIT_SYNC();
-    }
-    for (long c = 0; c < n_chunks; c++) {
-        const long c0 = c * FIT_CH;
-        const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
-        if (!overlap) {
-            for (int i = FIT_TID; i < len; i += FIT_NT) { sh->buf[0][c & 1][i] = a[c0 + i]; sh->buf[1][c & 1][i] = b[c0 + i]; }
+    } else {
+        const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;
+        const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
+        long nmax = 0;
+        for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
+        const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
+        for (long c = -1; c < n_chunks; c++) {
+            if (FIT_TID >= first_loader) {
+                const long c1 = (c + 1) * FIT_CH;
+                for (int v = 0; v < nv; v++) {
+                    if (c1 >= n[v]) continue;
+                    const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
+                    for (int i = FIT_TID - first_loader; i < len; i += n_loaders)
+                        sh->buf[v][(c + 1) & 1][i] = FMUL(a[v][c1 + i], b[v][c1 + i]);
+                }
+            } else if (c >= 0 && my_v >= 0 && my_v < nv) {
+                const long c0 = c * FIT_CH;
+                if (c0 < n[my_v]) {
+                    const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
+                    sum = fit_ordered_sum(sum, sh->buf[my_v][c & 1], len);
+                }
+            }
             FIT_SYNC();
         }
-        if (overlap && FIT_TID >= first_loader) {
-            const long c1 = c0 + FIT_CH;
-            if (c1 < n) {
-                const int l1 = (int)((n - c1) < FIT_CH ? (n - c1) : FIT_CH);
-                for (int i = FIT_TID - first_loader; i < l1; i += n_loaders) sh->buf[0][(c + 1) & 1][i] = FMUL(a[c1 + i], b[c1 + i]);
-            }
-        } else if (overlap && FIT_TID == 0) {
-            sum = fit_ordered_sum(sum, sh->buf[0][c & 1], len);
-        } else if (FIT_TID == 0) {
-            const double* pa = sh->buf[0][c & 1];
-            const double* pb = sh->buf[1][c & 1];
-            int i = 0;
-            for (; i + 8 <= len; i += 8) {
-                double q[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) q[k] = FMUL(pa[i + k], pb[i + k]);
-#pragma unroll
-                for (int k = 0; k < 8; k++) sum = FADD(sum, q[k]);
-            }
-            for (; i < len; i++) sum = FADD(sum, FMUL(pa[i], pb[i]));
-        }
-        FIT_SYNC();
+        if (my_v >= 0 && my_v < nv) sh->out[my_v] = sum;
     }
-    if (FIT_TID == 0) sh->out[0] = sum;
     FIT_SYNC();
-    const double r = sh->out[0];
+    for (int v = 0; v < nv; v++) out[v] = sh->out[v];
     FIT_SYNC();
-    return r;
+}
+
+FIT_FN double fit_dot_big(const double* a, const double* b, long n, FitShared* sh)
+{
+    const double* as[1] = {a};
+    const double* bs[1] = {b};
+    long ns[1] = {n};
+    double o[1];
+    fit_dot_multi(1, as, bs, ns, sh, o);
+    return o[0];
 }
 
 // f(x,a,b) - y with f = a*log10(x) + b : three separately rounded operations (gathering.py:82)
@@ -431,6 +439,8 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             ipvt[j] = j;
         }
         const int minmn = m < 2 ? (int)m : 2;
+        double qtf_dot0 = 0.0;
+        bool have_qtf_dot0 = false;
         for (int j = 0; j < minmn; j++) {
             int kmax = j;
             for (int k = j; k < 2; k++) if (rdiag[k] > rdiag[kmax]) kmax = k;
@@ -452,7 +462,16 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
                 FIT_SYNC();
                 for (int k = j + 1; k < 2; k++) {
                     double* ck = col[k];
-                    const double sum = fit_dot_big(cj + j, ck + j, m - j, sh);
+                    // the first Householder vector is final here: its product with the residual (needed for
+                    // qtf below) rides along with its product with the second column
+                    const double* das[2] = {cj + j, cj + j};
+                    const double* dbs[2] = {ck + j, fvec + j};
+                    long dns[2] = {m - j, m - j};
+                    double dout[2];
+                    fit_dot_multi(2, das, dbs, dns, sh, dout);
+                    const double sum = dout[0];
+                    qtf_dot0 = dout[1];
+                    have_qtf_dot0 = true;
                     const double temp = FDIV(sum, cj[j]);
                     for (long i = j + FIT_TID; i < m; i += FIT_NT) ck[i] = FSUB(ck[i], FMUL(temp, cj[i]));
                     FIT_SYNC();
@@ -482,7 +501,7 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
         for (int j = 0; j < 2; j++) {
             double* cj = col[j];
             if (j < m && cj[j] != 0.0) {
-                const double sum = fit_dot_big(cj + j, wa4 + j, m - j, sh);
+                const double sum = (j == 0 && have_qtf_dot0) ? qtf_dot0 : fit_dot_big(cj + j, wa4 + j, m - j, sh);
                 const double temp = FDIV(-sum, cj[j]);
                 for (long i = j + FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(wa4[i], FMUL(cj[i], temp));
                 FIT_SYNC();
