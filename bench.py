@@ -234,9 +234,17 @@ def run_ours(args):
             if best is None and ab:
                 best = (k, gbs, per, ab)
         out["kernels"] = rows
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            t = tj.get(best[0]) if best else None
+            if t and abs(t["workload_lines"] - c["lines"]) <= 0.01 * c["lines"]:
+                traffic = t["dram_bytes_per_launch"]  # from the committed ncu --set full capture of this workload
+        except Exception:
+            pass
         if best:
             out["roofline"] = {"bound": "hbm", "kernel": best[0], "achieved": best[1], "peak": peak, "unit": "GB/s",
-                               "frac": best[1] / peak, "traffic": None, "peak_source": how,
+                               "frac": best[1] / peak, "traffic": traffic, "peak_source": how,
                                "ms_per_launch": best[2], "alg_bytes_per_launch": best[3]}
         # whole-path figure of SURVEY.md §8(d): B_alg = T + 124 bytes per line
         T = text_bytes_all / max(c["lines"], 1)

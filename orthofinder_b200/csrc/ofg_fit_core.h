@@ -43,22 +43,43 @@
 #define FIT_CH 512   // doubles staged per chunk and buffer for the sequential chains
 #define FIT_MAXV 3   // chains that can run side by side (one per warp)
 
-struct FitShared {  // lives in shared memory on the device (24.6 KB)
-    double buf[FIT_MAXV][2][FIT_CH];  // staged squares (enorm) / products (dot), double buffered
+#define FIT_RING 3    // staging ring depth: chunk c+2 is being fetched while chunk c is accumulated
+
+struct FitShared {  // lives in shared memory on the device (36.9 KB)
+    double buf[FIT_MAXV][FIT_RING][FIT_CH];  // staged squares (enorm) / products (dot)
     double out[FIT_MAXV];
-    int tag[FIT_MAXV][2];             // chunk tag set when a staged chunk holds a value outside MINPACK's mid range
+    int tag[FIT_MAXV][FIT_RING];      // chunk tag set when a staged chunk holds a value outside MINPACK's mid range
 };
 
-// ordered sum of n staged terms (n even-aligned buffer), two per 16-byte shared-memory load
+// ordered sum of the staged terms q[0..len): strictly left to right.  On the device the next eight terms
+// are fetched (four 16-byte shared-memory loads) while the current eight are being added, so that the loop
+// runs at the latency of the dependent fp64 additions and nothing else.
+FIT_FN double fit_ordered_sum_var(double s, const double* q, int len);
+
+// Full chunks take the constant-trip-count instance (the compiler keeps the loads one batch ahead of the
+// additions there: 8.1 cycles per term measured on B200, the latency of a dependent DADD).
 FIT_FN double fit_ordered_sum(double s, const double* q, int len)
+{
+    if (len == FIT_CH) return fit_ordered_sum_var(s, q, FIT_CH);
+    return fit_ordered_sum_var(s, q, len);
+}
+
+FIT_FN double fit_ordered_sum_var(double s, const double* q, int len)
 {
     int i = 0;
 #if defined(__CUDACC__)
-    const double2* q2 = reinterpret_cast<const double2*>(q);
-    for (; i + 8 <= len; i += 8) {
-        const double2 a = q2[(i >> 1)], b = q2[(i >> 1) + 1], c = q2[(i >> 1) + 2], d = q2[(i >> 1) + 3];
+    if (len >= 8) {
+        const double2* q2 = reinterpret_cast<const double2*>(q);
+        double2 a = q2[0], b = q2[1], c = q2[2], d = q2[3];
+        for (; i + 16 <= len; i += 8) {
+            const double2 na = q2[(i >> 1) + 4], nb = q2[(i >> 1) + 5], nc = q2[(i >> 1) + 6], nd = q2[(i >> 1) + 7];
+            s = FADD(s, a.x); s = FADD(s, a.y); s = FADD(s, b.x); s = FADD(s, b.y);
+            s = FADD(s, c.x); s = FADD(s, c.y); s = FADD(s, d.x); s = FADD(s, d.y);
+            a = na; b = nb; c = nc; d = nd;
+        }
         s = FADD(s, a.x); s = FADD(s, a.y); s = FADD(s, b.x); s = FADD(s, b.y);
         s = FADD(s, c.x); s = FADD(s, c.y); s = FADD(s, d.x); s = FADD(s, d.y);
+        i += 8;
     }
 #endif
     for (; i < len; i++) s = FADD(s, q[i]);
@@ -154,33 +175,60 @@ FIT_FN void fit_enorm_multi(int nv, const double* const* x, const long* n, FitSh
         // squares of chunk c in index order: same operations as FitEnormAcc::add for mid-range values.  A chunk
         // holding a value outside the mid range is tagged and accumulated from the raw values instead.
         const double rdwarf = 3.834e-20;
-        for (long c = -1; c < n_chunks; c++) {
+        const int lt = FIT_TID - first_loader;  // loader index
+        for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
             if (FIT_TID >= first_loader) {
-                const long c1 = (c + 1) * FIT_CH;
+                const long cl = c + (FIT_RING - 1);          // chunk to stage now
+                const long c1 = cl * FIT_CH;
+                const int slot = (int)(cl % FIT_RING);
                 for (int v = 0; v < nv; v++) {
                     if (c1 >= n[v]) continue;
                     const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
                     const double agiant = FDIV(1.304e19, (double)n[v]);
                     bool odd = false;
-                    for (int i = FIT_TID - first_loader; i < len; i += n_loaders) {
-                        const double xa = fabs(x[v][c1 + i]);
-                        odd = odd || !(xa > rdwarf && xa < agiant);
-                        sh->buf[v][(c + 1) & 1][i] = FMUL(xa, xa);
+                    for (int i0 = 0; i0 < len; i0 += 4 * n_loaders) {
+                        double xv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {  // four independent loads in flight per loader
+                            const int i = i0 + u * n_loaders + lt;
+                            xv[u] = i < len ? fabs(x[v][c1 + i]) : 1.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = i0 + u * n_loaders + lt;
+                            if (i < len) {
+                                odd = odd || !(xv[u] > rdwarf && xv[u] < agiant);
+                                sh->buf[v][slot][i] = FMUL(xv[u], xv[u]);
+                            }
+                        }
                     }
-                    if (odd) sh->tag[v][(c + 1) & 1] = (int)(c + 2);
+                    if (odd) sh->tag[v][slot] = (int)(cl + 1);
                 }
             } else if (c >= 0 && my_v >= 0 && my_v < nv) {
                 const long c0 = c * FIT_CH;
                 if (c0 < n[my_v]) {
                     const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
-                    if (sh->tag[my_v][c & 1] == (int)(c + 1)) {
+                    const int slot = (int)(c % FIT_RING);
+                    if (sh->tag[my_v][slot] == (int)(c + 1)) {
                         for (int i = 0; i < len; i++) acc.add(x[my_v][c0 + i]);
                     } else {
-                        acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][c & 1], len);
+#ifdef FIT_PROFILE
+                        const long long tp0 = clock64();
+#endif
+                        acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][slot], len);
+#ifdef FIT_PROFILE
+                        if (my_v == 0) { g_t_sum += clock64() - tp0; g_n_chunks++; }
+#endif
                     }
                 }
             }
+#ifdef FIT_PROFILE
+            const long long tp1 = clock64();
+#endif
             FIT_SYNC();
+#ifdef FIT_PROFILE
+            if (FIT_TID == 0) g_t_wait += clock64() - tp1;
+#endif
         }
         if (my_v >= 0 && my_v < nv) sh->out[my_v] = acc.result();
     }
@@ -223,20 +271,35 @@ FIT_FN void fit_dot_multi(int nv, const double* const* a, const double* const* b
         long nmax = 0;
         for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
         const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
-        for (long c = -1; c < n_chunks; c++) {
+        const int lt = FIT_TID - first_loader;
+        for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
             if (FIT_TID >= first_loader) {
-                const long c1 = (c + 1) * FIT_CH;
+                const long cl = c + (FIT_RING - 1);
+                const long c1 = cl * FIT_CH;
+                const int slot = (int)(cl % FIT_RING);
                 for (int v = 0; v < nv; v++) {
                     if (c1 >= n[v]) continue;
                     const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
-                    for (int i = FIT_TID - first_loader; i < len; i += n_loaders)
-                        sh->buf[v][(c + 1) & 1][i] = FMUL(a[v][c1 + i], b[v][c1 + i]);
+                    for (int i0 = 0; i0 < len; i0 += 4 * n_loaders) {
+                        double av[4], bv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = i0 + u * n_loaders + lt;
+                            av[u] = i < len ? a[v][c1 + i] : 0.0;
+                            bv[u] = i < len ? b[v][c1 + i] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = i0 + u * n_loaders + lt;
+                            if (i < len) sh->buf[v][slot][i] = FMUL(av[u], bv[u]);
+                        }
+                    }
                 }
             } else if (c >= 0 && my_v >= 0 && my_v < nv) {
                 const long c0 = c * FIT_CH;
                 if (c0 < n[my_v]) {
                     const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
-                    sum = fit_ordered_sum(sum, sh->buf[my_v][c & 1], len);
+                    sum = fit_ordered_sum(sum, sh->buf[my_v][c % FIT_RING], len);
                 }
             }
             FIT_SYNC();
