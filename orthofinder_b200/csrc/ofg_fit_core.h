@@ -473,16 +473,27 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
     double fnorm = 0.0;
     bool have_fnorm = false;
     for (;;) {
-        // fdjac2
-        for (int j = 0; j < 2; j++) {
-            const double temp = x[j];
-            double h = FMUL(eps, fabs(temp));
-            if (h == 0.0) h = eps;
-            double xp[2] = {x[0], x[1]};
-            xp[j] = FADD(temp, h);
-            fit_resid(lx, ly, m, xp[0], xp[1], wa4);
-            double* cj = col[j];
-            for (long i = FIT_TID; i < m; i += FIT_NT) cj[i] = FDIV(FSUB(wa4[i], fvec[i]), h);
+        // fdjac2: both forward-difference columns in one pass (same per-element operations as evaluating
+        // f at x + h_j e_j into a scratch vector first)
+        {
+            double h[2], xp[2][2];
+            for (int j = 0; j < 2; j++) {
+                const double temp = x[j];
+                h[j] = FMUL(eps, fabs(temp));
+                if (h[j] == 0.0) h[j] = eps;
+                xp[j][0] = x[0];
+                xp[j][1] = x[1];
+                xp[j][j] = FADD(temp, h[j]);
+            }
+            double* cA = col[0];
+            double* cB = col[1];
+            for (long i = FIT_TID; i < m; i += FIT_NT) {
+                const double lxi = lx[i], lyi = ly[i], f = fvec[i];
+                const double w0 = FSUB(FADD(FMUL(xp[0][0], lxi), xp[0][1]), lyi);
+                const double w1 = FSUB(FADD(FMUL(xp[1][0], lxi), xp[1][1]), lyi);
+                cA[i] = FDIV(FSUB(w0, f), h[0]);
+                cB[i] = FDIV(FSUB(w1, f), h[1]);
+            }
             FIT_SYNC();
         }
         nfev += 2;
@@ -558,16 +569,31 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             delta = FMUL(factor, xnorm);
             if (delta == 0.0) delta = factor;
         }
-        // qtf
-        for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = fvec[i];
-        FIT_SYNC();
+        // qtf (wa4 = fvec, then the two Householder reflections; the copy is folded into the first one)
+        bool wa4_ready = false;
         for (int j = 0; j < 2; j++) {
             double* cj = col[j];
             if (j < m && cj[j] != 0.0) {
-                const double sum = (j == 0 && have_qtf_dot0) ? qtf_dot0 : fit_dot_big(cj + j, wa4 + j, m - j, sh);
-                const double temp = FDIV(-sum, cj[j]);
-                for (long i = j + FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(wa4[i], FMUL(cj[i], temp));
+                if (j == 0 && have_qtf_dot0) {
+                    const double temp = FDIV(-qtf_dot0, cj[0]);
+                    for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(fvec[i], FMUL(cj[i], temp));
+                    FIT_SYNC();
+                    wa4_ready = true;
+                } else {
+                    if (!wa4_ready) {
+                        for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = fvec[i];
+                        FIT_SYNC();
+                        wa4_ready = true;
+                    }
+                    const double sum = fit_dot_big(cj + j, wa4 + j, m - j, sh);
+                    const double temp = FDIV(-sum, cj[j]);
+                    for (long i = j + FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(wa4[i], FMUL(cj[i], temp));
+                    FIT_SYNC();
+                }
+            } else if (!wa4_ready) {
+                for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = fvec[i];
                 FIT_SYNC();
+                wa4_ready = true;
             }
             FIT_SYNC();
             if (FIT_TID == 0 && j < m) cj[j] = rdiag[j];
@@ -629,8 +655,7 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             }
             if (ratio >= 1e-4) {
                 for (int j = 0; j < 2; j++) { x[j] = wa2[j]; wa2[j] = FMUL(diag[j], x[j]); }
-                for (long i = FIT_TID; i < m; i += FIT_NT) fvec[i] = wa4[i];
-                FIT_SYNC();
+                { double* t = fvec; fvec = wa4; wa4 = t; }  // fvec <- f(x_new): swap the two work vectors
                 xnorm = fit_enorm_small(2, wa2);
                 fnorm = fnorm1;
                 iter++;
