@@ -141,9 +141,12 @@ def run_ours(args):
     ids = list(range(S))
     gb = waterfall.GraphBuilder(local)
     gb.set_species([G] * S, L)
-    owned = sharding.partition_rows(S, world)[rank]
+    parts = sharding.partition_rows(S, world)
+    owned = parts[rank]
+    species_rank = sharding.species_owner(parts, S)
+    lists = args.exchange == "lists"
     if world > 1:
-        gb.set_partition(owned, True)
+        gb.set_partition(owned, not lists)
     t0 = time.time()
     gb.synth_hits(P, ids)
     log("[rank %d] generated hit text on device in %.1fs" % (rank, time.time() - t0))
@@ -152,9 +155,17 @@ def run_ours(args):
     def step():
         if world == 1:
             gb.build(_lib.STAGE_GRAPH)
+        elif lists:
+            # design B: rows only; the transposed best-hit and connect index lists travel over NVLink
+            gb.build(_lib.STAGE_NORM)
+            sharding.exchange_lists(gb, 0, species_rank, rank, world, local)
+            gb.build(_lib.STAGE_CONNECT)
+            sharding.exchange_lists(gb, 1, species_rank, rank, world, local)
+            gb.build(_lib.STAGE_GRAPH)
         else:
+            # design A (north star): column pairs re-parsed locally, one all-reduce(MIN) of per-gene thresholds
             gb.build(_lib.STAGE_THRESH)
-            sharding.exchange_thresholds(gb, local)  # one NCCL all-reduce(MIN): owned entries finite, the rest +inf
+            sharding.exchange_thresholds(gb, local)
             gb.build(_lib.STAGE_GRAPH)
 
     def barrier():
@@ -169,7 +180,7 @@ def run_ours(args):
     sizes = {}
     text_bytes_all = 0
     pairs_here = [(p, j) for p in owned for j in range(S)]
-    if world > 1:
+    if world > 1 and not lists:
         pairs_here += sharding.rank_pairs(owned, S)[1]
     for (p, j) in pairs_here:
         sizes[(p, j)] = gb.hits_text_size(p, j)
@@ -214,8 +225,11 @@ def run_ours(args):
                args.config, S, G, P.hq, S * S, int(lines_all), text_bytes_all * (world if world > 1 else 1) / 1e9,
                ", per-rank text incl. column pairs" if world > 1 else ""),
                "species": S, "genes_per_species": G, "hits_per_query_per_pair": P.hq, "lines": int(lines_all),
-               "parallelism": "1 GPU" if world == 1 else "query species sharded over %d GPUs, column pairs re-parsed, "
-                                                        "thresholds all-reduced (min) over NCCL" % world,
+               "parallelism": "1 GPU" if world == 1 else (
+                   "query species sharded over %d GPUs, rows only; transposed best-hit and connect index lists "
+                   "exchanged with NCCL all-to-all (design B)" % world if lists else
+                   "query species sharded over %d GPUs, column pairs re-parsed, thresholds all-reduced (min) over "
+                   "NCCL (design A)" % world),
                "l2": "inputs (%.1f GB text per GPU) larger than L2, no flush needed" % (text_bytes_all / 1e9)},
            "gpu_launches": int(launches * args.steps) if world == 1 else int(launches * args.steps),
            "clocks": clk.summary(), "counts": c, "stage_ms_last_step": gb.timing()}
@@ -369,6 +383,8 @@ def main():
     ap.add_argument("--species", type=int, default=0)
     ap.add_argument("--genes", type=int, default=0)
     ap.add_argument("--hq", type=int, default=0)
+    ap.add_argument("--exchange", default="lists", choices=["lists", "thresholds"],
+                    help="multi-GPU: 'lists' = design B (sparse all-to-all), 'thresholds' = design A (column re-parse + all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-species", type=int, default=4, help="species in the cpu_baseline sample")

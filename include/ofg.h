@@ -47,14 +47,16 @@ enum {
     OFG_STAGE_RAW = 1,      /* GetBLAST6Scores for every pair (blast_file_processor.py:38-104) */
     OFG_STAGE_NORM = 2,     /* NormaliseScores + GetBH_s -> "B", "BH" (gathering.py:140-155,213-248) */
     OFG_STAGE_THRESH = 3,   /* RBH + GetMostDistant_s for owned species (gathering.py:251-259,294-310) */
-    OFG_STAGE_GRAPH = 4     /* ConnectAllBetterThanCutoff_s + WriteGraph_perSpecies (:391-408, :23-49) */
+    OFG_STAGE_CONNECT = 4,  /* ConnectAllBetterThanCutoff_s -> "connect" (gathering.py:391-408) */
+    OFG_STAGE_GRAPH = 5     /* WriteGraph_perSpecies: (connect + connect^T) .* B, CSR + text (gathering.py:23-49) */
 };
 
 /* flag bits stored in the top of the column word returned by ofg_pair_csr */
 #define OFG_FLAG_BH 0x80000000u      /* entry of BH_pj   (gathering.py:213-248) */
 #define OFG_FLAG_CONNECT 0x40000000u /* entry of connect_pj (gathering.py:391-408) */
 #define OFG_FLAG_REVERSE 0x20000000u /* connect_jp[c,r] is set (gathering.py:30, m2tr) */
-#define OFG_COL_MASK 0x1fffffffu
+#define OFG_FLAG_TBH 0x10000000u     /* BH_jp[c,r] is set, imported from the context that owns species j */
+#define OFG_COL_MASK 0x0fffffffu
 
 /* synthetic hit-file parameters (orthofinder_b200/csrc/synth_hits.h) */
 typedef struct {
@@ -103,7 +105,8 @@ int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
 
 /* Run the path up to and including `stop_after` (OFG_STAGE_*).  OFG_STAGE_THRESH stops before the
  * thresholds of other ranks are needed; call ofg_thresholds_get / _set around the exchange and then
- * ofg_build(ctx, OFG_STAGE_GRAPH) to finish.  Single GPU: ofg_build(ctx, OFG_STAGE_GRAPH). */
+ * ofg_build(ctx, OFG_STAGE_GRAPH) to finish.  Single GPU: ofg_build(ctx, OFG_STAGE_GRAPH).  A later stage
+ * includes every earlier one that has not run yet. */
 int ofg_build(ofg_ctx* ctx, int stop_after);
 
 /* Per-gene cut-off "mostDistant" (gathering.py:294-310), global gene indexing (seqStartingIndices).
@@ -112,6 +115,18 @@ int ofg_build(ofg_ctx* ctx, int stop_after);
 int ofg_thresholds_dev(ofg_ctx* ctx, double** dev_ptr, int64_t* n);
 int ofg_thresholds_mark_complete(ofg_ctx* ctx);
 int ofg_thresholds_copy(ofg_ctx* ctx, double* host_dst, int64_t n);
+
+/* Sparse exchange between contexts that own disjoint query species and do NOT ingest column pairs
+ * (design B of SURVEY.md 8e): instead of re-reading Blast{j}_{p}, the owner of species j ships the index
+ * lists the reference reads back from the transposed pickles — BH_jp (matrices.LoadMatrixArray(...,
+ * row=False), gathering.py:254) after OFG_STAGE_NORM, connect_jp (gathering.py:30) after OFG_STAGE_CONNECT.
+ * which = 0: best hits, 1: connect.  species_rank[S] gives the owner rank of every species.  The list holds
+ * one (gene of the remote species, gene of the local species) pair of global gene ids (2 x int32) per flagged
+ * entry, grouped by destination rank; counts[r] entries go to rank r.  The device buffer stays owned by the
+ * context until the next export.  ofg_import_flags marks the received entries (TBH / REVERSE flags). */
+int ofg_export_flags(ofg_ctx* ctx, int which, int n_ranks, const int32_t* species_rank, int my_rank, int64_t* counts,
+                     int32_t** dev_list);
+int ofg_import_flags(ofg_ctx* ctx, int which, const int32_t* dev_list, int64_t n_entries);
 
 /* Totals after a build: lines = non-empty records seen, records = lines kept after the self-hit and
  * score > 0 filters, nnz = stored (q,s) after max-dedup, edges = entries of the final graph. */

@@ -9,13 +9,14 @@ OFG_OK = 0
 ERR_NAMES = {-1: "OFG_ERR_CUDA", -2: "OFG_ERR_ARG", -3: "OFG_ERR_PARSE", -4: "OFG_ERR_INCONSISTENT", -5: "OFG_ERR_FIT",
              -6: "OFG_ERR_CAPACITY", -7: "OFG_ERR_UNSUPPORTED", -8: "OFG_ERR_MISSING"}
 ERR_PARSE, ERR_INCONSISTENT, ERR_FIT, ERR_UNSUPPORTED, ERR_MISSING = -3, -4, -5, -7, -8
-STAGE_RAW, STAGE_NORM, STAGE_THRESH, STAGE_GRAPH = 1, 2, 3, 4
-FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, COL_MASK = 0x80000000, 0x40000000, 0x20000000, 0x1FFFFFFF
+STAGE_RAW, STAGE_NORM, STAGE_THRESH, STAGE_CONNECT, STAGE_GRAPH = 1, 2, 3, 4, 5
+FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, FLAG_TBH, COL_MASK = 0x80000000, 0x40000000, 0x20000000, 0x10000000, 0x0FFFFFFF
 
 # every symbol include/ofg.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "ofg_set_partition", "ofg_add_hits_text",
            "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_build",
-           "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_counts", "ofg_pair_csr",
+           "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_export_flags",
+           "ofg_import_flags", "ofg_counts", "ofg_pair_csr",
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
            "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
@@ -52,6 +53,8 @@ def load():
         "ofg_thresholds_dev": [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)],
         "ofg_thresholds_mark_complete": [vp],
         "ofg_thresholds_copy": [vp, vp, i64],
+        "ofg_export_flags": [vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp)],
+        "ofg_import_flags": [vp, i32, vp, i64],
         "ofg_counts": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
         "ofg_pair_csr": [vp, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), vp, vp, vp],
         "ofg_pair_fit": [vp, i32, i32, vp],

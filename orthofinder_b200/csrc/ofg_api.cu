@@ -634,14 +634,12 @@ int stage_thresh(ofg_ctx* c)
     return 0;
 }
 
-int stage_graph(ofg_ctx* c)
+int stage_connect(ofg_ctx* c)
 {
     mark_timeline(c);
     const int P = (int)c->pairs.size();
-    if (!c->thresholds_complete)
+    if (!c->thresholds_complete && c->with_columns)
         return fail(c, OFG_ERR_ARG, "thresholds of species owned by other contexts are missing: exchange them and call ofg_thresholds_mark_complete");
-    u64* sm = c->d_small.as<u64>();
-    u32* err_flags = (u32*)(sm + 2);
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
@@ -651,6 +649,20 @@ int stage_graph(ofg_ctx* c)
         CKL("connect_kernel");
     }
     CK(cudaEventRecord(c->ev[8], c->stream));
+    c->stage_done = OFG_STAGE_CONNECT;
+    return 0;
+}
+
+int stage_emit(ofg_ctx* c)
+{
+    mark_timeline(c);
+    const int P = (int)c->pairs.size();
+    u64* sm = c->d_small.as<u64>();
+    u32* err_flags = (u32*)(sm + 2);
+    GraphArgs g;
+    g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
+    g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
     // emission units: owned genes (list order) x S
     std::vector<int64_t> gene_of;
     std::vector<int32_t> sp_of;
@@ -932,9 +944,14 @@ int ofg_build(ofg_ctx* c, int stop_after)
         if (int rc = stage_thresh(c)) { c->stage_done = 0; return rc; }
         last_ev = 7;
     }
-    if (stop_after >= OFG_STAGE_GRAPH && c->stage_done < OFG_STAGE_GRAPH) {
+    if (stop_after >= OFG_STAGE_CONNECT && c->stage_done < OFG_STAGE_CONNECT) {
         if (first_ev < 0) { CK(cudaEventRecord(c->ev[7], c->stream)); first_ev = 7; }
-        if (int rc = stage_graph(c)) return rc;
+        if (int rc = stage_connect(c)) return rc;
+        last_ev = 8;
+    }
+    if (stop_after >= OFG_STAGE_GRAPH && c->stage_done < OFG_STAGE_GRAPH) {
+        if (first_ev < 0) { CK(cudaEventRecord(c->ev[8], c->stream)); first_ev = 8; }
+        if (int rc = stage_emit(c)) return rc;
         last_ev = 9;
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1006,6 +1023,78 @@ int ofg_thresholds_copy(ofg_ctx* c, double* host_dst, int64_t n)
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(host_dst, c->most.p, (size_t)std::min<int64_t>(n, c->N) * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return OFG_OK;
+}
+
+int ofg_export_flags(ofg_ctx* c, int which, int n_ranks, const int32_t* species_rank, int my_rank, int64_t* counts, int32_t** dev_list)
+{
+    if (!c || !species_rank || !counts || !dev_list || n_ranks <= 0) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int need = which == 0 ? OFG_STAGE_NORM : OFG_STAGE_CONNECT;
+    if (c->stage_done < need) return fail(c, OFG_ERR_ARG, "export of %s lists needs stage %d", which == 0 ? "best-hit" : "connect", need);
+    const int P = (int)c->pairs.size();
+    std::vector<uint8_t> ex(P, 0);
+    for (int i = 0; i < P; i++) {
+        const PairDesc& d = c->pairs[i];
+        ex[i] = d.owned_row && species_rank[d.j] != my_rank;  // (k, p): column species p lives elsewhere
+    }
+    DevBuf& flagbuf = c->synth_bytes;  // scratch buffers of the generator are free at this point
+    DevBuf& cntbuf = c->synth_off;
+    if (upload(c, flagbuf, ex.data(), (size_t)P)) return OFG_ERR_CUDA;
+    CK(cntbuf.ensure((size_t)(2 * P + 2) * 8));
+    CK(cudaMemsetAsync(cntbuf.p, 0, (size_t)(2 * P + 2) * 8, c->stream));
+    ExportArgs a;
+    a.n_rows = c->n_rows; a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>();
+    a.pairs = c->d_pairs.as<PairDesc>(); a.pair_row_base = c->d_pair_row_base.as<int64_t>(); a.P = P;
+    a.pair_export = flagbuf.as<uint8_t>(); a.flag = which == 0 ? OFG_FLAG_BH : OFG_FLAG_CONNECT;
+    a.pair_count = cntbuf.as<u64>(); a.pair_off = cntbuf.as<u64>() + P; a.out = nullptr;
+    for (int r = 0; r < n_ranks; r++) counts[r] = 0;
+    *dev_list = nullptr;
+    if (P == 0 || c->n_rows == 0) return OFG_OK;
+    const int g = grid_for(c, c->n_rows, 8, 8);
+    export_flags_kernel<false><<<g, 256, 0, c->stream>>>(a);
+    CKL("export_flags_kernel<false>");
+    std::vector<u64> pc(P);
+    CK(cudaMemcpyAsync(pc.data(), a.pair_count, sizeof(u64) * P, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // lay the pairs out grouped by destination rank
+    std::vector<u64> off(P, 0);
+    u64 total = 0;
+    for (int r = 0; r < n_ranks; r++)
+        for (int i = 0; i < P; i++)
+            if (ex[i] && species_rank[c->pairs[i].j] == r) { off[i] = total; total += pc[i]; counts[r] += (int64_t)pc[i]; }
+    CK(c->unit_bytes.ensure((size_t)(total + 1) * 8));  // list buffer (free until the emit stage)
+    CK(cudaMemcpyAsync(cntbuf.as<u64>() + P, off.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(cntbuf.p, 0, sizeof(u64) * P, c->stream));
+    a.out = c->unit_bytes.as<int2>();
+    if (total > 0) {
+        export_flags_kernel<true><<<g, 256, 0, c->stream>>>(a);
+        CKL("export_flags_kernel<true>");
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    *dev_list = c->unit_bytes.as<int32_t>();
+    return OFG_OK;
+}
+
+int ofg_import_flags(ofg_ctx* c, int which, const int32_t* dev_list, int64_t n_entries)
+{
+    if (!c || n_entries < 0 || (n_entries > 0 && !dev_list)) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    const int need = which == 0 ? OFG_STAGE_NORM : OFG_STAGE_CONNECT;
+    if (c->stage_done < need) return fail(c, OFG_ERR_ARG, "import of %s lists needs stage %d", which == 0 ? "best-hit" : "connect", need);
+    if (n_entries == 0) return OFG_OK;
+    u32* err_flags = (u32*)(c->d_small.as<u64>() + 2);
+    ImportArgs a;
+    a.list = reinterpret_cast<const int2*>(dev_list); a.n = n_entries; a.seq_start = c->d_seq_start.as<int64_t>(); a.S = c->S;
+    a.pair_of = c->d_pair_of.as<int32_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.row_start = c->row_start.as<u32>();
+    a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>(); a.set_flag = which == 0 ? OFG_FLAG_TBH : OFG_FLAG_REVERSE;
+    a.err_flags = err_flags;
+    import_flags_kernel<<<grid_for(c, n_entries, 256, 8), 256, 0, c->stream>>>(a);
+    CKL("import_flags_kernel");
+    u32 flags = 0;
+    CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (flags & 8u) return fail(c, OFG_ERR_ARG, "imported list addresses a species pair this context does not hold");
     return OFG_OK;
 }
 

@@ -205,8 +205,6 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
         const PairDesc& pd = a.pairs[pair];
         if (pd.same || !pd.owned_row) continue;
         const int tp = a.pair_of[pd.j * a.S + pd.p];
-        if (tp < 0) continue;
-        const PairDesc& td = a.pairs[tp];
         const u32 s0 = a.row_start[row];
         const u32 r = (u32)(row - pd.row_base);
         int last = -1;  // largest k (column order) with an RBH
@@ -216,9 +214,14 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
             if (k < n) {
                 const u32 cw = a.cols[s0 + k];
                 if (cw & OFG_FLAG_BH) {
-                    const int64_t trow = td.row_base + (cw & OFG_COL_MASK);
-                    const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
-                    rbh = e >= 0 && (a.cols[e] & OFG_FLAG_BH);
+                    if (tp >= 0) {
+                        const PairDesc& td = a.pairs[tp];
+                        const int64_t trow = td.row_base + (cw & OFG_COL_MASK);
+                        const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
+                        rbh = e >= 0 && (a.cols[e] & OFG_FLAG_BH);
+                    } else {
+                        rbh = (cw & OFG_FLAG_TBH) != 0;  // transposed pair lives in another context: flag was imported
+                    }
                 }
             }
             const u32 bal = __ballot_sync(OFG_FULL, rbh);
@@ -265,6 +268,82 @@ __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------- sparse exchange (design B)
+struct ExportArgs {
+    int64_t n_rows;
+    const u32* row_start;
+    const u32* rowlen;
+    const u32* cols;
+    const PairDesc* pairs;
+    const int64_t* pair_row_base;
+    int P;
+    const uint8_t* pair_export;  // [P] 1: pair (k, p) whose column species p is owned by another context
+    u32 flag;                    // OFG_FLAG_BH or OFG_FLAG_CONNECT
+    u64* pair_count;             // [P] COUNT pass out / FILL pass: running fill
+    const u64* pair_off;         // [P] FILL pass: first list slot of the pair
+    int2* out;                   // (gene of remote species p, gene of local species k), global ids
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) export_flags_kernel(ExportArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int pair = -1;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const int n = (int)a.rowlen[row];
+        if (n == 0) continue;
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
+        if (!a.pair_export[pair]) continue;
+        const PairDesc& pd = a.pairs[pair];
+        const u32 s0 = a.row_start[row];
+        const int r = (int)(row - pd.row_base);
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const u32 cw = k < n ? a.cols[s0 + k] : 0u;
+            const bool on = (cw & a.flag) != 0;
+            const u32 bal = __ballot_sync(OFG_FULL, on);
+            if (!bal) continue;
+            u64 base = 0;
+            if (lane == 0) base = atomicAdd(&a.pair_count[pair], (u64)__popc(bal));
+            base = __shfl_sync(OFG_FULL, base, 0);
+            if (FILL && on) {
+                const u64 pos = a.pair_off[pair] + base + __popc(bal & lanemask_lt());
+                a.out[pos] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
+            }
+        }
+    }
+}
+
+struct ImportArgs {
+    const int2* list;
+    int64_t n;
+    const int64_t* seq_start;  // [S]
+    int S;
+    const int32_t* pair_of;
+    const PairDesc* pairs;
+    const u32* row_start;
+    const u32* rowlen;
+    u32* cols;
+    u32 set_flag;              // OFG_FLAG_TBH or OFG_FLAG_REVERSE
+    u32* err_flags;            // bit 3: an entry addressed a pair this context does not hold
+};
+
+__global__ void __launch_bounds__(256) import_flags_kernel(ImportArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 e = a.list[i];
+        const int p = upper_bound_dev(a.seq_start, a.S, (int64_t)e.x) - 1;  // local (row) species
+        const int k = upper_bound_dev(a.seq_start, a.S, (int64_t)e.y) - 1;  // species of the sender
+        const int pair = a.pair_of[p * a.S + k];
+        if (pair < 0) { atomicOr(a.err_flags, 8u); continue; }
+        const PairDesc& pd = a.pairs[pair];
+        const int64_t row = pd.row_base + ((int64_t)e.x - pd.gi_start);
+        const int64_t slot = find_col(a.cols, a.row_start[row], (int)a.rowlen[row], (u32)((int64_t)e.y - pd.gj_start));
+        if (slot >= 0) atomicOr(&a.cols[slot], a.set_flag);  // no stored hit in this direction: nothing to mark
     }
 }
 

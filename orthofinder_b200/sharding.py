@@ -44,10 +44,41 @@ def merge_thresholds_host(parts):
 
 
 class _DeviceVector:
-    """Zero-copy view of a device fp64 vector for torch.as_tensor (CUDA array interface)."""
+    """Zero-copy view of a device vector for torch.as_tensor (CUDA array interface)."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def species_owner(owned_per_rank, n_species):
+    """owner rank of every species from partition_rows' output."""
+    out = np.full(n_species, -1, np.int32)
+    for r, o in enumerate(owned_per_rank):
+        out[o] = r
+    return out
+
+
+def exchange_lists(gb, which, species_rank, rank, world, device_index):
+    """Design B (no column pairs): all-to-all of the index lists the reference reads from the transposed
+    pickles — best hits (which=0, gathering.py:254) or connect (which=1, gathering.py:30).  Two NCCL calls:
+    the per-rank counts, then the variable-size lists (one int64 = two packed int32 gene ids per entry)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", device_index)
+    ptr, counts = gb.export_flags(which, species_rank, rank)
+    send_counts = torch.from_numpy(np.ascontiguousarray(counts[:world], dtype=np.int64)).to(dev)
+    recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_counts, send_counts)
+    rc = [int(x) for x in recv_counts.cpu()]
+    sc = [int(x) for x in counts[:world]]
+    n_send = sum(sc)
+    send = (torch.as_tensor(_DeviceVector(ptr, n_send, "<i8"), device=dev) if n_send
+            else torch.empty(0, dtype=torch.int64, device=dev))
+    recv = torch.empty(sum(rc), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
+    torch.cuda.synchronize()
+    gb.import_flags(which, recv.data_ptr(), recv.numel())
+    return n_send, recv.numel()
 
 
 def exchange_thresholds(gb, device_index):

@@ -184,6 +184,19 @@ class GraphBuilder:
     def thresholds_mark_complete(self):
         self._ck(self.lib.ofg_thresholds_mark_complete(self.h))
 
+    def export_flags(self, which, species_rank, my_rank):
+        """Design B exchange: (device pointer, counts per destination rank) of the best-hit (which=0) or
+        connect (which=1) index lists for species pairs whose column species another rank owns."""
+        sr = np.ascontiguousarray(species_rank, dtype=np.int32)
+        n_ranks = int(sr.max()) + 1 if sr.size else 1
+        counts = np.zeros(n_ranks, np.int64)
+        ptr = ctypes.c_void_p()
+        self._ck(self.lib.ofg_export_flags(self.h, int(which), n_ranks, _vp(sr), int(my_rank), _vp(counts), ctypes.byref(ptr)))
+        return ptr.value, counts
+
+    def import_flags(self, which, dev_ptr, n_entries):
+        self._ck(self.lib.ofg_import_flags(self.h, int(which), ctypes.c_void_p(dev_ptr), int(n_entries)))
+
     def graph_csr(self):
         nr, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
         self._ck(self.lib.ofg_graph_csr_size(self.h, ctypes.byref(nr), ctypes.byref(nnz)))

@@ -328,6 +328,74 @@ def test_two_partitions_stitch_to_the_single_context_graph():
     whole.close()
 
 
+@pytest.mark.parametrize("name", ["synth_C5_small", "ref_AddTwoSpecies"])
+def test_row_partitions_with_list_exchange_stitch_to_the_single_context_graph(name):
+    """Design B of SURVEY.md §8e on one GPU: two contexts own disjoint query species and ingest NO column
+    pairs; the transposed best-hit lists (after NORM) and connect lists (after CONNECT) are exported,
+    handed over and imported — the stitched graph must equal the single-context graph exactly."""
+    import torch
+    from orthofinder_b200 import sharding
+    g = Golden(name)
+    S = len(g.n_seqs)
+    whole = waterfall.GraphBuilder(0)
+    _load(whole, g.n_seqs, g.lengths, g.hit_text)
+    whole.build()
+    w_rows, w_indptr, w_idx, w_dat = whole.graph_csr()
+    w_md = whole.thresholds()
+    parts = sharding.partition_rows(S, 2, [sum(len(g.hit_text(p, j)) for j in range(S)) for p in range(S)])
+    owner = sharding.species_owner(parts, S)
+    ctxs = []
+    for owned in parts:
+        c = waterfall.GraphBuilder(0)
+        c.set_species(g.n_seqs, g.lengths)
+        c.set_partition(owned, False)
+        for p in owned:
+            for j in range(S):
+                c.add_hits(p, j, g.hit_text(p, j))
+        ctxs.append(c)
+
+    def exchange(which):
+        outbox = []
+        for r, c in enumerate(ctxs):
+            ptr, counts = c.export_flags(which, owner, r)
+            assert counts[r] == 0
+            n = int(counts.sum())
+            t = (torch.as_tensor(sharding._DeviceVector(ptr, n, "<i8"), device="cuda:0").clone() if n
+                 else torch.empty(0, dtype=torch.int64, device="cuda:0"))
+            outbox.append((t, counts))
+        for r, c in enumerate(ctxs):
+            src = 1 - r
+            t, counts = outbox[src]
+            off = int(counts[:r].sum())
+            part = t[off:off + int(counts[r])].contiguous()
+            c.import_flags(which, part.data_ptr(), part.numel())
+        return sum(int(cn.sum()) for _, cn in outbox)
+
+    for c in ctxs:
+        c.build(_lib.STAGE_NORM)
+    n_bh = exchange(0)
+    for c in ctxs:
+        c.build(_lib.STAGE_CONNECT)
+    n_conn = exchange(1)
+    assert n_bh > 0 and n_conn > 0
+    seen = []
+    starts = np.concatenate(([0], np.cumsum(g.n_seqs)))
+    for owned, c in zip(parts, ctxs):
+        c.build(_lib.STAGE_GRAPH)
+        md = c.thresholds()
+        for p in owned:
+            assert np.array_equal(md[starts[p]:starts[p + 1]], w_md[starts[p]:starts[p + 1]])
+        rows, indptr, idx, dat = c.graph_csr()
+        for k, r in enumerate(rows):
+            a, b = w_indptr[r], w_indptr[r + 1]
+            assert np.array_equal(idx[indptr[k]:indptr[k + 1]], w_idx[a:b]), (name, r)
+            assert np.array_equal(dat[indptr[k]:indptr[k + 1]], w_dat[a:b]), (name, r)
+        seen += list(rows)
+        c.close()
+    assert sorted(seen) == list(range(sum(g.n_seqs)))
+    whole.close()
+
+
 def test_mid_size_job_equals_oracle(gb):
     """8 species x 2000 genes x 50 hits/query/pair (7 M lines, bins of 1000, m ~ 5 k points per fit): the whole
     graph against the CPU oracle — edge set and indices exact, fits bit-equal, weights within 1e-9."""
