@@ -223,7 +223,7 @@ def run_ours(args):
            "data": "synthetic",
            "config": {"workload": "%s: %d species x %d genes, hq=%d (%d pairs, %d hit lines, %.2f GB text%s)" % (
                args.config, S, G, P.hq, S * S, int(lines_all), text_bytes_all * (world if world > 1 else 1) / 1e9,
-               ", per-rank text incl. column pairs" if world > 1 else ""),
+               ", per-rank text incl. column pairs" if (world > 1 and not lists) else ""),
                "species": S, "genes_per_species": G, "hits_per_query_per_pair": P.hq, "lines": int(lines_all),
                "parallelism": "1 GPU" if world == 1 else (
                    "query species sharded over %d GPUs, rows only; transposed best-hit and connect index lists "
