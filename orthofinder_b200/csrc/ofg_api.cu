@@ -87,7 +87,7 @@ struct ofg_ctx {
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
     DevBuf lx, ly, fvec, wa4, c0, c1, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
-    DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off;
+    DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
     std::vector<u64> pair_lines, pair_valid, pair_nnz;
     std::vector<double> fit_host;
@@ -571,6 +571,9 @@ int stage_norm(ofg_ctx* c)
         sa.pair_row_base = c->d_pair_row_base.as<int64_t>(); sa.P = P; sa.fit = c->fit.as<double>();
         sa.rowfac = c->rowfac.as<double>(); sa.colfac = c->colfac.as<double>(); sa.rowmax = c->rowmax.as<double>();
         sa.best = c->best.as<double>();
+        CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
+        CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
+        sa.row_flagcnt = c->row_flagcnt.as<u32>();
         const int g2 = grid_for(c, c->n_rows, 8, 8);
         scale_bh_kernel<<<g2, 256, 0, c->stream>>>(sa);
         CKL("scale_bh_kernel");
@@ -621,7 +624,7 @@ int stage_thresh(ofg_ctx* c)
         GraphArgs g;
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
         g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-        g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
+        g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
         rbh_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(g);
         CKL("rbh_kernel");
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
@@ -643,8 +646,11 @@ int stage_connect(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
     if (P > 0 && c->n_rows > 0) {
+        CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
+        CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
+        g.row_flagcnt = c->row_flagcnt.as<u32>();
         connect_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(g);
         CKL("connect_kernel");
     }
@@ -662,7 +668,7 @@ int stage_emit(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>();
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
     // emission units: owned genes (list order) x S
     std::vector<int64_t> gene_of;
     std::vector<int32_t> sp_of;
@@ -748,7 +754,7 @@ void ofg_destroy(ofg_ctx* c)
                       &c->wa4, &c->c0, &c->c1, &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
-                      &c->file_off, &c->pair_sel_off};
+                      &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -1039,37 +1045,39 @@ int ofg_export_flags(ofg_ctx* c, int which, int n_ranks, const int32_t* species_
         ex[i] = d.owned_row && species_rank[d.j] != my_rank;  // (k, p): column species p lives elsewhere
     }
     DevBuf& flagbuf = c->synth_bytes;  // scratch buffers of the generator are free at this point
-    DevBuf& cntbuf = c->synth_off;
-    if (upload(c, flagbuf, ex.data(), (size_t)P)) return OFG_ERR_CUDA;
-    CK(cntbuf.ensure((size_t)(2 * P + 2) * 8));
-    CK(cudaMemsetAsync(cntbuf.p, 0, (size_t)(2 * P + 2) * 8, c->stream));
-    ExportArgs a;
-    a.n_rows = c->n_rows; a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>();
-    a.pairs = c->d_pairs.as<PairDesc>(); a.pair_row_base = c->d_pair_row_base.as<int64_t>(); a.P = P;
-    a.pair_export = flagbuf.as<uint8_t>(); a.flag = which == 0 ? OFG_FLAG_BH : OFG_FLAG_CONNECT;
-    a.pair_count = cntbuf.as<u64>(); a.pair_off = cntbuf.as<u64>() + P; a.out = nullptr;
+    DevBuf& offbuf = c->synth_off;
     for (int r = 0; r < n_ranks; r++) counts[r] = 0;
     *dev_list = nullptr;
     if (P == 0 || c->n_rows == 0) return OFG_OK;
-    const int g = grid_for(c, c->n_rows, 8, 8);
-    export_flags_kernel<false><<<g, 256, 0, c->stream>>>(a);
-    CKL("export_flags_kernel<false>");
-    std::vector<u64> pc(P);
-    CK(cudaMemcpyAsync(pc.data(), a.pair_count, sizeof(u64) * P, cudaMemcpyDeviceToHost, c->stream));
+    if (upload(c, flagbuf, ex.data(), (size_t)P)) return OFG_ERR_CUDA;
+    // per-row counts were written by scale_bh_kernel (best hits) / connect_kernel (connect): scan them
+    CK(c->row_flagoff.ensure((size_t)(c->n_rows + 2) * 8));
+    if (device_scan<u64>(c, c->row_flagcnt.as<u32>(), c->n_rows, c->row_flagoff.as<u64>(), 1)) return OFG_ERR_CUDA;
+    CK(offbuf.ensure((size_t)(2 * P + 4) * 8));
+    std::vector<u64> bidx(P + 1);
+    for (int i = 0; i <= P; i++) bidx[i] = (u64)c->pair_row_base[i];
+    CK(cudaMemcpyAsync(offbuf.as<u64>() + P + 2, bidx.data(), sizeof(u64) * (P + 1), cudaMemcpyHostToDevice, c->stream));
+    gather_u64_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(c->row_flagoff.as<u64>(), offbuf.as<u64>() + P + 2, P + 1, offbuf.as<u64>());
+    CKL("gather_u64_kernel");
+    std::vector<u64> pb(P + 1);
+    CK(cudaMemcpyAsync(pb.data(), offbuf.p, sizeof(u64) * (P + 1), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    // lay the pairs out grouped by destination rank
+    // lay the exported pairs out grouped by destination rank
     std::vector<u64> off(P, 0);
     u64 total = 0;
     for (int r = 0; r < n_ranks; r++)
         for (int i = 0; i < P; i++)
-            if (ex[i] && species_rank[c->pairs[i].j] == r) { off[i] = total; total += pc[i]; counts[r] += (int64_t)pc[i]; }
+            if (ex[i] && species_rank[c->pairs[i].j] == r) { off[i] = total; total += pb[i + 1] - pb[i]; counts[r] += (int64_t)(pb[i + 1] - pb[i]); }
     CK(c->unit_bytes.ensure((size_t)(total + 1) * 8));  // list buffer (free until the emit stage)
-    CK(cudaMemcpyAsync(cntbuf.as<u64>() + P, off.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(cntbuf.p, 0, sizeof(u64) * P, c->stream));
-    a.out = c->unit_bytes.as<int2>();
+    CK(cudaMemcpyAsync(offbuf.p, off.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, c->stream));
+    ExportArgs a;
+    a.n_rows = c->n_rows; a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>();
+    a.pairs = c->d_pairs.as<PairDesc>(); a.pair_row_base = c->d_pair_row_base.as<int64_t>(); a.P = P;
+    a.pair_export = flagbuf.as<uint8_t>(); a.flag = which == 0 ? OFG_FLAG_BH : OFG_FLAG_CONNECT;
+    a.row_off = c->row_flagoff.as<u64>(); a.pair_off = offbuf.as<u64>(); a.out = c->unit_bytes.as<int2>();
     if (total > 0) {
-        export_flags_kernel<true><<<g, 256, 0, c->stream>>>(a);
-        CKL("export_flags_kernel<true>");
+        export_flags_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(a);
+        CKL("export_flags_kernel");
     }
     CK(cudaStreamSynchronize(c->stream));
     *dev_list = c->unit_bytes.as<int32_t>();

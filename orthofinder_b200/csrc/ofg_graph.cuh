@@ -107,6 +107,7 @@ struct ScaleArgs {
     const double* colfac;
     double* rowmax;  // [n_rows]
     double* best;    // [nSeqs] bit patterns, 0 = no hit in another species
+    u32* row_flagcnt;  // [n_rows] best hits per row (pre-zeroed): sizes of the design-B export lists
 };
 
 __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
@@ -138,8 +139,12 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
         if (lane == 0) a.rowmax[row] = m;
         if (!pd.same) {
             const double thr = __dsub_rn(m, 1e-3);
+            u32 nbh = 0;
             for (int k = lane; k < n; k += 32)
-                if (a.vals[s0 + k] > thr) a.cols[s0 + k] |= OFG_FLAG_BH;
+                if (a.vals[s0 + k] > thr) { a.cols[s0 + k] |= OFG_FLAG_BH; nbh++; }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) nbh += __shfl_xor_sync(OFG_FULL, nbh, d);
+            if (lane == 0) a.row_flagcnt[row] = nbh;
             if (lane == 0 && pd.owned_row && m > 0.0) atomic_max_pos_double(&a.best[pd.gi_start + (row - pd.row_base)], m);
         }
     }
@@ -178,6 +183,7 @@ struct GraphArgs {
     int S;
     double* most;            // [nSeqs] thresholds (bit patterns while being reduced)
     const double* best;
+    u32* row_flagcnt;        // [n_rows] connect entries per row (connect_kernel; pre-zeroed)
 };
 
 // index of column `want` in the row [s0, s0+n) of the slotted CSR, or -1
@@ -255,10 +261,12 @@ __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
         const u32 r = (u32)(row - pd.row_base);
         const double md = a.most[pd.gi_start + r];
         const int tp = a.pair_of[pd.j * a.S + pd.p];
+        u32 nconn = 0;
         for (int k = lane; k < n; k += 32) {
             const u32 cw = a.cols[s0 + k];
             const u32 c = cw & OFG_COL_MASK;
             if (a.vals[s0 + k] >= md && !(pd.same && c == r)) {
+                nconn++;
                 atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
                 if (tp >= 0) {
                     const PairDesc& td = a.pairs[tp];
@@ -268,6 +276,9 @@ __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
                 }
             }
         }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nconn += __shfl_xor_sync(OFG_FULL, nconn, d);
+        if (lane == 0) a.row_flagcnt[row] = nconn;
     }
 }
 
@@ -282,38 +293,35 @@ struct ExportArgs {
     int P;
     const uint8_t* pair_export;  // [P] 1: pair (k, p) whose column species p is owned by another context
     u32 flag;                    // OFG_FLAG_BH or OFG_FLAG_CONNECT
-    u64* pair_count;             // [P] COUNT pass out / FILL pass: running fill
-    const u64* pair_off;         // [P] FILL pass: first list slot of the pair
+    const u64* row_off;          // [n_rows + 1] exclusive scan of the per-row flag counts
+    const u64* pair_off;         // [P] first list slot of the pair (pairs grouped by destination rank)
     int2* out;                   // (gene of remote species p, gene of local species k), global ids
 };
 
-template <bool FILL>
+// Deterministic single pass: every flagged entry of an exported pair goes to
+// pair_off[pair] + (entries of earlier rows of the pair) + (rank inside the row).
 __global__ void __launch_bounds__(256) export_flags_kernel(ExportArgs a)
 {
     const int lane = lane_id();
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int pair = -1;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const int n = (int)a.rowlen[row];
-        if (n == 0) continue;
+        const u64 o0 = a.row_off[row];
+        if (a.row_off[row + 1] == o0) continue;  // nothing flagged in this row
         pair = advance_pair(a.pair_row_base, a.P, pair, row);
         if (!a.pair_export[pair]) continue;
         const PairDesc& pd = a.pairs[pair];
+        const int n = (int)a.rowlen[row];
         const u32 s0 = a.row_start[row];
         const int r = (int)(row - pd.row_base);
+        u64 pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
         for (int k0 = 0; k0 < n; k0 += 32) {
             const int k = k0 + lane;
             const u32 cw = k < n ? a.cols[s0 + k] : 0u;
             const bool on = (cw & a.flag) != 0;
             const u32 bal = __ballot_sync(OFG_FULL, on);
-            if (!bal) continue;
-            u64 base = 0;
-            if (lane == 0) base = atomicAdd(&a.pair_count[pair], (u64)__popc(bal));
-            base = __shfl_sync(OFG_FULL, base, 0);
-            if (FILL && on) {
-                const u64 pos = a.pair_off[pair] + base + __popc(bal & lanemask_lt());
-                a.out[pos] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
-            }
+            if (on) a.out[pos + __popc(bal & lanemask_lt())] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
+            pos += __popc(bal);
         }
     }
 }
