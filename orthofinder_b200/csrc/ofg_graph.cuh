@@ -110,42 +110,73 @@ struct ScaleArgs {
     u32* row_flagcnt;  // [n_rows] best hits per row (pre-zeroed): sizes of the design-B export lists
 };
 
+// Row kernels below give HALF a warp (16 lanes) to each matrix row: rows hold ~50 entries, the work per row is
+// a short dependent chain of loads, and two rows in flight per warp hide that latency better than one.  Both
+// halves run the same trip counts (max of the two rows) so that warp-wide shuffles stay converged.
+constexpr int ROW_G = 16;
+
+__device__ __forceinline__ double group_max(double v)
+{
+#pragma unroll
+    for (int d = ROW_G / 2; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(OFG_FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ u32 group_sum(u32 v)
+{
+#pragma unroll
+    for (int d = ROW_G / 2; d > 0; d >>= 1) v += __shfl_xor_sync(OFG_FULL, v, d);
+    return v;
+}
+
 __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
 {
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     int pair = -1;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const int n = (int)a.rowlen[row];
-        if (n == 0) continue;
-        pair = advance_pair(a.pair_row_base, a.P, pair, row);
-        const PairDesc& pd = a.pairs[pair];
-        if (a.fit[(size_t)pair * 8 + 6] == 0.0) {  // zeroed pair: sparse.lil_matrix(B.get_shape())
-            if (lane == 0) a.rowlen[row] = 0;
-            continue;
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
+        u32 s0 = 0;
+        double rf = 0.0;
+        const double* cf = nullptr;
+        bool same = true, owned = false;
+        int64_t gene = 0;
+        if (n > 0) {
+            pair = advance_pair(a.pair_row_base, a.P, pair, row);
+            const PairDesc& pd = a.pairs[pair];
+            if (a.fit[(size_t)pair * 8 + 6] == 0.0) {  // zeroed pair: sparse.lil_matrix(B.get_shape())
+                if (gl == 0) a.rowlen[row] = 0;
+                n = 0;
+            } else {
+                s0 = a.row_start[row];
+                rf = a.rowfac[row];
+                cf = a.colfac + pd.col_base;
+                same = pd.same != 0;
+                owned = pd.owned_row != 0;
+                gene = pd.gi_start + (row - pd.row_base);
+            }
         }
-        const u32 s0 = a.row_start[row];
-        const double rf = a.rowfac[row];
-        const double* cf = a.colfac + pd.col_base;
+        const int nmax = max(n, __shfl_xor_sync(OFG_FULL, n, ROW_G));
         double m = 0.0;
-        for (int k = lane; k < n; k += 32) {
-            const u32 c = a.cols[s0 + k];
-            const double v = __dmul_rn(__dmul_rn(rf, a.vals[s0 + k]), cf[c]);
-            a.vals[s0 + k] = v;
-            m = fmax(m, v);
+        for (int k = gl; k < nmax; k += ROW_G) {
+            if (k < n) {
+                const u32 c = a.cols[s0 + k];
+                const double v = __dmul_rn(__dmul_rn(rf, a.vals[s0 + k]), cf[c]);
+                a.vals[s0 + k] = v;
+                m = fmax(m, v);
+            }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) m = fmax(m, __shfl_xor_sync(OFG_FULL, m, d));
-        if (lane == 0) a.rowmax[row] = m;
-        if (!pd.same) {
-            const double thr = __dsub_rn(m, 1e-3);
-            u32 nbh = 0;
-            for (int k = lane; k < n; k += 32)
+        m = group_max(m);
+        if (gl == 0 && n > 0) a.rowmax[row] = m;
+        const double thr = __dsub_rn(m, 1e-3);
+        u32 nbh = 0;
+        if (!same)
+            for (int k = gl; k < n; k += ROW_G)
                 if (a.vals[s0 + k] > thr) { a.cols[s0 + k] |= OFG_FLAG_BH; nbh++; }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) nbh += __shfl_xor_sync(OFG_FULL, nbh, d);
-            if (lane == 0) a.row_flagcnt[row] = nbh;
-            if (lane == 0 && pd.owned_row && m > 0.0) atomic_max_pos_double(&a.best[pd.gi_start + (row - pd.row_base)], m);
+        nbh = group_sum(nbh);
+        if (gl == 0 && n > 0 && !same) {
+            a.row_flagcnt[row] = nbh;
+            if (owned && m > 0.0) atomic_max_pos_double(&a.best[gene], m);
         }
     }
 }
@@ -201,21 +232,31 @@ __device__ __forceinline__ int64_t find_col(const u32* cols, u32 s0, int n, u32 
 
 __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
 {
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     int pair = -1;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const int n = (int)a.rowlen[row];
-        if (n == 0) continue;
-        pair = advance_pair(a.pair_row_base, a.P, pair, row);
-        const PairDesc& pd = a.pairs[pair];
-        if (pd.same || !pd.owned_row) continue;
-        const int tp = a.pair_of[pd.j * a.S + pd.p];
-        const u32 s0 = a.row_start[row];
-        const u32 r = (u32)(row - pd.row_base);
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
+        int tp = -1;
+        u32 s0 = 0, r = 0;
+        int64_t gene = 0;
+        if (n > 0) {
+            pair = advance_pair(a.pair_row_base, a.P, pair, row);
+            const PairDesc& pd = a.pairs[pair];
+            if (pd.same || !pd.owned_row) {
+                n = 0;
+            } else {
+                tp = a.pair_of[pd.j * a.S + pd.p];
+                s0 = a.row_start[row];
+                r = (u32)(row - pd.row_base);
+                gene = pd.gi_start + r;
+            }
+        }
+        const int nmax = max(n, __shfl_xor_sync(OFG_FULL, n, ROW_G));
         int last = -1;  // largest k (column order) with an RBH
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
+        for (int k0 = 0; k0 < nmax; k0 += ROW_G) {
+            const int k = k0 + gl;
             bool rbh = false;
             if (k < n) {
                 const u32 cw = a.cols[s0 + k];
@@ -230,10 +271,10 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
                     }
                 }
             }
-            const u32 bal = __ballot_sync(OFG_FULL, rbh);
+            const u32 bal = (__ballot_sync(OFG_FULL, rbh) >> (sub * ROW_G)) & ((1u << ROW_G) - 1u);
             if (bal) last = k0 + (31 - __clz(bal));
         }
-        if (last >= 0 && lane == 0) atomic_min_pos_double(&a.most[pd.gi_start + r], a.vals[s0 + last]);
+        if (last >= 0 && gl == 0) atomic_min_pos_double(&a.most[gene], a.vals[s0 + last]);
     }
 }
 
@@ -249,36 +290,37 @@ __global__ void thresh_final_kernel(double* most, const double* best, const uint
 // ---------------------------------------------------------------- connect
 __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
 {
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     int pair = -1;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const int n = (int)a.rowlen[row];
-        if (n == 0) continue;
-        pair = advance_pair(a.pair_row_base, a.P, pair, row);
-        const PairDesc& pd = a.pairs[pair];
-        const u32 s0 = a.row_start[row];
-        const u32 r = (u32)(row - pd.row_base);
-        const double md = a.most[pd.gi_start + r];
-        const int tp = a.pair_of[pd.j * a.S + pd.p];
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        const int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
         u32 nconn = 0;
-        for (int k = lane; k < n; k += 32) {
-            const u32 cw = a.cols[s0 + k];
-            const u32 c = cw & OFG_COL_MASK;
-            if (a.vals[s0 + k] >= md && !(pd.same && c == r)) {
-                nconn++;
-                atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
-                if (tp >= 0) {
-                    const PairDesc& td = a.pairs[tp];
-                    const int64_t trow = td.row_base + c;
-                    const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
-                    if (e >= 0) atomicOr(&a.cols[e], OFG_FLAG_REVERSE);
+        if (n > 0) {
+            pair = advance_pair(a.pair_row_base, a.P, pair, row);
+            const PairDesc& pd = a.pairs[pair];
+            const u32 s0 = a.row_start[row];
+            const u32 r = (u32)(row - pd.row_base);
+            const double md = a.most[pd.gi_start + r];
+            const int tp = a.pair_of[pd.j * a.S + pd.p];
+            for (int k = gl; k < n; k += ROW_G) {
+                const u32 cw = a.cols[s0 + k];
+                const u32 c = cw & OFG_COL_MASK;
+                if (a.vals[s0 + k] >= md && !(pd.same && c == r)) {
+                    nconn++;
+                    atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
+                    if (tp >= 0) {
+                        const PairDesc& td = a.pairs[tp];
+                        const int64_t trow = td.row_base + c;
+                        const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
+                        if (e >= 0) atomicOr(&a.cols[e], OFG_FLAG_REVERSE);
+                    }
                 }
             }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) nconn += __shfl_xor_sync(OFG_FULL, nconn, d);
-        if (lane == 0) a.row_flagcnt[row] = nconn;
+        nconn = group_sum(nconn);
+        if (gl == 0 && n > 0) a.row_flagcnt[row] = nconn;
     }
 }
 
