@@ -575,7 +575,7 @@ int stage_norm(ofg_ctx* c)
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
         sa.row_flagcnt = c->row_flagcnt.as<u32>();
         const int g2 = grid_for(c, c->n_rows, 16, 8);
-        scale_bh_kernel<<<g2, 256, 0, c->stream>>>(sa);
+        scale_bh_kernel<16><<<g2, 256, 0, c->stream>>>(sa);
         CKL("scale_bh_kernel");
         std::vector<int32_t> diag;
         int64_t max_gi = 1;
@@ -625,7 +625,7 @@ int stage_thresh(ofg_ctx* c)
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
         g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
         g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
-        rbh_kernel<<<grid_for(c, c->n_rows, 16, 8), 256, 0, c->stream>>>(g);
+        rbh_kernel<8><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
         CKL("rbh_kernel");
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
                                                                                c->owned_gene.as<uint8_t>(), c->N);
@@ -651,7 +651,7 @@ int stage_connect(ofg_ctx* c)
         CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
         g.row_flagcnt = c->row_flagcnt.as<u32>();
-        connect_kernel<<<grid_for(c, c->n_rows, 16, 8), 256, 0, c->stream>>>(g);
+        connect_kernel<16><<<grid_for(c, c->n_rows, 16, 8), 256, 0, c->stream>>>(g);
         CKL("connect_kernel");
     }
     CK(cudaEventRecord(c->ev[8], c->stream));

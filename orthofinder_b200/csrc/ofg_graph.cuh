@@ -110,17 +110,26 @@ struct ScaleArgs {
     u32* row_flagcnt;  // [n_rows] best hits per row (pre-zeroed): sizes of the design-B export lists
 };
 
-// Row kernels below give HALF a warp (16 lanes) to each matrix row: rows hold ~50 entries, the work per row is
-// a short dependent chain of loads, and two rows in flight per warp hide that latency better than one.  Both
-// halves run the same trip counts (max of the two rows) so that warp-wide shuffles stay converged.
-constexpr int ROW_G = 16;
+// Row kernels below give a part of a warp (ROW_G = 16 or 8 lanes) to each matrix row: rows hold ~50 entries, the work per row is
+// a short dependent chain of loads, and several rows in flight per warp hide that latency better than one.  All
+// groups run the same trip counts (max over the warp's rows) so that warp-wide shuffles stay converged.
 
+// largest value of n over the groups of a warp (uniform trip counts)
+template <int ROW_G>
+__device__ __forceinline__ int warp_max_over_groups(int n)
+{
+#pragma unroll
+    for (int d = ROW_G; d < 32; d <<= 1) n = max(n, __shfl_xor_sync(OFG_FULL, n, d));
+    return n;
+}
+template <int ROW_G>
 __device__ __forceinline__ double group_max(double v)
 {
 #pragma unroll
     for (int d = ROW_G / 2; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(OFG_FULL, v, d));
     return v;
 }
+template <int ROW_G>
 __device__ __forceinline__ u32 group_sum(u32 v)
 {
 #pragma unroll
@@ -128,6 +137,7 @@ __device__ __forceinline__ u32 group_sum(u32 v)
     return v;
 }
 
+template <int ROW_G>
 __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
 {
     const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
                 gene = pd.gi_start + (row - pd.row_base);
             }
         }
-        const int nmax = max(n, __shfl_xor_sync(OFG_FULL, n, ROW_G));
+        const int nmax = warp_max_over_groups<ROW_G>(n);
         double m = 0.0;
         for (int k = gl; k < nmax; k += ROW_G) {
             if (k < n) {
@@ -166,14 +176,14 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
                 m = fmax(m, v);
             }
         }
-        m = group_max(m);
+        m = group_max<ROW_G>(m);
         if (gl == 0 && n > 0) a.rowmax[row] = m;
         const double thr = __dsub_rn(m, 1e-3);
         u32 nbh = 0;
         if (!same)
             for (int k = gl; k < n; k += ROW_G)
                 if (a.vals[s0 + k] > thr) { a.cols[s0 + k] |= OFG_FLAG_BH; nbh++; }
-        nbh = group_sum(nbh);
+        nbh = group_sum<ROW_G>(nbh);
         if (gl == 0 && n > 0 && !same) {
             a.row_flagcnt[row] = nbh;
             if (owned && m > 0.0) atomic_max_pos_double(&a.best[gene], m);
@@ -230,6 +240,7 @@ __device__ __forceinline__ int64_t find_col(const u32* cols, u32 s0, int n, u32 
     return -1;
 }
 
+template <int ROW_G>
 __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
 {
     const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
                 gene = pd.gi_start + r;
             }
         }
-        const int nmax = max(n, __shfl_xor_sync(OFG_FULL, n, ROW_G));
+        const int nmax = warp_max_over_groups<ROW_G>(n);
         int last = -1;  // largest k (column order) with an RBH
         for (int k0 = 0; k0 < nmax; k0 += ROW_G) {
             const int k = k0 + gl;
@@ -288,6 +299,7 @@ __global__ void thresh_final_kernel(double* most, const double* best, const uint
 }
 
 // ---------------------------------------------------------------- connect
+template <int ROW_G>
 __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
 {
     const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
@@ -319,7 +331,7 @@ __global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
                 }
             }
         }
-        nconn = group_sum(nconn);
+        nconn = group_sum<ROW_G>(nconn);
         if (gl == 0 && n > 0) a.row_flagcnt[row] = nconn;
     }
 }
