@@ -16,10 +16,8 @@ extern "C" {
 
 int ofg_hostcheck_fit(const double* lx, const double* ly, long m, double* out)
 {
-    double* buf = (double*)malloc(sizeof(double) * 4 * (size_t)(m > 0 ? m : 1));
     static FitShared sh;
-    int info = fit_loglinear(lx, ly, m, buf, buf + m, buf + 2 * m, buf + 3 * m, &sh, out);
-    free(buf);
+    int info = fit_loglinear(lx, ly, m, &sh, out);
     return info;
 }
 

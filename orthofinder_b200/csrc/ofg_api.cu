@@ -85,7 +85,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf lx, ly, fvec, wa4, c0, c1, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -181,10 +181,10 @@ __global__ void test_score_kernel(const uint8_t* text, int64_t nbytes, const int
         y[i] = v;
     }
 }
-__global__ void __launch_bounds__(FIT_THREADS) test_fit_kernel(const double* lx, const double* ly, long m, double* scratch, double* out)
+__global__ void __launch_bounds__(FIT_THREADS) test_fit_kernel(const double* lx, const double* ly, long m, double* out)
 {
     __shared__ __align__(16) FitShared sh;
-    fit_loglinear(lx, ly, m, scratch, scratch + m, scratch + 2 * m, scratch + 3 * m, &sh, out);
+    fit_loglinear(lx, ly, m, &sh, out);
 }
 
 template <typename TO>
@@ -508,8 +508,6 @@ int stage_norm(ofg_ctx* c)
     c->sel_cap = std::max<u64>(n_slots / (u64)std::max<int64_t>(c->sel_frac_inv, 1), 1u << 16);
     if (c->sel_cap > n_slots + 1) c->sel_cap = n_slots + 1;
     CK(c->lx.ensure(c->sel_cap * 8)); CK(c->ly.ensure(c->sel_cap * 8));
-    CK(c->fvec.ensure(c->sel_cap * 8)); CK(c->wa4.ensure(c->sel_cap * 8));
-    CK(c->c0.ensure(c->sel_cap * 8)); CK(c->c1.ensure(c->sel_cap * 8));
     CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
     CK(cudaMemsetAsync(c->fit.p, 0, (size_t)P * 8 * 8, c->stream));
     BinArgs b;
@@ -542,7 +540,6 @@ int stage_norm(ofg_ctx* c)
     CKL("gather_u64_kernel");
     FitArgs f;
     f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
-    f.fvec = c->fvec.as<double>(); f.wa4 = c->wa4.as<double>(); f.c0 = c->c0.as<double>(); f.c1 = c->c1.as<double>();
     f.fit = c->fit.as<double>(); f.err_flags = err_flags;
     if (P > 0) {
         fit_kernel<<<P, FIT_THREADS, 0, c->stream>>>(f);
@@ -750,8 +747,8 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->fvec,
-                      &c->wa4, &c->c0, &c->c1, &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly,
+                      &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
                       &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff};
@@ -1274,17 +1271,17 @@ int ofg_test_lmfit(ofg_ctx* c, const double* host_lx, const double* host_ly, int
 {
     if (!c || m < 2) return OFG_ERR_ARG;
     cudaSetDevice(c->device);
-    DevBuf x, y, s, o;
-    CK(x.ensure((size_t)m * 8)); CK(y.ensure((size_t)m * 8)); CK(s.ensure((size_t)m * 32)); CK(o.ensure(64));
+    DevBuf x, y, o;
+    CK(x.ensure((size_t)m * 8)); CK(y.ensure((size_t)m * 8)); CK(o.ensure(64));
     CK(cudaMemcpyAsync(x.p, host_lx, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(y.p, host_ly, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
-    test_fit_kernel<<<1, FIT_THREADS, 0, c->stream>>>(x.as<double>(), y.as<double>(), (long)m, s.as<double>(), o.as<double>());
+    test_fit_kernel<<<1, FIT_THREADS, 0, c->stream>>>(x.as<double>(), y.as<double>(), (long)m, o.as<double>());
     CKL("test_fit_kernel");
     double h[8];
     CK(cudaMemcpyAsync(h, o.p, 48, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[3]; out[3] = h[4];
-    x.release(); y.release(); s.release(); o.release();
+    x.release(); y.release(); o.release();
     return OFG_OK;
 }
 

@@ -144,188 +144,180 @@ FIT_FN double fit_enorm_small(int n, const double* x)
     return acc.result();
 }
 
-// enorm of up to FIT_MAXV long vectors side by side.  Vector v is accumulated in index order by lane 0
-// of warp v while the warps >= FIT_MAXV stage the next chunk of every vector (double buffering).  With
-// fewer than 128 threads (the host build) staging and accumulation simply alternate.
-FIT_FN void fit_enorm_multi(int nv, const double* const* x, const long* n, FitShared* sh, double* out)
+// ---- vectors as pure functions -------------------------------------------------------------------------
+// Every long vector of the algorithm (residual, the two Jacobian columns, the Householder vectors, Q^T f) is
+// an element-wise function of (log10 Lf_i, log10 S_i) and a handful of scalars.  They are therefore never
+// stored: the warps that stage a chain recompute the needed term from lx[i], ly[i] with exactly the
+// operations MINPACK would have applied to the stored arrays, in the same order.  This removes all O(m)
+// scratch traffic; the fit costs the latency of its ordered sums and nothing else.
+enum { FIT_K_F = 0,      // f_i = (x0*lx + x1) - ly                       (enorm term)
+       FIT_K_J0,         // forward-difference column of parameter 0      (enorm term)
+       FIT_K_J1,         // forward-difference column of parameter 1      (enorm term)
+       FIT_K_AB,         // A'_i * B_i   first Householder vector times second (pivoted) column   (dot term)
+       FIT_K_AF,         // A'_i * f_i                                                           (dot term)
+       FIT_K_B1,         // B'_i = B_i - t*A'_i   second column after the first reflection       (enorm term)
+       FIT_K_B2W,        // B''_i * w'_i  second Householder vector times once-reflected residual (dot term)
+       FIT_K_FNEW };     // residual at the trial point                   (enorm term)
+
+struct FitState {
+    double x0, x1;               // current iterate
+    double xp00, xp01, h0;       // x + h0*e0 and h0
+    double xp10, xp11, h1;       // x + h1*e1 and h1
+    double aj0, t, aj1, temp0;   // signed column norms, reflection coefficients
+    double xn0, xn1;             // trial point
+    int piv, hh1, hh2;           // columns swapped; first / second reflection applied
+};
+
+FIT_FN bool fit_kind_is_enorm(int kind) { return kind == FIT_K_F || kind == FIT_K_J0 || kind == FIT_K_J1 || kind == FIT_K_B1 || kind == FIT_K_FNEW; }
+
+FIT_FN double fit_elem_f(const FitState& S, double lx, double ly) { return FSUB(FADD(FMUL(S.x0, lx), S.x1), ly); }
+FIT_FN double fit_elem_j0(const FitState& S, double lx, double ly, double f) { return FDIV(FSUB(FSUB(FADD(FMUL(S.xp00, lx), S.xp01), ly), f), S.h0); }
+FIT_FN double fit_elem_j1(const FitState& S, double lx, double ly, double f) { return FDIV(FSUB(FSUB(FADD(FMUL(S.xp10, lx), S.xp11), ly), f), S.h1); }
+FIT_FN double fit_elem_ap(const FitState& S, long i, double A)
 {
-    FitEnormAcc acc;
-    acc.init(1.0);
+    if (!S.hh1) return A;
+    const double ap = FDIV(A, S.aj0);
+    return i == 0 ? FADD(ap, 1.0) : ap;
+}
+FIT_FN double fit_elem_bp(const FitState& S, double B, double Ap) { return S.hh1 ? FSUB(B, FMUL(S.t, Ap)) : B; }
+FIT_FN double fit_elem_bpp(const FitState& S, long i, double Bp)
+{
+    if (!S.hh2 || i < 1) return Bp;
+    const double b = FDIV(Bp, S.aj1);
+    return i == 1 ? FADD(b, 1.0) : b;
+}
+FIT_FN double fit_elem_wp(const FitState& S, double f, double Ap) { return S.hh1 ? FADD(f, FMUL(Ap, S.temp0)) : f; }
+
+// value of the chain term `kind` at absolute index i
+FIT_FN double fit_term(int kind, long i, double lx, double ly, const FitState& S)
+{
+    if (kind == FIT_K_FNEW) return FSUB(FADD(FMUL(S.xn0, lx), S.xn1), ly);
+    const double f = fit_elem_f(S, lx, ly);
+    if (kind == FIT_K_F) return f;
+    if (kind == FIT_K_J0) return fit_elem_j0(S, lx, ly, f);
+    if (kind == FIT_K_J1) return fit_elem_j1(S, lx, ly, f);
+    const double J0 = fit_elem_j0(S, lx, ly, f), J1 = fit_elem_j1(S, lx, ly, f);
+    const double A = S.piv ? J1 : J0, B = S.piv ? J0 : J1;
+    const double Ap = fit_elem_ap(S, i, A);
+    if (kind == FIT_K_AB) return FMUL(Ap, B);
+    if (kind == FIT_K_AF) return FMUL(Ap, f);
+    const double Bp = fit_elem_bp(S, B, Ap);
+    if (kind == FIT_K_B1) return Bp;
+    return FMUL(fit_elem_bpp(S, i, Bp), fit_elem_wp(S, f, Ap));  // FIT_K_B2W
+}
+
+// Up to FIT_MAXV chains side by side over the absolute index ranges [i0[v], i0[v] + n[v]).  Chain v is an
+// enorm (MINPACK's scaled 2-norm) or a plain ordered sum depending on kinds[v]; it is accumulated in index
+// order by lane 0 of warp v from terms staged through a ring of shared-memory chunks by the warps >=
+// FIT_MAXV.  With fewer than 128 threads (the host build) staging and accumulation simply alternate.
+FIT_FN void fit_chain_multi(int nv, const int* kinds, const long* i0, const long* n, const double* lx, const double* ly,
+                            const FitState& S, FitShared* sh, double* out)
+{
+    const double rdwarf = 3.834e-20;
     const bool overlap = FIT_NT >= 128;
-    const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;  // chain this thread accumulates (device)
-    long nmax = 0;
-    for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
     if (!overlap) {
         for (int v = 0; v < nv; v++) {
+            const bool en = fit_kind_is_enorm(kinds[v]);
+            FitEnormAcc acc;
             acc.init((double)n[v]);
+            double sum = 0.0;
             for (long c0 = 0; c0 < n[v]; c0 += FIT_CH) {
                 const int len = (int)((n[v] - c0) < FIT_CH ? (n[v] - c0) : FIT_CH);
-                for (int i = FIT_TID; i < len; i += FIT_NT) sh->buf[0][0][i] = x[v][c0 + i];
+                for (int i = FIT_TID; i < len; i += FIT_NT) {
+                    const long gi = i0[v] + c0 + i;
+                    sh->buf[0][0][i] = fit_term(kinds[v], gi, lx[gi], ly[gi], S);
+                }
                 FIT_SYNC();
-                if (FIT_TID == 0) acc.add_run(sh->buf[0][0], len);
+                if (FIT_TID == 0) {
+                    if (en) acc.add_run(sh->buf[0][0], len);
+                    else sum = fit_ordered_sum(sum, sh->buf[0][0], len);
+                }
                 FIT_SYNC();
             }
-            if (FIT_TID == 0) sh->out[v] = acc.result();
+            if (FIT_TID == 0) sh->out[v] = en ? acc.result() : sum;
         }
     } else {
-        if (my_v >= 0 && my_v < nv) acc.init((double)n[my_v]);
+        const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;
+        const bool summer = my_v >= 0 && my_v < nv;
+        const bool my_en = summer && fit_kind_is_enorm(kinds[my_v]);
+        FitEnormAcc acc;
+        acc.init(summer ? (double)n[my_v] : 1.0);
+        double sum = 0.0;
         const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
+        const int lt = FIT_TID - first_loader;
+        long nmax = 0;
+        for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
         const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
-        // The loaders stage the SQUARES of chunk c+1 (independent, any order) while lane 0 of warp v adds the
-        // squares of chunk c in index order: same operations as FitEnormAcc::add for mid-range values.  A chunk
-        // holding a value outside the mid range is tagged and accumulated from the raw values instead.
-        const double rdwarf = 3.834e-20;
-        const int lt = FIT_TID - first_loader;  // loader index
         for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
             if (FIT_TID >= first_loader) {
-                const long cl = c + (FIT_RING - 1);          // chunk to stage now
+                const long cl = c + (FIT_RING - 1);  // chunk to stage now
                 const long c1 = cl * FIT_CH;
                 const int slot = (int)(cl % FIT_RING);
                 for (int v = 0; v < nv; v++) {
                     if (c1 >= n[v]) continue;
                     const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
+                    const bool en = fit_kind_is_enorm(kinds[v]);
                     const double agiant = FDIV(1.304e19, (double)n[v]);
                     bool odd = false;
-                    for (int i0 = 0; i0 < len; i0 += 4 * n_loaders) {
-                        double xv[4];
+                    for (int b0 = 0; b0 < len; b0 += 4 * n_loaders) {
+                        double xa[4], ya[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {  // four independent loads in flight per loader
-                            const int i = i0 + u * n_loaders + lt;
-                            xv[u] = i < len ? fabs(x[v][c1 + i]) : 1.0;
+                        for (int u = 0; u < 4; u++) {  // four independent element loads in flight per loader
+                            const int i = b0 + u * n_loaders + lt;
+                            const long gi = i0[v] + c1 + (i < len ? i : 0);
+                            xa[u] = lx[gi];
+                            ya[u] = ly[gi];
                         }
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            const int i = i0 + u * n_loaders + lt;
+                            const int i = b0 + u * n_loaders + lt;
                             if (i < len) {
-                                odd = odd || !(xv[u] > rdwarf && xv[u] < agiant);
-                                sh->buf[v][slot][i] = FMUL(xv[u], xv[u]);
+                                const double tv = fit_term(kinds[v], i0[v] + c1 + i, xa[u], ya[u], S);
+                                if (en) {
+                                    const double av = fabs(tv);
+                                    odd = odd || !(av > rdwarf && av < agiant);
+                                    sh->buf[v][slot][i] = FMUL(av, av);
+                                } else {
+                                    sh->buf[v][slot][i] = tv;
+                                }
                             }
                         }
                     }
                     if (odd) sh->tag[v][slot] = (int)(cl + 1);
                 }
-            } else if (c >= 0 && my_v >= 0 && my_v < nv) {
+            } else if (c >= 0 && summer) {
                 const long c0 = c * FIT_CH;
                 if (c0 < n[my_v]) {
                     const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
                     const int slot = (int)(c % FIT_RING);
-                    if (sh->tag[my_v][slot] == (int)(c + 1)) {
-                        for (int i = 0; i < len; i++) acc.add(x[my_v][c0 + i]);
+                    if (!my_en) {
+                        sum = fit_ordered_sum(sum, sh->buf[my_v][slot], len);
+                    } else if (sh->tag[my_v][slot] == (int)(c + 1)) {  // a value outside MINPACK's mid range: exact slow path
+                        for (int i = 0; i < len; i++) {
+                            const long gi = i0[my_v] + c0 + i;
+                            acc.add(fit_term(kinds[my_v], gi, lx[gi], ly[gi], S));
+                        }
                     } else {
-#ifdef FIT_PROFILE
-                        const long long tp0 = clock64();
-#endif
                         acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][slot], len);
-#ifdef FIT_PROFILE
-                        if (my_v == 0) { g_t_sum += clock64() - tp0; g_n_chunks++; }
-#endif
                     }
                 }
             }
-#ifdef FIT_PROFILE
-            const long long tp1 = clock64();
-#endif
             FIT_SYNC();
-#ifdef FIT_PROFILE
-            if (FIT_TID == 0) g_t_wait += clock64() - tp1;
-#endif
         }
-        if (my_v >= 0 && my_v < nv) sh->out[my_v] = acc.result();
+        if (summer) sh->out[my_v] = my_en ? acc.result() : sum;
     }
     FIT_SYNC();
     for (int v = 0; v < nv; v++) out[v] = sh->out[v];
     FIT_SYNC();
 }
 
-FIT_FN double fit_enorm_big(const double* x, long n, FitShared* sh)
+FIT_FN double fit_chain_one(int kind, long i0, long n, const double* lx, const double* ly, const FitState& S, FitShared* sh)
 {
-    const double* xs[1] = {x};
-    long ns[1] = {n};
+    int ks[1] = {kind};
+    long is[1] = {i0}, ns[1] = {n};
     double o[1];
-    fit_enorm_multi(1, xs, ns, sh, o);
+    fit_chain_multi(1, ks, is, ns, lx, ly, S, sh, o);
     return o[0];
-}
-
-// Up to FIT_MAXV dot products side by side: out[v] = sum_i a[v][i]*b[v][i], index order, product rounded
-// before the add.  Chain v is accumulated by lane 0 of warp v from products staged (double buffered) by the
-// warps >= FIT_MAXV; the host build alternates staging and accumulation.
-FIT_FN void fit_dot_multi(int nv, const double* const* a, const double* const* b, const long* n, FitShared* sh, double* out)
-{
-    const bool overlap = FIT_NT >= 128;
-    double sum = 0.0;
-    if (!overlap) {
-        for (int v = 0; v < nv; v++) {
-            sum = 0.0;
-            for (long c0 = 0; c0 < n[v]; c0 += FIT_CH) {
-                const int len = (int)((n[v] - c0) < FIT_CH ? (n[v] - c0) : FIT_CH);
-                for (int i = FIT_TID; i < len; i += FIT_NT) sh->buf[0][0][i] = FMUL(a[v][c0 + i], b[v][c0 + i]);
-                FIT_SYNC();
-                if (FIT_TID == 0) sum = fit_ordered_sum(sum, sh->buf[0][0], len);
-                FIT_SYNC();
-            }
-            if (FIT_TID == 0) sh->out[v] = sum;
-        }
-    } else {
-        const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;
-        const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
-        long nmax = 0;
-        for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
-        const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
-        const int lt = FIT_TID - first_loader;
-        for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
-            if (FIT_TID >= first_loader) {
-                const long cl = c + (FIT_RING - 1);
-                const long c1 = cl * FIT_CH;
-                const int slot = (int)(cl % FIT_RING);
-                for (int v = 0; v < nv; v++) {
-                    if (c1 >= n[v]) continue;
-                    const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
-                    for (int i0 = 0; i0 < len; i0 += 4 * n_loaders) {
-                        double av[4], bv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int i = i0 + u * n_loaders + lt;
-                            av[u] = i < len ? a[v][c1 + i] : 0.0;
-                            bv[u] = i < len ? b[v][c1 + i] : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int i = i0 + u * n_loaders + lt;
-                            if (i < len) sh->buf[v][slot][i] = FMUL(av[u], bv[u]);
-                        }
-                    }
-                }
-            } else if (c >= 0 && my_v >= 0 && my_v < nv) {
-                const long c0 = c * FIT_CH;
-                if (c0 < n[my_v]) {
-                    const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
-                    sum = fit_ordered_sum(sum, sh->buf[my_v][c % FIT_RING], len);
-                }
-            }
-            FIT_SYNC();
-        }
-        if (my_v >= 0 && my_v < nv) sh->out[my_v] = sum;
-    }
-    FIT_SYNC();
-    for (int v = 0; v < nv; v++) out[v] = sh->out[v];
-    FIT_SYNC();
-}
-
-FIT_FN double fit_dot_big(const double* a, const double* b, long n, FitShared* sh)
-{
-    const double* as[1] = {a};
-    const double* bs[1] = {b};
-    long ns[1] = {n};
-    double o[1];
-    fit_dot_multi(1, as, bs, ns, sh, o);
-    return o[0];
-}
-
-// f(x,a,b) - y with f = a*log10(x) + b : three separately rounded operations (gathering.py:82)
-FIT_FN void fit_resid(const double* lx, const double* ly, long m, double pa, double pb, double* out)
-{
-    for (long k = FIT_TID; k < m; k += FIT_NT) out[k] = FSUB(FADD(FMUL(pa, lx[k]), pb), ly[k]);
-    FIT_SYNC();
 }
 
 FIT_FN void fit_qrsolv(double r[2][2], const int* ipvt, const double* diag, const double* qtb, double* x, double* sdiag)
@@ -454,55 +446,44 @@ FIT_FN void fit_lmpar(double r[2][2], const int* ipvt, const double* diag, const
     if (iter == 0) *par = 0.0;
 }
 
-// lx, ly: m selected points in the reference's order.  fvec, wa4, c0, c1: m doubles of scratch each.
-// out[0..5] = a, b, m, info, nfev, iterative-lmpar flag.  Returns MINPACK info.
-FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fvec, double* wa4, double* c0, double* c1,
-                         FitShared* sh, double* out)
+// lx, ly: m selected points in the reference's order.  out[0..5] = a, b, m, info, nfev, iterative-lmpar flag.
+// Returns MINPACK info.
+FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* sh, double* out)
 {
     const double ftol = 1.49012e-08, xtol = 1.49012e-08, gtol = 0.0, factor = 100.0, epsmch = DBL_EPSILON;
     const int maxfev = 600;
-    double* col[2] = {c0, c1};
     double x[2] = {1.0, 1.0}, diag[2], qtf[2], wa1[2], wa2[2], wa3[2], acnorm[2], rdiag[2], wa[2];
     int ipvt[2];
     int info = 0, nfev = 0, iterative = 0, iter = 1;
     double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
     const double eps = FSQRT(epsmch);
+    const double lx0 = lx[0], ly0 = ly[0], lx1 = m > 1 ? lx[1] : 0.0, ly1 = m > 1 ? ly[1] : 0.0;
+    FitState S;
+    S.xn0 = S.xn1 = 0.0;
 
-    fit_resid(lx, ly, m, x[0], x[1], fvec);
     nfev = 1;
     double fnorm = 0.0;
     bool have_fnorm = false;
     for (;;) {
-        // fdjac2: both forward-difference columns in one pass (same per-element operations as evaluating
-        // f at x + h_j e_j into a scratch vector first)
+        // fdjac2: forward differences, h_j = eps*|x_j|
+        S.x0 = x[0]; S.x1 = x[1];
+        S.piv = 0; S.hh1 = 0; S.hh2 = 0; S.aj0 = S.aj1 = 1.0; S.t = S.temp0 = 0.0;
         {
-            double h[2], xp[2][2];
+            double h[2];
             for (int j = 0; j < 2; j++) {
-                const double temp = x[j];
-                h[j] = FMUL(eps, fabs(temp));
+                h[j] = FMUL(eps, fabs(x[j]));
                 if (h[j] == 0.0) h[j] = eps;
-                xp[j][0] = x[0];
-                xp[j][1] = x[1];
-                xp[j][j] = FADD(temp, h[j]);
             }
-            double* cA = col[0];
-            double* cB = col[1];
-            for (long i = FIT_TID; i < m; i += FIT_NT) {
-                const double lxi = lx[i], lyi = ly[i], f = fvec[i];
-                const double w0 = FSUB(FADD(FMUL(xp[0][0], lxi), xp[0][1]), lyi);
-                const double w1 = FSUB(FADD(FMUL(xp[1][0], lxi), xp[1][1]), lyi);
-                cA[i] = FDIV(FSUB(w0, f), h[0]);
-                cB[i] = FDIV(FSUB(w1, f), h[1]);
-            }
-            FIT_SYNC();
+            S.h0 = h[0]; S.xp00 = FADD(x[0], h[0]); S.xp01 = x[1];
+            S.h1 = h[1]; S.xp10 = x[0]; S.xp11 = FADD(x[1], h[1]);
         }
         nfev += 2;
         // qrfac with column pivoting; the initial |fvec| rides along with the two column norms
         {
-            const double* xs[3] = {col[0], col[1], fvec};
-            long ns[3] = {m, m, m};
+            int ks[3] = {FIT_K_J0, FIT_K_J1, FIT_K_F};
+            long is[3] = {0, 0, 0}, ns[3] = {m, m, m};
             double o[3];
-            fit_enorm_multi(have_fnorm ? 2 : 3, xs, ns, sh, o);
+            fit_chain_multi(have_fnorm ? 2 : 3, ks, is, ns, lx, ly, S, sh, o);
             acnorm[0] = o[0];
             acnorm[1] = o[1];
             if (!have_fnorm) { fnorm = o[2]; have_fnorm = true; }
@@ -512,55 +493,62 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             wa[j] = rdiag[j];
             ipvt[j] = j;
         }
-        const int minmn = m < 2 ? (int)m : 2;
+        // j = 0: pivot, first Householder reflection
         double qtf_dot0 = 0.0;
-        bool have_qtf_dot0 = false;
-        for (int j = 0; j < minmn; j++) {
-            int kmax = j;
-            for (int k = j; k < 2; k++) if (rdiag[k] > rdiag[kmax]) kmax = k;
-            if (kmax != j) {
-                double* t = col[j]; col[j] = col[kmax]; col[kmax] = t;
-                rdiag[kmax] = rdiag[j];
-                wa[kmax] = wa[j];
-                const int k = ipvt[j]; ipvt[j] = ipvt[kmax]; ipvt[kmax] = k;
+        double r01 = 0.0;  // element (0,1) of R: second column's first entry after the first reflection
+        {
+            if (rdiag[1] > rdiag[0]) {
+                S.piv = 1;
+                rdiag[1] = rdiag[0];
+                wa[1] = wa[0];
+                ipvt[0] = 1; ipvt[1] = 0;
             }
-            double* cj = col[j];
-            // enorm(a[j:, j]); for j = 0 this is the full (pivoted) column, already computed as acnorm
-            double ajnorm = (j == 0) ? acnorm[ipvt[0]] : fit_enorm_big(cj + j, m - j, sh);
+            // elements 0 and 1 of the pivoted raw columns
+            const double f0 = fit_elem_f(S, lx0, ly0), f1 = fit_elem_f(S, lx1, ly1);
+            const double J00 = fit_elem_j0(S, lx0, ly0, f0), J10 = fit_elem_j1(S, lx0, ly0, f0);
+            const double A0 = S.piv ? J10 : J00, B0 = S.piv ? J00 : J10;
+            double ajnorm = acnorm[ipvt[0]];  // enorm(a[0:, 0]) of the pivoted column
             if (ajnorm != 0.0) {
-                if (cj[j] < 0.0) ajnorm = -ajnorm;
-                FIT_SYNC();
-                for (long i = j + FIT_TID; i < m; i += FIT_NT) cj[i] = FDIV(cj[i], ajnorm);
-                FIT_SYNC();
-                if (FIT_TID == 0) cj[j] = FADD(cj[j], 1.0);
-                FIT_SYNC();
-                for (int k = j + 1; k < 2; k++) {
-                    double* ck = col[k];
-                    // the first Householder vector is final here: its product with the residual (needed for
-                    // qtf below) rides along with its product with the second column
-                    const double* das[2] = {cj + j, cj + j};
-                    const double* dbs[2] = {ck + j, fvec + j};
-                    long dns[2] = {m - j, m - j};
-                    double dout[2];
-                    fit_dot_multi(2, das, dbs, dns, sh, dout);
-                    const double sum = dout[0];
-                    qtf_dot0 = dout[1];
-                    have_qtf_dot0 = true;
-                    const double temp = FDIV(sum, cj[j]);
-                    for (long i = j + FIT_TID; i < m; i += FIT_NT) ck[i] = FSUB(ck[i], FMUL(temp, cj[i]));
-                    FIT_SYNC();
-                    if (rdiag[k] != 0.0) {
-                        const double t2 = FDIV(ck[j], rdiag[k]);
-                        rdiag[k] = FMUL(rdiag[k], FSQRT(fmax(0.0, FSUB(1.0, FMUL(t2, t2)))));
-                        const double q = FDIV(rdiag[k], wa[k]);
-                        if (FMUL(0.05, FMUL(q, q)) <= epsmch) {
-                            rdiag[k] = fit_enorm_big(ck + j + 1, m - j - 1, sh);
-                            wa[k] = rdiag[k];
-                        }
+                if (A0 < 0.0) ajnorm = -ajnorm;
+                S.aj0 = ajnorm;
+                S.hh1 = 1;
+                const double Ap0 = fit_elem_ap(S, 0, A0);
+                // A'.B and A'.f (the latter is needed for qtf) side by side
+                int ks[2] = {FIT_K_AB, FIT_K_AF};
+                long is[2] = {0, 0}, ns[2] = {m, m};
+                double o[2];
+                fit_chain_multi(2, ks, is, ns, lx, ly, S, sh, o);
+                qtf_dot0 = o[1];
+                S.t = FDIV(o[0], Ap0);
+                r01 = fit_elem_bp(S, B0, Ap0);
+                if (rdiag[1] != 0.0) {
+                    const double t2 = FDIV(r01, rdiag[1]);
+                    rdiag[1] = FMUL(rdiag[1], FSQRT(fmax(0.0, FSUB(1.0, FMUL(t2, t2)))));
+                    const double q = FDIV(rdiag[1], wa[1]);
+                    if (FMUL(0.05, FMUL(q, q)) <= epsmch) {
+                        rdiag[1] = fit_chain_one(FIT_K_B1, 1, m - 1, lx, ly, S, sh);
+                        wa[1] = rdiag[1];
                     }
                 }
+            } else {
+                r01 = B0;
             }
-            rdiag[j] = -ajnorm;
+            rdiag[0] = -ajnorm;
+            (void)f1;
+        }
+        // j = 1: second Householder reflection (no pivot choice left)
+        if (m >= 2) {
+            double ajnorm = fit_chain_one(FIT_K_B1, 1, m - 1, lx, ly, S, sh);
+            if (ajnorm != 0.0) {
+                const double f1 = fit_elem_f(S, lx1, ly1);
+                const double J01 = fit_elem_j0(S, lx1, ly1, f1), J11 = fit_elem_j1(S, lx1, ly1, f1);
+                const double A1 = S.piv ? J11 : J01, B1 = S.piv ? J01 : J11;
+                const double Bp1 = fit_elem_bp(S, B1, fit_elem_ap(S, 1, A1));
+                if (Bp1 < 0.0) ajnorm = -ajnorm;
+                S.aj1 = ajnorm;
+                S.hh2 = 1;
+            }
+            rdiag[1] = -ajnorm;
         }
         if (iter == 1) {
             for (int j = 0; j < 2; j++) { diag[j] = acnorm[j]; if (acnorm[j] == 0.0) diag[j] = 1.0; }
@@ -569,40 +557,25 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             delta = FMUL(factor, xnorm);
             if (delta == 0.0) delta = factor;
         }
-        // qtf (wa4 = fvec, then the two Householder reflections; the copy is folded into the first one)
-        bool wa4_ready = false;
-        for (int j = 0; j < 2; j++) {
-            double* cj = col[j];
-            if (j < m && cj[j] != 0.0) {
-                if (j == 0 && have_qtf_dot0) {
-                    const double temp = FDIV(-qtf_dot0, cj[0]);
-                    for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(fvec[i], FMUL(cj[i], temp));
-                    FIT_SYNC();
-                    wa4_ready = true;
-                } else {
-                    if (!wa4_ready) {
-                        for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = fvec[i];
-                        FIT_SYNC();
-                        wa4_ready = true;
-                    }
-                    const double sum = fit_dot_big(cj + j, wa4 + j, m - j, sh);
-                    const double temp = FDIV(-sum, cj[j]);
-                    for (long i = j + FIT_TID; i < m; i += FIT_NT) wa4[i] = FADD(wa4[i], FMUL(cj[i], temp));
-                    FIT_SYNC();
-                }
-            } else if (!wa4_ready) {
-                for (long i = FIT_TID; i < m; i += FIT_NT) wa4[i] = fvec[i];
-                FIT_SYNC();
-                wa4_ready = true;
+        // qtf: Q^T f through the two reflections
+        {
+            const double f0 = fit_elem_f(S, lx0, ly0), f1 = fit_elem_f(S, lx1, ly1);
+            const double J00 = fit_elem_j0(S, lx0, ly0, f0), J10 = fit_elem_j1(S, lx0, ly0, f0);
+            const double J01 = fit_elem_j0(S, lx1, ly1, f1), J11 = fit_elem_j1(S, lx1, ly1, f1);
+            const double A0 = S.piv ? J10 : J00, A1 = S.piv ? J11 : J01, B1 = S.piv ? J01 : J11;
+            const double Ap0 = fit_elem_ap(S, 0, A0), Ap1 = fit_elem_ap(S, 1, A1);
+            if (S.hh1) S.temp0 = FDIV(-qtf_dot0, Ap0);
+            qtf[0] = fit_elem_wp(S, f0, Ap0);
+            double w1 = fit_elem_wp(S, f1, Ap1);
+            if (S.hh2) {
+                const double Bpp1 = fit_elem_bpp(S, 1, fit_elem_bp(S, B1, Ap1));
+                const double sum = fit_chain_one(FIT_K_B2W, 1, m - 1, lx, ly, S, sh);
+                const double temp = FDIV(-sum, Bpp1);
+                w1 = FADD(w1, FMUL(Bpp1, temp));
             }
-            FIT_SYNC();
-            if (FIT_TID == 0 && j < m) cj[j] = rdiag[j];
-            FIT_SYNC();
-            qtf[j] = j < m ? wa4[j] : 0.0;
+            qtf[1] = w1;
         }
-        double r[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-        for (int j = 0; j < 2; j++)
-            for (int i = 0; i <= j; i++) r[i][j] = (i < m) ? col[j][i] : 0.0;
+        double r[2][2] = {{rdiag[0], r01}, {0.0, rdiag[1]}};
         gnorm = 0.0;
         if (fnorm != 0.0) {
             for (int j = 0; j < 2; j++) {
@@ -627,9 +600,9 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
             }
             const double pnorm = fit_enorm_small(2, wa3);
             if (iter == 1) delta = fmin(delta, pnorm);
-            fit_resid(lx, ly, m, wa2[0], wa2[1], wa4);
+            S.xn0 = wa2[0]; S.xn1 = wa2[1];
             nfev++;
-            const double fnorm1 = fit_enorm_big(wa4, m, sh);
+            const double fnorm1 = fit_chain_one(FIT_K_FNEW, 0, m, lx, ly, S, sh);
             double actred = -1.0;
             if (FMUL(0.1, fnorm1) < fnorm) { const double q = FDIV(fnorm1, fnorm); actred = FSUB(1.0, FMUL(q, q)); }
             for (int j = 0; j < 2; j++) {
@@ -654,8 +627,7 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, double* fve
                 par = FMUL(0.5, par);
             }
             if (ratio >= 1e-4) {
-                for (int j = 0; j < 2; j++) { x[j] = wa2[j]; wa2[j] = FMUL(diag[j], x[j]); }
-                { double* t = fvec; fvec = wa4; wa4 = t; }  // fvec <- f(x_new): swap the two work vectors
+                for (int j = 0; j < 2; j++) { x[j] = wa2[j]; wa2[j] = FMUL(diag[j], x[j]); }  // f(x) follows implicitly
                 xnorm = fit_enorm_small(2, wa2);
                 fnorm = fnorm1;
                 iter++;

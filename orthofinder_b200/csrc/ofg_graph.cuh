@@ -25,10 +25,6 @@ struct FitArgs {
     u64 sel_cap;
     const double* lx;
     const double* ly;
-    double* fvec;
-    double* wa4;
-    double* c0;
-    double* c1;
     double* fit;      // [P][8]: a, b, m, info, nfev, iterative, ok, pad
     u32* err_flags;   // bit 0: a fit failed (curve_fit would raise); bit 1: selection overflowed sel_cap
 };
@@ -48,7 +44,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(FitArgs a)
             if (threadIdx.x == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = (double)m; out[3] = 0.0; out[4] = 0.0; out[5] = 0.0; out[6] = 0.0; }
             continue;
         }
-        const int info = fit_loglinear(a.lx + o0, a.ly + o0, m, a.fvec + o0, a.wa4 + o0, a.c0 + o0, a.c1 + o0, &sh, out);
+        const int info = fit_loglinear(a.lx + o0, a.ly + o0, m, &sh, out);
         if (threadIdx.x == 0) {
             const bool ok = info >= 1 && info <= 4;
             out[6] = ok ? 1.0 : 0.0;
