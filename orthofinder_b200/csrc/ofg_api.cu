@@ -85,7 +85,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf sort_desc, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -466,13 +466,19 @@ int stage_norm(ofg_ctx* c)
     u32* kin = c->key.as<u32>(); double* vin = c->keyval.as<double>();
     u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
     if (n_tiles > 0) {
+        CK(c->sort_desc.ensure((size_t)n_tiles * sizeof(RsTileDesc)));
         for (int pass = 0; pass < n_pass; pass++) {
             RadixArgs a;
             a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
             a.tile_prefix = c->sort_tile_prefix.as<int64_t>(); a.pair_slot = c->pair_slot.as<int64_t>();
             a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
-            const int g = grid_for(c, n_tiles, 1, 3);
-            radix_hist_kernel<<<g, RS_THREADS, 0, c->stream>>>(a);
+            a.desc = c->sort_desc.as<RsTileDesc>();
+            if (pass == 0) {
+                rs_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(a, c->sort_desc.as<RsTileDesc>());
+                CKL("rs_desc_kernel");
+            }
+            const int g = grid_for(c, n_tiles, 1, 2);  // scatter: two resident CTAs per SM (registers, shared memory)
+            radix_hist_kernel<<<grid_for(c, n_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
             CKL("radix_hist_kernel");
             if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
             CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
@@ -747,7 +753,7 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,

@@ -33,20 +33,40 @@ struct RadixArgs {
     int64_t n_tiles;
     int shift, bits;               // digit = (key >> shift) & ((1 << bits) - 1)
     u32* counters;                 // [n_tiles << bits], layout [pair][digit][tile in pair]
+    const struct RsTileDesc* desc; // [n_tiles]
 };
 
-__device__ __forceinline__ void rs_tile_range(const RadixArgs& a, int64_t tile, int& pair, int64_t& e0, int& cnt,
-                                              int64_t& cidx0, int64_t& ntp)
+// Per-tile constants, computed once per sort by rs_desc_kernel so that the per-tile path of the three passes
+// has no dependent global loads: every thread prefetches the next tile's descriptor while it works.
+struct __align__(16) RsTileDesc {
+    int64_t e0;     // first slot of the tile
+    int64_t cidx0;  // counter index of (digit 0, this tile);  + digit * ntp
+    int cnt;        // records in the tile
+    int ntp;        // tiles in the tile's pair
+};
+
+__global__ void rs_desc_kernel(RadixArgs a, RsTileDesc* desc)
 {
-    // tiles are visited in increasing order: the pair index only moves forward
-    if (pair < 0) pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
-    while (tile >= a.tile_prefix[pair + 1]) pair++;
-    const int64_t t = tile - a.tile_prefix[pair];
-    ntp = a.tile_prefix[pair + 1] - a.tile_prefix[pair];
-    e0 = a.pair_slot[pair] + t * RS_TILE;
-    const int64_t rem = a.pair_slot[pair + 1] - e0;
-    cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
-    cidx0 = (a.tile_prefix[pair] << a.bits) + t;  // + digit * ntp
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= a.n_tiles) return;
+    const int pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
+    const int64_t tp0 = a.tile_prefix[pair], tp1 = a.tile_prefix[pair + 1];
+    const int64_t t = tile - tp0;
+    RsTileDesc d;
+    d.e0 = a.pair_slot[pair] + t * RS_TILE;
+    const int64_t rem = a.pair_slot[pair + 1] - d.e0;
+    d.cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
+    d.cidx0 = (tp0 << a.bits) + t;
+    d.ntp = (int)(tp1 - tp0);
+    desc[tile] = d;
+}
+
+__device__ __forceinline__ RsTileDesc rs_load_desc(const RsTileDesc* desc, int64_t tile, int64_t n_tiles)
+{
+    RsTileDesc d;
+    d.e0 = 0; d.cidx0 = 0; d.cnt = 0; d.ntp = 0;
+    if (tile < n_tiles) d = desc[tile];
+    return d;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(RadixArgs a)
@@ -54,11 +74,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(RadixArgs a)
     __shared__ u32 s_hist[RS_MAX_DIGITS];
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
-    int pair = -1;
+    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, a.n_tiles);
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        int cnt;
-        int64_t e0, cidx0, ntp;
-        rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
+        const RsTileDesc td = next;
+        next = rs_load_desc(a.desc, tile + gridDim.x, a.n_tiles);
+        const int cnt = td.cnt;
+        const int64_t e0 = td.e0, cidx0 = td.cidx0, ntp = td.ntp;
         s_hist[threadIdx.x] = 0;
         __syncthreads();
         for (int k = threadIdx.x; k < cnt; k += RS_THREADS) atomicAdd(&s_hist[(a.key_in[e0 + k] >> a.shift) & mask], 1u);
@@ -88,17 +109,18 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
     const int w = threadIdx.x >> 5, lane = lane_id();
-    int pair = -1;
+    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, a.n_tiles);
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        int cnt;
-        int64_t e0, cidx0, ntp;
-        rs_tile_range(a, tile, pair, e0, cnt, cidx0, ntp);
+        const RsTileDesc td = next;
+        next = rs_load_desc(a.desc, tile + gridDim.x, a.n_tiles);
+        const int cnt = td.cnt;
+        const int64_t e0 = td.e0, cidx0 = td.cidx0, ntp = td.ntp;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ww++) sm.cnt[ww][threadIdx.x] = 0;
         sm.gbase[threadIdx.x] = (int)threadIdx.x < nd ? a.counters[cidx0 + (int64_t)threadIdx.x * ntp] : 0u;
         u32 key[RS_ITEMS];
         double val[RS_ITEMS];
-        unsigned short loc[RS_ITEMS];
+        u32 rk[RS_ITEMS];  // peer mask, then the record's rank among its warp's records of the same digit
         const int kbase = w * (RS_ITEMS * 32) + lane;  // warp w owns records [w*256, w*256+256) of the tile
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
@@ -106,13 +128,20 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
             key[it] = k < cnt ? a.key_in[e0 + k] : 0u;
             val[it] = k < cnt ? a.val_in[e0 + k] : 0.0;
         }
+        // all match operations first: they are independent and their latency overlaps
+#pragma unroll
+        for (int it = 0; it < RS_ITEMS; it++) {
+            const int k = kbase + it * 32;
+            const u32 d = k < cnt ? ((key[it] >> a.shift) & mask) : 0xffffffffu;
+            rk[it] = __match_any_sync(OFG_FULL, d);
+        }
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < RS_ITEMS; it++) {
             const int k = kbase + it * 32;
             const bool valid = k < cnt;
-            const u32 d = valid ? ((key[it] >> a.shift) & mask) : 0xffffffffu;
-            const u32 peers = __match_any_sync(OFG_FULL, d);
+            const u32 d = (key[it] >> a.shift) & mask;
+            const u32 peers = rk[it];
             const int leader = __ffs(peers) - 1;
             u32 old = 0;
             if (valid && lane == leader) {
@@ -120,7 +149,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
                 sm.cnt[w][d] = (unsigned short)(old + (u32)__popc(peers));
             }
             old = __shfl_sync(OFG_FULL, old, leader);
-            loc[it] = (unsigned short)(old + (u32)__popc(peers & lanemask_lt()));
+            rk[it] = old + (u32)__popc(peers & lanemask_lt());
             __syncwarp();
         }
         __syncthreads();
@@ -144,7 +173,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
             const int k = kbase + it * 32;
             if (k < cnt) {
                 const u32 d = (key[it] >> a.shift) & mask;
-                const u32 tpos = sm.tbase[d] + sm.cnt[w][d] + loc[it];
+                const u32 tpos = sm.tbase[d] + sm.cnt[w][d] + rk[it];
                 sm.key[tpos] = key[it];
                 sm.val[tpos] = val[it];
             }
