@@ -102,7 +102,7 @@ struct RadixSmem {
 // counters must hold the exclusive scan (global destination of the first record of each (pair, digit, tile)
 // group) when this runs.  Stable: ranks follow (warp, iteration, lane) == input order.  Records are first
 // permuted into tile-sorted order in shared memory so that every digit run leaves as one coalesced write.
-__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(RadixArgs a)
+__global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(RadixArgs a)
 {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RadixSmem& sm = *reinterpret_cast<RadixSmem*>(rs_smem_raw);

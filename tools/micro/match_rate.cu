@@ -1,0 +1,85 @@
+// Throughput of __match_any_sync vs a ballot-based peer mask for 9-bit digits (B200).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o match_rate match_rate.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned u32;
+template <int BITS>
+__device__ __forceinline__ u32 ballot_peers(u32 d)
+{
+    u32 m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const u32 bal = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        m &= ((d >> b) & 1u) ? bal : ~bal;
+    }
+    return m;
+}
+template <int MODE>
+__global__ void k(const u32* in, u32* out, int iters)
+{
+    u32 v[8];
+    for (int i = 0; i < 8; i++) v[i] = in[(threadIdx.x + i * 97 + blockIdx.x) & 4095];
+    u32 acc = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 d = (v[i] + it * 7 + acc) & 511u;
+            u32 p;
+            if (MODE == 0) p = __match_any_sync(0xffffffffu, d);
+            else if (MODE == 1) p = ballot_peers<9>(d);
+            else p = d;
+            acc += __popc(p);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+// independent matches (no serial dependency through acc)
+template <int MODE>
+__global__ void k_indep(const u32* in, u32* out, int iters)
+{
+    u32 v[8];
+    for (int i = 0; i < 8; i++) v[i] = in[(threadIdx.x + i * 97 + blockIdx.x) & 4095];
+    u32 acc = 0;
+    for (int it = 0; it < iters; it++) {
+        u32 p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 d = (v[i] + it * 7) & 511u;
+            if (MODE == 0) p[i] = __match_any_sync(0xffffffffu, d);
+            else p[i] = ballot_peers<9>(d);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc += __popc(p[i]);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+int main()
+{
+    u32 *in, *out;
+    cudaMalloc(&in, 4096 * 4); cudaMalloc(&out, 148 * 8 * 1024 * 4);
+    u32 h[4096]; for (int i = 0; i < 4096; i++) h[i] = (u32)(i * 2654435761u >> 7);
+    cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 2000;
+    for (int warps = 1; warps <= 32; warps *= 2) {
+        for (int mode = 0; mode < 5; mode++) {
+            const int threads = warps * 32 > 1024 ? 1024 : warps * 32;
+            const int blocks = 148 * (warps * 32 / threads);
+            for (int rep = 0; rep < 2; rep++) {
+                cudaEventRecord(e0);
+                if (mode == 0) k<0><<<blocks, threads>>>(in, out, iters);
+                if (mode == 1) k<1><<<blocks, threads>>>(in, out, iters);
+                if (mode == 2) k<2><<<blocks, threads>>>(in, out, iters);
+                if (mode == 3) k_indep<0><<<blocks, threads>>>(in, out, iters);
+                if (mode == 4) k_indep<1><<<blocks, threads>>>(in, out, iters);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+            }
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            const double cyc = ms * 1e-3 * 1.965e9;  // assumes boost clock
+            const char* nm[] = {"match dep", "ballot9 dep", "none", "match indep", "ballot9 indep"};
+            printf("warps/SM %2d  %-14s  %8.1f cycles per warp-item (per warp)  %7.2f SM-cycles per warp-item\n", warps, nm[mode],
+                   cyc / (iters * 8.0), cyc / (iters * 8.0) / warps);
+        }
+    }
+    return 0;
+}
