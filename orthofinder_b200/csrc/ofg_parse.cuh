@@ -332,9 +332,15 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
                     a.coo_val[idx] = score;
                 }
             }
-            // row histogram, warp aggregated
-            const u32 peers = __match_any_sync(OFG_FULL, row);
-            if (row != OFG_ROW_SENTINEL && (int)lane_id() == __ffs(peers) - 1) atomicAdd(&a.rowcount[row], (u32)__popc(peers));
+            // row histogram, aggregated over runs of equal rows (a query's hits are consecutive lines); MATCH.ANY
+            // would cost ~64 SM cycles per warp instruction on B200 (tools/micro/match_rate.cu)
+            const u32 prev_row = __shfl_up_sync(OFG_FULL, row, 1);
+            const u32 heads = __ballot_sync(OFG_FULL, lane_id() == 0 || row != prev_row);
+            if (row != OFG_ROW_SENTINEL && ((heads >> lane_id()) & 1u)) {
+                const u32 later = heads & ~lanemask_lt() & ~(1u << lane_id());  // heads after this lane
+                const int run_end = later ? __ffs(later) - 1 : 32;
+                atomicAdd(&a.rowcount[row], (u32)(run_end - (int)lane_id()));
+            }
             const u32 vb = __ballot_sync(OFG_FULL, row != OFG_ROW_SENTINEL);
             if (lane_id() == 0 && vb) atomicAdd(&s_valid, (u32)__popc(vb));
         }
