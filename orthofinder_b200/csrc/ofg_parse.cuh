@@ -63,6 +63,50 @@ __device__ __forceinline__ u32 bytes_eq_hi(u32 w, u32 pattern)
 // gathers the four 0x80 flags into bits 0..3 (the partial products never collide below bit 32)
 __device__ __forceinline__ u32 hi_to_nibble(u32 t) { return (t * 0x00204081u) >> 28; }
 
+// a * b + c on the FMA pipe (the kernel is bound by the integer ALU pipe)
+__device__ __forceinline__ u32 umad32(u32 a, u32 b, u32 c)
+{
+    u32 r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// Structural bitmaps of one 32-byte chunk (bit i = byte i): line terminators (\n, \r) and tabs.
+// Fast form: for bytes below 0x80, (byte ^ c) + 0x7f has its top bit clear exactly when byte == c, with no
+// carries between bytes.  Returns false if the chunk holds a byte >= 0x80 (carries possible) or a double
+// quote (csv quoting is not supported); the caller then uses the exact, carry-free form.
+__device__ __forceinline__ bool chunk_masks_fast(const u32 (&xs)[8], u32* term, u32* tabs)
+{
+    const u32 H = 0x80808080u, A = 0x7f7f7f7fu;
+    u32 good = H, tm = 0, tb = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const u32 x = xs[b];
+        const u32 n_nl = (x ^ 0x0a0a0a0au) + A, n_cr = (x ^ 0x0d0d0d0du) + A;
+        const u32 n_tb = (x ^ 0x09090909u) + A, n_qu = (x ^ 0x22222222u) + A;
+        good = good & n_qu & ~x;
+        tm = umad32(hi_to_nibble(~(n_nl & n_cr) & H), 1u << (4 * b), tm);   // nibbles do not overlap: multiply-add == shift-or
+        tb = umad32(hi_to_nibble(~n_tb & H), 1u << (4 * b), tb);
+    }
+    *term = tm;
+    *tabs = tb;
+    return good == H;
+}
+__device__ __forceinline__ void chunk_masks_exact(const u32 (&xs)[8], u32* term, u32* tabs, u32* quotes)
+{
+    u32 tm = 0, tb = 0, qu = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        const u32 x = xs[b];
+        tm |= hi_to_nibble(bytes_eq_hi(x, 0x0a0a0a0au) | bytes_eq_hi(x, 0x0d0d0d0du)) << (4 * b);
+        tb |= hi_to_nibble(bytes_eq_hi(x, 0x09090909u)) << (4 * b);
+        qu |= hi_to_nibble(bytes_eq_hi(x, 0x22222222u)) << (4 * b);
+    }
+    *term = tm;
+    *tabs = tb;
+    *quotes = qu;
+}
+
 // ---- warp-converged fast path --------------------------------------------------------------------------
 // Every lane of a warp holds one record (or none).  All loops below have warp-uniform trip counts and use
 // predication instead of early exits, so the 32 records are parsed in lock step; a record that does not fit
@@ -184,7 +228,7 @@ __device__ __forceinline__ bool swar_score(const uint8_t* s_text, int end, int l
     return act && shape && dig;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
+__global__ void __launch_bounds__(PARSE_THREADS, 5) parse_kernel(ParseArgs a)
 {
     __shared__ __align__(16) uint8_t s_text_raw[16 + PARSE_TILE + PARSE_OVERLAP];  // 16-byte front pad for load8_ending_at
     uint8_t* const s_text = s_text_raw + 16;
@@ -221,9 +265,21 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
         {
             const uint4* g16 = reinterpret_cast<const uint4*>(gfile + t0);
             uint4* s16 = reinterpret_cast<uint4*>(s_text);
-            for (int i = tid; i < nload / 16; i += PARSE_THREADS) s16[i] = __ldg(g16 + i);
-            const uint4 nl = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-            for (int i = nload / 16 + tid; i < (PARSE_TILE + PARSE_OVERLAP) / 16; i += PARSE_THREADS) s16[i] = nl;
+            constexpr int FULL16 = (PARSE_TILE + PARSE_OVERLAP) / 16;
+            if (nload == PARSE_TILE + PARSE_OVERLAP) {  // every tile but a file's last: fixed trip count, loads in flight together
+                uint4 v[FULL16 / PARSE_THREADS + 1];
+#pragma unroll
+                for (int k = 0; k < FULL16 / PARSE_THREADS; k++) v[k] = __ldg(g16 + (k * PARSE_THREADS + tid));
+                constexpr int REST = FULL16 % PARSE_THREADS;
+                if (REST && tid < REST) v[FULL16 / PARSE_THREADS] = __ldg(g16 + ((FULL16 / PARSE_THREADS) * PARSE_THREADS + tid));
+#pragma unroll
+                for (int k = 0; k < FULL16 / PARSE_THREADS; k++) s16[k * PARSE_THREADS + tid] = v[k];
+                if (REST && tid < REST) s16[(FULL16 / PARSE_THREADS) * PARSE_THREADS + tid] = v[FULL16 / PARSE_THREADS];
+            } else {
+                for (int i = tid; i < nload / 16; i += PARSE_THREADS) s16[i] = __ldg(g16 + i);
+                const uint4 nl = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+                for (int i = nload / 16 + tid; i < FULL16; i += PARSE_THREADS) s16[i] = nl;
+            }
             if (tid == 0) {
                 s_prev_term = (t0 == 0) ? 1 : (int)ofg_is_term(gfile[t0 - 1]);
                 s_valid = 0;
@@ -244,15 +300,8 @@ __global__ void __launch_bounds__(PARSE_THREADS) parse_kernel(ParseArgs a)
             const uint4* w4 = reinterpret_cast<const uint4*>(s_text + ch * 32);
             const uint4 lo4 = w4[0], hi4 = w4[1];
             const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-            u32 term = 0, tabs = 0, qu = 0;
-#pragma unroll
-            for (int b = 0; b < 8; b++) {
-                const u32 x = xs[b];
-                term |= hi_to_nibble(bytes_eq_hi(x, 0x0a0a0a0au) | bytes_eq_hi(x, 0x0d0d0d0du)) << (4 * b);
-                tabs |= hi_to_nibble(bytes_eq_hi(x, 0x09090909u)) << (4 * b);
-                const u32 tq = bytes_eq_hi(x, 0x22222222u);
-                if (tq) qu |= hi_to_nibble(tq) << (4 * b);
-            }
+            u32 term, tabs, qu = 0;
+            if (!chunk_masks_fast(xs, &term, &tabs)) chunk_masks_exact(xs, &term, &tabs, &qu);
             s_term[ch] = term;
             s_tab[ch] = tabs;
             if (k < PARSE_CPT) {  // body word: line starts
