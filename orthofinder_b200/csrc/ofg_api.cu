@@ -266,7 +266,7 @@ int ensure_pairs(ofg_ctx* c)
 int text_reserve(ofg_ctx* c, int64_t need)
 {
     // tail pad so that staged overlap reads never leave the arena
-    const int64_t tail = PARSE_TILE + PARSE_OVERLAP + 64;
+    const int64_t tail = PS_RING + 64;
     if ((size_t)(need + tail) <= c->text.cap) return 0;
     DevBuf nb;
     int64_t want = std::max<int64_t>(need + tail, (int64_t)(c->text.cap + c->text.cap / 2));
@@ -323,9 +323,10 @@ int stage_raw(ofg_ctx* c)
         }
         total_padded += d.text_len;
     }
-    std::vector<int64_t> tile_prefix(P + 1, 0);
-    for (int i = 0; i < P; i++) tile_prefix[i + 1] = tile_prefix[i] + (c->pairs[i].text_len + PARSE_TILE - 1) / PARSE_TILE;
+    std::vector<int64_t> tile_prefix(P + 1, 0);  // parse segments before each pair
+    for (int i = 0; i < P; i++) tile_prefix[i + 1] = tile_prefix[i] + (c->pairs[i].text_len + PS_SEG - 1) / PS_SEG;
     const int64_t n_tiles = tile_prefix[P];
+    const int parse_grid = grid_for(c, (n_tiles + PS_WARPS - 1) / PS_WARPS, 1, 4);
     if (upload(c, c->d_pairs, c->pairs.data(), sizeof(PairDesc) * P)) return OFG_ERR_CUDA;
     if (upload(c, c->d_pair_row_base, c->pair_row_base.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
     if (upload(c, c->d_pair_of, c->pair_of.data(), sizeof(int32_t) * c->pair_of.size())) return OFG_ERR_CUDA;
@@ -333,7 +334,8 @@ int stage_raw(ofg_ctx* c)
     if (upload(c, c->d_tile_prefix, tile_prefix.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
     if (upload(c, c->d_seq_start, c->seq_start.data(), sizeof(int64_t) * c->S)) return OFG_ERR_CUDA;
 
-    const u64 cap = (u64)(total_padded / std::max<int64_t>(c->bytes_per_line_inv, 2)) + 1024;
+    // every parse warp may leave up to PS_RESERVE - 1 reserved slots unused
+    const u64 cap = (u64)(total_padded / std::max<int64_t>(c->bytes_per_line_inv, 2)) + 1024 + (u64)parse_grid * PS_WARPS * PS_RESERVE;
     if (cap >= 0xfffffff0ULL) return fail(c, OFG_ERR_CAPACITY, "more than 2^32 records in one context (%llu); shard by query species", (unsigned long long)cap);
     CK(c->coo_row.ensure(cap * 4));
     CK(c->coo_col.ensure(cap * 4));
@@ -358,11 +360,13 @@ int stage_raw(ofg_ctx* c)
     if (n_tiles > 0) {
         ParseArgs a;
         a.text = c->text.as<uint8_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.P = P;
-        a.tile_prefix = c->d_tile_prefix.as<int64_t>(); a.n_tiles = n_tiles;
+        a.seg_prefix = c->d_tile_prefix.as<int64_t>(); a.n_segs = n_tiles;
         a.coo_row = c->coo_row.as<u32>(); a.coo_col = c->coo_col.as<u32>(); a.coo_val = c->coo_val.as<double>();
         a.cap = cap; a.coo_count = sm; a.rowcount = c->rowcount.as<u32>();
         a.pair_lines = d_pair_lines; a.pair_valid = d_pair_valid; a.pair_err = d_pair_err;
-        parse_kernel<<<grid_for(c, n_tiles, 1, 8), PARSE_THREADS, 0, c->stream>>>(a);
+        const int parse_smem = (int)(sizeof(PsWarp) * PS_WARPS);
+        CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_smem));
+        parse_kernel<<<parse_grid, PARSE_THREADS, parse_smem, c->stream>>>(a);
         CKL("parse_kernel");
     }
     CK(cudaEventRecord(c->ev[1], c->stream));
@@ -891,7 +895,7 @@ int ofg_synth_hits(ofg_ctx* c, const ofg_synth_params* params, const int32_t* sp
         used = off + padded;
     }
     if (int rc = text_reserve(c, used)) return rc;
-    CK(cudaMemsetAsync(c->text.p, '\n', (size_t)used + PARSE_TILE + PARSE_OVERLAP + 64, c->stream));
+    CK(cudaMemsetAsync(c->text.p, '\n', (size_t)used + PS_RING + 64, c->stream));
     if (upload(c, c->file_off, file_off.data(), sizeof(int64_t) * P)) return OFG_ERR_CUDA;
     a.text = c->text.as<uint8_t>();
     synth_kernel<true><<<g, 128, 0, c->stream>>>(a);

@@ -4,55 +4,77 @@
 //
 // Layout: all files of the context live back to back in one text arena, each padded with '\n' to a
 // multiple of 16 bytes (blank lines are skipped by the reference, :68-69, so padding is neutral).
-// A CTA takes a 16 KB tile of one file, stages it (plus 1 KB of overlap for the line that crosses
-// the tile end) in shared memory with 16-byte loads, marks line starts with SIMD-in-word byte
-// compares + a CTA scan, then parses one line per thread out of shared memory.  Records are written
-// at (tile base + line index), the tile base coming from one atomicAdd per tile; lines that are
-// dropped (self hits, score <= 0) leave a sentinel row id.  Row histogram (hits per query gene)
-// is accumulated with warp-aggregated atomics (consecutive lines share the query).
+//
+// Streaming warps: the unit of work is the set of lines that START inside one 64 KB segment of one file, and
+// one WARP owns it from the first byte to the last - there is no CTA-level barrier anywhere.  The warp keeps
+// the last 4 KB of text in a private shared-memory ring that it refills 1 KB at a time with cp.async, one step
+// ahead of use.  Per step every lane builds the structural bitmaps (line terminators, tabs) of one 32-byte
+// chunk with SIMD-in-word compares, the line starts are ranked with a warp scan and appended to a queue, and
+// whenever 32 complete lines are queued they are parsed in lock step, one line per lane (full lanes except for
+// the final flush of a segment).  Lines are never re-read: the ring is contiguous across steps, so a line
+// that crosses a step boundary is simply parsed once its terminator has arrived.  Records go to slots reserved
+// 256 at a time per warp (one atomicAdd per 8 rounds); lines that are dropped (self hits, score <= 0) and the
+// unused tail of the last reservation carry a sentinel row id.  The row histogram (hits per query gene) is
+// accumulated over runs of equal rows (a query's hits are consecutive lines).
 #pragma once
 #include "ofg_common.cuh"
 #include "ofg_parse_line.h"
 
-constexpr int PARSE_TILE = 16384;
-constexpr int PARSE_OVERLAP = 1024;
-constexpr int PARSE_THREADS = 256;
-constexpr int PARSE_CPT = PARSE_TILE / 32 / PARSE_THREADS;  // 32-byte chunks of the tile body per thread (adjacent)
-static_assert(PARSE_CPT * 32 * PARSE_THREADS == PARSE_TILE, "tile must split evenly");
-constexpr int PARSE_WORDS = (PARSE_TILE + PARSE_OVERLAP) / 32;
+constexpr int PS_RING = 4096;            // bytes of text a warp keeps staged (power of two)
+constexpr int PS_STEP = 1024;            // bytes per refill: 32 chunks of 32 bytes, one per lane
+constexpr int PS_SEG = 65536;            // lines starting in a 64 KB segment of one file are one warp's unit of work
+constexpr int PS_WARPS = 8;
+constexpr int PARSE_THREADS = PS_WARPS * 32;
+constexpr int PS_QCAP = 32 + PS_STEP / 2;  // pending (< 32) + the most line starts one step can add
+constexpr int PS_RESERVE = 256;          // record slots reserved per atomicAdd
+constexpr u32 PS_RMASK = PS_RING - 1;
+constexpr u32 PS_WMASK = PS_RING / 32 - 1;
+static_assert(PS_SEG <= 65536, "queued line starts are 16-bit stream offsets");
 
 struct ParseArgs {
     const uint8_t* text;
     const PairDesc* pairs;
     int P;
-    const int64_t* tile_prefix;  // [P+1] tiles before each pair
-    int64_t n_tiles;
+    const int64_t* seg_prefix;   // [P+1] segments before each pair
+    int64_t n_segs;
     u32* coo_row;
     u32* coo_col;
     double* coo_val;
     u64 cap;
-    u64* coo_count;   // records reserved so far (may exceed cap: host checks)
+    u64* coo_count;   // record slots reserved so far (may exceed cap: host checks)
     u32* rowcount;    // [total rows] kept records per (pair, query)
     u64* pair_lines;  // [P]
     u64* pair_valid;  // [P]
     u64* pair_err;    // [P] min over offending lines of (byte offset << 4 | kind), ~0 if none
 };
 
-struct SmemSrc {
+// One warp's staging area.  Positions are "stream offsets": bytes from the start of the segment; the ring index
+// is the offset modulo PS_RING, the bitmap word index is (offset / 32) modulo (PS_RING / 32).
+struct __align__(16) PsWarp {
+    uint8_t text[PS_RING];
+    u32 term[PS_RING / 32];   // bit i of word w: byte 32 w + i is '\n' or '\r'
+    u32 tab[PS_RING / 32];
+    uint16_t q[PS_QCAP];      // stream offsets of the line starts not parsed yet, ascending
+};
+
+struct RingSrc {  // generic parser over the ring
     const uint8_t* s;
-    int limit;
-    bool truncated;
-    __device__ __forceinline__ int get(int64_t pos)
-    {
-        if (pos >= limit) { truncated = true; return '\n'; }
-        return s[pos];
-    }
+    int64_t limit;            // stream offset one past the staged text
+    __device__ __forceinline__ int get(int64_t pos) { return pos >= limit ? '\n' : s[(u32)pos & PS_RMASK]; }
 };
 struct GlobalSrc {
     const uint8_t* g;
     int64_t limit;
     __device__ __forceinline__ int get(int64_t pos) { return pos >= limit ? '\n' : g[pos]; }
 };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // 0x80 in every byte of w that equals the pattern byte (exact, no cross-byte carries)
 __device__ __forceinline__ u32 bytes_eq_hi(u32 w, u32 pattern)
@@ -113,11 +135,13 @@ __device__ __forceinline__ void chunk_masks_exact(const u32 (&xs)[8], u32* term,
 // the plain shapes BLAST / DIAMOND / MMseqs2 write ("<species>_<digits>", "<digits>[.<digits>]", <= 9 digits,
 // 12+ fields within 128 bytes) is handed to the generic parser afterwards.
 
-// 128-bit window of a bitmap starting at byte st (bit i = byte st + i)
-__device__ __forceinline__ void rel_mask128(const u32* m, int st, u64* lo, u64* hi)
+// 128-bit window of a ring bitmap starting at stream offset st (bit i = byte st + i)
+__device__ __forceinline__ void rel_mask128(const u32* m, u32 st, u64* lo, u64* hi)
 {
-    const int w0 = st >> 5, sh = st & 31;
-    const u32 a0 = m[w0], a1 = m[w0 + 1], a2 = m[w0 + 2], a3 = m[w0 + 3], a4 = m[w0 + 4];
+    const u32 w0 = st >> 5;
+    const int sh = (int)(st & 31u);
+    const u32 a0 = m[w0 & PS_WMASK], a1 = m[(w0 + 1) & PS_WMASK], a2 = m[(w0 + 2) & PS_WMASK], a3 = m[(w0 + 3) & PS_WMASK],
+              a4 = m[(w0 + 4) & PS_WMASK];
     const u32 r0 = __funnelshift_r(a0, a1, sh), r1 = __funnelshift_r(a1, a2, sh);
     const u32 r2 = __funnelshift_r(a2, a3, sh), r3 = __funnelshift_r(a3, a4, sh);
     *lo = (u64)r0 | ((u64)r1 << 32);
@@ -128,14 +152,14 @@ __device__ __forceinline__ int ctz128(u64 lo, u64 hi) { return lo ? __ffsll((lon
 // Field boundaries relative to the record start for a record with EXACTLY 12 fields inside a 128-byte
 // window: first and second tab, the last (11th) tab and the line end.  Anything else is left to the
 // generic parser.
-__device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* s_term, int st, bool act, int* tab1, int* tab2,
+__device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* s_term, u32 st, bool act, int* tab1, int* tab2,
                                                    int* tab11, int* line_end)
 {
     u64 ea, eb, ta, tb;
     rel_mask128(s_term, st, &ea, &eb);
     rel_mask128(s_tab, st, &ta, &tb);
     const int le = (ea | eb) ? ctz128(ea, eb) : 128;
-    bool ok = act && le < 128 && st + le < PARSE_TILE + PARSE_OVERLAP;
+    bool ok = act && le < 128;  // the caller only hands over complete lines: every bit up to the terminator is valid
     // tabs of this record only
     if (le < 64) { ta &= (1ULL << le) - 1ULL; tb = 0; }
     else if (le < 128) { tb &= (1ULL << (le - 64)) - 1ULL; }
@@ -149,14 +173,15 @@ __device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* 
     return ok;
 }
 
-// 8 bytes [end - 8, end) of the staged text as a little-endian u64 (byte end-1 is the most significant).
-// The buffer has a 16-byte front pad, so end >= 0 is enough.
-__device__ __forceinline__ u64 load8_ending_at(const uint8_t* s_text, int end)
+// 8 bytes [end - 8, end) of the ring as a little-endian u64 (byte end-1 is the most significant); end is a
+// stream offset.  Bytes before the line's first byte may be stale: callers mask them by the field length.
+__device__ __forceinline__ u64 load8_ending_at(const uint8_t* s_text, u32 end)
 {
-    const int a = end - 8;
-    const u32* wp = reinterpret_cast<const u32*>(s_text + (a & ~3));  // (a & ~3) >= -16: inside the pad
-    const u32 a0 = wp[0], a1 = wp[1], a2 = wp[2];
-    const int sh = (a & 3) * 8;
+    const u32 a = end - 8u;
+    const u32* wp = reinterpret_cast<const u32*>(s_text);
+    const u32 wi = a >> 2;
+    const u32 a0 = wp[wi & (PS_RMASK >> 2)], a1 = wp[(wi + 1) & (PS_RMASK >> 2)], a2 = wp[(wi + 2) & (PS_RMASK >> 2)];
+    const int sh = (int)(a & 3u) * 8;
     return (u64)__funnelshift_r(a0, a1, sh) | ((u64)__funnelshift_r(a1, a2, sh) << 32);
 }
 
@@ -181,10 +206,11 @@ __device__ __forceinline__ bool swar_digits8(u64 X, u32* out)
 }
 
 // "<anything>_<1..7 digits>" of length 2..8 with exactly one underscore, ending at byte `end` (the tab).
-__device__ __forceinline__ bool swar_id(const uint8_t* s_text, int end, int len, bool act, u32* out)
+__device__ __forceinline__ bool swar_id(const uint8_t* s_text, u32 end, int len, bool act, u32* out)
 {
     act = act && len >= 2 && len <= 8;
-    const int l = act ? len : 8, e = act ? end : 8;
+    const int l = act ? len : 8;
+    const u32 e = act ? end : 8u;
     const u64 w = load8_ending_at(s_text, e);
     const u64 vm = ~0ULL << (8 * (8 - l));
     const u64 us = zero_bytes64(w ^ 0x5f5f5f5f5f5f5f5fULL) & vm;
@@ -202,10 +228,11 @@ __device__ __forceinline__ bool swar_id(const uint8_t* s_text, int end, int len,
 }
 
 // "<digits>[.<digits>]" of length 1..8 ending at byte `end`, at most 8 digits: exact fp64 value.
-__device__ __forceinline__ bool swar_score(const uint8_t* s_text, int end, int len, bool act, double* out)
+__device__ __forceinline__ bool swar_score(const uint8_t* s_text, u32 end, int len, bool act, double* out)
 {
     act = act && len >= 1 && len <= 8;
-    const int l = act ? len : 8, e = act ? end : 8;
+    const int l = act ? len : 8;
+    const u32 e = act ? end : 8u;
     const u64 w = load8_ending_at(s_text, e);
     const u64 vm = ~0ULL << (8 * (8 - l));
     const u64 dots = zero_bytes64(w ^ 0x2e2e2e2e2e2e2e2eULL) & vm;
@@ -228,173 +255,272 @@ __device__ __forceinline__ bool swar_score(const uint8_t* s_text, int end, int l
     return act && shape && dig;
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS, 5) parse_kernel(ParseArgs a)
-{
-    __shared__ __align__(16) uint8_t s_text_raw[16 + PARSE_TILE + PARSE_OVERLAP];  // 16-byte front pad for load8_ending_at
-    uint8_t* const s_text = s_text_raw + 16;
-    __shared__ uint16_t s_lstart[PARSE_TILE / 2];
-    __shared__ u32 s_term[PARSE_WORDS + 8];  // + padding read by the 128-bit windows: all terminators
-    __shared__ u32 s_tab[PARSE_WORDS + 8];
-    __shared__ u32 s_scan[PARSE_THREADS / 32 + 1];
-    __shared__ u64 s_base;
-    __shared__ u32 s_valid;
-    __shared__ int s_prev_term;
-    const int tid = threadIdx.x;
-    if (tid < 8) { s_term[PARSE_WORDS + tid] = 0xffffffffu; s_tab[PARSE_WORDS + tid] = 0u; }
 
-    int pair = -1;
-    // per-pair constants, reloaded only when the tile loop crosses into another file
-    int64_t p_tile0 = 0, p_tile1 = 0, p_text_len = 0, p_row_base = 0;
-    const uint8_t* gfile = nullptr;
-    u32 p_Gi = 0, p_Gj = 0;
-    bool p_same = false, p_swap = false;
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        // tiles are visited in increasing order: the pair index only moves forward
-        if (pair < 0 || tile >= p_tile1) {
-            if (pair < 0) pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
-            while (tile >= a.tile_prefix[pair + 1]) pair++;
-            const PairDesc& d = a.pairs[pair];
-            p_tile0 = a.tile_prefix[pair]; p_tile1 = a.tile_prefix[pair + 1];
-            p_text_len = d.text_len; p_row_base = d.row_base; gfile = a.text + d.text_off;
-            p_Gi = (u32)d.Gi; p_Gj = (u32)d.Gj; p_same = d.same != 0; p_swap = d.swap != 0;
-        }
-        const int64_t t0 = (tile - p_tile0) * (int64_t)PARSE_TILE;
-        const int64_t remain = p_text_len - t0;
-        const int nload = (int)(remain < (int64_t)(PARSE_TILE + PARSE_OVERLAP) ? remain : (int64_t)(PARSE_TILE + PARSE_OVERLAP));
-        const int body = (int)(remain < (int64_t)PARSE_TILE ? remain : (int64_t)PARSE_TILE);
-        {
-            const uint4* g16 = reinterpret_cast<const uint4*>(gfile + t0);
-            uint4* s16 = reinterpret_cast<uint4*>(s_text);
-            constexpr int FULL16 = (PARSE_TILE + PARSE_OVERLAP) / 16;
-            if (nload == PARSE_TILE + PARSE_OVERLAP) {  // every tile but a file's last: fixed trip count, loads in flight together
-                uint4 v[FULL16 / PARSE_THREADS + 1];
-#pragma unroll
-                for (int k = 0; k < FULL16 / PARSE_THREADS; k++) v[k] = __ldg(g16 + (k * PARSE_THREADS + tid));
-                constexpr int REST = FULL16 % PARSE_THREADS;
-                if (REST && tid < REST) v[FULL16 / PARSE_THREADS] = __ldg(g16 + ((FULL16 / PARSE_THREADS) * PARSE_THREADS + tid));
-#pragma unroll
-                for (int k = 0; k < FULL16 / PARSE_THREADS; k++) s16[k * PARSE_THREADS + tid] = v[k];
-                if (REST && tid < REST) s16[(FULL16 / PARSE_THREADS) * PARSE_THREADS + tid] = v[FULL16 / PARSE_THREADS];
+// Per-file constants a warp keeps while it works on a segment
+struct PsFile {
+    const uint8_t* gfile;
+    int64_t text_len;   // padded file length
+    int64_t seg_a;      // file offset of the segment's first byte
+    u32 row_base, Gi, Gj;
+    bool same, swap;
+    int pair;
+};
+
+struct PsOut {  // record slots of this warp (warp-uniform)
+    u64 base;
+    u32 left;
+};
+
+// Parses up to 32 queued lines in lock step: lane l takes queue entry first + l (n entries are live).
+// open_last: the newest entry has not been terminated inside the ring (it is being evicted): parse it from
+// global memory.  loaded_end: stream offset one past the staged text.
+__device__ __forceinline__ void ps_round(const ParseArgs& a, PsWarp& sw, const PsFile& f, PsOut& out, int first, int n, bool open_last,
+                                         u32 loaded_end, u32& n_valid)
+{
+    const int lane = (int)lane_id();
+    if (out.left == 0) {  // warp-uniform
+        u64 b = 0;
+        if (lane == 0) b = atomicAdd(reinterpret_cast<unsigned long long*>(a.coo_count), (unsigned long long)PS_RESERVE);
+        out.base = __shfl_sync(OFG_FULL, b, 0);
+        out.left = PS_RESERVE;
+    }
+    const bool act = lane < n;
+    const u32 st = act ? (u32)sw.q[first + lane] : 0u;
+    const bool from_global = open_last && lane == n - 1;
+    u32 row = OFG_ROW_SENTINEL, col = 0;
+    double score = 0.0;
+    u32 f0 = 0, f1 = 0;
+    int tab1, tab2, tab11, lend;
+    bool fast = locate_fields_conv(sw.tab, sw.term, st, act && !from_global, &tab1, &tab2, &tab11, &lend);
+    const bool ok0 = swar_id(sw.text, st + (u32)tab1, tab1, fast, &f0);
+    const bool ok1 = swar_id(sw.text, st + (u32)tab2, tab2 - tab1 - 1, fast, &f1);
+    const bool ok2 = swar_score(sw.text, st + (u32)lend, lend - tab11 - 1, fast, &score);
+    fast = fast && ok0 && ok1 && ok2;
+    if (act) {
+        int rc = OFG_PL_OK;
+        if (!fast) {  // anything unusual: the generic record parser decides (and names the error)
+            if (from_global) {
+                GlobalSrc gs{f.gfile, f.text_len};
+                rc = ofg_parse_record(gs, f.seg_a + (int64_t)st, &f0, &f1, &score);
             } else {
-                for (int i = tid; i < nload / 16; i += PARSE_THREADS) s16[i] = __ldg(g16 + i);
-                const uint4 nl = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-                for (int i = nload / 16 + tid; i < FULL16; i += PARSE_THREADS) s16[i] = nl;
-            }
-            if (tid == 0) {
-                s_prev_term = (t0 == 0) ? 1 : (int)ofg_is_term(gfile[t0 - 1]);
-                s_valid = 0;
+                RingSrc rs{sw.text, (int64_t)loaded_end};
+                rc = ofg_parse_record(rs, (int64_t)st, &f0, &f1, &score);
             }
         }
-        __syncthreads();
-        // structural bitmaps of the whole staged window (32 bytes per word): terminators and tabs.
-        // Thread t owns the adjacent body words [t*CPT, (t+1)*CPT) (their line starts come out in order);
-        // the overlap words are shared out to the first threads.
-        u32 starts[PARSE_CPT];
-        u32 quotes = 0;
-        int n_starts = 0;
-#pragma unroll
-        for (int k = 0; k < PARSE_CPT + 1; k++) {
-            int ch;
-            if (k < PARSE_CPT) ch = tid * PARSE_CPT + k;
-            else { ch = PARSE_TILE / 32 + tid; if (ch >= PARSE_WORDS) break; }
-            const uint4* w4 = reinterpret_cast<const uint4*>(s_text + ch * 32);
-            const uint4 lo4 = w4[0], hi4 = w4[1];
-            const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-            u32 term, tabs, qu = 0;
-            if (!chunk_masks_fast(xs, &term, &tabs)) chunk_masks_exact(xs, &term, &tabs, &qu);
-            s_term[ch] = term;
-            s_tab[ch] = tabs;
-            if (k < PARSE_CPT) {  // body word: line starts
-                const int off = ch * 32;
-                const u32 prev = (ch == 0) ? (u32)s_prev_term : (u32)ofg_is_term(s_text[off - 1]);
-                u32 st = ~term & ((term << 1) | prev);
-                const int nvalid = body - off;  // bytes of this word inside the body
-                if (nvalid <= 0) { st = 0; qu = 0; }
-                else if (nvalid < 32) { st &= (1u << nvalid) - 1u; qu &= (1u << nvalid) - 1u; }
-                starts[k] = st;
-                n_starts += __popc(st);
-                if (qu && !quotes) quotes = ((u32)off + (u32)__ffs(qu) - 1u) | 0x80000000u;
+        int kind = rc;
+        if (rc == OFG_PL_OK) {
+            const u32 q = f.swap ? f1 : f0, s = f.swap ? f0 : f1;
+            if (f.same && q == s) {
+                // self hit: skipped before any range check (:83-84)
+            } else if (q >= f.Gi) {
+                kind = OFG_LINE_RANGE_Q;
+            } else if (s >= f.Gj) {
+                kind = OFG_LINE_RANGE_S;
+            } else if (score > 0.0) {  // stored only if score > current (initially 0) (:87)
+                row = f.row_base + q;
+                col = s;
             }
         }
-        if (quotes)  // csv quoting is not supported: report the byte offset of the quote
-            atomicMin(&a.pair_err[pair], ((u64)(t0 + (quotes & 0x7fffffffu)) << 4) | (u64)OFG_LINE_QUOTE);
-        u32 nl_total;
-        u32 pos = block_excl_scan<PARSE_THREADS>((u32)n_starts, s_scan, &nl_total);
-#pragma unroll
-        for (int k = 0; k < PARSE_CPT; k++) {
-            u32 st = starts[k];
-            while (st) {
-                const int b = __ffs(st) - 1;
-                s_lstart[pos++] = (uint16_t)((tid * PARSE_CPT + k) * 32 + b);
-                st &= st - 1;
-            }
-        }
-        if (tid == 0) {
-            s_base = atomicAdd(a.coo_count, (u64)nl_total);
-            atomicAdd(&a.pair_lines[pair], (u64)nl_total);
-        }
-        __syncthreads();
-        const u64 base = s_base;
-        for (u32 li0 = 0; li0 < nl_total; li0 += PARSE_THREADS) {
-            if (li0 + (u32)(tid & ~31) >= nl_total) continue;  // warp without records (warp-uniform)
-            const u32 li = li0 + tid;
-            u32 row = OFG_ROW_SENTINEL, col = 0;
-            double score = 0.0;
-            const bool act = li < nl_total;
-            const int st = act ? (int)s_lstart[li] : 0;
-            u32 f0 = 0, f1 = 0;
-            int tab1, tab2, tab11, lend;
-            bool fast = locate_fields_conv(s_tab, s_term, st, act, &tab1, &tab2, &tab11, &lend);
-            const bool ok0 = swar_id(s_text, st + tab1, tab1, fast, &f0);
-            const bool ok1 = swar_id(s_text, st + tab2, tab2 - tab1 - 1, fast, &f1);
-            const bool ok2 = swar_score(s_text, st + lend, lend - tab11 - 1, fast, &score);
-            fast = fast && ok0 && ok1 && ok2;
+        if (kind != OFG_LINE_OK) atomicMin(reinterpret_cast<unsigned long long*>(&a.pair_err[f.pair]),
+                                           (unsigned long long)(((u64)(f.seg_a + (int64_t)st) << 4) | (u64)kind));
+    }
+    {
+        const u64 idx = out.base + (u64)(PS_RESERVE - out.left) + (u64)lane;
+        if (idx < a.cap) {
+            a.coo_row[idx] = row;
             if (act) {
-                int rc = OFG_PL_OK;
-                if (!fast) {  // anything unusual: the generic record parser decides (and names the error)
-                    SmemSrc ss{s_text, PARSE_TILE + PARSE_OVERLAP, false};
-                    rc = ofg_parse_record(ss, (int64_t)st, &f0, &f1, &score);
-                    if (ss.truncated) {  // line longer than the staged window: re-parse from global memory
-                        GlobalSrc gs{gfile, p_text_len};
-                        rc = ofg_parse_record(gs, t0 + st, &f0, &f1, &score);
-                    }
-                }
-                int kind = rc;
-                if (rc == OFG_PL_OK) {
-                    const u32 q = p_swap ? f1 : f0, s = p_swap ? f0 : f1;
-                    if (p_same && q == s) {
-                        // self hit: skipped before any range check (:83-84)
-                    } else if (q >= p_Gi) {
-                        kind = OFG_LINE_RANGE_Q;
-                    } else if (s >= p_Gj) {
-                        kind = OFG_LINE_RANGE_S;
-                    } else if (score > 0.0) {  // stored only if score > current (initially 0) (:87)
-                        row = (u32)p_row_base + q;
-                        col = s;
-                    }
-                }
-                if (kind != OFG_LINE_OK) atomicMin(&a.pair_err[pair], ((u64)(t0 + st) << 4) | (u64)kind);
-                const u64 idx = base + li;
-                if (idx < a.cap) {
-                    a.coo_row[idx] = row;
-                    a.coo_col[idx] = col;
-                    a.coo_val[idx] = score;
-                }
+                a.coo_col[idx] = col;
+                a.coo_val[idx] = score;
             }
-            // row histogram, aggregated over runs of equal rows (a query's hits are consecutive lines); MATCH.ANY
-            // would cost ~64 SM cycles per warp instruction on B200 (tools/micro/match_rate.cu)
-            const u32 prev_row = __shfl_up_sync(OFG_FULL, row, 1);
-            const u32 heads = __ballot_sync(OFG_FULL, lane_id() == 0 || row != prev_row);
-            if (row != OFG_ROW_SENTINEL && ((heads >> lane_id()) & 1u)) {
-                const u32 later = heads & ~lanemask_lt() & ~(1u << lane_id());  // heads after this lane
-                const int run_end = later ? __ffs(later) - 1 : 32;
-                atomicAdd(&a.rowcount[row], (u32)(run_end - (int)lane_id()));
-            }
-            const u32 vb = __ballot_sync(OFG_FULL, row != OFG_ROW_SENTINEL);
-            if (lane_id() == 0 && vb) atomicAdd(&s_valid, (u32)__popc(vb));
         }
-        __syncthreads();
-        if (tid == 0 && s_valid) atomicAdd(&a.pair_valid[pair], (u64)s_valid);
-        __syncthreads();
+        out.left -= 32;
+    }
+    // row histogram, aggregated over runs of equal rows (a query's hits are consecutive lines); MATCH.ANY
+    // would cost ~64 SM cycles per warp instruction on B200 (tools/micro/match_rate.cu)
+    const u32 prev_row = __shfl_up_sync(OFG_FULL, row, 1);
+    const u32 heads = __ballot_sync(OFG_FULL, lane == 0 || row != prev_row);
+    if (row != OFG_ROW_SENTINEL && ((heads >> lane) & 1u)) {
+        const u32 later = heads & ~lanemask_lt() & ~(1u << lane);  // heads after this lane
+        const int run_end = later ? __ffs(later) - 1 : 32;
+        atomicAdd(&a.rowcount[row], (u32)(run_end - lane));
+    }
+    n_valid += (u32)__popc(__ballot_sync(OFG_FULL, row != OFG_ROW_SENTINEL));
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
+{
+    extern __shared__ __align__(16) unsigned char ps_smem_raw[];
+    PsWarp& sw = reinterpret_cast<PsWarp*>(ps_smem_raw)[threadIdx.x >> 5];
+    const int lane = (int)lane_id();
+    const int64_t n_warps = (int64_t)gridDim.x * PS_WARPS;
+    PsOut out{0, 0};
+    for (int64_t seg = (int64_t)blockIdx.x * PS_WARPS + (threadIdx.x >> 5); seg < a.n_segs; seg += n_warps) {
+        PsFile f;
+        {
+            const int pair = upper_bound_dev(a.seg_prefix, a.P + 1, seg) - 1;
+            const PairDesc& d = a.pairs[pair];
+            f.pair = pair;
+            f.gfile = a.text + d.text_off;
+            f.text_len = d.text_len;
+            f.seg_a = (seg - a.seg_prefix[pair]) * (int64_t)PS_SEG;
+            f.row_base = (u32)d.row_base; f.Gi = (u32)d.Gi; f.Gj = (u32)d.Gj;
+            f.same = d.same != 0; f.swap = d.swap != 0;
+        }
+        const int64_t len_rel64 = f.text_len - f.seg_a;  // bytes of the file from the segment start on (multiple of 16)
+        const u32 b_rel = (u32)(len_rel64 < (int64_t)PS_SEG ? len_rel64 : (int64_t)PS_SEG);  // starts below this offset are ours
+        // steps of PS_STEP bytes the file still has from here: the first full_steps are whole, then at most one partial
+        const int64_t cl = len_rel64 < (int64_t)0x40000000 ? len_rel64 : (int64_t)0x40000000;  // far beyond any step this segment reads
+        const u32 full_steps = (u32)cl / PS_STEP, tail_bytes = (u32)cl % PS_STEP;
+        const u32 file_steps = full_steps + (tail_bytes ? 1u : 0u);
+        u32 prev_term = (f.seg_a == 0) ? 1u : (u32)ofg_is_term(f.gfile[f.seg_a - 1]);
+        int qn = 0;                         // queued line starts
+        bool tail_open = false;             // the newest queued line has not seen its terminator yet
+        bool foreign_open = prev_term == 0; // the line running into the staged text is not in the queue
+        u32 n_lines = 0, n_valid = 0;
+        const uint8_t* glane = f.gfile + f.seg_a + lane * 16;  // this lane's first 16-byte piece of step 0
+        auto issue_step = [&](u32 k) {  // two 16-byte pieces per lane; pieces past the end of the file become '\n'
+            uint8_t* dst = sw.text + ((k * PS_STEP) & PS_RMASK) + lane * 16;
+            const uint8_t* src = glane + (size_t)k * PS_STEP;
+            if (k < full_steps) {
+                cp_async16(dst, src);
+                cp_async16(dst + 512, src + 512);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if ((u32)(lane * 16 + 512 * h) < tail_bytes) cp_async16(dst + 512 * h, src + 512 * h);
+                    else *reinterpret_cast<uint4*>(dst + 512 * h) = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+                }
+            }
+            cp_async_commit();
+        };
+        issue_step(0);
+        for (u32 k = 0;; k++) {
+            cp_async_wait_all();
+            __syncwarp();
+            const u32 step_so = k * PS_STEP;
+            const u32 loaded_end = step_so + PS_STEP;   // bytes past the file end are staged as '\n'
+            const bool more = k + 1 < file_steps;
+            if (more) {
+                // the next refill overwrites stream bytes [step_so - 3 KB, step_so - 2 KB): lines starting there go now
+                if (qn > 0 && (int)sw.q[0] < (int)step_so - 2 * PS_STEP) {
+                    for (int r0 = 0; r0 < qn; r0 += 32) {
+                        const int n = qn - r0 < 32 ? qn - r0 : 32;
+                        ps_round(a, sw, f, out, r0, n, tail_open && r0 + n == qn, step_so, n_valid);
+                        n_lines += (u32)n;
+                    }
+                    qn = 0;
+                    foreign_open = foreign_open || tail_open;
+                    tail_open = false;
+                    __syncwarp();
+                }
+                issue_step(k + 1);
+            }
+            // ---- structural bitmaps of this step: lane l owns the chunk at stream offset step_so + 32 l
+            const u32 so = step_so + (u32)lane * 32u;
+            u32 term, tabs;
+            {
+                const uint4* w4 = reinterpret_cast<const uint4*>(sw.text + (so & PS_RMASK));
+                const uint4 lo4 = w4[0], hi4 = w4[1];
+                const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                if (!chunk_masks_fast(xs, &term, &tabs)) {
+                    u32 qu;
+                    chunk_masks_exact(xs, &term, &tabs, &qu);
+                    const u32 nv = k < full_steps ? (u32)PS_STEP : (k == full_steps ? tail_bytes : 0u);
+                    const u32 inside = so < step_so + nv ? (step_so + nv - so >= 32u ? 0xffffffffu : (1u << (step_so + nv - so)) - 1u) : 0u;
+                    qu &= inside;
+                    if (qu)  // csv quoting is not supported: report the byte offset of the quote
+                        atomicMin(reinterpret_cast<unsigned long long*>(&a.pair_err[f.pair]),
+                                  (unsigned long long)(((u64)(f.seg_a + (int64_t)so + (int64_t)(__ffs(qu) - 1)) << 4) | (u64)OFG_LINE_QUOTE));
+                }
+                sw.term[(so >> 5) & PS_WMASK] = term;
+                sw.tab[(so >> 5) & PS_WMASK] = tabs;
+            }
+            // ---- line starts: first byte after a terminator that is not itself a terminator
+            const u32 up = __shfl_up_sync(OFG_FULL, term, 1);
+            const u32 prev = lane == 0 ? prev_term : (up >> 31);
+            u32 stb = ~term & ((term << 1) | prev);
+            const u32 any_term = __ballot_sync(OFG_FULL, term != 0u);
+            prev_term = (any_term >> 31) ? (__shfl_sync(OFG_FULL, term, 31) >> 31) : 0u;
+            if (loaded_end <= b_rel) {
+                // common case: every start of this step is ours
+                const u32 has_start = __ballot_sync(OFG_FULL, stb != 0u);
+                const u32 multi = __ballot_sync(OFG_FULL, (stb & (stb - 1u)) != 0u);
+                if (multi == 0u) {  // at most one start per 32-byte chunk (lines longer than 32 bytes)
+                    if (stb) sw.q[qn + __popc(has_start & lanemask_lt())] = (uint16_t)(so + (u32)__ffs(stb) - 1u);
+                    qn += __popc(has_start);
+                } else {
+                    const u32 cnt = (u32)__popc(stb);
+                    const u32 inc = warp_incl_scan(cnt);
+                    int pos = qn + (int)(inc - cnt);
+                    u32 t = stb;
+                    while (t) {
+                        sw.q[pos++] = (uint16_t)(so + (u32)__ffs(t) - 1u);
+                        t &= t - 1;
+                    }
+                    qn += (int)__shfl_sync(OFG_FULL, inc, 31);
+                }
+                if (any_term) foreign_open = false;
+                tail_open = prev_term == 0u && !foreign_open;  // the line open at the end of the step is the newest queued one
+            } else {
+                // last steps of the segment: starts at or beyond b_rel belong to the next segment
+                if (so >= b_rel) stb = 0;
+                else if (b_rel - so < 32u) stb &= (1u << (b_rel - so)) - 1u;
+                const u32 has_start = __ballot_sync(OFG_FULL, stb != 0u);
+                if (has_start) {
+                    const u32 cnt = (u32)__popc(stb);
+                    const u32 inc = warp_incl_scan(cnt);
+                    int pos = qn + (int)(inc - cnt);
+                    u32 t = stb;
+                    while (t) {
+                        sw.q[pos++] = (uint16_t)(so + (u32)__ffs(t) - 1u);
+                        t &= t - 1;
+                    }
+                    qn += (int)__shfl_sync(OFG_FULL, inc, 31);
+                    // is the newest queued start followed by a terminator?
+                    const int last_lane = 31 - __clz(has_start);
+                    const int hb = 31 - __clz(stb | 1u);  // highest start bit of this lane (used on last_lane)
+                    const bool closed_here = (hb < 31 && (term >> (hb + 1)) != 0u) || (last_lane < 31 && (any_term >> (last_lane + 1)) != 0u);
+                    tail_open = !__shfl_sync(OFG_FULL, (int)closed_here, last_lane);
+                } else if (any_term) {
+                    tail_open = false;
+                }
+                if (tail_open && !more && tail_bytes == 0u) {
+                    // the file ends exactly at this step without a final newline: plant a terminator after it
+                    if (lane == 0) { sw.term[(loaded_end >> 5) & PS_WMASK] = 0xffffffffu; sw.tab[(loaded_end >> 5) & PS_WMASK] = 0u; }
+                    tail_open = false;
+                }
+            }
+            __syncwarp();
+            // ---- parse complete lines, 32 at a time
+            const bool seg_done = loaded_end >= b_rel && !tail_open;
+            const int ready = tail_open ? qn - 1 : qn;
+            int done = 0;
+            while (ready - done >= 32 || (seg_done && done < qn)) {
+                const int n = qn - done < 32 ? qn - done : 32;
+                ps_round(a, sw, f, out, done, n, false, loaded_end, n_valid);
+                done += n;
+                n_lines += (u32)n;
+            }
+            if (seg_done) break;
+            if (done > 0) {  // keep the < 32 (+ the open one) leftovers at the front of the queue
+                const int left = qn - done;
+                uint16_t v = 0;  // left <= 32: at most 31 complete lines and the open one
+                if (lane < left) v = sw.q[done + lane];
+                __syncwarp();
+                if (lane < left) sw.q[lane] = v;
+                qn = left;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (n_lines) atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_lines[f.pair]), (unsigned long long)n_lines);
+            if (n_valid) atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_valid[f.pair]), (unsigned long long)n_valid);
+        }
+        __syncwarp();
+    }
+    // unused tail of the last reservation: sentinel rows
+    for (u32 i = (u32)lane; i < out.left; i += 32) {
+        const u64 idx = out.base + (u64)(PS_RESERVE - out.left) + (u64)i;
+        if (idx < a.cap) a.coo_row[idx] = OFG_ROW_SENTINEL;
     }
 }
