@@ -363,7 +363,7 @@ int stage_raw(ofg_ctx* c)
         a.seg_prefix = c->d_tile_prefix.as<int64_t>(); a.n_segs = n_tiles;
         a.coo_row = c->coo_row.as<u32>(); a.coo_col = c->coo_col.as<u32>(); a.coo_val = c->coo_val.as<double>();
         a.cap = cap; a.coo_count = sm; a.rowcount = c->rowcount.as<u32>();
-        a.pair_lines = d_pair_lines; a.pair_valid = d_pair_valid; a.pair_err = d_pair_err;
+        a.pair_lines = d_pair_lines; a.pair_valid = d_pair_valid; a.pair_err = d_pair_err; a.one = 1u;
         const int parse_smem = (int)(sizeof(PsWarp) * PS_WARPS);
         CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_smem));
         parse_kernel<<<parse_grid, PARSE_THREADS, parse_smem, c->stream>>>(a);

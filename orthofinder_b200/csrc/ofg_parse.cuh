@@ -46,6 +46,7 @@ struct ParseArgs {
     u64* pair_lines;  // [P]
     u64* pair_valid;  // [P]
     u64* pair_err;    // [P] min over offending lines of (byte offset << 4 | kind), ~0 if none
+    u32 one;          // 1 (opaque to the compiler: see chunk_masks_fast)
 };
 
 // One warp's staging area.  Positions are "stream offsets": bytes from the start of the segment; the ring index
@@ -97,15 +98,16 @@ __device__ __forceinline__ u32 umad32(u32 a, u32 b, u32 c)
 // Fast form: for bytes below 0x80, (byte ^ c) + 0x7f has its top bit clear exactly when byte == c, with no
 // carries between bytes.  Returns false if the chunk holds a byte >= 0x80 (carries possible) or a double
 // quote (csv quoting is not supported); the caller then uses the exact, carry-free form.
-__device__ __forceinline__ bool chunk_masks_fast(const u32 (&xs)[8], u32* term, u32* tabs)
+__device__ __forceinline__ bool chunk_masks_fast(const u32 (&xs)[8], u32 one, u32* term, u32* tabs)
 {
     const u32 H = 0x80808080u, A = 0x7f7f7f7fu;
     u32 good = H, tm = 0, tb = 0;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
         const u32 x = xs[b];
-        const u32 n_nl = (x ^ 0x0a0a0a0au) + A, n_cr = (x ^ 0x0d0d0d0du) + A;
-        const u32 n_tb = (x ^ 0x09090909u) + A, n_qu = (x ^ 0x22222222u) + A;
+        // (y * one + A): `one` is a kernel parameter equal to 1, which keeps the add a multiply-add on the FMA pipe
+        const u32 n_nl = umad32(x ^ 0x0a0a0a0au, one, A), n_cr = umad32(x ^ 0x0d0d0d0du, one, A);
+        const u32 n_tb = umad32(x ^ 0x09090909u, one, A), n_qu = umad32(x ^ 0x22222222u, one, A);
         good = good & n_qu & ~x;
         tm = umad32(hi_to_nibble(~(n_nl & n_cr) & H), 1u << (4 * b), tm);   // nibbles do not overlap: multiply-add == shift-or
         tb = umad32(hi_to_nibble(~n_tb & H), 1u << (4 * b), tb);
@@ -193,15 +195,18 @@ __device__ __forceinline__ u64 zero_bytes64(u64 y)
 }
 
 // X holds 8 ASCII characters, first character in the lowest byte.  Returns false unless all are digits;
-// *out = their decimal value (SWAR, three multiplies).
+// *out = their decimal value (SWAR on the two 32-bit halves, two multiplies each).
+__device__ __forceinline__ u32 swar_digits4(u32 w)
+{
+    u32 v = w & 0x0f0f0f0fu;
+    v = ((v * 2561u) >> 8) & 0x00ff00ffu;   // (10 a + b) | (10 c + d) << 16
+    return (v * 6553601u) >> 16;            // 100 (10 a + b) + (10 c + d)
+}
 __device__ __forceinline__ bool swar_digits8(u64 X, u32* out)
 {
-    const bool ok = (((X + 0x4646464646464646ULL) | (X - 0x3030303030303030ULL)) & 0x8080808080808080ULL) == 0;
-    u64 v = X & 0x0F0F0F0F0F0F0F0FULL;
-    v = (v * 2561ULL) >> 8;
-    v = ((v & 0x00FF00FF00FF00FFULL) * 6553601ULL) >> 16;
-    v = ((v & 0x0000FFFF0000FFFFULL) * 42949672960001ULL) >> 32;
-    *out = (u32)v;
+    const u32 lo = (u32)X, hi = (u32)(X >> 32);
+    const bool ok = ((((lo + 0x46464646u) | (lo - 0x30303030u)) | ((hi + 0x46464646u) | (hi - 0x30303030u))) & 0x80808080u) == 0;
+    *out = swar_digits4(lo) * 10000u + swar_digits4(hi);
     return ok;
 }
 
@@ -251,7 +256,11 @@ __device__ __forceinline__ bool swar_score(const uint8_t* s_text, u32 end, int l
     u32 m;
     const bool dig = swar_digits8(X, &m);
     const double v = (double)m;
-    *out = frac > 0 ? v / OFG_POW10_DEV[frac] : v;  // exact: m < 10^8, one correctly rounded division
+    // m / 10^frac, correctly rounded, without the division routine: for m < 10^8 and frac <= 8 one Newton step
+    // on the rounded product is exact (exhaustive check: tools/micro/div_pow10_check.c)
+    const double p = OFG_POW10_DEV[frac], r = OFG_RCP10_DEV[frac];
+    const double q0 = __dmul_rn(v, r);
+    *out = __fma_rn(__fma_rn(-q0, p, v), r, q0);
     return act && shape && dig;
 }
 
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
                 const uint4* w4 = reinterpret_cast<const uint4*>(sw.text + (so & PS_RMASK));
                 const uint4 lo4 = w4[0], hi4 = w4[1];
                 const u32 xs[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                if (!chunk_masks_fast(xs, &term, &tabs)) {
+                if (!chunk_masks_fast(xs, a.one, &term, &tabs)) {
                     u32 qu;
                     chunk_masks_exact(xs, &term, &tabs, &qu);
                     const u32 nv = k < full_steps ? (u32)PS_STEP : (k == full_steps ? tail_bytes : 0u);

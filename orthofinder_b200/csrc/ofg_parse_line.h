@@ -32,6 +32,10 @@ OFG_HD_INLINE bool ofg_is_space(int c) { return c == ' ' || c == '\v' || c == '\
 __device__ __constant__ double OFG_POW10_DEV[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
                                                     1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 #endif
+#if defined(__CUDACC__)
+// correctly rounded 1 / 10^k, 0 <= k <= 8
+__device__ __constant__ double OFG_RCP10_DEV[9] = {1.0, 1.0 / 1e1, 1.0 / 1e2, 1.0 / 1e3, 1.0 / 1e4, 1.0 / 1e5, 1.0 / 1e6, 1.0 / 1e7, 1.0 / 1e8};
+#endif
 OFG_HD_INLINE double ofg_pow10_exact(int k)
 {
 #if defined(__CUDA_ARCH__)

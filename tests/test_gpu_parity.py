@@ -220,6 +220,52 @@ def test_shuffled_lines_long_rows_and_long_lines(gb):
     _oracle_vs_device(gb, g.n_seqs, g.lengths, texts)
 
 
+def test_streaming_parser_boundaries(gb):
+    """The parse warps stream 64 KB segments through a 4 KB ring in 1 KB steps (csrc/ofg_parse.cuh).  Cover:
+    a file that ends on a step boundary without a final newline, lines crossing step and segment boundaries,
+    a line longer than the ring (parsed from global memory once evicted), lines longer than the 128-byte fast
+    window, runs of blank lines (several line starts per 32-byte chunk), bytes >= 0x80 and CR line ends."""
+    n_seqs = [40, 30]
+    L = [np.arange(100., 140.), np.arange(200., 230.)]
+    rng = random.Random(11)
+
+    def lines(n, sp, nq, ns, pad=0):
+        out = []
+        for _ in range(n):
+            q, t = rng.randrange(nq), rng.randrange(ns)
+            ln = _mk(q, t, b"%d.%d" % (rng.randrange(20, 900), rng.randrange(10)), sp)
+            if pad and rng.random() < 0.1:  # widen a middle column: line longer than 128 bytes
+                ln = ln.replace(b"\t10\t1\t0", b"\t" + b"7" * rng.randrange(80, 400) + b"\t1\t0")
+            out.append(ln)
+        return out
+
+    # (0,0): ends exactly at a multiple of 1024 bytes, no trailing newline
+    body = b"".join(lines(200, (0, 0), 40, 40))
+    last = _mk(3, 4, b"77.7", (0, 0))[:-1]
+    fill = (-(len(body) + len(last))) % 1024
+    t00 = body + b"\n" * fill + last
+    assert len(t00) % 1024 == 0 and not t00.endswith(b"\n")
+    # (0,1): > 3 segments, long lines, a 6000-byte line (prefix before the underscore is ignored), blank runs, CR
+    ls = lines(3500, (0, 1), 40, 30, pad=1)
+    ls.insert(1000, b"x" * 6000 + b"_5\t1_6\t50.0\t10\t1\t0\t1\t10\t1\t10\t1e-5\t123.5\n")
+    ls.insert(2000, b"\n" * 300)
+    ls.insert(2500, b"\r\n\r\r\n")
+    for i, sc in enumerate([b"0.0000123", b"1234.5678", b"99999.999", b"7.1234567", b"0.3", b"12345678", b"1e2", b"2.5e+01", b".5", b"5."]):
+        ls.insert(100 + 7 * i, _mk(i, i + 1, sc))
+    ls.insert(3000, b"caf\xc3\xa9_7\t1_8\t50.0\t10\t1\t0\t1\t10\t1\t10\t1e-5\t 64.25\n")
+    t01 = b"".join(ls)
+    assert len(t01) > 3 * 65536
+    # (1,0): a line that straddles the first segment boundary exactly, CRLF line ends
+    ls = lines(1200, (1, 0), 30, 40)
+    t10 = b"".join(ls).replace(b"\n", b"\r\n")
+    # (1,1): tiny
+    t11 = _mk(1, 2, b"55", (1, 1)) + _mk(2, 1, b"56", (1, 1))
+    texts = {(0, 0): t00, (0, 1): t01, (1, 0): t10, (1, 1): t11}
+    _oracle_vs_device(gb, n_seqs, L, texts)
+    want = sum(sum(1 for ln in t.replace(b"\r", b"\n").split(b"\n") if ln) for t in texts.values())
+    assert gb.counts()["lines"] == want
+
+
 def test_one_way_mode_reads_swapped_columns(gb):
     """-1 mode (blast_file_processor.py:41-54): for i > j the file Blast{j}_{i} is read with columns swapped."""
     g = Golden("synth_C2_tiny")
