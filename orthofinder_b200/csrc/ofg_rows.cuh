@@ -119,13 +119,19 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const u32* __restrict
     const u64 n_round = (n + 31) & ~(u64)31;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const u32 row = i < n ? coo_row[i] : OFG_ROW_SENTINEL;
-        const u32 peers = __match_any_sync(OFG_FULL, row);
-        const int leader = __ffs(peers) - 1;
+        // records of one query are consecutive: aggregate the slot reservation over runs of equal rows
+        // (MATCH.ANY retires one warp instruction per ~64 SM cycles on B200, tools/micro/match_rate.cu)
+        const int lane = (int)lane_id();
+        const u32 prev_row = __shfl_up_sync(OFG_FULL, row, 1);
+        const u32 heads = __ballot_sync(OFG_FULL, lane == 0 || row != prev_row);
+        const int leader = 31 - __clz(heads & (lanemask_lt() | (1u << lane)));   // first lane of this lane's run
+        const u32 later = heads & ~(lanemask_lt() | (1u << lane));
+        const int run_end = later ? __ffs(later) - 1 : 32;
         u32 basev = 0;
-        if (row != OFG_ROW_SENTINEL && (int)lane_id() == leader) basev = atomicAdd(&rowfill[row], (u32)__popc(peers));
+        if (row != OFG_ROW_SENTINEL && lane == leader) basev = atomicAdd(&rowfill[row], (u32)(run_end - leader));
         basev = __shfl_sync(OFG_FULL, basev, leader);
         if (row != OFG_ROW_SENTINEL) {
-            const u32 pos = row_start[row] + basev + (u32)__popc(peers & lanemask_lt());
+            const u32 pos = row_start[row] + basev + (u32)(lane - leader);
             cols[pos] = coo_col[i];
             vals[pos] = coo_val[i];
         }
