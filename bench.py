@@ -278,14 +278,29 @@ def run_ours(args):
         step()
         out_pinned = torch.empty(gb.graph_text_size() + (1 << 20), dtype=torch.uint8).pin_memory()
         out_np = out_pinned.numpy()
-        gb.set_option("reserve_text_bytes", total + 16 * len(sizes) + 4096)
+        want_text = gb.graph_text_body().tobytes() if args.e2e_check else None
+        pipelined = world == 1 and args.e2e_parts > 1
+        if pipelined:
+            # the public pipelined builder: row partitions in separate contexts of this GPU, host->device copies of
+            # partition g+1 overlapped with the parse/normalise of partition g
+            pb = waterfall.PipelinedGraphBuilder(local, args.e2e_parts)
+            pb.set_species([G] * S, L, [sum(sizes[(p, j)] for j in range(S)) for p in range(S)])
+            for c_, owned_ in zip(pb.ctxs, pb.parts):
+                c_.set_option("reserve_text_bytes", sum(sizes[(p, j)] + 16 for p in owned_ for j in range(S)) + 4096)
 
-        def e2e_step():
-            gb.clear_hits()
-            for k, n in sizes.items():
-                gb.add_hits_ptr(k[0], k[1], base + offs[k], n)
-            step()
-            return gb.graph_text_body(out_np).size
+            def e2e_step():
+                pb.load(lambda p, j: (base + offs[(p, j)], sizes[(p, j)]))
+                pb.build()
+                return pb.graph_text_body(out_np).size
+        else:
+            gb.set_option("reserve_text_bytes", total + 16 * len(sizes) + 4096)
+
+            def e2e_step():
+                gb.clear_hits()
+                for k, n in sizes.items():
+                    gb.add_hits_ptr(k[0], k[1], base + offs[k], n)
+                step()
+                return gb.graph_text_body(out_np).size
 
         e2e_step()
         barrier()
@@ -301,7 +316,14 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         out["e2e"] = {"value": lines_all / float(tt[0]), "unit": UNIT, "h2d_bytes_per_step": int(total), "d2h_bytes_per_step": int(d2h),
                       "ms_per_step": float(tt[0]) * 1e3, "steps": n_e2e,
-                      "note": "pinned host text -> ofg_add_hits_text (H2D) -> ofg_build -> graph text D2H, per rank"}
+                      "note": ("pinned host text -> PipelinedGraphBuilder (%d row partitions on the GPU: H2D of partition g+1 "
+                               "overlaps ofg_build of partition g) -> graph text D2H" % len(pb.parts)) if pipelined else
+                              "pinned host text -> ofg_add_hits_text (H2D) -> ofg_build -> graph text D2H, per rank"}
+        if want_text is not None:
+            got = out_np[:d2h].tobytes()
+            out["e2e"]["text_equals_device_resident_run"] = bool(got == want_text)
+        if pipelined:
+            pb.close()
         del pinned
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload (rank 0, N = 1)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -386,6 +408,8 @@ def main():
     ap.add_argument("--exchange", default="lists", choices=["lists", "thresholds"],
                     help="multi-GPU: 'lists' = design B (sparse all-to-all), 'thresholds' = design A (column re-parse + all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-parts", type=int, default=4, help="row partitions of the pipelined e2e run (1 = single context)")
+    ap.add_argument("--e2e-check", action="store_true", help="compare the e2e graph text with the device-resident run's")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-species", type=int, default=4, help="species in the cpu_baseline sample")
     ap.add_argument("--ref-species", type=int, default=6, help="species in the reference-arm sample")

@@ -25,6 +25,41 @@ def partition_rows(n_species, world, weights=None):
     return [sorted(o) for o in owned]
 
 
+def contiguous_partitions(n_species, n_parts, weights=None):
+    """Split species 0..S-1 into n_parts contiguous ranges of roughly equal weight (used by the single-GPU
+    copy/compute pipeline, where the stitched graph is the plain concatenation of the parts)."""
+    n_parts = max(1, min(n_parts, n_species))
+    w = np.ones(n_species) if weights is None else np.asarray(weights, dtype=np.float64)
+    cum = np.concatenate(([0.0], np.cumsum(w)))
+    cuts = [0]
+    for g in range(1, n_parts):
+        k = int(np.searchsorted(cum, cum[-1] * g / n_parts, side="left"))
+        k = min(max(k, cuts[-1] + 1), n_species - (n_parts - g))
+        cuts.append(k)
+    cuts.append(n_species)
+    return [list(range(cuts[g], cuts[g + 1])) for g in range(n_parts)]
+
+
+def exchange_lists_local(ctxs, which, owner):
+    """Design B exchange between row partitions that live in separate contexts of ONE process / GPU: every
+    context exports its best-hit (which=0) or connect (which=1) lists grouped by destination and the
+    destinations import them straight from the exporter's device buffer (no collective, no host copy)."""
+    outbox = []
+    for r, c in enumerate(ctxs):
+        ptr, counts = c.export_flags(which, owner, r)   # synchronises c's stream: the lists are complete
+        outbox.append((ptr, counts))
+    total = 0
+    for src, (ptr, counts) in enumerate(outbox):
+        off = 0
+        for dst in range(len(counts)):
+            n = int(counts[dst])
+            if n and dst != src and dst < len(ctxs):
+                ctxs[dst].import_flags(which, ptr + off * 8, n)
+            off += n
+            total += n
+    return total
+
+
 def rank_pairs(owned, n_species):
     """(row pairs, column pairs) a rank ingests: (p, j) for owned p and every j, plus (j, p) for j it does
     not own."""

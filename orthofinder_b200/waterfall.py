@@ -220,6 +220,102 @@ class GraphBuilder:
         return buf[:n]
 
 
+class PipelinedGraphBuilder:
+    """The whole job on one GPU with the host->device copy hidden behind the compute.
+
+    The query species are cut into `n_parts` contiguous row partitions, each in its own context (own stream,
+    SURVEY.md §8e design B: rows only).  All copies are queued up front, partition after partition (a
+    partition's copies wait for the previous partition's, so the PCIe link serves them in order at full
+    rate), and partition g is parsed and normalised while partitions g+1.. are still in flight.  The
+    transposed best-hit and connect lists are then handed between the contexts on the device
+    (sharding.exchange_lists_local) and the stitched graph text is the concatenation of the parts - byte
+    for byte the single-context result (tests/test_gpu_parity.py)."""
+
+    def __init__(self, device=0, n_parts=4):
+        self.device = device
+        self.n_parts_req = n_parts
+        self.ctxs = []
+        self.parts = []
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    def set_species(self, n_seqs, lengths, weights=None):
+        from . import sharding
+        S = len(n_seqs)
+        self.S = S
+        parts = sharding.contiguous_partitions(S, self.n_parts_req, weights)
+        if [len(x) for x in parts] != [len(x) for x in self.parts] or not self.ctxs:
+            self.close()
+            self.ctxs = [GraphBuilder(self.device) for _ in parts]
+        self.parts = parts
+        self.owner = sharding.species_owner(parts, S)
+        for c, owned in zip(self.ctxs, parts):
+            c.set_species(n_seqs, lengths)
+            c.set_partition(owned, False)
+
+    def set_option(self, name, value):
+        for c in self.ctxs:
+            c.set_option(name, value)
+
+    def load(self, host_buffer_of):
+        """host_buffer_of(p, j) -> (host pointer, nbytes) (pinned memory for an asynchronous copy) or a
+        bytes-like object.  Queues every copy; returns immediately."""
+        import torch
+        prev = None
+        for c, owned in zip(self.ctxs, self.parts):
+            c.clear_hits()
+            st = torch.cuda.ExternalStream(c.lib.ofg_stream(c.h), device=torch.device("cuda", self.device))
+            if prev is not None:
+                st.wait_event(prev)
+            for p in owned:
+                for j in range(self.S):
+                    d = host_buffer_of(p, j)
+                    if isinstance(d, tuple):
+                        c.add_hits_ptr(p, j, d[0], d[1])
+                    else:
+                        c.add_hits(p, j, d)
+            prev = torch.cuda.Event()
+            prev.record(st)
+
+    def build(self):
+        from . import sharding
+        for c in self.ctxs:
+            c.build(_lib.STAGE_NORM)
+        if len(self.ctxs) > 1:
+            sharding.exchange_lists_local(self.ctxs, 0, self.owner)
+        for c in self.ctxs:
+            c.build(_lib.STAGE_CONNECT)
+        if len(self.ctxs) > 1:
+            sharding.exchange_lists_local(self.ctxs, 1, self.owner)
+        for c in self.ctxs:
+            c.build(_lib.STAGE_GRAPH)
+
+    def counts(self):
+        out = dict(lines=0, records=0, nnz=0, edges=0)
+        for c in self.ctxs:
+            for k, v in c.counts().items():
+                out[k] += v
+        return out
+
+    def graph_text_size(self):
+        return sum(c.graph_text_size() for c in self.ctxs)
+
+    def graph_text_body(self, out=None):
+        n = self.graph_text_size()
+        buf = out if out is not None else np.empty(max(n, 1), np.uint8)
+        assert buf.size >= n
+        o = 0
+        for c in self.ctxs:
+            k = c.graph_text_size()
+            if k:
+                c.graph_text_body(buf[o:o + k])
+            o += k
+        return buf[:n]
+
+
 def graph_header(n_seqs_total):
     """gathering.py:279-280."""
     return ("(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (n_seqs_total, n_seqs_total)).encode() + \

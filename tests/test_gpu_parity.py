@@ -442,6 +442,29 @@ def test_row_partitions_with_list_exchange_stitch_to_the_single_context_graph(na
     whole.close()
 
 
+@pytest.mark.parametrize("name,n_parts", [("synth_C5_small", 2), ("synth_C5_small", 3), ("ref_AddTwoSpecies", 4)])
+def test_pipelined_builder_equals_single_context(name, n_parts):
+    """waterfall.PipelinedGraphBuilder (row partitions in separate contexts of one GPU, copies overlapped with
+    compute, lists exchanged on the device) must produce the single-context graph text byte for byte."""
+    g = Golden(name)
+    S = len(g.n_seqs)
+    whole = waterfall.GraphBuilder(0)
+    _load(whole, g.n_seqs, g.lengths, g.hit_text)
+    whole.build()
+    want = whole.graph_text_body().tobytes()
+    want_counts = whole.counts()
+    whole.close()
+    pb = waterfall.PipelinedGraphBuilder(0, n_parts)
+    pb.set_species(g.n_seqs, g.lengths, [sum(len(g.hit_text(p, j)) for j in range(S)) for p in range(S)])
+    for _ in range(2):  # twice: the contexts are reused
+        pb.load(lambda p, j: g.hit_text(p, j))
+        pb.build()
+        assert pb.graph_text_body().tobytes() == want
+        assert pb.counts() == want_counts
+    assert waterfall.graph_header(sum(g.n_seqs)) + want + waterfall.GRAPH_FOOTER == g.graph
+    pb.close()
+
+
 def test_mid_size_job_equals_oracle(gb):
     """8 species x 2000 genes x 50 hits/query/pair (7 M lines, bins of 1000, m ~ 5 k points per fit): the whole
     graph against the CPU oracle — edge set and indices exact, fits bit-equal, weights within 1e-9."""
