@@ -167,77 +167,225 @@ __device__ __forceinline__ bool rs_before(u32 cj, double vj, int j, u32 ck, doub
     return (cj < ck) || (cj == ck && (vj > vk || (vj == vk && j < k)));
 }
 
+// Shared memory of one warp of rowsort_kernel
+struct RowSortWarp {
+    u32 c[ROWSORT_MAXN + 4];   // staged columns (padded for the 4-wide compares of the medium path)
+    double v[ROWSORT_MAXN];    // staged scores, by input index
+    u32 lf[ROWSORT_MAXN];      // Lq * Lh[col] per input index
+    u32 oc[ROWSORT_MAXN];      // column per output slot
+    u32 okey[ROWSORT_MAXN];    // Lf per output slot
+    u64 ov[ROWSORT_MAXN];      // best score (bit pattern, > 0) per output slot
+};
+
+// Medium rows (64 < n <= ROWSORT_MAXN): O(n^2) rank sort out of shared memory, duplicates of a column share a slot.
+__device__ __forceinline__ int rowsort_medium(const RowSortArgs& a, RowSortWarp& sw, u32 s0, int n, double Lq, const double* Lh)
+{
+    const int lane = (int)lane_id();
+    for (int k = lane; k < n; k += 32) {
+        const u32 col = a.cols[s0 + k];
+        sw.c[k] = col;
+        sw.v[k] = a.vals[s0 + k];
+        sw.lf[k] = (u32)(Lq * Lh[col]);
+        sw.ov[k] = 0ULL;
+    }
+    if (lane < 4) sw.c[n + lane] = 0xffffffffu;  // padding for the 4-wide compares (never < a real column)
+    __syncwarp();
+    const uint4* c4 = reinterpret_cast<const uint4*>(sw.c);
+    const int n4 = (n + 3) >> 2;
+    for (int k = lane; k < n; k += 32) {
+        const u32 ck = sw.c[k];
+        int rank = 0;  // number of strictly smaller columns: duplicates of a column share the slot
+        for (int j4 = 0; j4 < n4; j4++) {
+            const uint4 q = c4[j4];
+            rank += (q.x < ck) + (q.y < ck) + (q.z < ck) + (q.w < ck);
+        }
+        sw.oc[rank] = ck;
+        sw.okey[rank] = sw.lf[k];
+        atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[rank]), (unsigned long long)__double_as_longlong(sw.v[k]));  // max over duplicate HSP lines
+    }
+    __syncwarp();
+    // compact the used slots (ascending column) to the front
+    int outn = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        const bool h = k < n && sw.ov[k] != 0ULL;
+        const u32 bal = __ballot_sync(OFG_FULL, h);
+        u32 col = 0, key = 0;
+        u64 val = 0;
+        if (h) { col = sw.oc[k]; key = sw.okey[k]; val = sw.ov[k]; }
+        __syncwarp();
+        if (h) {
+            const int o = outn + __popc(bal & lanemask_lt());
+            sw.oc[o] = col; sw.okey[o] = key; sw.ov[o] = val;
+        }
+        outn += __popc(bal);
+        __syncwarp();
+    }
+    return outn;
+}
+
+// compare-exchange step of the 64-element bitonic network: element i = 32 h + lane, partner i ^ j
+__device__ __forceinline__ u32 bitonic_cx(u32 mine, u32 other, bool keep_min) { return keep_min ? min(mine, other) : max(mine, other); }
+
+// Per-row sort by column + max-dedup, one warp per row.  Rows of up to 64 records (practically all: a query has
+// a few dozen hits per target species) stay in registers: two records per lane, prefetched one row ahead
+// (row extents two rows ahead), sorted as packed (column, input index) words by a bitonic network of shuffles;
+// duplicates of a column are adjacent afterwards and share an output slot (max score).  The length product
+// Lq * Lh[col] that keys the later length sort is gathered right after the columns arrive, so no load
+// depends on the sort result.
 __global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs a)
 {
-    __shared__ __align__(16) u32 s_c[ROWSORT_WARPS][ROWSORT_MAXN + 4];
-    __shared__ double s_v[ROWSORT_WARPS][ROWSORT_MAXN];
-    __shared__ u32 s_oc[ROWSORT_WARPS][ROWSORT_MAXN];
-    __shared__ u64 s_ov[ROWSORT_WARPS][ROWSORT_MAXN];  // best score (bit pattern, > 0) per output slot
-    const int w = threadIdx.x >> 5, lane = lane_id();
-    u32* c = s_c[w];
-    double* v = s_v[w];
-    u32* oc = s_oc[w];
-    u64* ov = s_ov[w];
-    const int64_t n_warps = (int64_t)gridDim.x * ROWSORT_WARPS;
-    int pair = -1;
-    for (int64_t row = (int64_t)blockIdx.x * ROWSORT_WARPS + w; row < a.n_rows; row += n_warps) {
-        const u32 s0 = a.row_start[row];
-        const int n = (int)(a.row_start[row + 1] - s0);
+    __shared__ __align__(16) RowSortWarp s_w[ROWSORT_WARPS];
+    const int w = threadIdx.x >> 5, lane = (int)lane_id();
+    RowSortWarp& sw = s_w[w];
+    // every CTA owns a contiguous run of rows (the pair changes rarely), its warps interleave inside it
+    const int64_t rows_per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
+    const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t row_end = row_begin + rows_per_cta < a.n_rows ? row_begin + rows_per_cta : a.n_rows;
+    int64_t row = row_begin + w;
+    if (row >= row_end) return;
+    // ---- prefetch state
+    int pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;   // pair of the row being prefetched
+    int64_t pair_end = a.pair_row_base[pair + 1];
+    int64_t p_li = 0, p_lj = 0, p_rb = 0;
+    {
+        const PairDesc& pd = a.pairs[pair];
+        p_li = pd.li_off; p_lj = pd.lj_off; p_rb = pd.row_base;
+    }
+    auto advance_pair = [&](int64_t r) {
+        if (r >= pair_end) {
+            while (r >= a.pair_row_base[pair + 1]) pair++;
+            pair_end = a.pair_row_base[pair + 1];
+            const PairDesc& pd = a.pairs[pair];
+            p_li = pd.li_off; p_lj = pd.lj_off; p_rb = pd.row_base;
+        }
+    };
+    // extents of the row two steps ahead, records of the row one step ahead
+    u32 nx_s0 = a.row_start[row];
+    int nx_n = (int)(a.row_start[row + 1] - nx_s0);
+    u32 nn_s0 = 0;
+    int nn_n = 0;
+    if (row + ROWSORT_WARPS < row_end) { nn_s0 = a.row_start[row + ROWSORT_WARPS]; nn_n = (int)(a.row_start[row + ROWSORT_WARPS + 1] - nn_s0); }
+    u32 nx_c0 = 0, nx_c1 = 0;
+    double nx_v0 = 0.0, nx_v1 = 0.0, nx_Lq;
+    int64_t nx_lj;
+    int nx_pair;
+    auto fetch_records = [&]() {  // records + per-row constants of row `row` (extents nx_s0, nx_n) into the nx_* registers
+        advance_pair(row);
+        nx_pair = pair;
+        nx_lj = p_lj;
+        nx_Lq = a.lengths[p_li + (row - p_rb)];
+        if (nx_n <= 64) {
+            if (lane < nx_n) { nx_c0 = a.cols[nx_s0 + lane]; nx_v0 = a.vals[nx_s0 + lane]; }
+            if (lane + 32 < nx_n) { nx_c1 = a.cols[nx_s0 + lane + 32]; nx_v1 = a.vals[nx_s0 + lane + 32]; }
+        }
+    };
+    fetch_records();
+    for (; row < row_end; row += ROWSORT_WARPS) {
+        // ---- rotate the pipeline: current <- next, next <- next-next, issue the loads two rows ahead
+        const u32 s0 = nx_s0;
+        const int n = nx_n;
+        const u32 c0 = nx_c0, c1 = nx_c1;
+        const double v0 = nx_v0, v1 = nx_v1, Lq = nx_Lq;
+        const double* Lh = a.lengths + nx_lj;
+        const int cur_pair = nx_pair;
+        const int64_t cur_row = row;
+        nx_s0 = nn_s0; nx_n = nn_n;
+        if (row + ROWSORT_WARPS < row_end) {
+            const int64_t r2 = row + 2 * ROWSORT_WARPS;
+            if (r2 < row_end) { nn_s0 = a.row_start[r2]; nn_n = (int)(a.row_start[r2 + 1] - nn_s0); }
+            row += ROWSORT_WARPS;   // fetch_records works on `row`
+            fetch_records();
+            row -= ROWSORT_WARPS;
+        }
         if (n == 0) {
-            if (lane == 0) a.rowlen[row] = 0;
+            if (lane == 0) a.rowlen[cur_row] = 0;
             continue;
         }
         if (n > ROWSORT_MAXN) {
-            if (lane == 0) a.long_rows[atomicAdd(a.n_long, 1u)] = (u32)row;
+            if (lane == 0) a.long_rows[atomicAdd(a.n_long, 1u)] = (u32)cur_row;
             continue;
         }
-        // rows are visited in increasing order: the pair index only moves forward
-        if (pair < 0) pair = upper_bound_dev(a.pair_row_base, a.P + 1, row) - 1;
-        while (row >= a.pair_row_base[pair + 1]) pair++;
-        const PairDesc& pd = a.pairs[pair];
-        const double Lq = a.lengths[pd.li_off + (row - pd.row_base)];
-        const double* Lh = a.lengths + pd.lj_off;
-        for (int k = lane; k < n; k += 32) {
-            c[k] = a.cols[s0 + k];
-            v[k] = a.vals[s0 + k];
-            ov[k] = 0ULL;
-        }
-        if (lane < 4) c[n + lane] = 0xffffffffu;  // padding for the 4-wide compares (never < or == a real column)
-        __syncwarp();
-        const uint4* c4 = reinterpret_cast<const uint4*>(c);
-        const int n4 = (n + 3) >> 2;
-        for (int k = lane; k < n; k += 32) {
-            const u32 ck = c[k];
-            const double vk = v[k];
-            int rank = 0;  // number of strictly smaller columns: duplicates of a column share the slot
-            for (int j4 = 0; j4 < n4; j4++) {
-                const uint4 q = c4[j4];
-                rank += (q.x < ck) + (q.y < ck) + (q.z < ck) + (q.w < ck);
+        int outn;
+        const bool v0ok = lane < n, v1ok = lane + 32 < n;
+        if (n <= 64 && !__any_sync(OFG_FULL, (v0ok && c0 >= (1u << 26)) || (v1ok && c1 >= (1u << 26)))) {
+            // ---- register path
+            const double l0 = v0ok ? Lh[c0] : 0.0, l1 = v1ok ? Lh[c1] : 0.0;   // gathers in flight during the sort
+            u32 k0 = v0ok ? ((c0 << 6) | (u32)lane) : 0xffffffffu;
+            u32 k1 = v1ok ? ((c1 << 6) | (u32)(lane + 32)) : 0xffffffffu;
+            sw.v[lane] = v0; sw.v[lane + 32] = v1;
+            sw.ov[lane] = 0ULL; sw.ov[lane + 32] = 0ULL;
+            if (n <= 32) {
+                // 32-element network on k0 only
+#pragma unroll
+                for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        const u32 o = __shfl_xor_sync(OFG_FULL, k0, j);
+                        const bool lower = (lane & j) == 0, asc = (lane & k) == 0 || k == 32;
+                        k0 = bitonic_cx(k0, o, lower == asc);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        if (j == 32) {  // partner is the lane's other element; k == 64: ascending
+                            const u32 lo = min(k0, k1), hi = max(k0, k1);
+                            k0 = lo; k1 = hi;
+                        } else {
+                            const u32 o0 = __shfl_xor_sync(OFG_FULL, k0, j), o1 = __shfl_xor_sync(OFG_FULL, k1, j);
+                            const bool lower = (lane & j) == 0;
+                            // direction of element i = 32 h + lane: ascending iff (i & k) == 0
+                            const bool asc0 = k == 64 || (k == 32 ? true : (lane & k) == 0);
+                            const bool asc1 = k == 64 || (k == 32 ? false : (lane & k) == 0);
+                            k0 = bitonic_cx(k0, o0, lower == asc0);
+                            k1 = bitonic_cx(k1, o1, lower == asc1);
+                        }
+                    }
+                }
             }
-            oc[rank] = ck;
-            atomicMax(&ov[rank], (u64)__double_as_longlong(vk));  // B[q,s] = max over duplicate HSP lines
-        }
-        __syncwarp();
-        int outn = 0;
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            const bool h = k < n && ov[k] != 0ULL;
-            const u32 bal = __ballot_sync(OFG_FULL, h);
-            if (h) {
-                const u32 pos = s0 + outn + __popc(bal & lanemask_lt());
-                const u32 col = oc[k];
-                const double val = __longlong_as_double((long long)ov[k]);
-                a.cols[pos] = col;
-                a.vals[pos] = val;
-                a.key[pos] = (u32)(Lq * Lh[col]);
-                a.keyval[pos] = val;
+            sw.lf[lane] = (u32)(Lq * l0); sw.lf[lane + 32] = (u32)(Lq * l1);
+            __syncwarp();
+            // sorted position i = 32 h + lane holds k_h; duplicates of a column are adjacent
+            const u32 p0 = __shfl_up_sync(OFG_FULL, k0, 1), p1u = __shfl_up_sync(OFG_FULL, k1, 1), last0 = __shfl_sync(OFG_FULL, k0, 31);
+            const u32 p1 = lane == 0 ? last0 : p1u;
+            const bool in0 = k0 != 0xffffffffu, in1 = k1 != 0xffffffffu;
+            const bool h0 = in0 && (lane == 0 || (p0 >> 6) != (k0 >> 6));
+            const bool h1 = in1 && ((p1 >> 6) != (k1 >> 6));
+            const u32 hb0 = __ballot_sync(OFG_FULL, h0), hb1 = __ballot_sync(OFG_FULL, h1);
+            const u32 le = lanemask_lt() | (1u << lane);
+            const int n_h0 = __popc(hb0);
+            if (in0) {
+                const int slot = __popc(hb0 & le) - 1;
+                const int idx = (int)(k0 & 63u);
+                if (h0) { sw.oc[slot] = k0 >> 6; sw.okey[slot] = sw.lf[idx]; }
+                atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot]), (unsigned long long)__double_as_longlong(sw.v[idx]));
             }
-            outn += __popc(bal);
+            if (in1) {
+                const int slot = n_h0 + __popc(hb1 & le) - 1;
+                const int idx = (int)(k1 & 63u);
+                if (h1) { sw.oc[slot] = k1 >> 6; sw.okey[slot] = sw.lf[idx]; }
+                atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot]), (unsigned long long)__double_as_longlong(sw.v[idx]));
+            }
+            outn = n_h0 + __popc(hb1);
+            __syncwarp();
+        } else {
+            outn = rowsort_medium(a, sw, s0, n, Lq, Lh);
+        }
+        for (int k = lane; k < outn; k += 32) {
+            const u32 pos = s0 + (u32)k;
+            const double val = __longlong_as_double((long long)sw.ov[k]);
+            a.cols[pos] = sw.oc[k];
+            a.vals[pos] = val;
+            a.key[pos] = sw.okey[k];
+            a.keyval[pos] = val;
         }
         for (int k = outn + lane; k < n; k += 32) a.key[s0 + k] = a.key_sentinel;
         if (lane == 0) {
-            a.rowlen[row] = (u32)outn;
-            atomicAdd(&a.pair_nnz[pair], (u64)outn);
+            a.rowlen[cur_row] = (u32)outn;
+            atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_nnz[cur_pair]), (unsigned long long)outn);
         }
         __syncwarp();
     }
