@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const u32* __restrict
 }
 
 // ---------------------------------------------------------------- per-row sort + max-dedup
-constexpr int ROWSORT_MAXN = 256;
+constexpr int ROWSORT_MAXN = 128;
 constexpr int ROWSORT_WARPS = 4;
 
 struct RowSortArgs {
@@ -233,7 +233,7 @@ __device__ __forceinline__ u32 bitonic_cx(u32 mine, u32 other, bool keep_min) { 
 // duplicates of a column are adjacent afterwards and share an output slot (max score).  The length product
 // Lq * Lh[col] that keys the later length sort is gathered right after the columns arrive, so no load
 // depends on the sort result.
-__global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs a)
+__global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortArgs a)
 {
     __shared__ __align__(16) RowSortWarp s_w[ROWSORT_WARPS];
     const int w = threadIdx.x >> 5, lane = (int)lane_id();
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs
             u32 k0 = v0ok ? ((c0 << 6) | (u32)lane) : 0xffffffffu;
             u32 k1 = v1ok ? ((c1 << 6) | (u32)(lane + 32)) : 0xffffffffu;
             sw.v[lane] = v0; sw.v[lane + 32] = v1;
-            sw.ov[lane] = 0ULL; sw.ov[lane + 32] = 0ULL;
             if (n <= 32) {
                 // 32-element network on k0 only
 #pragma unroll
@@ -357,17 +356,15 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32) rowsort_kernel(RowSortArgs
             const u32 hb0 = __ballot_sync(OFG_FULL, h0), hb1 = __ballot_sync(OFG_FULL, h1);
             const u32 le = lanemask_lt() | (1u << lane);
             const int n_h0 = __popc(hb0);
-            if (in0) {
-                const int slot = __popc(hb0 & le) - 1;
-                const int idx = (int)(k0 & 63u);
-                if (h0) { sw.oc[slot] = k0 >> 6; sw.okey[slot] = sw.lf[idx]; }
-                atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot]), (unsigned long long)__double_as_longlong(sw.v[idx]));
-            }
-            if (in1) {
-                const int slot = n_h0 + __popc(hb1 & le) - 1;
-                const int idx = (int)(k1 & 63u);
-                if (h1) { sw.oc[slot] = k1 >> 6; sw.okey[slot] = sw.lf[idx]; }
-                atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot]), (unsigned long long)__double_as_longlong(sw.v[idx]));
+            const int slot0 = __popc(hb0 & le) - 1, slot1 = n_h0 + __popc(hb1 & le) - 1;
+            // the first record of every column run opens its slot ...
+            if (h0) { const int idx = (int)(k0 & 63u); sw.oc[slot0] = k0 >> 6; sw.okey[slot0] = sw.lf[idx]; sw.ov[slot0] = (u64)__double_as_longlong(sw.v[idx]); }
+            if (h1) { const int idx = (int)(k1 & 63u); sw.oc[slot1] = k1 >> 6; sw.okey[slot1] = sw.lf[idx]; sw.ov[slot1] = (u64)__double_as_longlong(sw.v[idx]); }
+            // ... and duplicate HSP lines of a column (rare) raise it to their maximum
+            if (__any_sync(OFG_FULL, (in0 && !h0) || (in1 && !h1))) {
+                __syncwarp();
+                if (in0 && !h0) atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot0]), (unsigned long long)__double_as_longlong(sw.v[k0 & 63u]));
+                if (in1 && !h1) atomicMax(reinterpret_cast<unsigned long long*>(&sw.ov[slot1]), (unsigned long long)__double_as_longlong(sw.v[k1 & 63u]));
             }
             outn = n_h0 + __popc(hb1);
             __syncwarp();
