@@ -532,6 +532,8 @@ int stage_norm(ofg_ctx* c)
     }
     b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
     b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
+    // staging: two free fp64 arrays of at least n_slots entries - the parse output scores and the idle sort buffer
+    b.stage_lx = c->coo_val.as<double>(); b.stage_ly = vout;
     if (n_tasks > 0) {
         const int g = grid_for(c, n_tasks, BIN_WARPS, 6);
         bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);

@@ -219,136 +219,186 @@ struct BinArgs {
     double* lx;            // out: log10(Lf) of selected hits, reference order
     double* ly;            // out: log10(score)
     u64 sel_cap;
+    double* stage_lx;      // [n_slots] per-bin staging of the selected hits (bin_cut -> bin_select)
+    double* stage_ly;
 };
 
-// One WARP per length bin (no CTA barriers).  k-th smallest (0-based) of n positive doubles held in this
-// warp's shared-memory slice as bit patterns, by an 8-pass radix select with a warp-private histogram;
-// also returns how many values are <= it.
-__device__ __forceinline__ u64 warp_kth(const u64* s_bits, int n, int k, u32* s_hist, int* n_le)
+// One WARP per length bin (no CTA barriers).  k-th smallest (0-based) of n positive doubles held in this warp's
+// shared-memory slice as bit patterns (unsigned order == numeric order), by a radix select over 8-bit digits with
+// a warp-private histogram.  The select starts at the highest byte in which the bin's minimum and maximum
+// differ (the bytes above are common to all values) and stops as soon as the k-th value is alone in its
+// bucket, which for bit scores happens after two or three digits.  Also returns how many values are <= it.
+__device__ __forceinline__ u64 warp_kth(const u64* s_bits, int n, int k, u64 vmin, u64 vmax, u32* s_hist, int* n_le)
 {
     const int lane = lane_id();
-    u64 prefix = 0;
-    int kk = k;
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    u64 result;
+    if (vmin == vmax) {
+        result = vmin;
+    } else {
+        const int top = 63 - __clzll((long long)(vmin ^ vmax));
+        int shift = top & ~7;
+        u64 prefix = (shift + 8 >= 64) ? 0ULL : (vmin >> (shift + 8));  // the common high bytes
+        int kk = k;
+        bool found = false;
+        result = 0;
+        for (; shift >= 0; shift -= 8) {
 #pragma unroll
-        for (int t = 0; t < 8; t++) s_hist[lane * 8 + t] = 0;
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const u64 b = s_bits[i];
-            const bool match = (shift == 56) || ((b >> (shift + 8)) == prefix);
-            if (match) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
-        }
-        __syncwarp();
-        // lane l owns buckets [8l, 8l+8)
-        u32 h[8], sum = 0;
+            for (int t = 0; t < 8; t++) s_hist[lane * 8 + t] = 0;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                const u64 b = s_bits[i];
+                const bool match = (shift + 8 >= 64) || ((b >> (shift + 8)) == prefix);
+                if (match) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
+            }
+            __syncwarp();
+            // lane l owns buckets [8l, 8l+8)
+            u32 h[8], sum = 0;
 #pragma unroll
-        for (int t = 0; t < 8; t++) { h[t] = s_hist[lane * 8 + t]; sum += h[t]; }
-        const u32 inc = warp_incl_scan(sum);
-        const u32 exc = inc - sum;
-        const bool mine = (u32)kk >= exc && (u32)kk < inc;
-        u32 bsel = 0, below = exc;
-        if (mine) {
-            u32 run = exc;
+            for (int t = 0; t < 8; t++) { h[t] = s_hist[lane * 8 + t]; sum += h[t]; }
+            const u32 inc = warp_incl_scan(sum);
+            const u32 exc = inc - sum;
+            const bool mine = (u32)kk >= exc && (u32)kk < inc;
+            u32 bsel = 0, below = exc, hsel = 0;
+            if (mine) {
+                u32 run = exc;
+                hsel = h[0];
 #pragma unroll
-            for (int t = 0; t < 8; t++) {
-                if ((u32)kk >= run + h[t]) { below = run + h[t]; bsel = t + 1; }
-                run += h[t];
+                for (int t = 0; t < 8; t++) {
+                    if ((u32)kk >= run + h[t]) { below = run + h[t]; bsel = t + 1; hsel = t + 1 < 8 ? h[t + 1] : 0u; }
+                    run += h[t];
+                }
+            }
+            const u32 src = __ffs(__ballot_sync(OFG_FULL, mine)) - 1;
+            const u32 bucket = __shfl_sync(OFG_FULL, (u32)(lane * 8) + bsel, src);
+            const u32 blw = __shfl_sync(OFG_FULL, below, src);
+            const u32 alone = __shfl_sync(OFG_FULL, hsel, src);
+            prefix = (prefix << 8) | (u64)bucket;
+            kk -= (int)blw;
+            __syncwarp();
+            if (alone == 1u && shift > 0) {  // the k-th value is the only one with this prefix: fetch it
+                u64 cand = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const u64 b = s_bits[i];
+                    if ((b >> shift) == prefix) cand = b;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const u64 o = __shfl_xor_sync(OFG_FULL, cand, d);
+                    cand = o > cand ? o : cand;
+                }
+                result = cand;
+                found = true;
+                break;
             }
         }
-        const u32 src = __ffs(__ballot_sync(OFG_FULL, mine)) - 1;
-        const u32 bucket = __shfl_sync(OFG_FULL, (u32)(lane * 8) + bsel, src);
-        const u32 blw = __shfl_sync(OFG_FULL, below, src);
-        prefix = (prefix << 8) | (u64)bucket;
-        kk -= (int)blw;
-        __syncwarp();
+        if (!found) result = prefix;
     }
     u32 c = 0;
-    for (int i = lane; i < n; i += 32) c += (s_bits[i] <= prefix);
+    for (int i = lane; i < n; i += 32) c += (s_bits[i] <= result);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(OFG_FULL, c, d);
     *n_le = (int)c;
-    return prefix;
+    return result;
 }
 
 constexpr int BIN_WARPS = 4;
 static_assert(BIN_WARPS * 32 == BIN_THREADS, "one warp per bin");
 
+// Per bin: the 95th-percentile cut-off (numpy 'linear'), the number of hits >= cut-off, and those hits themselves
+// - log10(Lf), log10(score) in sorted order - staged at the bin's own slot range (stage_lx / stage_ly [first ..]).
+// The selected hits are first compacted in shared memory so that the two log10 evaluations run on full lanes.
 __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
 {
     __shared__ u64 s_bits_all[BIN_WARPS][BIN_MAXN];
     __shared__ u32 s_hist_all[BIN_WARPS][256];
+    __shared__ uint16_t s_idx_all[BIN_WARPS][BIN_MAXN];
     const int w = threadIdx.x >> 5, lane = lane_id();
     u64* s_bits = s_bits_all[w];
     u32* s_hist = s_hist_all[w];
+    uint16_t* s_idx = s_idx_all[w];
     const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
     for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
         const BinTask bt = a.tasks[t];
-        if (bt.take_all) {
-            if (lane == 0) { a.cut[t] = 0.0; a.cnt[t] = bt.n; }
-            continue;
-        }
         const int n = (int)bt.n;
-        for (int i = lane; i < n; i += 32) s_bits[i] = (u64)__double_as_longlong(a.val[bt.first + i]);
-        __syncwarp();
-        const int k = n == 1000 ? a.k1000 : (n == 200 ? a.k200 : a.k20);
-        const double g = n == 1000 ? a.g1000 : (n == 200 ? a.g200 : a.g20);
-        int n_le;
-        const u64 ak = warp_kth(s_bits, n, k, s_hist, &n_le);
-        u64 ak1 = ak;
-        if (n_le <= k + 1) {  // a[k+1] is the smallest value above a[k]
-            u64 m = ~0ULL;
-            for (int i = lane; i < n; i += 32) {
-                const u64 b = s_bits[i];
-                if (b > ak && b < m) m = b;
-            }
+        u64 vmin = ~0ULL, vmax = 0ULL;
+        for (int i = lane; i < n; i += 32) {
+            const u64 b = (u64)__double_as_longlong(a.val[bt.first + i]);
+            s_bits[i] = b;
+            vmin = b < vmin ? b : vmin;
+            vmax = b > vmax ? b : vmax;
+        }
+        double cut = 0.0;
+        if (!bt.take_all) {
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) {
-                const u64 o = __shfl_xor_sync(OFG_FULL, m, d);
-                m = o < m ? o : m;
+                const u64 o1 = __shfl_xor_sync(OFG_FULL, vmin, d), o2 = __shfl_xor_sync(OFG_FULL, vmax, d);
+                vmin = o1 < vmin ? o1 : vmin;
+                vmax = o2 > vmax ? o2 : vmax;
             }
-            ak1 = (m == ~0ULL) ? ak : m;
-        }
-        const double va = __longlong_as_double((long long)ak), vb = __longlong_as_double((long long)ak1);
-        // numpy _lerp for gamma < 0.5: a + (b - a) * gamma, separately rounded
-        const double cut = __dadd_rn(va, __dmul_rn(__dsub_rn(vb, va), g));
-        u32 c = 0;
-        for (int i = lane; i < n; i += 32) c += (__longlong_as_double((long long)s_bits[i]) >= cut);
+            __syncwarp();
+            const int k = n == 1000 ? a.k1000 : (n == 200 ? a.k200 : a.k20);
+            const double g = n == 1000 ? a.g1000 : (n == 200 ? a.g200 : a.g20);
+            int n_le;
+            const u64 ak = warp_kth(s_bits, n, k, vmin, vmax, s_hist, &n_le);
+            u64 ak1 = ak;
+            if (n_le <= k + 1) {  // a[k+1] is the smallest value above a[k]
+                u64 m = ~0ULL;
+                for (int i = lane; i < n; i += 32) {
+                    const u64 b = s_bits[i];
+                    if (b > ak && b < m) m = b;
+                }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(OFG_FULL, c, d);
-        if (lane == 0) { a.cut[t] = cut; a.cnt[t] = c; }
+                for (int d = 16; d > 0; d >>= 1) {
+                    const u64 o = __shfl_xor_sync(OFG_FULL, m, d);
+                    m = o < m ? o : m;
+                }
+                ak1 = (m == ~0ULL) ? ak : m;
+            }
+            const double va = __longlong_as_double((long long)ak), vb = __longlong_as_double((long long)ak1);
+            // numpy _lerp for gamma < 0.5: a + (b - a) * gamma, separately rounded
+            cut = __dadd_rn(va, __dmul_rn(__dsub_rn(vb, va), g));
+        }
+        __syncwarp();
+        // order-preserving compaction of the selected hits, in place (the write position never passes the read position)
+        int cnt = 0;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const u64 b = i < n ? s_bits[i] : 0ULL;
+            const bool sel = i < n && (bt.take_all || __longlong_as_double((long long)b) >= cut);
+            const u32 bal = __ballot_sync(OFG_FULL, sel);
+            __syncwarp();
+            if (sel) {
+                const int o = cnt + __popc(bal & lanemask_lt());
+                s_bits[o] = b;
+                s_idx[o] = (uint16_t)i;
+            }
+            cnt += __popc(bal);
+            __syncwarp();
+        }
+        if (lane == 0) { a.cut[t] = cut; a.cnt[t] = (u32)cnt; }
+        for (int r = lane; r < cnt; r += 32) {
+            const u32 i = s_idx[r];
+            a.stage_lx[bt.first + r] = ofg_log10_svml((double)a.key[bt.first + i]);
+            a.stage_ly[bt.first + r] = ofg_log10_svml(__longlong_as_double((long long)s_bits[r]));
+        }
         __syncwarp();
     }
 }
 
+// Concatenates the staged selections of all bins (exclusive scan of their counts in sel_off) into lx / ly.
 __global__ void __launch_bounds__(BIN_THREADS) bin_select_kernel(BinArgs a)
 {
     const int w = threadIdx.x >> 5, lane = lane_id();
     const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
     for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
-        const BinTask bt = a.tasks[t];
-        const double cut = a.cut[t];
-        u64 out = a.sel_off[t];
-        for (u32 i0 = 0; i0 < bt.n; i0 += 128) {
-            double sc[4];
-            bool sel[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {  // four independent loads in flight
-                const u32 i = i0 + u * 32 + lane;
-                sc[u] = i < bt.n ? a.val[bt.first + i] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const u32 i = i0 + u * 32 + lane;
-                sel[u] = i < bt.n && (bt.take_all || sc[u] >= cut);
-                const u32 bal = __ballot_sync(OFG_FULL, sel[u]);
-                if (sel[u]) {
-                    const u64 o = out + __popc(bal & lanemask_lt());
-                    if (o < a.sel_cap) {
-                        a.lx[o] = ofg_log10_svml((double)a.key[bt.first + i]);
-                        a.ly[o] = ofg_log10_svml(sc[u]);
-                    }
-                }
-                out += __popc(bal);
+        const u32 first = a.tasks[t].first;
+        const u64 o0 = a.sel_off[t];
+        const u32 cnt = (u32)(a.sel_off[t + 1] - o0);
+        for (u32 r = lane; r < cnt; r += 32) {
+            const u64 o = o0 + r;
+            if (o < a.sel_cap) {
+                a.lx[o] = a.stage_lx[first + r];
+                a.ly[o] = a.stage_ly[first + r];
             }
         }
     }
