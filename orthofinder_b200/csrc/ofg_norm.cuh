@@ -231,74 +231,72 @@ struct BinArgs {
 __device__ __forceinline__ u64 warp_kth(const u64* s_bits, int n, int k, u64 vmin, u64 vmax, u32* s_hist, int* n_le)
 {
     const int lane = lane_id();
-    u64 result;
     if (vmin == vmax) {
-        result = vmin;
-    } else {
-        const int top = 63 - __clzll((long long)(vmin ^ vmax));
-        int shift = top & ~7;
-        u64 prefix = (shift + 8 >= 64) ? 0ULL : (vmin >> (shift + 8));  // the common high bytes
-        int kk = k;
-        bool found = false;
-        result = 0;
-        for (; shift >= 0; shift -= 8) {
+        *n_le = n;
+        return vmin;
+    }
+    // digits of up to 8 bits, the first one starting at the highest bit in which minimum and maximum differ
+    int hi = 64 - __clzll((long long)(vmin ^ vmax));   // bits [hi, 64) are common to all values
+    u64 prefix = hi >= 64 ? 0ULL : (vmin >> hi);
+    int kk = k;
+    while (hi > 0) {
+        const int width = hi < 8 ? hi : 8;
+        const int shift = hi - width;
+        const u32 dmask = (1u << width) - 1u;
 #pragma unroll
-            for (int t = 0; t < 8; t++) s_hist[lane * 8 + t] = 0;
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
-                const u64 b = s_bits[i];
-                const bool match = (shift + 8 >= 64) || ((b >> (shift + 8)) == prefix);
-                if (match) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
-            }
-            __syncwarp();
-            // lane l owns buckets [8l, 8l+8)
-            u32 h[8], sum = 0;
+        for (int t = 0; t < 8; t++) s_hist[lane * 8 + t] = 0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const u64 b = s_bits[i];
+            const bool match = hi >= 64 || (b >> hi) == prefix;
+            if (match) atomicAdd(&s_hist[(u32)(b >> shift) & dmask], 1u);
+        }
+        __syncwarp();
+        // lane l owns buckets [8l, 8l+8)
+        u32 h[8], sum = 0;
 #pragma unroll
-            for (int t = 0; t < 8; t++) { h[t] = s_hist[lane * 8 + t]; sum += h[t]; }
-            const u32 inc = warp_incl_scan(sum);
-            const u32 exc = inc - sum;
-            const bool mine = (u32)kk >= exc && (u32)kk < inc;
-            u32 bsel = 0, below = exc, hsel = 0;
-            if (mine) {
-                u32 run = exc;
-                hsel = h[0];
+        for (int t = 0; t < 8; t++) { h[t] = s_hist[lane * 8 + t]; sum += h[t]; }
+        const u32 inc = warp_incl_scan(sum);
+        const u32 exc = inc - sum;
+        const bool mine = (u32)kk >= exc && (u32)kk < inc;
+        u32 bsel = 0, below = exc, hsel = h[0];
+        if (mine) {
+            u32 run = exc;
 #pragma unroll
-                for (int t = 0; t < 8; t++) {
-                    if ((u32)kk >= run + h[t]) { below = run + h[t]; bsel = t + 1; hsel = t + 1 < 8 ? h[t + 1] : 0u; }
-                    run += h[t];
-                }
-            }
-            const u32 src = __ffs(__ballot_sync(OFG_FULL, mine)) - 1;
-            const u32 bucket = __shfl_sync(OFG_FULL, (u32)(lane * 8) + bsel, src);
-            const u32 blw = __shfl_sync(OFG_FULL, below, src);
-            const u32 alone = __shfl_sync(OFG_FULL, hsel, src);
-            prefix = (prefix << 8) | (u64)bucket;
-            kk -= (int)blw;
-            __syncwarp();
-            if (alone == 1u && shift > 0) {  // the k-th value is the only one with this prefix: fetch it
-                u64 cand = 0;
-                for (int i = lane; i < n; i += 32) {
-                    const u64 b = s_bits[i];
-                    if ((b >> shift) == prefix) cand = b;
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    const u64 o = __shfl_xor_sync(OFG_FULL, cand, d);
-                    cand = o > cand ? o : cand;
-                }
-                result = cand;
-                found = true;
-                break;
+            for (int t = 0; t < 7; t++) {
+                if ((u32)kk >= run + h[t]) { below = run + h[t]; bsel = t + 1; hsel = h[t + 1]; }
+                run += h[t];
             }
         }
-        if (!found) result = prefix;
+        const u32 src = __ffs(__ballot_sync(OFG_FULL, mine)) - 1;
+        const u32 bucket = __shfl_sync(OFG_FULL, (u32)(lane * 8) + bsel, src);
+        const u32 blw = __shfl_sync(OFG_FULL, below, src);
+        const u32 alone = __shfl_sync(OFG_FULL, hsel, src);
+        prefix = (prefix << width) | (u64)bucket;
+        kk -= (int)blw;
+        hi = shift;
+        __syncwarp();
+        if (alone == 1u && hi > 0) {  // the k-th value is the only one with this prefix: fetch it
+            u64 cand = 0;
+            for (int i = lane; i < n; i += 32) {
+                const u64 b = s_bits[i];
+                if ((b >> hi) == prefix) cand = b;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const u64 o = __shfl_xor_sync(OFG_FULL, cand, d);
+                cand = o > cand ? o : cand;
+            }
+            *n_le = k + 1;   // k values are smaller, this one is unique
+            return cand;
+        }
     }
     u32 c = 0;
-    for (int i = lane; i < n; i += 32) c += (s_bits[i] <= result);
+    for (int i = lane; i < n; i += 32) c += (s_bits[i] <= prefix);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(OFG_FULL, c, d);
     *n_le = (int)c;
-    return result;
+    return prefix;
 }
 
 constexpr int BIN_WARPS = 4;
@@ -321,11 +319,22 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
         const BinTask bt = a.tasks[t];
         const int n = (int)bt.n;
         u64 vmin = ~0ULL, vmax = 0ULL;
-        for (int i = lane; i < n; i += 32) {
-            const u64 b = (u64)__double_as_longlong(a.val[bt.first + i]);
-            s_bits[i] = b;
-            vmin = b < vmin ? b : vmin;
-            vmax = b > vmax ? b : vmax;
+        for (int i0 = 0; i0 < n; i0 += 256) {  // eight independent loads in flight per lane
+            u64 tb[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * 32 + lane;
+                tb[u] = i < n ? (u64)__double_as_longlong(a.val[bt.first + i]) : 0ULL;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * 32 + lane;
+                if (i < n) {
+                    s_bits[i] = tb[u];
+                    vmin = tb[u] < vmin ? tb[u] : vmin;
+                    vmax = tb[u] > vmax ? tb[u] : vmax;
+                }
+            }
         }
         double cut = 0.0;
         if (!bt.take_all) {
