@@ -53,6 +53,40 @@ __global__ void k_indep(const u32* in, u32* out, int iters)
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
+// one match + two ballot-based peer masks per three items: do MATCH and VOTE overlap?
+__global__ void k_mixed(const u32* in, u32* out, int iters)
+{
+    u32 v[9];
+    for (int i = 0; i < 9; i++) v[i] = in[(threadIdx.x + i * 97 + blockIdx.x) & 4095];
+    u32 acc = 0;
+    for (int it = 0; it < iters; it++) {
+        u32 p[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const u32 d = (v[i] + it * 7) & 511u;
+            if (i % 3 == 0) p[i] = __match_any_sync(0xffffffffu, d);
+            else p[i] = ballot_peers<9>(d);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) acc += __popc(p[i]);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+// number of distinct values per warp: does MATCH.ANY cost depend on it?
+template <int DISTINCT>
+__global__ void k_distinct(u32* out, int iters)
+{
+    u32 acc = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 d = ((threadIdx.x + it + i) % DISTINCT) + (acc & 0u);
+            acc += __popc(__match_any_sync(0xffffffffu, d));
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 int main()
 {
     u32 *in, *out;
@@ -80,6 +114,16 @@ int main()
             printf("warps/SM %2d  %-14s  %8.1f cycles per warp-item (per warp)  %7.2f SM-cycles per warp-item\n", warps, nm[mode],
                    cyc / (iters * 8.0), cyc / (iters * 8.0) / warps);
         }
+    }
+    {
+        const int threads = 1024, blocks = 148;
+        float ms;
+        for (int rep = 0; rep < 2; rep++) { cudaEventRecord(e0); k_mixed<<<blocks, threads>>>(in, out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); }
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("mixed (1 match + 2 ballot9 per 3 items), 32 warps/SM: %7.2f SM-cycles per warp-item\n", ms * 1e-3 * 1.965e9 / (iters * 9.0) / 32);
+#define DIST(N) for (int rep = 0; rep < 2; rep++) { cudaEventRecord(e0); k_distinct<N><<<blocks, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); } \
+        cudaEventElapsedTime(&ms, e0, e1); printf("match.any with %2d distinct values per warp: %7.2f SM-cycles per warp-instruction\n", N, ms * 1e-3 * 1.965e9 / (iters * 8.0) / 32);
+        DIST(1) DIST(2) DIST(4) DIST(8) DIST(16) DIST(32)
     }
     return 0;
 }
