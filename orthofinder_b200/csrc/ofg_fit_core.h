@@ -27,6 +27,7 @@
 #define FMUL(a, b) __dmul_rn((a), (b))
 #define FDIV(a, b) __ddiv_rn((a), (b))
 #define FSQRT(a) __dsqrt_rn((a))
+#define FFMA(a, b, c) __fma_rn((a), (b), (c))
 #else
 #define FIT_FN static
 #define FIT_MFN
@@ -38,6 +39,7 @@
 #define FMUL(a, b) ((a) * (b))
 #define FDIV(a, b) ((a) / (b))
 #define FSQRT(a) sqrt((a))
+#define FFMA(a, b, c) fma((a), (b), (c))
 #endif
 
 #define FIT_CH 512   // doubles staged per chunk and buffer for the sequential chains
@@ -45,10 +47,42 @@
 
 #define FIT_RING 3    // staging ring depth: chunk c+2 is being fetched while chunk c is accumulated
 
-struct FitShared {  // lives in shared memory on the device (36.9 KB)
+// Exact division by a divisor that is reused for a whole chain.  With r = RN(1/d), q0 = RN(x r) is within one ulp
+// of x / d and the correction q0 + (x - q0 d) r, the residual taken exactly by an fma, rounds to RN(x / d)
+// (Markstein's theorem; 5e9 random pairs and the all-ones significand checked in tools/micro/div_fast_check.c).
+// Three fp64 instructions instead of the ~45 of the division routine - the staging warps are bound by the fp64
+// pipe.  Only used when divisor, dividend and quotient are comfortably normal; anything else divides for real.
+FIT_FN double fit_rcp(double d)
+{
+    const double ad = fabs(d);
+    return (ad > 1e-150 && ad < 1e150) ? FDIV(1.0, d) : 0.0;  // 0: no fast path for this divisor
+}
+FIT_FN double fit_div(double x, double d, double r)
+{
+    const double ax = fabs(x);
+    if (r != 0.0 && ax > 1e-150 && ax < 1e150) {
+        const double q0 = FMUL(x, r);
+        return FFMA(FFMA(-q0, d, x), r, q0);
+    }
+    return FDIV(x, d);
+}
+
+struct FitState {
+    double x0, x1;               // current iterate
+    double xp00, xp01, h0;       // x + h0*e0 and h0
+    double xp10, xp11, h1;       // x + h1*e1 and h1
+    double aj0, t, aj1, temp0;   // signed column norms, reflection coefficients
+    double xn0, xn1;             // trial point
+    double xnp0, hn0, xnp1, hn1; // its forward-difference points (xn0 + hn0, xn1 + hn1) and steps
+    double rh0, rh1, raj0, raj1, rhn0, rhn1;  // fit_rcp of the six divisors (0 = divide for real)
+    int piv, hh1, hh2;           // columns swapped; first / second reflection applied
+};
+
+struct FitShared {  // lives in shared memory on the device (37 KB)
     double buf[FIT_MAXV][FIT_RING][FIT_CH];  // staged squares (enorm) / products (dot)
     double out[FIT_MAXV];
     int tag[FIT_MAXV][FIT_RING];      // chunk tag set when a staged chunk holds a value outside MINPACK's mid range
+    FitState st;                      // the scalars the staging warps read (published before every chain)
 };
 
 // ordered sum of the staged terms q[0..len): strictly left to right.  On the device the next eight terms
@@ -157,33 +191,27 @@ enum { FIT_K_F = 0,      // f_i = (x0*lx + x1) - ly                       (enorm
        FIT_K_AF,         // A'_i * f_i                                                           (dot term)
        FIT_K_B1,         // B'_i = B_i - t*A'_i   second column after the first reflection       (enorm term)
        FIT_K_B2W,        // B''_i * w'_i  second Householder vector times once-reflected residual (dot term)
-       FIT_K_FNEW };     // residual at the trial point                   (enorm term)
+       FIT_K_FNEW,       // residual at the trial point                   (enorm term)
+       FIT_K_J0N,        // forward-difference columns AT the trial point: the next iteration's column norms,
+       FIT_K_J1N };      // summed speculatively next to FIT_K_FNEW (they are needed iff the step is accepted)
 
-struct FitState {
-    double x0, x1;               // current iterate
-    double xp00, xp01, h0;       // x + h0*e0 and h0
-    double xp10, xp11, h1;       // x + h1*e1 and h1
-    double aj0, t, aj1, temp0;   // signed column norms, reflection coefficients
-    double xn0, xn1;             // trial point
-    int piv, hh1, hh2;           // columns swapped; first / second reflection applied
-};
 
-FIT_FN bool fit_kind_is_enorm(int kind) { return kind == FIT_K_F || kind == FIT_K_J0 || kind == FIT_K_J1 || kind == FIT_K_B1 || kind == FIT_K_FNEW; }
+FIT_FN bool fit_kind_is_enorm(int kind) { return kind == FIT_K_F || kind == FIT_K_J0 || kind == FIT_K_J1 || kind == FIT_K_B1 || kind >= FIT_K_FNEW; }
 
 FIT_FN double fit_elem_f(const FitState& S, double lx, double ly) { return FSUB(FADD(FMUL(S.x0, lx), S.x1), ly); }
-FIT_FN double fit_elem_j0(const FitState& S, double lx, double ly, double f) { return FDIV(FSUB(FSUB(FADD(FMUL(S.xp00, lx), S.xp01), ly), f), S.h0); }
-FIT_FN double fit_elem_j1(const FitState& S, double lx, double ly, double f) { return FDIV(FSUB(FSUB(FADD(FMUL(S.xp10, lx), S.xp11), ly), f), S.h1); }
+FIT_FN double fit_elem_j0(const FitState& S, double lx, double ly, double f) { return fit_div(FSUB(FSUB(FADD(FMUL(S.xp00, lx), S.xp01), ly), f), S.h0, S.rh0); }
+FIT_FN double fit_elem_j1(const FitState& S, double lx, double ly, double f) { return fit_div(FSUB(FSUB(FADD(FMUL(S.xp10, lx), S.xp11), ly), f), S.h1, S.rh1); }
 FIT_FN double fit_elem_ap(const FitState& S, long i, double A)
 {
     if (!S.hh1) return A;
-    const double ap = FDIV(A, S.aj0);
+    const double ap = fit_div(A, S.aj0, S.raj0);
     return i == 0 ? FADD(ap, 1.0) : ap;
 }
 FIT_FN double fit_elem_bp(const FitState& S, double B, double Ap) { return S.hh1 ? FSUB(B, FMUL(S.t, Ap)) : B; }
 FIT_FN double fit_elem_bpp(const FitState& S, long i, double Bp)
 {
     if (!S.hh2 || i < 1) return Bp;
-    const double b = FDIV(Bp, S.aj1);
+    const double b = fit_div(Bp, S.aj1, S.raj1);
     return i == 1 ? FADD(b, 1.0) : b;
 }
 FIT_FN double fit_elem_wp(const FitState& S, double f, double Ap) { return S.hh1 ? FADD(f, FMUL(Ap, S.temp0)) : f; }
@@ -191,7 +219,12 @@ FIT_FN double fit_elem_wp(const FitState& S, double f, double Ap) { return S.hh1
 // value of the chain term `kind` at absolute index i
 FIT_FN double fit_term(int kind, long i, double lx, double ly, const FitState& S)
 {
-    if (kind == FIT_K_FNEW) return FSUB(FADD(FMUL(S.xn0, lx), S.xn1), ly);
+    if (kind >= FIT_K_FNEW) {
+        const double fn = FSUB(FADD(FMUL(S.xn0, lx), S.xn1), ly);
+        if (kind == FIT_K_FNEW) return fn;
+        if (kind == FIT_K_J0N) return fit_div(FSUB(FSUB(FADD(FMUL(S.xnp0, lx), S.xn1), ly), fn), S.hn0, S.rhn0);
+        return fit_div(FSUB(FSUB(FADD(FMUL(S.xn0, lx), S.xnp1), ly), fn), S.hn1, S.rhn1);
+    }
     const double f = fit_elem_f(S, lx, ly);
     if (kind == FIT_K_F) return f;
     if (kind == FIT_K_J0) return fit_elem_j0(S, lx, ly, f);
@@ -206,26 +239,82 @@ FIT_FN double fit_term(int kind, long i, double lx, double ly, const FitState& S
     return FMUL(fit_elem_bpp(S, i, Bp), fit_elem_wp(S, f, Ap));  // FIT_K_B2W
 }
 
-// Up to FIT_MAXV chains side by side over the absolute index ranges [i0[v], i0[v] + n[v]).  Chain v is an
-// enorm (MINPACK's scaled 2-norm) or a plain ordered sum depending on kinds[v]; it is accumulated in index
-// order by lane 0 of warp v from terms staged through a ring of shared-memory chunks by the warps >=
-// FIT_MAXV.  With fewer than 128 threads (the host build) staging and accumulation simply alternate.
-FIT_FN void fit_chain_multi(int nv, const int* kinds, const long* i0, const long* n, const double* lx, const double* ly,
-                            const FitState& S, FitShared* sh, double* out)
+// All terms of one element for the (up to three) chains of a call, sharing the sub-expressions they have in
+// common (the residual, the two difference quotients, the Householder vector element).  Same operations, same
+// order as fit_term.
+FIT_FN void fit_terms(int nv, int k0, int k1, int k2, long i, double lx, double ly, const FitState& S, double* tv)
 {
+    const int ks[3] = {k0, k1, k2};
+    const int kmax = nv == 1 ? k0 : (nv == 2 ? (k0 > k1 ? k0 : k1) : (k0 > k1 ? (k0 > k2 ? k0 : k2) : (k1 > k2 ? k1 : k2)));
+    const int kmin = nv == 1 ? k0 : (nv == 2 ? (k0 < k1 ? k0 : k1) : (k0 < k1 ? (k0 < k2 ? k0 : k2) : (k1 < k2 ? k1 : k2)));
+    double fn = 0.0, j0n = 0.0, j1n = 0.0;
+    if (kmax >= FIT_K_FNEW) {
+        fn = FSUB(FADD(FMUL(S.xn0, lx), S.xn1), ly);
+        if (kmax >= FIT_K_J0N) {
+            j0n = fit_div(FSUB(FSUB(FADD(FMUL(S.xnp0, lx), S.xn1), ly), fn), S.hn0, S.rhn0);
+            j1n = fit_div(FSUB(FSUB(FADD(FMUL(S.xn0, lx), S.xnp1), ly), fn), S.hn1, S.rhn1);
+        }
+    }
+    double f = 0.0, J0 = 0.0, J1 = 0.0, Ap = 0.0, B = 0.0, Bp = 0.0, b2w = 0.0;
+    if (kmin < FIT_K_FNEW) {
+        f = fit_elem_f(S, lx, ly);
+        const int kc = kmax < FIT_K_FNEW ? kmax : FIT_K_B2W;  // highest current-point kind that may be present
+        if (kc >= FIT_K_J0) {
+            J0 = fit_elem_j0(S, lx, ly, f);
+            J1 = fit_elem_j1(S, lx, ly, f);
+        }
+        if (kc >= FIT_K_AB) {
+            const double A = S.piv ? J1 : J0;
+            B = S.piv ? J0 : J1;
+            Ap = fit_elem_ap(S, i, A);
+            if (kc >= FIT_K_B1) Bp = fit_elem_bp(S, B, Ap);
+            if (kc >= FIT_K_B2W) b2w = FMUL(fit_elem_bpp(S, i, Bp), fit_elem_wp(S, f, Ap));
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        if (v < nv) {
+            const int k = ks[v];
+            tv[v] = k == FIT_K_F ? f : k == FIT_K_J0 ? J0 : k == FIT_K_J1 ? J1 : k == FIT_K_AB ? FMUL(Ap, B) : k == FIT_K_AF ? FMUL(Ap, f)
+                  : k == FIT_K_B1 ? Bp : k == FIT_K_B2W ? b2w : k == FIT_K_FNEW ? fn : k == FIT_K_J0N ? j0n : j1n;
+        }
+    }
+}
+
+#ifndef FIT_SKIP_SUMS
+#define FIT_SKIP_SUMS 0   // tools/micro/fit_timing.cu sets 1 to time the staging warps alone
+#endif
+
+// Up to FIT_MAXV chains side by side over the absolute index range [i0, i0 + n).  Chain v is an enorm (MINPACK's
+// scaled 2-norm) or a plain ordered sum depending on its kind; it is accumulated in index order by lane 0 of
+// warp v from terms staged through a ring of shared-memory chunks by the warps >= FIT_MAXV.  With fewer than 128
+// threads (the host build) staging and accumulation simply alternate.
+FIT_FN void fit_chain_multi(int nv, int k0, int k1, int k2, long i0, long n, const double* lx, const double* ly,
+                            const FitState& S_local, FitShared* sh, double* out)
+{
+    // every thread carries the same scalars; the staging loops read them from shared memory, which keeps them out
+    // of the registers of the hot loops
+    if (FIT_TID == 0) sh->st = S_local;
+    FIT_SYNC();
+    const FitState& S = sh->st;
     const double rdwarf = 3.834e-20;
+    const double agiant = FDIV(1.304e19, (double)n);
+    const bool en0 = fit_kind_is_enorm(k0), en1 = fit_kind_is_enorm(k1), en2 = fit_kind_is_enorm(k2);
     const bool overlap = FIT_NT >= 128;
     if (!overlap) {
         for (int v = 0; v < nv; v++) {
-            const bool en = fit_kind_is_enorm(kinds[v]);
+            const int kind = v == 0 ? k0 : (v == 1 ? k1 : k2);
+            const bool en = fit_kind_is_enorm(kind);
             FitEnormAcc acc;
-            acc.init((double)n[v]);
+            acc.init((double)n);
             double sum = 0.0;
-            for (long c0 = 0; c0 < n[v]; c0 += FIT_CH) {
-                const int len = (int)((n[v] - c0) < FIT_CH ? (n[v] - c0) : FIT_CH);
+            for (long c0 = 0; c0 < n; c0 += FIT_CH) {
+                const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
                 for (int i = FIT_TID; i < len; i += FIT_NT) {
-                    const long gi = i0[v] + c0 + i;
-                    sh->buf[0][0][i] = fit_term(kinds[v], gi, lx[gi], ly[gi], S);
+                    const long gi = i0 + c0 + i;
+                    double tv[3];
+                    fit_terms(nv, k0, k1, k2, gi, lx[gi], ly[gi], S, tv);
+                    sh->buf[0][0][i] = tv[v];
                 }
                 FIT_SYNC();
                 if (FIT_TID == 0) {
@@ -239,32 +328,28 @@ FIT_FN void fit_chain_multi(int nv, const int* kinds, const long* i0, const long
     } else {
         const int my_v = (FIT_TID & 31) == 0 ? (FIT_TID >> 5) : -1;
         const bool summer = my_v >= 0 && my_v < nv;
-        const bool my_en = summer && fit_kind_is_enorm(kinds[my_v]);
+        const int my_kind = my_v == 0 ? k0 : (my_v == 1 ? k1 : k2);
+        const bool my_en = summer && fit_kind_is_enorm(my_kind);
         FitEnormAcc acc;
-        acc.init(summer ? (double)n[my_v] : 1.0);
+        acc.init((double)n);
         double sum = 0.0;
         const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
         const int lt = FIT_TID - first_loader;
-        long nmax = 0;
-        for (int v = 0; v < nv; v++) nmax = n[v] > nmax ? n[v] : nmax;
-        const long n_chunks = (nmax + FIT_CH - 1) / FIT_CH;
+        const long n_chunks = (n + FIT_CH - 1) / FIT_CH;
         for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
             if (FIT_TID >= first_loader) {
                 const long cl = c + (FIT_RING - 1);  // chunk to stage now
                 const long c1 = cl * FIT_CH;
-                const int slot = (int)(cl % FIT_RING);
-                for (int v = 0; v < nv; v++) {
-                    if (c1 >= n[v]) continue;
-                    const int len = (int)((n[v] - c1) < FIT_CH ? (n[v] - c1) : FIT_CH);
-                    const bool en = fit_kind_is_enorm(kinds[v]);
-                    const double agiant = FDIV(1.304e19, (double)n[v]);
-                    bool odd = false;
+                if (c1 < n) {
+                    const int slot = (int)(cl % FIT_RING);
+                    const int len = (int)((n - c1) < FIT_CH ? (n - c1) : FIT_CH);
+                    bool odd0 = false, odd1 = false, odd2 = false;
                     for (int b0 = 0; b0 < len; b0 += 4 * n_loaders) {
                         double xa[4], ya[4];
 #pragma unroll
                         for (int u = 0; u < 4; u++) {  // four independent element loads in flight per loader
                             const int i = b0 + u * n_loaders + lt;
-                            const long gi = i0[v] + c1 + (i < len ? i : 0);
+                            const long gi = i0 + c1 + (i < len ? i : 0);
                             xa[u] = lx[gi];
                             ya[u] = ly[gi];
                         }
@@ -272,34 +357,43 @@ FIT_FN void fit_chain_multi(int nv, const int* kinds, const long* i0, const long
                         for (int u = 0; u < 4; u++) {
                             const int i = b0 + u * n_loaders + lt;
                             if (i < len) {
-                                const double tv = fit_term(kinds[v], i0[v] + c1 + i, xa[u], ya[u], S);
-                                if (en) {
-                                    const double av = fabs(tv);
-                                    odd = odd || !(av > rdwarf && av < agiant);
-                                    sh->buf[v][slot][i] = FMUL(av, av);
-                                } else {
-                                    sh->buf[v][slot][i] = tv;
+                                double tv[3];
+                                fit_terms(nv, k0, k1, k2, i0 + c1 + i, xa[u], ya[u], S, tv);
+                                {
+                                    const double av = fabs(tv[0]);
+                                    if (en0) odd0 = odd0 || !(av > rdwarf && av < agiant);
+                                    sh->buf[0][slot][i] = en0 ? FMUL(av, av) : tv[0];
+                                }
+                                if (nv > 1) {
+                                    const double av = fabs(tv[1]);
+                                    if (en1) odd1 = odd1 || !(av > rdwarf && av < agiant);
+                                    sh->buf[1][slot][i] = en1 ? FMUL(av, av) : tv[1];
+                                }
+                                if (nv > 2) {
+                                    const double av = fabs(tv[2]);
+                                    if (en2) odd2 = odd2 || !(av > rdwarf && av < agiant);
+                                    sh->buf[2][slot][i] = en2 ? FMUL(av, av) : tv[2];
                                 }
                             }
                         }
                     }
-                    if (odd) sh->tag[v][slot] = (int)(cl + 1);
+                    if (odd0) sh->tag[0][slot] = (int)(cl + 1);
+                    if (odd1) sh->tag[1][slot] = (int)(cl + 1);
+                    if (odd2) sh->tag[2][slot] = (int)(cl + 1);
                 }
-            } else if (c >= 0 && summer) {
+            } else if (c >= 0 && summer && !FIT_SKIP_SUMS) {
                 const long c0 = c * FIT_CH;
-                if (c0 < n[my_v]) {
-                    const int len = (int)((n[my_v] - c0) < FIT_CH ? (n[my_v] - c0) : FIT_CH);
-                    const int slot = (int)(c % FIT_RING);
-                    if (!my_en) {
-                        sum = fit_ordered_sum(sum, sh->buf[my_v][slot], len);
-                    } else if (sh->tag[my_v][slot] == (int)(c + 1)) {  // a value outside MINPACK's mid range: exact slow path
-                        for (int i = 0; i < len; i++) {
-                            const long gi = i0[my_v] + c0 + i;
-                            acc.add(fit_term(kinds[my_v], gi, lx[gi], ly[gi], S));
-                        }
-                    } else {
-                        acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][slot], len);
+                const int len = (int)((n - c0) < FIT_CH ? (n - c0) : FIT_CH);
+                const int slot = (int)(c % FIT_RING);
+                if (!my_en) {
+                    sum = fit_ordered_sum(sum, sh->buf[my_v][slot], len);
+                } else if (sh->tag[my_v][slot] == (int)(c + 1)) {  // a value outside MINPACK's mid range: exact slow path
+                    for (int i = 0; i < len; i++) {
+                        const long gi = i0 + c0 + i;
+                        acc.add(fit_term(my_kind, gi, lx[gi], ly[gi], S));
                     }
+                } else {
+                    acc.s2 = fit_ordered_sum(acc.s2, sh->buf[my_v][slot], len);
                 }
             }
             FIT_SYNC();
@@ -313,10 +407,8 @@ FIT_FN void fit_chain_multi(int nv, const int* kinds, const long* i0, const long
 
 FIT_FN double fit_chain_one(int kind, long i0, long n, const double* lx, const double* ly, const FitState& S, FitShared* sh)
 {
-    int ks[1] = {kind};
-    long is[1] = {i0}, ns[1] = {n};
-    double o[1];
-    fit_chain_multi(1, ks, is, ns, lx, ly, S, sh, o);
+    double o[3];
+    fit_chain_multi(1, kind, kind, kind, i0, n, lx, ly, S, sh, o);
     return o[0];
 }
 
@@ -460,30 +552,35 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* 
     const double lx0 = lx[0], ly0 = ly[0], lx1 = m > 1 ? lx[1] : 0.0, ly1 = m > 1 ? ly[1] : 0.0;
     FitState S;
     S.xn0 = S.xn1 = 0.0;
+    S.xnp0 = S.xnp1 = 0.0; S.hn0 = S.hn1 = 1.0; S.rhn0 = S.rhn1 = 0.0;
 
     nfev = 1;
     double fnorm = 0.0;
     bool have_fnorm = false;
+    bool spec_valid = false;      // spec_acnorm holds the column norms at the current x
+    double spec_acnorm[2] = {0.0, 0.0};
     for (;;) {
         // fdjac2: forward differences, h_j = eps*|x_j|
         S.x0 = x[0]; S.x1 = x[1];
-        S.piv = 0; S.hh1 = 0; S.hh2 = 0; S.aj0 = S.aj1 = 1.0; S.t = S.temp0 = 0.0;
+        S.piv = 0; S.hh1 = 0; S.hh2 = 0; S.aj0 = S.aj1 = 1.0; S.raj0 = S.raj1 = 0.0; S.t = S.temp0 = 0.0;
         {
             double h[2];
             for (int j = 0; j < 2; j++) {
                 h[j] = FMUL(eps, fabs(x[j]));
                 if (h[j] == 0.0) h[j] = eps;
             }
-            S.h0 = h[0]; S.xp00 = FADD(x[0], h[0]); S.xp01 = x[1];
+            S.h0 = h[0]; S.xp00 = FADD(x[0], h[0]); S.xp01 = x[1]; S.rh0 = fit_rcp(h[0]); S.rh1 = fit_rcp(h[1]);
             S.h1 = h[1]; S.xp10 = x[0]; S.xp11 = FADD(x[1], h[1]);
         }
         nfev += 2;
         // qrfac with column pivoting; the initial |fvec| rides along with the two column norms
-        {
-            int ks[3] = {FIT_K_J0, FIT_K_J1, FIT_K_F};
-            long is[3] = {0, 0, 0}, ns[3] = {m, m, m};
+        if (spec_valid) {  // summed next to the accepted trial residual
+            acnorm[0] = spec_acnorm[0];
+            acnorm[1] = spec_acnorm[1];
+            spec_valid = false;
+        } else {
             double o[3];
-            fit_chain_multi(have_fnorm ? 2 : 3, ks, is, ns, lx, ly, S, sh, o);
+            fit_chain_multi(have_fnorm ? 2 : 3, FIT_K_J0, FIT_K_J1, FIT_K_F, 0, m, lx, ly, S, sh, o);
             acnorm[0] = o[0];
             acnorm[1] = o[1];
             if (!have_fnorm) { fnorm = o[2]; have_fnorm = true; }
@@ -510,14 +607,12 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* 
             double ajnorm = acnorm[ipvt[0]];  // enorm(a[0:, 0]) of the pivoted column
             if (ajnorm != 0.0) {
                 if (A0 < 0.0) ajnorm = -ajnorm;
-                S.aj0 = ajnorm;
+                S.aj0 = ajnorm; S.raj0 = fit_rcp(ajnorm);
                 S.hh1 = 1;
                 const double Ap0 = fit_elem_ap(S, 0, A0);
                 // A'.B and A'.f (the latter is needed for qtf) side by side
-                int ks[2] = {FIT_K_AB, FIT_K_AF};
-                long is[2] = {0, 0}, ns[2] = {m, m};
-                double o[2];
-                fit_chain_multi(2, ks, is, ns, lx, ly, S, sh, o);
+                double o[3];
+                fit_chain_multi(2, FIT_K_AB, FIT_K_AF, FIT_K_AF, 0, m, lx, ly, S, sh, o);
                 qtf_dot0 = o[1];
                 S.t = FDIV(o[0], Ap0);
                 r01 = fit_elem_bp(S, B0, Ap0);
@@ -545,7 +640,7 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* 
                 const double A1 = S.piv ? J11 : J01, B1 = S.piv ? J01 : J11;
                 const double Bp1 = fit_elem_bp(S, B1, fit_elem_ap(S, 1, A1));
                 if (Bp1 < 0.0) ajnorm = -ajnorm;
-                S.aj1 = ajnorm;
+                S.aj1 = ajnorm; S.raj1 = fit_rcp(ajnorm);
                 S.hh2 = 1;
             }
             rdiag[1] = -ajnorm;
@@ -601,8 +696,22 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* 
             const double pnorm = fit_enorm_small(2, wa3);
             if (iter == 1) delta = fmin(delta, pnorm);
             S.xn0 = wa2[0]; S.xn1 = wa2[1];
+            {   // fdjac2's steps at the trial point
+                double hn0 = FMUL(eps, fabs(wa2[0])), hn1 = FMUL(eps, fabs(wa2[1]));
+                if (hn0 == 0.0) hn0 = eps;
+                if (hn1 == 0.0) hn1 = eps;
+                S.hn0 = hn0; S.xnp0 = FADD(wa2[0], hn0); S.rhn0 = fit_rcp(hn0);
+                S.hn1 = hn1; S.xnp1 = FADD(wa2[1], hn1); S.rhn1 = fit_rcp(hn1);
+            }
             nfev++;
-            const double fnorm1 = fit_chain_one(FIT_K_FNEW, 0, m, lx, ly, S, sh);
+            double fnorm1;
+            {
+                double o[3];
+                fit_chain_multi(3, FIT_K_FNEW, FIT_K_J0N, FIT_K_J1N, 0, m, lx, ly, S, sh, o);
+                fnorm1 = o[0];
+                spec_acnorm[0] = o[1];
+                spec_acnorm[1] = o[2];
+            }
             double actred = -1.0;
             if (FMUL(0.1, fnorm1) < fnorm) { const double q = FDIV(fnorm1, fnorm); actred = FSUB(1.0, FMUL(q, q)); }
             for (int j = 0; j < 2; j++) {
@@ -631,6 +740,7 @@ FIT_FN int fit_loglinear(const double* lx, const double* ly, long m, FitShared* 
                 xnorm = fit_enorm_small(2, wa2);
                 fnorm = fnorm1;
                 iter++;
+                spec_valid = true;
             }
             if (fabs(actred) <= ftol && prered <= ftol && FMUL(0.5, ratio) <= 1.0) info = 1;
             if (delta <= FMUL(xtol, xnorm)) info = 2;

@@ -1,88 +1,46 @@
-// microbenchmark: where does fit_kernel spend its time?  One CTA, m points, instrumented copies of the
-// chain primitives (clock64 on the accumulating thread).
+// microbenchmark: cycles per element of the ordered-sum chains of fit_kernel, by term kind and by number of
+// chains running side by side; 296 CTAs (2 per SM, like production), m points each.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 [-DFIT_SKIP_SUMS=1] -o fit_timing fit_timing.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
-#define FIT_PROFILE 1
-__device__ long long g_t_sum, g_t_wait, g_t_total, g_n_chunks;
 #include "../../orthofinder_b200/csrc/ofg_fit_core.h"
 
-__global__ void __launch_bounds__(256) k_enorm(const double* x, long m, double* out, int reps)
+__global__ void __launch_bounds__(256, 2) k_chain(const double* lx, const double* ly, long m, int nv, int k0, int k1, int k2, double* out, int reps)
 {
     __shared__ __align__(16) FitShared sh;
+    FitState S;
+    S.x0 = 0.46; S.x1 = 0.4; S.h0 = 1e-8; S.h1 = 1e-8; S.xp00 = S.x0 + S.h0; S.xp01 = S.x1; S.xp10 = S.x0; S.xp11 = S.x1 + S.h1;
+    S.aj0 = 3.0; S.t = 0.1; S.aj1 = 2.0; S.temp0 = 0.01; S.xn0 = 0.461; S.xn1 = 0.401; S.hn0 = 1e-8; S.hn1 = 1e-8;
+    S.xnp0 = S.xn0 + S.hn0; S.xnp1 = S.xn1 + S.hn1; S.piv = 0; S.hh1 = 1; S.hh2 = 1;
+    S.rh0 = fit_rcp(S.h0); S.rh1 = fit_rcp(S.h1); S.raj0 = fit_rcp(S.aj0); S.raj1 = fit_rcp(S.aj1); S.rhn0 = fit_rcp(S.hn0); S.rhn1 = fit_rcp(S.hn1);
+    double o[3], r = 0;
     long long t0 = clock64();
-    double r = 0;
-    for (int i = 0; i < reps; i++) r += fit_enorm_big(x, m, &sh);
+    for (int i = 0; i < reps; i++) { fit_chain_multi(nv, k0, k1, k2, 1, m - 1, lx, ly, S, &sh, o); r += o[0]; }
     long long t1 = clock64();
-    if (threadIdx.x == 0) { out[0] = r; out[1] = (double)(t1 - t0) / reps; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = r; out[1] = (double)(t1 - t0) / reps / (double)(m - 1); }
 }
-__global__ void __launch_bounds__(256) k_dot(const double* x, const double* y, long m, double* out, int reps)
+
+int main()
 {
-    __shared__ __align__(16) FitShared sh;
-    long long t0 = clock64();
-    double r = 0;
-    for (int i = 0; i < reps; i++) r += fit_dot_big(x, y, m, &sh);
-    long long t1 = clock64();
-    if (threadIdx.x == 0) { out[2] = r; out[3] = (double)(t1 - t0) / reps; }
-}
-__global__ void __launch_bounds__(256) k_osum(double* out, int reps)
-{
-    __shared__ __align__(16) double q[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) q[i] = 1.0 + i * 1e-9;
-    __syncthreads();
-    double s = 0.0;
-    long long t0 = clock64();
-    if (threadIdx.x == 0) for (int i = 0; i < reps; i++) s = fit_ordered_sum(s, q, 512);
-    long long t1 = clock64();
-    if (threadIdx.x == 0) { out[6] = s; out[7] = (double)(t1 - t0) / (reps * 512.0); }
-    // same with a barrier per chunk
-    __syncthreads();
-    t0 = clock64();
-    for (int i = 0; i < reps; i++) { if (threadIdx.x == 0) s = fit_ordered_sum(s, q, 512); __syncthreads(); }
-    t1 = clock64();
-    if (threadIdx.x == 0) { out[14] = s; out[15] = (double)(t1 - t0) / (reps * 512.0); }
-}
-__global__ void __launch_bounds__(256) k_elem(double* x, const double* y, long m, double* out, int reps)
-{
-    long long t0 = clock64();
-    for (int i = 0; i < reps; i++) {
-        for (long k = threadIdx.x; k < m; k += blockDim.x) x[k] = __ddiv_rn(__dsub_rn(x[k], y[k]), 1.0000001);
-        __syncthreads();
+    const long m = 50000;
+    std::vector<double> hx(m), hy(m);
+    for (long i = 0; i < m; i++) { hx[i] = 4.0 + 3.0 * (double)rand() / RAND_MAX; hy[i] = 0.46 * hx[i] + 0.4 + 0.1 * ((double)rand() / RAND_MAX - 0.5); }
+    double *dx, *dy, *dout;
+    cudaMalloc(&dx, m * 8); cudaMalloc(&dy, m * 8); cudaMalloc(&dout, 64);
+    cudaMemcpy(dx, hx.data(), m * 8, cudaMemcpyHostToDevice); cudaMemcpy(dy, hy.data(), m * 8, cudaMemcpyHostToDevice);
+    struct { const char* name; int nv, k0, k1, k2; } cases[] = {
+        {"FNEW", 1, FIT_K_FNEW, 0, 0}, {"F", 1, FIT_K_F, 0, 0}, {"B1", 1, FIT_K_B1, 0, 0}, {"B2W", 1, FIT_K_B2W, 0, 0},
+        {"AB+AF", 2, FIT_K_AB, FIT_K_AF, 0}, {"J0+J1", 2, FIT_K_J0, FIT_K_J1, 0}, {"J0+J1+F", 3, FIT_K_J0, FIT_K_J1, FIT_K_F},
+        {"FNEW+J0N+J1N", 3, FIT_K_FNEW, FIT_K_J0N, FIT_K_J1N}};
+    for (auto& c : cases) {
+        k_chain<<<296, 256>>>(dx, dy, m, c.nv, c.k0, c.k1, c.k2, dout, 3);
+        cudaDeviceSynchronize();
+        double h[2];
+        cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
+        printf("%-14s %d chain(s): %6.2f cycles per element%s\n", c.name, c.nv, h[1], FIT_SKIP_SUMS ? " (staging only)" : "");
     }
-    long long t1 = clock64();
-    if (threadIdx.x == 0) out[4] = (double)(t1 - t0) / reps;
-}
-__global__ void __launch_bounds__(256) k_fit(const double* lx, const double* ly, long m, double* scratch, double* out)
-{
-    __shared__ __align__(16) FitShared sh;
-    long long t0 = clock64();
-    fit_loglinear(lx, ly, m, scratch, scratch + m, scratch + 2 * m, scratch + 3 * m, &sh, out + 8);
-    long long t1 = clock64();
-    if (threadIdx.x == 0) out[5] = (double)(t1 - t0);
-}
-int main(int argc, char** argv)
-{
-    long m = argc > 1 ? atol(argv[1]) : 53000;
-    int nblk = argc > 2 ? atoi(argv[2]) : 1;
-    std::vector<double> lx(m), ly(m);
-    srand(1);
-    for (long i = 0; i < m; i++) { lx[i] = 3.0 + 3.0 * rand() / RAND_MAX; ly[i] = 0.46 * lx[i] + 0.4 + 0.3 * (rand() / (double)RAND_MAX - 0.5); }
-    double *dx, *dy, *ds, *dout;
-    cudaMalloc(&dx, m * 8 * nblk); cudaMalloc(&dy, m * 8 * nblk); cudaMalloc(&ds, 4 * m * 8 * nblk); cudaMalloc(&dout, 256 * nblk);
-    for (int b = 0; b < nblk; b++) { cudaMemcpy(dx + b * m, lx.data(), m * 8, cudaMemcpyHostToDevice); cudaMemcpy(dy + b * m, ly.data(), m * 8, cudaMemcpyHostToDevice); }
-    k_enorm<<<1, 256>>>(dx, m, dout, 10);
-    { long long a, b, c; cudaMemcpyFromSymbol(&a, g_t_sum, 8); cudaMemcpyFromSymbol(&b, g_t_wait, 8); cudaMemcpyFromSymbol(&c, g_n_chunks, 8);
-      printf("enorm: chunks %lld, cycles in ordered_sum %.0f per chunk, at barrier %.0f per chunk\n", c, (double)a / c, (double)b / c); }
-    k_dot<<<1, 256>>>(dx, dy, m, dout, 10);
-    k_elem<<<1, 256>>>(ds, dy, m, dout, 10);
-    k_osum<<<1, 256>>>(dout, 100);
-    k_fit<<<1, 256>>>(dx, dy, m, ds, dout);
-    double h[16];
-    cudaMemcpy(h, dout, 128, cudaMemcpyDeviceToHost);
-    printf("ordered_sum alone: %.2f cycles/elem; with __syncthreads per 512: %.2f\n", h[7], h[15]);
-    printf("m=%ld\nenorm chain: %.0f cycles (%.2f/elem)\ndot chain:   %.0f cycles (%.2f/elem)\nelementwise pass (load2, sub, div, store): %.0f cycles (%.2f/elem)\nwhole fit: %.0f cycles = %.3f ms @1.965GHz; a=%.12f b=%.12f info=%g nfev=%g\n",
-           m, h[1], h[1] / m, h[3], h[3] / m, h[4], h[4] / m, h[5], h[5] / 1.965e6, h[8], h[9], h[11], h[12]);
     return 0;
 }
