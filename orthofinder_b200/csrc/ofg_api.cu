@@ -183,7 +183,8 @@ __global__ void test_score_kernel(const uint8_t* text, int64_t nbytes, const int
 }
 __global__ void __launch_bounds__(FIT_THREADS) test_fit_kernel(const double* lx, const double* ly, long m, double* out)
 {
-    __shared__ __align__(16) FitShared sh;
+    extern __shared__ __align__(16) unsigned char fit_smem_raw[];  // sizeof(FitShared) > 48 KB: dynamic, opt-in
+    FitShared& sh = *reinterpret_cast<FitShared*>(fit_smem_raw);
     fit_loglinear(lx, ly, m, &sh, out);
 }
 
@@ -554,7 +555,8 @@ int stage_norm(ofg_ctx* c)
     f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
     f.fit = c->fit.as<double>(); f.err_flags = err_flags;
     if (P > 0) {
-        fit_kernel<<<P, FIT_THREADS, 0, c->stream>>>(f);
+        CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
+        fit_kernel<<<P, FIT_THREADS, sizeof(FitShared), c->stream>>>(f);
         CKL("fit_kernel");
     }
     CK(cudaEventRecord(c->ev[5], c->stream));
@@ -1287,7 +1289,8 @@ int ofg_test_lmfit(ofg_ctx* c, const double* host_lx, const double* host_ly, int
     CK(x.ensure((size_t)m * 8)); CK(y.ensure((size_t)m * 8)); CK(o.ensure(64));
     CK(cudaMemcpyAsync(x.p, host_lx, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(y.p, host_ly, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
-    test_fit_kernel<<<1, FIT_THREADS, 0, c->stream>>>(x.as<double>(), y.as<double>(), (long)m, o.as<double>());
+    CK(cudaFuncSetAttribute(test_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
+    test_fit_kernel<<<1, FIT_THREADS, sizeof(FitShared), c->stream>>>(x.as<double>(), y.as<double>(), (long)m, o.as<double>());
     CKL("test_fit_kernel");
     double h[8];
     CK(cudaMemcpyAsync(h, o.p, 48, cudaMemcpyDeviceToHost, c->stream));

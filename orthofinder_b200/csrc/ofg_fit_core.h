@@ -83,6 +83,8 @@ struct FitShared {  // lives in shared memory on the device (37 KB)
     double out[FIT_MAXV];
     int tag[FIT_MAXV][FIT_RING];      // chunk tag set when a staged chunk holds a value outside MINPACK's mid range
     FitState st;                      // the scalars the staging warps read (published before every chain)
+    double rx[FIT_RING][FIT_CH];      // raw (lx, ly) of the chunks being staged, filled one chunk ahead by cp.async
+    double ry[FIT_RING][FIT_CH];
 };
 
 // ordered sum of the staged terms q[0..len): strictly left to right.  On the device the next eight terms
@@ -239,6 +241,14 @@ FIT_FN double fit_term(int kind, long i, double lx, double ly, const FitState& S
     return FMUL(fit_elem_bpp(S, i, Bp), fit_elem_wp(S, f, Ap));  // FIT_K_B2W
 }
 
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void fit_cp_async8(void* smem, const void* gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+#endif
+
 // All terms of one element for the (up to three) chains of a call, sharing the sub-expressions they have in
 // common (the residual, the two difference quotients, the Householder vector element).  Same operations, same
 // order as fit_term.
@@ -287,7 +297,7 @@ FIT_FN void fit_terms(int nv, int k0, int k1, int k2, long i, double lx, double 
 
 // Up to FIT_MAXV chains side by side over the absolute index range [i0, i0 + n).  Chain v is an enorm (MINPACK's
 // scaled 2-norm) or a plain ordered sum depending on its kind; it is accumulated in index order by lane 0 of
-// warp v from terms staged through a ring of shared-memory chunks by the warps >= FIT_MAXV.  With fewer than 128
+// warp v from terms staged through a ring of shared-memory chunks by the remaining warps.  With fewer than 128
 // threads (the host build) staging and accumulation simply alternate.
 FIT_FN void fit_chain_multi(int nv, int k0, int k1, int k2, long i0, long n, const double* lx, const double* ly,
                             const FitState& S_local, FitShared* sh, double* out)
@@ -333,48 +343,62 @@ FIT_FN void fit_chain_multi(int nv, int k0, int k1, int k2, long i0, long n, con
         FitEnormAcc acc;
         acc.init((double)n);
         double sum = 0.0;
-        const int first_loader = FIT_MAXV * 32, n_loaders = FIT_NT - FIT_MAXV * 32;
+        const int first_loader = nv * 32, n_loaders = FIT_NT - nv * 32;  // warps without a chain to sum stage terms
         const int lt = FIT_TID - first_loader;
         const long n_chunks = (n + FIT_CH - 1) / FIT_CH;
+        // Staging warps: element k of a chunk belongs to loader (k mod n_loaders).  Its (lx, ly) are copied into shared
+        // memory by cp.async one chunk ahead of their use, so the global-memory latency hides behind the summing warps
+        // and costs no registers.
+        auto fetch_chunk = [&](long cl) {
+            const long c1 = cl * FIT_CH;
+            if (c1 < n) {
+                const int len = (int)((n - c1) < FIT_CH ? (n - c1) : FIT_CH);
+                const int rs = (int)(cl % FIT_RING);
+                for (int i = lt; i < len; i += n_loaders) {
+                    const long gi = i0 + c1 + i;
+#if defined(__CUDA_ARCH__)
+                    fit_cp_async8(&sh->rx[rs][i], lx + gi);
+                    fit_cp_async8(&sh->ry[rs][i], ly + gi);
+#else
+                    sh->rx[rs][i] = lx[gi];
+                    sh->ry[rs][i] = ly[gi];
+#endif
+                }
+            }
+#if defined(__CUDA_ARCH__)
+            asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+        };
+        if (FIT_TID >= first_loader) fetch_chunk(0);
         for (long c = -(FIT_RING - 1); c < n_chunks; c++) {
             if (FIT_TID >= first_loader) {
                 const long cl = c + (FIT_RING - 1);  // chunk to stage now
                 const long c1 = cl * FIT_CH;
+                fetch_chunk(cl + 1);
+#if defined(__CUDA_ARCH__)
+                asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the newest group has landed
+#endif
                 if (c1 < n) {
                     const int slot = (int)(cl % FIT_RING);
                     const int len = (int)((n - c1) < FIT_CH ? (n - c1) : FIT_CH);
                     bool odd0 = false, odd1 = false, odd2 = false;
-                    for (int b0 = 0; b0 < len; b0 += 4 * n_loaders) {
-                        double xa[4], ya[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {  // four independent element loads in flight per loader
-                            const int i = b0 + u * n_loaders + lt;
-                            const long gi = i0 + c1 + (i < len ? i : 0);
-                            xa[u] = lx[gi];
-                            ya[u] = ly[gi];
+                    for (int i = lt; i < len; i += n_loaders) {
+                        double tv[3];
+                        fit_terms(nv, k0, k1, k2, i0 + c1 + i, sh->rx[slot][i], sh->ry[slot][i], S, tv);
+                        {
+                            const double av = fabs(tv[0]);
+                            if (en0) odd0 = odd0 || !(av > rdwarf && av < agiant);
+                            sh->buf[0][slot][i] = en0 ? FMUL(av, av) : tv[0];
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int i = b0 + u * n_loaders + lt;
-                            if (i < len) {
-                                double tv[3];
-                                fit_terms(nv, k0, k1, k2, i0 + c1 + i, xa[u], ya[u], S, tv);
-                                {
-                                    const double av = fabs(tv[0]);
-                                    if (en0) odd0 = odd0 || !(av > rdwarf && av < agiant);
-                                    sh->buf[0][slot][i] = en0 ? FMUL(av, av) : tv[0];
-                                }
-                                if (nv > 1) {
-                                    const double av = fabs(tv[1]);
-                                    if (en1) odd1 = odd1 || !(av > rdwarf && av < agiant);
-                                    sh->buf[1][slot][i] = en1 ? FMUL(av, av) : tv[1];
-                                }
-                                if (nv > 2) {
-                                    const double av = fabs(tv[2]);
-                                    if (en2) odd2 = odd2 || !(av > rdwarf && av < agiant);
-                                    sh->buf[2][slot][i] = en2 ? FMUL(av, av) : tv[2];
-                                }
-                            }
+                        if (nv > 1) {
+                            const double av = fabs(tv[1]);
+                            if (en1) odd1 = odd1 || !(av > rdwarf && av < agiant);
+                            sh->buf[1][slot][i] = en1 ? FMUL(av, av) : tv[1];
+                        }
+                        if (nv > 2) {
+                            const double av = fabs(tv[2]);
+                            if (en2) odd2 = odd2 || !(av > rdwarf && av < agiant);
+                            sh->buf[2][slot][i] = en2 ? FMUL(av, av) : tv[2];
                         }
                     }
                     if (odd0) sh->tag[0][slot] = (int)(cl + 1);

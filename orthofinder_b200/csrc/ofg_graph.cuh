@@ -31,7 +31,8 @@ struct FitArgs {
 
 __global__ void __launch_bounds__(FIT_THREADS) fit_kernel(FitArgs a)
 {
-    __shared__ __align__(16) FitShared sh;
+    extern __shared__ __align__(16) unsigned char fit_smem_raw[];  // sizeof(FitShared) > 48 KB: dynamic, opt-in
+    FitShared& sh = *reinterpret_cast<FitShared*>(fit_smem_raw);
     for (int pair = blockIdx.x; pair < a.P; pair += gridDim.x) {
         const u64 o0 = a.pair_sel_off[pair], o1 = a.pair_sel_off[pair + 1];
         const long m = (long)(o1 - o0);

@@ -10,7 +10,8 @@
 
 __global__ void __launch_bounds__(256, 2) k_chain(const double* lx, const double* ly, long m, int nv, int k0, int k1, int k2, double* out, int reps)
 {
-    __shared__ __align__(16) FitShared sh;
+    extern __shared__ __align__(16) unsigned char fit_smem_raw[];  // sizeof(FitShared) > 48 KB: dynamic, opt-in
+    FitShared& sh = *reinterpret_cast<FitShared*>(fit_smem_raw);
     FitState S;
     S.x0 = 0.46; S.x1 = 0.4; S.h0 = 1e-8; S.h1 = 1e-8; S.xp00 = S.x0 + S.h0; S.xp01 = S.x1; S.xp10 = S.x0; S.xp11 = S.x1 + S.h1;
     S.aj0 = 3.0; S.t = 0.1; S.aj1 = 2.0; S.temp0 = 0.01; S.xn0 = 0.461; S.xn1 = 0.401; S.hn0 = 1e-8; S.hn1 = 1e-8;
@@ -36,7 +37,8 @@ int main()
         {"AB+AF", 2, FIT_K_AB, FIT_K_AF, 0}, {"J0+J1", 2, FIT_K_J0, FIT_K_J1, 0}, {"J0+J1+F", 3, FIT_K_J0, FIT_K_J1, FIT_K_F},
         {"FNEW+J0N+J1N", 3, FIT_K_FNEW, FIT_K_J0N, FIT_K_J1N}};
     for (auto& c : cases) {
-        k_chain<<<296, 256>>>(dx, dy, m, c.nv, c.k0, c.k1, c.k2, dout, 3);
+        cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared));
+        k_chain<<<296, 256, sizeof(FitShared)>>>(dx, dy, m, c.nv, c.k0, c.k1, c.k2, dout, 3);
         cudaDeviceSynchronize();
         double h[2];
         cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
