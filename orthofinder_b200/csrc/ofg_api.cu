@@ -573,7 +573,7 @@ int stage_norm(ofg_ctx* c)
         fa.rowfac = c->rowfac.as<double>(); fa.colfac = c->colfac.as<double>();
         int64_t maxg = 1;
         for (int i = 0; i < P; i++) maxg = std::max<int64_t>(maxg, (int64_t)c->pairs[i].Gi + c->pairs[i].Gj);
-        dim3 g((unsigned)std::min<int64_t>((maxg + 255) / 256, 64), (unsigned)P);
+        dim3 g((unsigned)P, (unsigned)std::min<int64_t>((maxg + 255) / 256, 64));
         factors_kernel<<<g, 256, 0, c->stream>>>(fa);
         CKL("factors_kernel");
         ScaleArgs sa;

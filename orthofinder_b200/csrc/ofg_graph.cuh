@@ -67,15 +67,15 @@ struct FactorArgs {
 
 __global__ void __launch_bounds__(256) factors_kernel(FactorArgs a)
 {
-    // grid.y = pair, grid.x strides over Gi + Gj genes
-    const int pair = blockIdx.y;
+    // grid.x = pair (S^2 pairs can exceed the 65535 limit of grid.y), grid.y strides over Gi + Gj genes
+    const int pair = blockIdx.x;
     const PairDesc pd = a.pairs[pair];
     const double* f = a.fit + (size_t)pair * 8;
     if (f[6] == 0.0) return;
     const double pa = f[0], pb = f[1];
     const double ten_mb = pow(10.0, -pb);  // 10**(-params[1])
     const int64_t n = (int64_t)pd.Gi + pd.Gj;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
         if (i < pd.Gi) a.rowfac[pd.row_base + i] = __dmul_rn(ten_mb, pow(a.lengths[pd.li_off + i], -pa));
         else a.colfac[pd.col_base + (i - pd.Gi)] = pow(a.lengths[pd.lj_off + (i - pd.Gi)], -pa);
     }

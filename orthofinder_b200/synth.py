@@ -33,6 +33,7 @@ CONFIGS = {
     "C2_tiny": dict(S=6, G=400, p=dict(seed=1, hq=24)),
     "C3": dict(S=64, G=20000, p=dict(seed=2, hq=50)),
     "C4": dict(S=256, G=20000, p=dict(seed=3, hq=8)),
+    "C4_tiny": dict(S=48, G=60, p=dict(seed=3, hq=6)),       # many species pairs (2304), few genes
     "C5": dict(S=6, G=5000, n_lengths=0, p=dict(seed=5, hq=12, integer_scores=1, ident_levels=16, p_missing=300,
                                                 p_nohit=50, p_selfonly=20, p_twin=50, single=(5, 4))),
     "C5_small": dict(S=5, G=600, p=dict(seed=5, hq=12, integer_scores=1, ident_levels=16, p_missing=300,

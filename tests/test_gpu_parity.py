@@ -488,6 +488,32 @@ def test_mid_size_job_equals_oracle(gb):
         assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
 
 
+def test_many_species_pairs_equal_oracle(gb):
+    """48 species x 60 genes (2304 species pairs, bins of 20): per-pair bookkeeping at scale - pair lookups, per-pair
+    kernels launched over thousands of pairs, one fit per pair - against the CPU oracle."""
+    ids, n_seqs, L, P = synth.config_inputs("C4_tiny")
+    S = len(ids)
+    gb.set_species(n_seqs, L)
+    gb.synth_hits(P, ids)
+    gb.build()
+    texts = {(p, j): gb.hits_text(p, j) for p in range(S) for j in range(S)}
+    from oracle import parallel
+    ref = parallel.waterfall_parallel(n_seqs, L, texts, None, want_text=True)
+    rows, indptr, idx, dat = gb.graph_csr()
+    assert np.array_equal(indptr, ref["indptr"]) and np.array_equal(idx, ref["indices"])
+    assert np.max(np.abs(dat - ref["data"]) / ref["data"]) <= REL_TOL
+    n_fit = 0
+    for (p, j), f in ref["fits"].items():
+        g = gb.pair_fit(p, j)
+        assert g["normalised"] and g["a"] == f[0] and g["b"] == f[1] and g["m"] == f[2], (p, j, g, f)
+        n_fit += 1
+    assert n_fit == S * S
+    text = waterfall.graph_header(sum(n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+    if text != ref["graph"]:
+        edge_diff, dec_diff = graph_text_diff(text, ref["graph"])
+        assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
+
+
 def test_rebuild_is_deterministic_and_sorted(gb):
     """Size-independent properties on a mid-size job (8 species x 2000 genes x 50 hits/query, 7 M lines):
     two builds give identical bytes; rows are strictly column-sorted; weights are positive and finite."""
