@@ -87,8 +87,9 @@ def workload(args, n_gpus):
     if args.hq:
         pk["hq"] = args.hq
     if n_gpus > 1 and not args.species:
-        # weak scaling: the pair grid (S^2) grows with the GPU count so that every GPU keeps ~256 owned pairs
-        S = int(round(cfg["S"] * n_gpus ** 0.5))
+        # weak scaling: the pair grid (S^2) grows with the GPU count so that every GPU keeps ~256 owned pairs; S is
+        # the multiple of the GPU count nearest to 16 sqrt(N), so every rank owns the same number of query species
+        S = n_gpus * max(1, int(round(cfg["S"] * n_gpus ** 0.5 / n_gpus)))
     P = synth.params(**pk)
     L = synth.make_lengths(S, G, P.seed, twins=P.p_twin_permille > 0, n_distinct=12 if P.ident_levels else 0)
     return S, G, P, L
@@ -175,6 +176,17 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
+    phase_ms = None
+    if world > 1 and lists and args.phase_timing:
+        # one instrumented step (outside the timed region): where does the multi-GPU step spend its time?
+        def lap(fn):
+            torch.cuda.synchronize(); t = time.perf_counter(); fn(); torch.cuda.synchronize(); return (time.perf_counter() - t) * 1e3
+        phase_ms = {
+            "build_norm": lap(lambda: gb.build(_lib.STAGE_NORM)),
+            "exchange_bh": lap(lambda: sharding.exchange_lists(gb, 0, species_rank, rank, world, local)),
+            "build_connect": lap(lambda: gb.build(_lib.STAGE_CONNECT)),
+            "exchange_connect": lap(lambda: sharding.exchange_lists(gb, 1, species_rank, rank, world, local)),
+            "build_graph": lap(lambda: gb.build(_lib.STAGE_GRAPH))}
     c = gb.counts()
     # owned lines: lines of the rows this rank owns (column-side re-parsing is implementation traffic, not work)
     sizes = {}
@@ -233,6 +245,8 @@ def run_ours(args):
                "l2": "inputs (%.1f GB text per GPU) larger than L2, no flush needed" % (text_bytes_all / 1e9)},
            "gpu_launches": int(launches * args.steps) if world == 1 else int(launches * args.steps),
            "clocks": clk.summary(), "counts": c, "stage_ms_last_step": gb.timing()}
+    if phase_ms:
+        out["phase_ms_rank0"] = phase_ms
     if rank == 0:
         # ---- roofline of the dominant kernel (per-launch CUDA-event time, averaged over the timed steps)
         peak, how = peaks()
@@ -408,6 +422,7 @@ def main():
     ap.add_argument("--exchange", default="lists", choices=["lists", "thresholds"],
                     help="multi-GPU: 'lists' = design B (sparse all-to-all), 'thresholds' = design A (column re-parse + all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--phase-timing", action="store_true", help="N > 1: add a per-phase wall-clock breakdown of one extra step")
     ap.add_argument("--e2e-parts", type=int, default=4, help="row partitions of the pipelined e2e run (1 = single context)")
     ap.add_argument("--e2e-check", action="store_true", help="compare the e2e graph text with the device-resident run's")
     ap.add_argument("--no-cpu", action="store_true")

@@ -45,7 +45,7 @@ def _import_reference_real():
     return gathering, util, files, matrices
 
 
-def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True):
+def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True, v2_scores=False):
     """Run the reference hot path on WorkingDirectory ``wd`` (must end with '/').
 
     Returns dict with: graph (bytes), seqsInfo fields, lengths, per-pair CSR of B (normalised),
@@ -92,9 +92,9 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True)
             with contextlib.redirect_stdout(buf):
                 for p in range(si.nSpecies):
                     norm_probe.p = p
-                    gathering.WaterfallMethod.ProcessBlastHits(si, [wd], L, p, pic, q_double_blast, False)
+                    gathering.WaterfallMethod.ProcessBlastHits(si, [wd], L, p, pic, q_double_blast, v2_scores)
                 for p in range(si.nSpecies):
-                    gathering.WaterfallMethod.ConnectCognates(si, p, pic)
+                    gathering.WaterfallMethod.ConnectCognates(si, p, pic, v2_scores)
                 mats = {}
                 if keep_matrices:
                     for p in range(si.nSpecies):

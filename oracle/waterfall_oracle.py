@@ -251,6 +251,19 @@ def normalise_scores(csr, Li, Lj):
     return empty, None
 
 
+def normalised_bit_score(csr, Li, Lj):
+    """gathering.py:157-174 NormalisedBitScore (A18, `--scores-v2`): diag(Lq**-0.5) * B * diag(Lh**-0.5), the two
+    sparse products evaluated left to right; no fit, no pair is ever zeroed.  Returns csr'."""
+    indptr, cols, vals = csr
+    if vals.size == 0:  # :165-166
+        return csr
+    n_i = len(indptr) - 1
+    rows = np.repeat(np.arange(n_i), np.diff(indptr))
+    li = Li ** (-0.5)  # :171-172
+    lj = Lj ** (-0.5)
+    return indptr, cols, (li[rows] * vals) * lj[cols]
+
+
 # ----------------------------------------------------------------------------------------------
 # A11: best hits with tolerance
 # ----------------------------------------------------------------------------------------------
@@ -289,32 +302,71 @@ def _entry_keys(indptr, cols, n_cols):
     return rows, rows * n_cols + cols
 
 
-def connect_cognates(B, BH, p, n_seqs):
+def _rbh_flags(B, BH, p, k, n_seqs):
+    """RBH_pk = BH_pk AND BH_kp^T (matrices.py:65-69) as a flag per stored entry of B[p][k]; also the entry rows."""
+    indptr, cols, vals = B[p][k]
+    rows, keys = _entry_keys(indptr, cols, n_seqs[k])
+    f = BH[p][k]
+    indptr2, cols2, _ = B[k][p]
+    rows2, _ = _entry_keys(indptr2, cols2, n_seqs[p])
+    f2 = BH[k][p]
+    tkeys = cols2[f2].astype(np.int64) * n_seqs[k] + rows2[f2]  # (row of p, col of k)
+    return f & np.isin(keys, tkeys), rows
+
+
+def rbh_conversion_factors(B, BH, p, n_seqs, pct=90):
+    """gathering.py:333-364, stage 1 of GetMostDistant_s_estimate_from_relative_rbhs: for query species p, the factor
+    per other species k (in species order) that converts an RBH score in k into the expected score of the most
+    distant RBH.  Z[k][i] is gene i's RBH score in species k if it has exactly ONE RBH there, else 0 (:340);
+    rs[a][b] is the (100 - pct)th percentile of Z[a] * (1 / Z[b]) over the genes where both exist (:344-357);
+    the factor of species b is the column minimum (:364)."""
+    others = [k for k in range(len(B[p])) if k != p]
+    n_i = n_seqs[p]
+    Z = np.zeros((len(others), n_i))
+    for a, k in enumerate(others):
+        rbh, rows = _rbh_flags(B, BH, p, k, n_seqs)
+        cnt = np.bincount(rows[rbh], minlength=n_i)
+        vals = B[p][k][2]
+        single = rbh & (cnt[rows] == 1)
+        Z[a, rows[single]] = vals[single]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Zr = 1.0 / Z  # :342
+        rs = np.ones((len(others), len(others)))
+        for a in range(len(others)):
+            for b in range(len(others)):
+                if a == b:
+                    continue
+                ratios = Z[a] * Zr[b]  # :349 (reciprocal first, then the product)
+                ok = np.isfinite(ratios) & (ratios > 0)
+                if ok.any():
+                    rs[a, b] = np.percentile(ratios[ok], 100 - pct)  # :355
+    return (rs.min(axis=0) if len(others) else np.zeros(0)), others
+
+
+def connect_cognates(B, BH, p, n_seqs, v2_scores=False):
     """gathering.py:251-259 ConnectCognates for query species p.
-    B[p][j], BH[p][j] and BH[j][p] for all j are read.  Returns (connect flags per j, mostDistant)."""
+    B[p][j], BH[p][j] and BH[j][p] for all j are read.  Returns (connect flags per j, mostDistant).
+    v2_scores: thresholds by GetMostDistant_s_estimate_from_relative_rbhs (:314-388) instead of GetMostDistant_s."""
     S = len(B[p])
     n_i = n_seqs[p]
-    most = np.ones(n_i) * 1e9  # :296
-    best = np.zeros(n_i)  # :298
+    most = np.ones(n_i) * 1e9  # :296 / :366
+    best = np.zeros(n_i)  # :298 / :368
+    factor = {}
+    if v2_scores:
+        C, others = rbh_conversion_factors(B, BH, p, n_seqs)
+        factor = {k: C[a] for a, k in enumerate(others)}
     for k in range(S):
         if k == p:
             continue
         indptr, cols, vals = B[p][k]
         m, _ = _row_max(indptr, vals, 0.0)  # matrices.py:75-78 sparse_max_row
         best = np.maximum(best, m)
-        # RBH_pk = BH_pk AND BH_kp^T (matrices.py:65-69)
-        rows, keys = _entry_keys(indptr, cols, n_seqs[k])
-        f = BH[p][k]
-        indptr2, cols2, _ = B[k][p]
-        rows2, _ = _entry_keys(indptr2, cols2, n_seqs[p])
-        f2 = BH[k][p]
-        tkeys = cols2[f2].astype(np.int64) * n_seqs[k] + rows2[f2]  # (row of p, col of k)
-        rbh = f & np.isin(keys, tkeys)
+        rbh, rows = _rbh_flags(B, BH, p, k, n_seqs)
         I = rows[rbh]
         if I.size:
-            # :304-306  mostDistant[I] = np.minimum(B[I,J], mostDistant[I]) : fancy assignment with
-            # repeated I is last-wins; entries are in (row, col) order so the last is the largest col
-            v = np.minimum(vals[rbh], most[I])
+            # :304-306 / :381-384  mostDistant[I] = np.minimum([factor *] B[I,J], mostDistant[I]) : fancy assignment
+            # with repeated I is last-wins; entries are in (row, col) order so the last is the largest col
+            v = np.minimum(factor[k] * vals[rbh] if v2_scores else vals[rbh], most[I])
             most[I] = v
     I = most > 1e8
     most[I] = best[I] + 1e-6  # :308-309
@@ -382,8 +434,8 @@ def graph_text(indptr, indices, data, n_total):
 # ----------------------------------------------------------------------------------------------
 # whole path
 # ----------------------------------------------------------------------------------------------
-def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False):
-    """WaterfallMethod end to end (gathering.py:476-512 of DoOrthogroups, v1 scores).
+def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False, v2_scores=False):
+    """WaterfallMethod end to end (gathering.py:476-512 of DoOrthogroups; v2_scores = `--scores-v2`, A18).
 
     n_seqs[p], lengths[p] per used species (list order); hit_text(p, j) -> bytes of Blast{p}_{j}
     (ids already translated to list positions by the caller) or None if absent.
@@ -399,13 +451,16 @@ def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False
             swap = (not q_double_blast) and p > j  # blast_file_processor.py:41-54
             txt = hit_text(j, p) if swap else hit_text(p, j)
             raw = get_blast6_scores(txt if txt is not None else b"", n_seqs[p], n_seqs[j], p == j, swap)
+            if v2_scores:
+                B[p][j], fits[(p, j)] = normalised_bit_score(raw, lengths[p], lengths[j]), None
+                continue
             B[p][j], fits[(p, j)] = normalise_scores(raw, lengths[p], lengths[j])
             if fits[(p, j)] is None:
                 warns.append((p, j, int(raw[0][-1])))
     BH = [get_bh(B[p], p) for p in range(S)]
     conn, most = [], []
     for p in range(S):
-        c, m = connect_cognates(B, BH, p, n_seqs)
+        c, m = connect_cognates(B, BH, p, n_seqs, v2_scores)
         conn.append(c)
         most.append(m)
     indptr, indices, data = assemble_graph(B, conn, starts, n_seqs)
@@ -415,7 +470,7 @@ def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False
     return out
 
 
-def waterfall_from_directory(wd, q_double_blast=True, return_parts=False):
+def waterfall_from_directory(wd, q_double_blast=True, return_parts=False, v2_scores=False):
     """Entry used by tests: reads SpeciesIDs.txt / Species*.fa / Blast*_*.txt like the reference."""
     import gzip
     use, n_all = get_species_to_use(os.path.join(wd, "SpeciesIDs.txt"))
@@ -431,7 +486,7 @@ def waterfall_from_directory(wd, q_double_blast=True, return_parts=False):
         with open(fn, "rb") as f:
             return f.read()
 
-    res = waterfall(n_seqs, L, hit_text, q_double_blast, return_parts)
+    res = waterfall(n_seqs, L, hit_text, q_double_blast, return_parts, v2_scores)
     res["seqsInfo"] = si
     res["lengths"] = L
     res["graph"] = graph_text(res["indptr"], res["indices"], res["data"], si.nSeqs)

@@ -16,6 +16,8 @@ class Golden:
         z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
         self.name = name
         self.graph = zlib.decompress(z["graph_z"].tobytes())
+        self.graph_v2 = zlib.decompress(z["graph_v2_z"].tobytes()) if "graph_v2_z" in z.files else None
+        self.most_distant_v2 = z["most_distant_v2"] if "most_distant_v2" in z.files else None
         self.fits = z["fits"]
         self.nnz = z["nnz"]
         self.n_seqs = [int(x) for x in z["n_seqs"]]

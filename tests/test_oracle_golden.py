@@ -24,6 +24,18 @@ def test_oracle_reproduces_reference_graph(name):
     np.testing.assert_array_equal(np.concatenate(res["most_distant"]), g.most_distant)
 
 
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_oracle_reproduces_reference_graph_with_v2_scores(name):
+    """`--scores-v2` (gathering.py:157-174 NormalisedBitScore, :314-388 percentile-ratio thresholds):
+    the golden graph comes from the live reference run with v2_scores=True (tools/make_golden.py)."""
+    g = Golden(name)
+    res = wo.waterfall(g.n_seqs, g.lengths, g.hit_text, v2_scores=True)
+    text = wo.graph_text(res["indptr"], res["indices"], res["data"], sum(g.n_seqs))
+    assert text == g.graph_v2, "oracle v2 graph differs from the live reference's (%s)" % g.provenance
+    assert np.array_equal(np.concatenate(res["most_distant"]), g.most_distant_v2)
+    assert all(f is None for f in res["fits"].values())   # no fit in this mode
+
+
 def test_oracle_matrix_counts_match_reference_pickles():
     g = Golden("ref_AddTwoSpecies")
     res = wo.waterfall(g.n_seqs, g.lengths, g.hit_text, return_parts=True)

@@ -5,7 +5,7 @@ Runs only where /root/reference exists (the build container).  For every dataset
   1. runs the reference in-process and keeps its OrthoFinder_graph.txt bytes, the curve_fit
      parameters of every species pair and the nnz of its B / BH / connect pickles,
   2. requires the CPU oracle (oracle/waterfall_oracle.py) to reproduce the graph byte for byte and the
-     fit parameters bit for bit (this is what pins the oracle),
+     fit parameters bit for bit (this is what pins the oracle), for the default scores and for `--scores-v2`,
   3. stores inputs (only for the reference's own fixtures — synthetic inputs are regenerated from
      orthofinder_b200/synth.py) and expected outputs, compressed.
 Provenance (numpy / scipy versions, CPU features) is recorded in each file.
@@ -68,6 +68,12 @@ def run_one(name, wd, store_inputs):
                 sizes.append(len(b))
         out["hits_z"] = np.frombuffer(zlib.compress(b"".join(blobs), 9), np.uint8)
         out["hit_sizes"] = np.array(sizes, np.int64)
+    # the `--scores-v2` variant of the same inputs: graph and thresholds of the live reference
+    ref2 = rh.run_reference(wd, capture_fit=False, keep_matrices=False, v2_scores=True)
+    mine2 = wo.waterfall_from_directory(wd, v2_scores=True)
+    assert ref2["graph"] == mine2["graph"], "%s: oracle v2 graph differs from the reference" % name
+    out["graph_v2_z"] = np.frombuffer(zlib.compress(ref2["graph"], 9), np.uint8)
+    out["most_distant_v2"] = np.concatenate(mine2["most_distant"])
     fn = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez(fn, **out)
     print("%-20s S=%d genes=%d graph=%d B  entries=%d  -> %s (%d KB)" % (
