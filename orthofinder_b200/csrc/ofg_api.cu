@@ -72,6 +72,7 @@ struct ofg_ctx {
     std::vector<FileInfo> files;
     // options
     int allow_empty = 0;
+    bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
     // text arena
@@ -85,7 +86,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf sort_desc, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf sort_desc, zrow, pair_factor, d_owned, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -454,112 +455,125 @@ int stage_norm(ofg_ctx* c)
     u32* err_flags = (u32*)(sm + 2);
     const int key_bits = c->key_bits;
     const u64 n_slots = (u64)c->tot_records;
-    // ---- segmented stable radix sort by Lf
-    std::vector<int64_t> pair_slot(P + 1, 0), tile_prefix(P + 1, 0);
-    for (int i = 0; i < P; i++) {
-        pair_slot[i + 1] = pair_slot[i] + (int64_t)c->pair_valid[i];
-        tile_prefix[i + 1] = tile_prefix[i] + ((int64_t)c->pair_valid[i] + RS_TILE - 1) / RS_TILE;
-    }
-    const int64_t n_tiles = tile_prefix[P];
-    if (upload(c, c->pair_slot, pair_slot.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
-    if (upload(c, c->sort_tile_prefix, tile_prefix.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
-    const int n_pass = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
-    const int pass_bits = (key_bits + n_pass - 1) / n_pass;
-    CK(c->key2.ensure((n_slots + 64) * 4));
-    CK(c->keyval2.ensure((n_slots + 64) * 8));
-    CK(c->counters.ensure(((size_t)n_tiles << pass_bits) * 4 + 64));
-    u32* kin = c->key.as<u32>(); double* vin = c->keyval.as<double>();
-    u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
-    if (n_tiles > 0) {
-        CK(c->sort_desc.ensure((size_t)n_tiles * sizeof(RsTileDesc)));
-        for (int pass = 0; pass < n_pass; pass++) {
-            RadixArgs a;
-            a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
-            a.tile_prefix = c->sort_tile_prefix.as<int64_t>(); a.pair_slot = c->pair_slot.as<int64_t>();
-            a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
-            a.desc = c->sort_desc.as<RsTileDesc>();
-            if (pass == 0) {
-                rs_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(a, c->sort_desc.as<RsTileDesc>());
-                CKL("rs_desc_kernel");
-            }
-            const int g = grid_for(c, n_tiles, 1, 2);  // scatter: two resident CTAs per SM (registers, shared memory)
-            radix_hist_kernel<<<grid_for(c, n_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
-            CKL("radix_hist_kernel");
-            if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
-            CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
-            radix_scatter_kernel<<<g, RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);
-            CKL("radix_scatter_kernel");
-            std::swap(kin, kout);
-            std::swap(vin, vout);
-        }
-    }
-    CK(cudaEventRecord(c->ev[3], c->stream));
-    // ---- bins
-    std::vector<BinTask> tasks;
-    std::vector<int64_t> task_prefix(P + 1, 0);
-    for (int i = 0; i < P; i++) {
-        const u64 H = c->pair_nnz[i];
-        const u32 first = (u32)pair_slot[i];
-        if (H > 0 && H < 100) {
-            tasks.push_back(BinTask{first, (u32)H, i, 1});
-        } else if (H >= 100) {
-            const u32 n_in = H > 5000 ? 1000u : (H > 1000 ? 200u : 20u);
-            const u64 n_bins = H / n_in;
-            for (u64 b = 0; b < n_bins; b++) tasks.push_back(BinTask{(u32)(first + b * n_in), n_in, i, 0});
-        }
-        task_prefix[i + 1] = (int64_t)tasks.size();
-    }
-    const int64_t n_tasks = (int64_t)tasks.size();
-    if (upload(c, c->bin_tasks, tasks.data(), sizeof(BinTask) * tasks.size())) return OFG_ERR_CUDA;
-    std::vector<u64> tp64(task_prefix.begin(), task_prefix.end());
-    if (upload(c, c->task_prefix, tp64.data(), sizeof(u64) * (P + 1))) return OFG_ERR_CUDA;
-    CK(c->bin_cut.ensure((size_t)(n_tasks + 1) * 8));
-    CK(c->bin_cnt.ensure((size_t)(n_tasks + 1) * 4));
-    CK(c->sel_off.ensure((size_t)(n_tasks + 2) * 8));
-    c->sel_cap = std::max<u64>(n_slots / (u64)std::max<int64_t>(c->sel_frac_inv, 1), 1u << 16);
-    if (c->sel_cap > n_slots + 1) c->sel_cap = n_slots + 1;
-    CK(c->lx.ensure(c->sel_cap * 8)); CK(c->ly.ensure(c->sel_cap * 8));
-    CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
-    CK(cudaMemsetAsync(c->fit.p, 0, (size_t)P * 8 * 8, c->stream));
-    BinArgs b;
-    b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks = n_tasks; b.key = kin; b.val = vin;
-    {
-        // numpy: virtual index (n-1)*q with q = 95/100, gamma = vi - floor(vi)
-        const double q = 95.0 / 100.0;
-        const double v20 = 19.0 * q, v200 = 199.0 * q, v1000 = 999.0 * q;
-        b.k20 = (int)floor(v20); b.g20 = v20 - floor(v20);
-        b.k200 = (int)floor(v200); b.g200 = v200 - floor(v200);
-        b.k1000 = (int)floor(v1000); b.g1000 = v1000 - floor(v1000);
-    }
-    b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
-    b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
-    // staging: two free fp64 arrays of at least n_slots entries - the parse output scores and the idle sort buffer
-    b.stage_lx = c->coo_val.as<double>(); b.stage_ly = vout;
-    if (n_tasks > 0) {
-        const int g = grid_for(c, n_tasks, BIN_WARPS, 6);
-        bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
-        CKL("bin_cut_kernel");
-        if (device_scan<u64>(c, b.cnt, n_tasks, c->sel_off.as<u64>(), 1)) return OFG_ERR_CUDA;
-        bin_select_kernel<<<grid_for(c, n_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
-        CKL("bin_select_kernel");
+    if (c->scores_v2) {
+        // --scores-v2 (gathering.py:157-174 NormalisedBitScore): B' = diag(Lq^-0.5) B diag(Lh^-0.5), no fit and no pair is
+        // zeroed.  Expressed through the same factor kernels as a fit with a = 0.5, b = 0 (10^-0 = 1 exactly).
+        std::vector<double> fv((size_t)P * 8, 0.0);
+        for (int i = 0; i < P; i++) { fv[(size_t)i * 8 + 0] = 0.5; fv[(size_t)i * 8 + 3] = 1.0; fv[(size_t)i * 8 + 6] = 1.0; }
+        CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
+        if (P > 0 && upload(c, c->fit, fv.data(), fv.size() * 8)) return OFG_ERR_CUDA;
+        CK(cudaStreamSynchronize(c->stream));  // fv goes out of scope
+        CK(cudaEventRecord(c->ev[3], c->stream));
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        CK(cudaEventRecord(c->ev[5], c->stream));
     } else {
-        CK(cudaMemsetAsync(c->sel_off.p, 0, 16, c->stream));
+        // ---- segmented stable radix sort by Lf
+        std::vector<int64_t> pair_slot(P + 1, 0), tile_prefix(P + 1, 0);
+        for (int i = 0; i < P; i++) {
+            pair_slot[i + 1] = pair_slot[i] + (int64_t)c->pair_valid[i];
+            tile_prefix[i + 1] = tile_prefix[i] + ((int64_t)c->pair_valid[i] + RS_TILE - 1) / RS_TILE;
+        }
+        const int64_t n_tiles = tile_prefix[P];
+        if (upload(c, c->pair_slot, pair_slot.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
+        if (upload(c, c->sort_tile_prefix, tile_prefix.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
+        const int n_pass = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+        const int pass_bits = (key_bits + n_pass - 1) / n_pass;
+        CK(c->key2.ensure((n_slots + 64) * 4));
+        CK(c->keyval2.ensure((n_slots + 64) * 8));
+        CK(c->counters.ensure(((size_t)n_tiles << pass_bits) * 4 + 64));
+        u32* kin = c->key.as<u32>(); double* vin = c->keyval.as<double>();
+        u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
+        if (n_tiles > 0) {
+            CK(c->sort_desc.ensure((size_t)n_tiles * sizeof(RsTileDesc)));
+            for (int pass = 0; pass < n_pass; pass++) {
+                RadixArgs a;
+                a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
+                a.tile_prefix = c->sort_tile_prefix.as<int64_t>(); a.pair_slot = c->pair_slot.as<int64_t>();
+                a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
+                a.desc = c->sort_desc.as<RsTileDesc>();
+                if (pass == 0) {
+                    rs_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(a, c->sort_desc.as<RsTileDesc>());
+                    CKL("rs_desc_kernel");
+                }
+                const int g = grid_for(c, n_tiles, 1, 2);  // scatter: two resident CTAs per SM (registers, shared memory)
+                radix_hist_kernel<<<grid_for(c, n_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
+                CKL("radix_hist_kernel");
+                if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
+                CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
+                radix_scatter_kernel<<<g, RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);
+                CKL("radix_scatter_kernel");
+                std::swap(kin, kout);
+                std::swap(vin, vout);
+            }
+        }
+        CK(cudaEventRecord(c->ev[3], c->stream));
+        // ---- bins
+        std::vector<BinTask> tasks;
+        std::vector<int64_t> task_prefix(P + 1, 0);
+        for (int i = 0; i < P; i++) {
+            const u64 H = c->pair_nnz[i];
+            const u32 first = (u32)pair_slot[i];
+            if (H > 0 && H < 100) {
+                tasks.push_back(BinTask{first, (u32)H, i, 1});
+            } else if (H >= 100) {
+                const u32 n_in = H > 5000 ? 1000u : (H > 1000 ? 200u : 20u);
+                const u64 n_bins = H / n_in;
+                for (u64 b = 0; b < n_bins; b++) tasks.push_back(BinTask{(u32)(first + b * n_in), n_in, i, 0});
+            }
+            task_prefix[i + 1] = (int64_t)tasks.size();
+        }
+        const int64_t n_tasks = (int64_t)tasks.size();
+        if (upload(c, c->bin_tasks, tasks.data(), sizeof(BinTask) * tasks.size())) return OFG_ERR_CUDA;
+        std::vector<u64> tp64(task_prefix.begin(), task_prefix.end());
+        if (upload(c, c->task_prefix, tp64.data(), sizeof(u64) * (P + 1))) return OFG_ERR_CUDA;
+        CK(c->bin_cut.ensure((size_t)(n_tasks + 1) * 8));
+        CK(c->bin_cnt.ensure((size_t)(n_tasks + 1) * 4));
+        CK(c->sel_off.ensure((size_t)(n_tasks + 2) * 8));
+        c->sel_cap = std::max<u64>(n_slots / (u64)std::max<int64_t>(c->sel_frac_inv, 1), 1u << 16);
+        if (c->sel_cap > n_slots + 1) c->sel_cap = n_slots + 1;
+        CK(c->lx.ensure(c->sel_cap * 8)); CK(c->ly.ensure(c->sel_cap * 8));
+        CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
+        CK(cudaMemsetAsync(c->fit.p, 0, (size_t)P * 8 * 8, c->stream));
+        BinArgs b;
+        b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks = n_tasks; b.key = kin; b.val = vin;
+        {
+            // numpy: virtual index (n-1)*q with q = 95/100, gamma = vi - floor(vi)
+            const double q = 95.0 / 100.0;
+            const double v20 = 19.0 * q, v200 = 199.0 * q, v1000 = 999.0 * q;
+            b.k20 = (int)floor(v20); b.g20 = v20 - floor(v20);
+            b.k200 = (int)floor(v200); b.g200 = v200 - floor(v200);
+            b.k1000 = (int)floor(v1000); b.g1000 = v1000 - floor(v1000);
+        }
+        b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
+        b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
+        // staging: two free fp64 arrays of at least n_slots entries - the parse output scores and the idle sort buffer
+        b.stage_lx = c->coo_val.as<double>(); b.stage_ly = vout;
+        if (n_tasks > 0) {
+            const int g = grid_for(c, n_tasks, BIN_WARPS, 6);
+            bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
+            CKL("bin_cut_kernel");
+            if (device_scan<u64>(c, b.cnt, n_tasks, c->sel_off.as<u64>(), 1)) return OFG_ERR_CUDA;
+            bin_select_kernel<<<grid_for(c, n_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
+            CKL("bin_select_kernel");
+        } else {
+            CK(cudaMemsetAsync(c->sel_off.p, 0, 16, c->stream));
+        }
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        // ---- fit
+        CK(c->pair_sel_off.ensure((size_t)(P + 2) * 8));
+        gather_u64_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(c->sel_off.as<u64>(), c->task_prefix.as<u64>(), P + 1,
+                                                                       c->pair_sel_off.as<u64>());
+        CKL("gather_u64_kernel");
+        FitArgs f;
+        f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
+        f.fit = c->fit.as<double>(); f.err_flags = err_flags;
+        if (P > 0) {
+            CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
+            fit_kernel<<<P, FIT_THREADS, sizeof(FitShared), c->stream>>>(f);
+            CKL("fit_kernel");
+        }
+        CK(cudaEventRecord(c->ev[5], c->stream));
     }
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    // ---- fit
-    CK(c->pair_sel_off.ensure((size_t)(P + 2) * 8));
-    gather_u64_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(c->sel_off.as<u64>(), c->task_prefix.as<u64>(), P + 1,
-                                                                   c->pair_sel_off.as<u64>());
-    CKL("gather_u64_kernel");
-    FitArgs f;
-    f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
-    f.fit = c->fit.as<double>(); f.err_flags = err_flags;
-    if (P > 0) {
-        CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
-        fit_kernel<<<P, FIT_THREADS, sizeof(FitShared), c->stream>>>(f);
-        CKL("fit_kernel");
-    }
-    CK(cudaEventRecord(c->ev[5], c->stream));
     // ---- factors, scale, best hits
     CK(c->rowfac.ensure((size_t)(c->n_rows + 1) * 8));
     CK(c->colfac.ensure((size_t)(c->n_cols + 1) * 8));
@@ -636,8 +650,35 @@ int stage_thresh(ofg_ctx* c)
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
         g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
         g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
-        rbh_kernel<8><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
-        CKL("rbh_kernel");
+        g.zrow = nullptr; g.pair_factor = nullptr;
+        if (c->scores_v2) {
+            // gathering.py:314-388 GetMostDistant_s_estimate_from_relative_rbhs
+            CK(c->zrow.ensure((size_t)(c->n_rows + 1) * 8));
+            CK(cudaMemsetAsync(c->zrow.p, 0, (size_t)(c->n_rows + 1) * 8, c->stream));
+            std::vector<double> ones((size_t)P, 1.0);
+            std::vector<int32_t> owned(c->owned.begin(), c->owned.end());
+            if (upload(c, c->pair_factor, ones.data(), ones.size() * 8)) return OFG_ERR_CUDA;
+            if (upload(c, c->d_owned, owned.data(), owned.size() * 4)) return OFG_ERR_CUDA;
+            CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+            g.zrow = c->zrow.as<double>(); g.pair_factor = c->pair_factor.as<double>();
+            rbh_kernel<8, 1><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
+            CKL("rbh_kernel");
+            RatioArgs ra;
+            ra.pairs = c->d_pairs.as<PairDesc>(); ra.pair_of = c->d_pair_of.as<int32_t>(); ra.S = c->S;
+            ra.owned = c->d_owned.as<int32_t>(); ra.n_owned = (int)owned.size(); ra.zrow = c->zrow.as<double>();
+            ra.pair_factor = c->pair_factor.as<double>();
+            const int64_t n_tasks = (int64_t)owned.size() * c->S * c->S;
+            if (n_tasks > 0x7fffffffLL) return fail(c, OFG_ERR_CAPACITY, "too many species for the --scores-v2 ratio table (%lld tasks)", (long long)n_tasks);
+            if (n_tasks > 0) {
+                v2_ratio_kernel<<<(unsigned)n_tasks, 256, 0, c->stream>>>(ra);
+                CKL("v2_ratio_kernel");
+            }
+            rbh_kernel<8, 2><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
+            CKL("rbh_kernel");
+        } else {
+            rbh_kernel<8, 0><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
+            CKL("rbh_kernel");
+        }
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
                                                                                c->owned_gene.as<uint8_t>(), c->N);
         CKL("thresh_final_kernel");
@@ -657,7 +698,7 @@ int stage_connect(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr;
     if (P > 0 && c->n_rows > 0) {
         CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
@@ -679,7 +720,7 @@ int stage_emit(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr;
     // emission units: owned genes (list order) x S
     std::vector<int64_t> gene_of;
     std::vector<int32_t> sp_of;
@@ -761,7 +802,7 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
@@ -822,6 +863,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
 {
     if (!c || !name) return OFG_ERR_ARG;
     if (!strcmp(name, "allow_empty")) c->allow_empty = (int)value;
+    else if (!strcmp(name, "scores_v2")) c->scores_v2 = value != 0;
     else if (!strcmp(name, "max_bytes_per_line_inv")) c->bytes_per_line_inv = value;
     else if (!strcmp(name, "sel_capacity_frac_inv")) c->sel_frac_inv = value;
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }

@@ -222,6 +222,8 @@ struct GraphArgs {
     double* most;            // [nSeqs] thresholds (bit patterns while being reduced)
     const double* best;
     u32* row_flagcnt;        // [n_rows] connect entries per row (connect_kernel; pre-zeroed)
+    double* zrow;            // [n_rows] --scores-v2: the row's RBH score if it has exactly one RBH, else 0
+    const double* pair_factor;  // [P] --scores-v2: conversion factor of the pair's target species
 };
 
 // index of column `want` in the row [s0, s0+n) of the slotted CSR, or -1
@@ -237,9 +239,11 @@ __device__ __forceinline__ int64_t find_col(const u32* cols, u32 s0, int n, u32 
     return -1;
 }
 
-template <int ROW_G>
+template <int ROW_G, int MODE>
 __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
 {
+    // MODE 0: default thresholds (gathering.py:294-306).  --scores-v2 (:314-388) runs MODE 1 (per-row RBH score Z,
+    // :340) before the percentile ratios and MODE 2 (thresholds scaled by the species factor, :381-384) after.
     const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
     const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     int pair = -1;
@@ -263,6 +267,9 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
         }
         const int nmax = warp_max_over_groups<ROW_G>(n);
         int last = -1;  // largest k (column order) with an RBH
+        int n_rbh = 0;
+        double factor = 1.0;
+        if (MODE == 2 && n > 0) factor = a.pair_factor[pair];
         for (int k0 = 0; k0 < nmax; k0 += ROW_G) {
             const int k = k0 + gl;
             bool rbh = false;
@@ -281,8 +288,131 @@ __global__ void __launch_bounds__(256) rbh_kernel(GraphArgs a)
             }
             const u32 bal = (__ballot_sync(OFG_FULL, rbh) >> (sub * ROW_G)) & ((1u << ROW_G) - 1u);
             if (bal) last = k0 + (31 - __clz(bal));
+            n_rbh += __popc(bal);
         }
-        if (last >= 0 && gl == 0) atomic_min_pos_double(&a.most[gene], a.vals[s0 + last]);
+        if (MODE == 1) {
+            if (n > 0 && gl == 0) a.zrow[row] = n_rbh == 1 ? a.vals[s0 + last] : 0.0;
+        } else if (last >= 0 && gl == 0) {
+            atomic_min_pos_double(&a.most[gene], MODE == 2 ? __dmul_rn(factor, a.vals[s0 + last]) : a.vals[s0 + last]);
+        }
+    }
+}
+
+// --scores-v2, gathering.py:344-364: for query species p and every ordered pair (a, b) of other species, the
+// (100 - 90)th percentile (numpy 'linear') of Z[a][i] * (1 / Z[b][i]) over the genes i where both RBH scores exist;
+// the factor of species b is the minimum over a (with 1.0 for a == b and for "no common gene").  One CTA per
+// (p, a, b): the ratios are recomputed from the two Z rows in every pass of an 8-bit radix select on their bit
+// patterns (they stay L2-resident), no scratch.  pair_factor must hold 1.0 when this starts.
+struct RatioArgs {
+    const PairDesc* pairs;
+    const int32_t* pair_of;     // [S*S]
+    int S;
+    const int32_t* owned;       // [n_owned] query species of this context
+    int n_owned;
+    const double* zrow;
+    double* pair_factor;        // [P]
+};
+
+__device__ __forceinline__ bool v2_ratio(const double* za, const double* zb, int64_t i, double* out)
+{
+    const double x = za[i], y = zb[i];
+    const double r = __dmul_rn(x, __ddiv_rn(1.0, y));  // Z[a] * Zr[b] with Zr = 1. / Z (:342,:349)
+    *out = r;
+    return r > 0.0 && r < INFINITY;                     // np.isfinite(ratios) & (ratios > 0); nan (0 * inf) fails both
+}
+
+__global__ void __launch_bounds__(256) v2_ratio_kernel(RatioArgs a)
+{
+    __shared__ u32 s_hist[256];
+    __shared__ u64 s_red[8];
+    __shared__ u32 s_cnt[8];
+    __shared__ u64 s_prefix;
+    __shared__ int s_kk;
+    const int S = a.S;
+    const int64_t task = blockIdx.x;
+    const int p = a.owned[task / ((int64_t)S * S)];
+    const int ka = (int)((task / S) % S), kb = (int)(task % S);
+    if (ka == p || kb == p || ka == kb) return;
+    const int pa = a.pair_of[p * S + ka], pb = a.pair_of[p * S + kb];
+    if (pa < 0 || pb < 0) return;  // a missing species pair has no RBHs: no conversion, factor 1.0 (:352-353)
+    const PairDesc& da = a.pairs[pa];
+    const double* za = a.zrow + da.row_base;
+    const double* zb = a.zrow + a.pairs[pb].row_base;
+    const int64_t n_i = da.Gi;
+    const int tid = threadIdx.x, lane = lane_id(), w = tid >> 5;
+    // ---- how many genes have both scores
+    u32 c = 0;
+    for (int64_t i = tid; i < n_i; i += 256) { double r; c += v2_ratio(za, zb, i, &r) ? 1u : 0u; }
+    c = warp_incl_scan(c);
+    if (lane == 31) s_cnt[w] = c;
+    __syncthreads();
+    u32 n = 0;
+    for (int i = 0; i < 8; i++) n += s_cnt[i];
+    if (n == 0) return;
+    // ---- numpy percentile(ratios, 10), method 'linear': virtual index (n - 1) * 0.1
+    const double vi = __dmul_rn((double)(n - 1), 10.0 / 100.0);
+    const bool top = vi >= (double)(n - 1);          // only n == 1: both neighbours are the last element
+    const u32 k = top ? n - 1 : (u32)floor(vi);
+    const double gamma = top ? 0.0 : __dsub_rn(vi, floor(vi));
+    // ---- k-th smallest by radix select over the 64-bit patterns (positive doubles: unsigned order == numeric order)
+    if (tid == 0) { s_prefix = 0; s_kk = (int)k; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        s_hist[tid] = 0;
+        __syncthreads();
+        const u64 prefix = s_prefix;
+        for (int64_t i = tid; i < n_i; i += 256) {
+            double r;
+            if (v2_ratio(za, zb, i, &r)) {
+                const u64 b = (u64)__double_as_longlong(r);
+                if (shift == 56 || (b >> (shift + 8)) == prefix) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int kk = s_kk;
+            u32 run = 0;
+            int bucket = 255;
+            for (int d = 0; d < 256; d++) {
+                if ((u32)kk < run + s_hist[d]) { bucket = d; break; }
+                run += s_hist[d];
+            }
+            s_kk = kk - (int)run;
+            s_prefix = (prefix << 8) | (u64)bucket;
+        }
+        __syncthreads();
+    }
+    const u64 ak = s_prefix;
+    // ---- the next order statistic: ak again if it has duplicates reaching index k + 1, else the smallest value above
+    u32 n_le = 0;
+    u64 above = ~0ULL;
+    for (int64_t i = tid; i < n_i; i += 256) {
+        double r;
+        if (v2_ratio(za, zb, i, &r)) {
+            const u64 b = (u64)__double_as_longlong(r);
+            n_le += b <= ak;
+            if (b > ak && b < above) above = b;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        n_le += __shfl_xor_sync(OFG_FULL, n_le, d);
+        const u64 o = __shfl_xor_sync(OFG_FULL, above, d);
+        above = o < above ? o : above;
+    }
+    __syncthreads();
+    if (lane == 0) { s_cnt[w] = n_le; s_red[w] = above; }
+    __syncthreads();
+    if (tid == 0) {
+        u32 tot = 0;
+        u64 m = ~0ULL;
+        for (int i = 0; i < 8; i++) { tot += s_cnt[i]; m = s_red[i] < m ? s_red[i] : m; }
+        const u64 ak1 = (top || tot > k + 1 || m == ~0ULL) ? ak : m;
+        const double va = __longlong_as_double((long long)ak), vb = __longlong_as_double((long long)ak1);
+        // numpy _lerp: a + (b - a) t, and b - (b - a)(1 - t) where t >= 0.5
+        const double diff = __dsub_rn(vb, va);
+        double r = __dadd_rn(va, __dmul_rn(diff, gamma));
+        if (gamma >= 0.5) r = __dsub_rn(vb, __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+        atomic_min_pos_double(&a.pair_factor[pb], r);  // column minimum over a (:364)
     }
 }
 

@@ -416,13 +416,12 @@ class WaterfallMethod:
                    builder=None):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
         the device-resident graph.  Returns the GraphBuilder holding it."""
-        if v2_scores:
-            raise NotImplementedError("--scores-v2 (gathering.py:157-174,314-388) is not on the device path yet")
         gb = builder or GraphBuilder(device)
         sp = list(seqsInfo.speciesToUse)
         n_seqs = [seqsInfo.nSeqsPerSpecies[k] for k in sp]
         gb.set_species(n_seqs, Lengths)
         gb.set_option("allow_empty", int(q_allow_empty))
+        gb.set_option("scores_v2", int(bool(v2_scores)))  # --scores-v2: gathering.py:157-174, :314-388
         for p, kp in enumerate(sp):
             for j, kj in enumerate(sp):
                 swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54

@@ -163,6 +163,26 @@ def test_graph_equals_reference(gb, name):
         assert edge_diff == 0 and dec_diff <= 2, (edge_diff, dec_diff)
 
 
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_graph_equals_reference_with_v2_scores(gb, name):
+    """`--scores-v2`: NormalisedBitScore + percentile-ratio thresholds on the device against the live
+    reference's v2 graph (tests/golden, byte for byte) and the oracle's thresholds."""
+    g = Golden(name)
+    gb.set_option("scores_v2", 1)
+    try:
+        _load(gb, g.n_seqs, g.lengths, g.hit_text)
+        gb.build()
+        md = gb.thresholds()
+        assert md.shape == g.most_distant_v2.shape
+        assert np.max(np.abs(md - g.most_distant_v2) / g.most_distant_v2) <= REL_TOL
+        text = waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+        if text != g.graph_v2:
+            edge_diff, dec_diff = graph_text_diff(text, g.graph_v2)
+            assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
+    finally:
+        gb.set_option("scores_v2", 0)
+
+
 def test_device_synth_is_byte_identical_to_host(gb):
     for cfg in ("C2_tiny", "C5_small"):
         ids, n_seqs, L, P = synth.config_inputs(cfg)
