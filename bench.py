@@ -141,6 +141,8 @@ def run_ours(args):
     S, G, P, L = workload(args, world)
     ids = list(range(S))
     gb = waterfall.GraphBuilder(local)
+    if args.scores_v2:
+        gb.set_option("scores_v2", 1)   # variant path, not the headline configuration
     gb.set_species([G] * S, L)
     parts = sharding.partition_rows(S, world)
     owned = parts[rank]
@@ -236,6 +238,7 @@ def run_ours(args):
            "config": {"workload": "%s: %d species x %d genes, hq=%d (%d pairs, %d hit lines, %.2f GB text%s)" % (
                args.config, S, G, P.hq, S * S, int(lines_all), text_bytes_all * (world if world > 1 else 1) / 1e9,
                ", per-rank text incl. column pairs" if (world > 1 and not lists) else ""),
+               "scores": "v2 (NormalisedBitScore, percentile-ratio thresholds)" if args.scores_v2 else "default (length-normalised fit)",
                "species": S, "genes_per_species": G, "hits_per_query_per_pair": P.hq, "lines": int(lines_all),
                "parallelism": "1 GPU" if world == 1 else (
                    "query species sharded over %d GPUs, rows only; transposed best-hit and connect index lists "
@@ -422,6 +425,7 @@ def main():
     ap.add_argument("--exchange", default="lists", choices=["lists", "thresholds"],
                     help="multi-GPU: 'lists' = design B (sparse all-to-all), 'thresholds' = design A (column re-parse + all-reduce)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scores-v2", action="store_true", help="measure the --scores-v2 variant of the path instead of the default scores")
     ap.add_argument("--phase-timing", action="store_true", help="N > 1: add a per-phase wall-clock breakdown of one extra step")
     ap.add_argument("--e2e-parts", type=int, default=4, help="row partitions of the pipelined e2e run (1 = single context)")
     ap.add_argument("--e2e-check", action="store_true", help="compare the e2e graph text with the device-resident run's")
