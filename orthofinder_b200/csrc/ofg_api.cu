@@ -86,7 +86,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf sort_desc, zrow, pair_factor, d_owned, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -650,7 +650,7 @@ int stage_thresh(ofg_ctx* c)
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
         g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
         g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr;
-        g.zrow = nullptr; g.pair_factor = nullptr;
+        g.zrow = nullptr; g.pair_factor = nullptr; g.gene_cnt = nullptr; g.gene_bytes = nullptr; g.err_flags = nullptr;
         if (c->scores_v2) {
             // gathering.py:314-388 GetMostDistant_s_estimate_from_relative_rbhs
             CK(c->zrow.ensure((size_t)(c->n_rows + 1) * 8));
@@ -698,11 +698,17 @@ int stage_connect(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr;
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr; g.gene_cnt = nullptr; g.gene_bytes = nullptr; g.err_flags = nullptr;
+    // per-gene edge / text-byte counters, maintained by connect_kernel and by REVERSE imports (edge_account)
+    CK(c->gene_cntg.ensure((size_t)(c->N + 1) * 4));
+    CK(c->gene_bytesg.ensure((size_t)(c->N + 1) * 4));
+    CK(cudaMemsetAsync(c->gene_cntg.p, 0, (size_t)(c->N + 1) * 4, c->stream));
+    CK(cudaMemsetAsync(c->gene_bytesg.p, 0, (size_t)(c->N + 1) * 4, c->stream));
     if (P > 0 && c->n_rows > 0) {
         CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
         g.row_flagcnt = c->row_flagcnt.as<u32>();
+        g.gene_cnt = c->gene_cntg.as<u32>(); g.gene_bytes = c->gene_bytesg.as<u32>(); g.err_flags = (u32*)(c->d_small.as<u64>() + 2);
         connect_kernel<16><<<grid_for(c, c->n_rows, 16, 8), 256, 0, c->stream>>>(g);
         CKL("connect_kernel");
     }
@@ -720,7 +726,7 @@ int stage_emit(ofg_ctx* c)
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
-    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr;
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr; g.gene_cnt = nullptr; g.gene_bytes = nullptr; g.err_flags = nullptr;
     // emission units: owned genes (list order) x S
     std::vector<int64_t> gene_of;
     std::vector<int32_t> sp_of;
@@ -746,8 +752,8 @@ int stage_emit(ofg_ctx* c)
     c->tot_edges = 0; c->tot_text = 0;
     if (n_units > 0) {
         const int ge = grid_for(c, n_units, EMIT_WARPS, 6);
-        emit_kernel<false><<<ge, EMIT_WARPS * 32, 0, c->stream>>>(e);
-        CKL("emit_kernel<false>");
+        emit_sizes_kernel<<<grid_for(c, n_units, 256, 4), 256, 0, c->stream>>>(e, c->gene_cntg.as<u32>(), c->gene_bytesg.as<u32>());
+        CKL("emit_sizes_kernel");
         if (device_scan<u64>(c, e.gene_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         if (device_scan<u64>(c, e.gene_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         u64 tots[2] = {0, 0};
@@ -802,7 +808,7 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
@@ -1149,7 +1155,7 @@ int ofg_import_flags(ofg_ctx* c, int which, const int32_t* dev_list, int64_t n_e
     a.list = reinterpret_cast<const int2*>(dev_list); a.n = n_entries; a.seq_start = c->d_seq_start.as<int64_t>(); a.S = c->S;
     a.pair_of = c->d_pair_of.as<int32_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.row_start = c->row_start.as<u32>();
     a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>(); a.set_flag = which == 0 ? OFG_FLAG_TBH : OFG_FLAG_REVERSE;
-    a.err_flags = err_flags;
+    a.err_flags = err_flags; a.vals = c->vals.as<double>(); a.gene_cnt = c->gene_cntg.as<u32>(); a.gene_bytes = c->gene_bytesg.as<u32>();
     import_flags_kernel<<<grid_for(c, n_entries, 256, 8), 256, 0, c->stream>>>(a);
     CKL("import_flags_kernel");
     u32 flags = 0;

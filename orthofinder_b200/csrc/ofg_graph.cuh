@@ -224,6 +224,9 @@ struct GraphArgs {
     u32* row_flagcnt;        // [n_rows] connect entries per row (connect_kernel; pre-zeroed)
     double* zrow;            // [n_rows] --scores-v2: the row's RBH score if it has exactly one RBH, else 0
     const double* pair_factor;  // [P] --scores-v2: conversion factor of the pair's target species
+    u32* gene_cnt;           // [nSeqs] edges of every graph row, [nSeqs] text bytes of its entries (edge_account)
+    u32* gene_bytes;
+    u32* err_flags;
 };
 
 // index of column `want` in the row [s0, s0+n) of the slotted CSR, or -1
@@ -426,117 +429,7 @@ __global__ void thresh_final_kernel(double* most, const double* best, const uint
 }
 
 // ---------------------------------------------------------------- connect
-template <int ROW_G>
-__global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
-{
-    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
-    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
-    int pair = -1;
-    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
-        const int64_t row = row0 + sub;
-        const int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
-        u32 nconn = 0;
-        if (n > 0) {
-            pair = advance_pair(a.pair_row_base, a.P, pair, row);
-            const PairDesc& pd = a.pairs[pair];
-            const u32 s0 = a.row_start[row];
-            const u32 r = (u32)(row - pd.row_base);
-            const double md = a.most[pd.gi_start + r];
-            const int tp = a.pair_of[pd.j * a.S + pd.p];
-            for (int k = gl; k < n; k += ROW_G) {
-                const u32 cw = a.cols[s0 + k];
-                const u32 c = cw & OFG_COL_MASK;
-                if (a.vals[s0 + k] >= md && !(pd.same && c == r)) {
-                    nconn++;
-                    atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
-                    if (tp >= 0) {
-                        const PairDesc& td = a.pairs[tp];
-                        const int64_t trow = td.row_base + c;
-                        const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
-                        if (e >= 0) atomicOr(&a.cols[e], OFG_FLAG_REVERSE);
-                    }
-                }
-            }
-        }
-        nconn = group_sum<ROW_G>(nconn);
-        if (gl == 0 && n > 0) a.row_flagcnt[row] = nconn;
-    }
-}
-
-// ---------------------------------------------------------------- sparse exchange (design B)
-struct ExportArgs {
-    int64_t n_rows;
-    const u32* row_start;
-    const u32* rowlen;
-    const u32* cols;
-    const PairDesc* pairs;
-    const int64_t* pair_row_base;
-    int P;
-    const uint8_t* pair_export;  // [P] 1: pair (k, p) whose column species p is owned by another context
-    u32 flag;                    // OFG_FLAG_BH or OFG_FLAG_CONNECT
-    const u64* row_off;          // [n_rows + 1] exclusive scan of the per-row flag counts
-    const u64* pair_off;         // [P] first list slot of the pair (pairs grouped by destination rank)
-    int2* out;                   // (gene of remote species p, gene of local species k), global ids
-};
-
-// Deterministic single pass: every flagged entry of an exported pair goes to
-// pair_off[pair] + (entries of earlier rows of the pair) + (rank inside the row).
-__global__ void __launch_bounds__(256) export_flags_kernel(ExportArgs a)
-{
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    int pair = -1;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const u64 o0 = a.row_off[row];
-        if (a.row_off[row + 1] == o0) continue;  // nothing flagged in this row
-        pair = advance_pair(a.pair_row_base, a.P, pair, row);
-        if (!a.pair_export[pair]) continue;
-        const PairDesc& pd = a.pairs[pair];
-        const int n = (int)a.rowlen[row];
-        const u32 s0 = a.row_start[row];
-        const int r = (int)(row - pd.row_base);
-        u64 pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
-            const u32 cw = k < n ? a.cols[s0 + k] : 0u;
-            const bool on = (cw & a.flag) != 0;
-            const u32 bal = __ballot_sync(OFG_FULL, on);
-            if (on) a.out[pos + __popc(bal & lanemask_lt())] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
-            pos += __popc(bal);
-        }
-    }
-}
-
-struct ImportArgs {
-    const int2* list;
-    int64_t n;
-    const int64_t* seq_start;  // [S]
-    int S;
-    const int32_t* pair_of;
-    const PairDesc* pairs;
-    const u32* row_start;
-    const u32* rowlen;
-    u32* cols;
-    u32 set_flag;              // OFG_FLAG_TBH or OFG_FLAG_REVERSE
-    u32* err_flags;            // bit 3: an entry addressed a pair this context does not hold
-};
-
-__global__ void __launch_bounds__(256) import_flags_kernel(ImportArgs a)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int2 e = a.list[i];
-        const int p = upper_bound_dev(a.seq_start, a.S, (int64_t)e.x) - 1;  // local (row) species
-        const int k = upper_bound_dev(a.seq_start, a.S, (int64_t)e.y) - 1;  // species of the sender
-        const int pair = a.pair_of[p * a.S + k];
-        if (pair < 0) { atomicOr(a.err_flags, 8u); continue; }
-        const PairDesc& pd = a.pairs[pair];
-        const int64_t row = pd.row_base + ((int64_t)e.x - pd.gi_start);
-        const int64_t slot = find_col(a.cols, a.row_start[row], (int)a.rowlen[row], (u32)((int64_t)e.y - pd.gj_start));
-        if (slot >= 0) atomicOr(&a.cols[slot], a.set_flag);  // no stored hit in this direction: nothing to mark
-    }
-}
-
-// ---------------------------------------------------------------- emission
+// ---------------------------------------------------------------- text formatting (used by connect and emit)
 // exact "%.3f" digits of a non-negative finite double: X = round-half-even(v * 1000) on the exact
 // binary value (what glibc printf does); returns false if it does not fit 64 bits.
 __host__ __device__ __forceinline__ bool ofg_fixed3(double v, unsigned long long* X)
@@ -601,6 +494,172 @@ __host__ __device__ __forceinline__ int ofg_format_entry(unsigned long long gcol
     return n;
 }
 
+// Length of "%d:%.3f " without formatting it.  The integer part of the printed weight has more than j digits iff
+// round-half-even(w * 1000) >= 10^(j+3), i.e. iff w >= T_j, the smallest double >= (2 * 10^(j+3) - 1) / 2000 (that
+// rational is never a double, so there is no tie to break); T_j computed with exact rational arithmetic.
+__device__ __constant__ double OFG_IP_DIGIT_THR[16] = {
+    0x1.3ffbe76c8b43ap+3, 0x1.8fff7ced91688p+6, 0x1.f3ffef9db22d1p+9, 0x1.387ffef9db22ep+13, 0x1.869fffdf3b646p+16,
+    0x1.e847fffbe76c9p+19, 0x1.312cffffbe76dp+23, 0x1.7d783ffff7ceep+26, 0x1.dcd64ffffef9ep+29, 0x1.2a05f1ffffefap+33,
+    0x1.74876e7ffffe0p+36, 0x1.d1a94a1fffffcp+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49,
+    0x1.1c37937e08000p+53};
+__device__ __forceinline__ int ofg_entry_len(unsigned long long gcol, double w, bool* ok)
+{
+    int nd = 1;
+#pragma unroll
+    for (int j = 0; j < 16; j++) nd += w >= OFG_IP_DIGIT_THR[j];
+    if (!(w < 18446744073709552.0)) *ok = false;  // w * 1000 >= 2^64: ofg_fixed3 does not fit (or w is not finite)
+    return ofg_ndigits(gcol) + 1 + nd + 1 + 3 + 1;
+}
+
+// Edge bookkeeping of the graph rows, kept while the flags are set so that no separate counting sweep is needed.
+// An entry is an edge if it or its transposed entry passes the threshold test.  The thread whose OWN entry passes
+// looks the transposed entry up anyway; it evaluates that entry's test as well and books (a) its own edge with weight
+// B or 2 B and (b) the transposed edge if the transposed test fails (otherwise the transposed thread books it).  No
+// atomic has to return a value.  When the transposed pair lives in another context the REVERSE import books the
+// second half (import_flags_kernel).
+__device__ __forceinline__ void edge_account(u32* gene_cnt, u32* gene_bytes, u32* err_flags, int64_t gene, u64 gcol, double w, bool new_edge,
+                                             double w_before)
+{
+    bool ok = true;
+    if (new_edge) {
+        atomicAdd(&gene_cnt[gene], 1u);
+        atomicAdd(&gene_bytes[gene], (u32)ofg_entry_len(gcol, w, &ok));
+    } else {  // the weight of an edge booked earlier changes from w_before to w
+        const int d = ofg_entry_len(gcol, w, &ok) - ofg_entry_len(gcol, w_before, &ok);
+        if (d) atomicAdd(&gene_bytes[gene], (u32)d);
+    }
+    if (!ok) atomicOr(err_flags, 4u);
+}
+
+template <int ROW_G>
+__global__ void __launch_bounds__(256) connect_kernel(GraphArgs a)
+{
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
+    int pair = -1;
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        const int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
+        u32 nconn = 0;
+        if (n > 0) {
+            pair = advance_pair(a.pair_row_base, a.P, pair, row);
+            const PairDesc& pd = a.pairs[pair];
+            const u32 s0 = a.row_start[row];
+            const u32 r = (u32)(row - pd.row_base);
+            const double md = a.most[pd.gi_start + r];
+            const int tp = a.pair_of[pd.j * a.S + pd.p];
+            for (int k = gl; k < n; k += ROW_G) {
+                const u32 cw = a.cols[s0 + k];
+                const u32 c = cw & OFG_COL_MASK;
+                const double v = a.vals[s0 + k];
+                if (v >= md && !(pd.same && c == r)) {
+                    nconn++;
+                    atomicOr(&a.cols[s0 + k], OFG_FLAG_CONNECT);
+                    bool t_pass = false;  // does the transposed entry pass its own test?
+                    if (tp >= 0) {
+                        const PairDesc& td = a.pairs[tp];
+                        const int64_t trow = td.row_base + c;
+                        const int64_t e = find_col(a.cols, a.row_start[trow], (int)a.rowlen[trow], r);
+                        if (e >= 0) {
+                            atomicOr(&a.cols[e], OFG_FLAG_REVERSE);
+                            const double tv = a.vals[e];
+                            t_pass = tv >= a.most[pd.gj_start + c];   // (c, r) is off the diagonal because (r, c) is
+                            if (!t_pass) edge_account(a.gene_cnt, a.gene_bytes, a.err_flags, pd.gj_start + c, (u64)(pd.gi_start + r), tv, true, 0.0);
+                        }
+                    }
+                    edge_account(a.gene_cnt, a.gene_bytes, a.err_flags, pd.gi_start + r, (u64)(pd.gj_start + c), t_pass ? __dmul_rn(2.0, v) : v, true, 0.0);
+                }
+            }
+        }
+        nconn = group_sum<ROW_G>(nconn);
+        if (gl == 0 && n > 0) a.row_flagcnt[row] = nconn;
+    }
+}
+
+// ---------------------------------------------------------------- sparse exchange (design B)
+struct ExportArgs {
+    int64_t n_rows;
+    const u32* row_start;
+    const u32* rowlen;
+    const u32* cols;
+    const PairDesc* pairs;
+    const int64_t* pair_row_base;
+    int P;
+    const uint8_t* pair_export;  // [P] 1: pair (k, p) whose column species p is owned by another context
+    u32 flag;                    // OFG_FLAG_BH or OFG_FLAG_CONNECT
+    const u64* row_off;          // [n_rows + 1] exclusive scan of the per-row flag counts
+    const u64* pair_off;         // [P] first list slot of the pair (pairs grouped by destination rank)
+    int2* out;                   // (gene of remote species p, gene of local species k), global ids
+};
+
+// Deterministic single pass: every flagged entry of an exported pair goes to
+// pair_off[pair] + (entries of earlier rows of the pair) + (rank inside the row).
+__global__ void __launch_bounds__(256) export_flags_kernel(ExportArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int pair = -1;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const u64 o0 = a.row_off[row];
+        if (a.row_off[row + 1] == o0) continue;  // nothing flagged in this row
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
+        if (!a.pair_export[pair]) continue;
+        const PairDesc& pd = a.pairs[pair];
+        const int n = (int)a.rowlen[row];
+        const u32 s0 = a.row_start[row];
+        const int r = (int)(row - pd.row_base);
+        u64 pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const u32 cw = k < n ? a.cols[s0 + k] : 0u;
+            const bool on = (cw & a.flag) != 0;
+            const u32 bal = __ballot_sync(OFG_FULL, on);
+            if (on) a.out[pos + __popc(bal & lanemask_lt())] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
+            pos += __popc(bal);
+        }
+    }
+}
+
+struct ImportArgs {
+    const int2* list;
+    int64_t n;
+    const int64_t* seq_start;  // [S]
+    int S;
+    const int32_t* pair_of;
+    const PairDesc* pairs;
+    const u32* row_start;
+    const u32* rowlen;
+    u32* cols;
+    u32 set_flag;              // OFG_FLAG_TBH or OFG_FLAG_REVERSE
+    u32* err_flags;            // bit 3: an entry addressed a pair this context does not hold
+    const double* vals;        // REVERSE imports also keep the edge bookkeeping (edge_account)
+    u32* gene_cnt;
+    u32* gene_bytes;
+};
+
+__global__ void __launch_bounds__(256) import_flags_kernel(ImportArgs a)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 e = a.list[i];
+        const int p = upper_bound_dev(a.seq_start, a.S, (int64_t)e.x) - 1;  // local (row) species
+        const int k = upper_bound_dev(a.seq_start, a.S, (int64_t)e.y) - 1;  // species of the sender
+        const int pair = a.pair_of[p * a.S + k];
+        if (pair < 0) { atomicOr(a.err_flags, 8u); continue; }
+        const PairDesc& pd = a.pairs[pair];
+        const int64_t row = pd.row_base + ((int64_t)e.x - pd.gi_start);
+        const int64_t slot = find_col(a.cols, a.row_start[row], (int)a.rowlen[row], (u32)((int64_t)e.y - pd.gj_start));
+        if (slot >= 0) {  // no stored hit in this direction: nothing to mark
+            const u32 old = atomicOr(&a.cols[slot], a.set_flag);
+            if (a.set_flag == OFG_FLAG_REVERSE && !(old & OFG_FLAG_REVERSE)) {  // connect_kernel has finished: CONNECT is final
+                const double v = a.vals[slot];
+                if (old & OFG_FLAG_CONNECT) edge_account(a.gene_cnt, a.gene_bytes, a.err_flags, (int64_t)e.x, (u64)e.y, __dmul_rn(2.0, v), false, v);
+                else edge_account(a.gene_cnt, a.gene_bytes, a.err_flags, (int64_t)e.x, (u64)e.y, v, true, 0.0);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- emission
 struct EmitArgs {
     GraphArgs g;
     int64_t n_genes;          // owned genes, list order
@@ -616,6 +675,17 @@ struct EmitArgs {
     char* out_text;
     u32* err_flags;           // bit 2: a weight could not be formatted
 };
+
+// Per graph row (owned gene, list order): number of edges and text bytes = "%d    " + entries + "$\n" (gathering.py:42-47),
+// from the counters kept by edge_account.
+__global__ void emit_sizes_kernel(EmitArgs a, const u32* gene_cnt_global, const u32* gene_bytes_global)
+{
+    for (int64_t lg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; lg < a.n_genes; lg += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gene = a.gene_of_local[lg];
+        a.gene_cnt[lg] = gene_cnt_global[gene];
+        a.gene_bytes[lg] = gene_bytes_global[gene] + (u32)ofg_ndigits((unsigned long long)gene) + 4u + 2u;
+    }
+}
 
 constexpr int EMIT_WARPS = 8;
 constexpr int EMIT_LIST = 64;  // edges buffered per warp before they are formatted
