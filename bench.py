@@ -88,8 +88,9 @@ def workload(args, n_gpus):
         pk["hq"] = args.hq
     if n_gpus > 1 and not args.species:
         # weak scaling: the pair grid (S^2) grows with the GPU count so that every GPU keeps ~256 owned pairs; S is
-        # the multiple of the GPU count nearest to 16 sqrt(N), so every rank owns the same number of query species
-        S = n_gpus * max(1, int(round(cfg["S"] * n_gpus ** 0.5 / n_gpus)))
+        # the largest multiple of the GPU count not above 16 sqrt(N), so every rank owns the same number of query
+        # species and never more text than the single-GPU job (the e2e leg pins every rank's text in host memory)
+        S = n_gpus * max(1, int(cfg["S"] * n_gpus ** 0.5 / n_gpus))
     P = synth.params(**pk)
     L = synth.make_lengths(S, G, P.seed, twins=P.p_twin_permille > 0, n_distinct=12 if P.ident_levels else 0)
     return S, G, P, L
