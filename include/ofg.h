@@ -100,7 +100,10 @@ int ofg_hits_text_size(ofg_ctx* ctx, int p, int j, size_t* nbytes);
 int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
 
 /* Options: "allow_empty" (0/1), "max_bytes_per_line_inv" (capacity: records <= bytes/this, default 24),
- * "sel_capacity_frac_inv" (fit scratch = records/this, default 4). */
+ * "sel_capacity_frac_inv" (selection capacity = records/this, default 4), "reserve_text_bytes" (size the text arena
+ * once), "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)
+ * instead of the length-bin fit and GetMostDistant_s_estimate_from_relative_rbhs (gathering.py:314-388) instead of
+ * GetMostDistant_s; what the reference passes as v2_scores to ProcessBlastHits / ConnectCognates (:177, :251). */
 int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
 
 /* Run the path up to and including `stop_after` (OFG_STAGE_*).  OFG_STAGE_THRESH stops before the
