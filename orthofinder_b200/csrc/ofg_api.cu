@@ -72,6 +72,7 @@ struct ofg_ctx {
     std::vector<FileInfo> files;
     // options
     int allow_empty = 0;
+    bool layout_dirty = true;   // species / partition changed: per-gene constant vectors must be rebuilt on the device
     bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
@@ -86,7 +87,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -636,15 +637,26 @@ int stage_thresh(ofg_ctx* c)
 {
     mark_timeline(c);
     const int P = (int)c->pairs.size();
-    // owned gene mask and initial thresholds: 1e9 for owned genes (gathering.py:296), +inf elsewhere
-    std::vector<uint8_t> og((size_t)c->N + 1, 0);
-    std::vector<double> init((size_t)c->N + 1, INFINITY);
-    for (int p : c->owned)
-        for (int64_t g = c->seq_start[p]; g < c->seq_start[p] + c->n_seqs[p]; g++) { og[g] = 1; init[g] = 1e9; }
-    if (upload(c, c->owned_gene, og.data(), og.size())) return OFG_ERR_CUDA;
-    if (upload(c, c->most, init.data(), init.size() * 8)) return OFG_ERR_CUDA;
-    CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);  // host vectors go out of scope
+    // owned gene mask and initial thresholds: 1e9 for owned genes (gathering.py:296), +inf elsewhere.  Both depend
+    // only on the species / partition layout: built once and kept on the device.
+    if (c->layout_dirty) {
+        std::vector<uint8_t> og((size_t)c->N + 1, 0);
+        std::vector<double> init((size_t)c->N + 1, INFINITY);
+        for (int p : c->owned)
+            for (int64_t g = c->seq_start[p]; g < c->seq_start[p] + c->n_seqs[p]; g++) { og[g] = 1; init[g] = 1e9; }
+        if (upload(c, c->owned_gene, og.data(), og.size())) return OFG_ERR_CUDA;
+        if (upload(c, c->most_init, init.data(), init.size() * 8)) return OFG_ERR_CUDA;
+        std::vector<int64_t> gene_of;
+        std::vector<int32_t> sp_of;
+        for (int p : c->owned)
+            for (int64_t q = 0; q < c->n_seqs[p]; q++) { gene_of.push_back(c->seq_start[p] + q); sp_of.push_back(p); }
+        if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
+        if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
+        CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+        c->layout_dirty = false;
+    }
+    CK(c->most.ensure((size_t)(c->N + 1) * 8));
+    CK(cudaMemcpyAsync(c->most.p, c->most_init.p, (size_t)(c->N + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
     if (P > 0 && c->n_rows > 0) {
         GraphArgs g;
         g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
@@ -727,18 +739,9 @@ int stage_emit(ofg_ctx* c)
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
     g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = c->most.as<double>(); g.best = c->best.as<double>(); g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr; g.gene_cnt = nullptr; g.gene_bytes = nullptr; g.err_flags = nullptr;
-    // emission units: owned genes (list order) x S
-    std::vector<int64_t> gene_of;
-    std::vector<int32_t> sp_of;
-    gene_of.reserve((size_t)c->n_owned_genes);
-    sp_of.reserve((size_t)c->n_owned_genes);
-    for (int p : c->owned)
-        for (int64_t q = 0; q < c->n_seqs[p]; q++) { gene_of.push_back(c->seq_start[p] + q); sp_of.push_back(p); }
-    const int64_t n_units = (int64_t)gene_of.size();  // one unit per graph row (gene)
-    if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
-    if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
-    CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);
+    // emission units: owned genes in list order, one per graph row (gene_of_local / species_of_local are layout
+    // constants uploaded by stage_thresh)
+    const int64_t n_units = c->n_owned_genes;
     CK(c->unit_cnt.ensure((size_t)(n_units + 1) * 4));
     CK(c->unit_bytes.ensure((size_t)(n_units + 1) * 4));
     CK(c->cnt_off.ensure((size_t)(n_units + 2) * 8));
@@ -808,7 +811,7 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg, &c->most_init,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
@@ -828,6 +831,7 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     if (!c || n_species <= 0 || !n_seqs || !lengths_concat) return c ? fail(c, OFG_ERR_ARG, "bad arguments to ofg_set_species") : OFG_ERR_ARG;
     cudaSetDevice(c->device);
     c->S = n_species;
+    c->layout_dirty = true;
     c->n_seqs.assign(n_seqs, n_seqs + n_species);
     c->seq_start.assign(n_species, 0);
     c->len_off.assign(n_species, 0);
@@ -854,6 +858,7 @@ int ofg_set_partition(ofg_ctx* c, int n_owned, const int32_t* owned_rows, int wi
 {
     if (!c) return OFG_ERR_ARG;
     if (c->S <= 0) return fail(c, OFG_ERR_ARG, "call ofg_set_species first");
+    c->layout_dirty = true;
     std::vector<int32_t> o;
     for (int i = 0; i < n_owned; i++) {
         if (owned_rows[i] < 0 || owned_rows[i] >= c->S) return fail(c, OFG_ERR_ARG, "owned row %d out of range", owned_rows[i]);
