@@ -118,3 +118,19 @@ def test_partition_is_balanced_and_complete():
     assert max(loads) - min(loads) <= 2
     rows, cols = sharding.rank_pairs(parts[0], 8)
     assert len(rows) == len(parts[0]) * 8 and len(cols) == len(parts[0]) * (8 - len(parts[0]))
+
+
+def test_contiguous_partitions_cover_all_species_in_order():
+    """sharding.contiguous_partitions (row partitions of the single-GPU copy/compute pipeline): contiguous, ordered,
+    non-empty, balanced by weight."""
+    from orthofinder_b200 import sharding
+    for S in (1, 2, 3, 5, 16, 23, 64):
+        for G in (1, 2, 4, 7, 100):
+            parts = sharding.contiguous_partitions(S, G)
+            assert len(parts) == min(S, G) and all(parts)
+            assert [p for part in parts for p in part] == list(range(S))
+            assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
+    parts = sharding.contiguous_partitions(6, 3, [100, 1, 1, 1, 1, 100])
+    assert parts[0] == [0] and parts[-1][-1] == 5 and [p for part in parts for p in part] == list(range(6))
+    owner = sharding.species_owner(parts, 6)
+    assert list(owner) == [g for g, part in enumerate(parts) for _ in part]
