@@ -87,6 +87,31 @@ __global__ void k_distinct(u32* out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// 9-bit digit matched as two narrower matches (low 5 bits, high 4 bits) whose results are ANDed
+template <int MODE>
+__global__ void k_split(const u32* in, u32* out, int iters)
+{
+    u32 v[8];
+    for (int i = 0; i < 8; i++) v[i] = in[(threadIdx.x + i * 97 + blockIdx.x) & 4095];
+    u32 acc = 0;
+    for (int it = 0; it < iters; it++) {
+        u32 p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 d = (v[i] + it * 7) & 511u;
+            if (MODE == 0) p[i] = __match_any_sync(0xffffffffu, d & 31u) & __match_any_sync(0xffffffffu, d >> 5);
+            else if (MODE == 1) p[i] = __match_any_sync(0xffffffffu, d & 15u) & __match_any_sync(0xffffffffu, (d >> 4) & 7u) & __match_any_sync(0xffffffffu, d >> 7);
+            else if (MODE == 3) p[i] = __match_any_sync(0xffffffffu, d & 7u) & __match_any_sync(0xffffffffu, (d >> 3) & 7u) & __match_any_sync(0xffffffffu, d >> 6);
+            else if (MODE == 4) p[i] = __match_any_sync(0xffffffffu, d & 3u) & __match_any_sync(0xffffffffu, (d >> 2) & 3u) & __match_any_sync(0xffffffffu, (d >> 4) & 3u)
+                                     & __match_any_sync(0xffffffffu, (d >> 6) & 3u) & __match_any_sync(0xffffffffu, d >> 8);
+            else p[i] = __match_any_sync(0xffffffffu, d);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc += __popc(p[i]);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 int main()
 {
     u32 *in, *out;
@@ -124,6 +149,9 @@ int main()
 #define DIST(N) for (int rep = 0; rep < 2; rep++) { cudaEventRecord(e0); k_distinct<N><<<blocks, threads>>>(out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); } \
         cudaEventElapsedTime(&ms, e0, e1); printf("match.any with %2d distinct values per warp: %7.2f SM-cycles per warp-instruction\n", N, ms * 1e-3 * 1.965e9 / (iters * 8.0) / 32);
         DIST(1) DIST(2) DIST(4) DIST(8) DIST(16) DIST(32)
+#define SPLIT(M, NAME) for (int rep = 0; rep < 2; rep++) { cudaEventRecord(e0); k_split<M><<<blocks, threads>>>(in, out, iters); cudaEventRecord(e1); cudaEventSynchronize(e1); } \
+        cudaEventElapsedTime(&ms, e0, e1); printf("random 9-bit digit, %s: %7.2f SM-cycles per warp-item\n", NAME, ms * 1e-3 * 1.965e9 / (iters * 8.0) / 32);
+        SPLIT(2, "one match") SPLIT(0, "match(5 bits) & match(4 bits)") SPLIT(1, "match(4) & match(3) & match(2)") SPLIT(3, "match(3) x 3") SPLIT(4, "match(2) x 4 & match(1)")
     }
     return 0;
 }
