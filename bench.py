@@ -110,7 +110,7 @@ def kernel_alg_bytes(name, c, text_bytes, n_pass):
     table = {
         "parse_kernel": text_bytes + 16 * lines,          # read text once, write (row, col, score)
         "scatter_rows_kernel": 16 * lines + 12 * rec,     # read COO, write (col, score) into row buckets
-        "rowsort_kernel": 12 * rec + 24 * nnz,            # read rows, write sorted CSR + (Lf, score) sort records
+        "rowsort_kernel": 12 * rec + 16 * nnz,            # read rows, write sorted CSR + the Lf sort keys
         "radix_hist_kernel": 4 * rec,                     # keys only
         "radix_scatter_kernel": 24 * rec,                 # read + write (Lf, score)
         "bin_cut_kernel": 8 * nnz,                        # scores of every bin

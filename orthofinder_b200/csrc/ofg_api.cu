@@ -482,7 +482,9 @@ int stage_norm(ofg_ctx* c)
         CK(c->key2.ensure((n_slots + 64) * 4));
         CK(c->keyval2.ensure((n_slots + 64) * 8));
         CK(c->counters.ensure(((size_t)n_tiles << pass_bits) * 4 + 64));
-        u32* kin = c->key.as<u32>(); double* vin = c->keyval.as<double>();
+        // the first pass reads the scores straight from the CSR values (same slots as the keys), so the row sort does
+        // not have to write a second copy; from then on the two sort buffers ping-pong
+        u32* kin = c->key.as<u32>(); double* vin = c->vals.as<double>();
         u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
         if (n_tiles > 0) {
             CK(c->sort_desc.ensure((size_t)n_tiles * sizeof(RsTileDesc)));
@@ -504,7 +506,7 @@ int stage_norm(ofg_ctx* c)
                 radix_scatter_kernel<<<g, RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);
                 CKL("radix_scatter_kernel");
                 std::swap(kin, kout);
-                std::swap(vin, vout);
+                if (pass == 0) { vin = vout; vout = c->keyval.as<double>(); } else std::swap(vin, vout);
             }
         }
         CK(cudaEventRecord(c->ev[3], c->stream));

@@ -153,7 +153,7 @@ struct RowSortArgs {
     int P;
     const double* lengths;
     u32* key;                  // out: Lf per slot (sentinel for unused slots)
-    double* keyval;            // out: score per slot
+    double* keyval;            // (unused: the first sort pass reads the scores from vals, which sits at the same slots)
     u32 key_sentinel;
     u32* long_rows;            // out: rows with more than ROWSORT_MAXN records
     u32* n_long;
@@ -377,7 +377,6 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
             a.cols[pos] = sw.oc[k];
             a.vals[pos] = val;
             a.key[pos] = sw.okey[k];
-            a.keyval[pos] = val;
         }
         for (int k = outn + lane; k < n; k += 32) a.key[s0 + k] = a.key_sentinel;
         if (lane == 0) {
@@ -433,8 +432,7 @@ __global__ void __launch_bounds__(256) rowsort_long_kernel(RowSortArgs a)
                 a.cols[pos] = col;
                 a.vals[pos] = val;
                 a.key[pos] = (u32)(Lq * Lh[col]);
-                a.keyval[pos] = val;
-            }
+                }
             __syncthreads();
             if (threadIdx.x == 0) s_outn = base + tot;
             __syncthreads();
