@@ -690,7 +690,7 @@ int stage_thresh(ofg_ctx* c)
             rbh_kernel<8, 2><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
             CKL("rbh_kernel");
         } else {
-            rbh_kernel<8, 0><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
+            rbh_kernel<4, 0><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(g);
             CKL("rbh_kernel");
         }
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
@@ -723,7 +723,7 @@ int stage_connect(ofg_ctx* c)
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
         g.row_flagcnt = c->row_flagcnt.as<u32>();
         g.gene_cnt = c->gene_cntg.as<u32>(); g.gene_bytes = c->gene_bytesg.as<u32>(); g.err_flags = (u32*)(c->d_small.as<u64>() + 2);
-        connect_kernel<4><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(g);
+        connect_kernel<2><<<grid_for(c, c->n_rows, 128, 8), 256, 0, c->stream>>>(g);
         CKL("connect_kernel");
     }
     CK(cudaEventRecord(c->ev[8], c->stream));
