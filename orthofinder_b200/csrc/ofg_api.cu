@@ -690,7 +690,7 @@ int stage_thresh(ofg_ctx* c)
             rbh_kernel<8, 2><<<grid_for(c, c->n_rows, 32, 8), 256, 0, c->stream>>>(g);
             CKL("rbh_kernel");
         } else {
-            rbh_kernel<4, 0><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(g);
+            rbh_kernel<2, 0><<<grid_for(c, c->n_rows, 128, 8), 256, 0, c->stream>>>(g);
             CKL("rbh_kernel");
         }
         thresh_final_kernel<<<grid_for(c, c->N, 256, 4), 256, 0, c->stream>>>(c->most.as<double>(), c->best.as<double>(),
