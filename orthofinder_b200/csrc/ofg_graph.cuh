@@ -9,9 +9,11 @@
 //                    "most distant" threshold with last-column-wins semantics (gathering.py:294-306)
 //  thresh_final    : genes without an RBH get bestHit + 1e-6 (gathering.py:308-309)
 //  connect_kernel  : connect_pj = B' >= threshold (gathering.py:391-408) and the reverse flag
-//                    connect_jp^T scattered into the transposed pair (gathering.py:27-31)
+//                    connect_jp^T scattered into the transposed pair (gathering.py:27-31); books the edge
+//                    count and text bytes of every graph row while it sets the flags (edge_account)
+//  v2_ratio_kernel : --scores-v2 only: percentile-ratio conversion factors (gathering.py:344-364)
 //  emit_*          : W = (connect + connect^T) .* B' as CSR with global gene ids and as MCL text with
-//                    glibc-exact "%d:%.3f " formatting (gathering.py:39-48)
+//                    glibc-exact "%d:%.3f " formatting (gathering.py:39-48); offsets from the booked sizes
 #pragma once
 #include "ofg_common.cuh"
 #include "ofg_fit_core.h"

@@ -5,10 +5,12 @@
 //               input order is the matrix order (row, col), so stability reproduces the reference's
 //               sorted(zip(L, range(n))) tie-break by original index (:96) without carrying an index.
 //               Unused slots carry a key one bit above the largest Lf and sink to the end of the pair.
-//  bin_cut    : one CTA per length bin: 95th percentile with numpy's linear interpolation via an
-//               8-pass radix select on the fp64 bit patterns; counts the hits >= cut-off.
-//  bin_select : order-preserving compaction of the selected hits, fused with the two np.log10 calls
-//               of gathering.py:82,120 (bit-exact SVML emulation, ofg_log10.cuh).
+//  bin_cut    : one warp per length bin: 95th percentile with numpy's linear interpolation via a radix select on
+//               the fp64 bit patterns (starting at the first bit where the bin's min and max differ, stopping
+//               once the k-th value is alone in its bucket); the hits >= cut-off are compacted in order, their
+//               two np.log10 values (gathering.py:82,120; bit-exact SVML emulation, ofg_log10.cuh) are taken
+//               on full lanes and staged at the bin's own slots.
+//  bin_select : concatenates the staged selections of all bins (exclusive scan of the counts).
 #pragma once
 #include "ofg_common.cuh"
 #include "ofg_log10.cuh"

@@ -4,9 +4,10 @@
 // ascending within a row).
 //
 //  scan      : device-wide exclusive scan of the row histogram -> row_start
-//  scatter   : counting sort by row (warp-aggregated slot allocation)
-//  rowsort   : one warp per row, rank sort in shared memory on (col asc, score desc), keep the head
-//              of every column run; also emits the length-product key Lf = L_i[q] * L_j[s]
+//  scatter   : counting sort by row (slots reserved per run of equal rows)
+//  rowsort   : one warp per row: rows of up to 64 records are sorted in registers by a bitonic shuffle network
+//              on packed (column, input index) words, longer ones by a rank sort in shared memory; duplicates
+//              of a column share a slot (max score); also emits the length-product key Lf = L_i[q] * L_j[s]
 //              (gathering.py:85-90,142) for the normalisation sort.
 #pragma once
 #include "ofg_common.cuh"
