@@ -485,6 +485,37 @@ def test_pipelined_builder_equals_single_context(name, n_parts):
     pb.close()
 
 
+@pytest.mark.parametrize("name,n_parts", [("synth_C5_small", 2), ("ref_AddTwoSpecies", 3)])
+def test_pipelined_builder_with_v2_scores(name, n_parts):
+    """`--scores-v2` through row partitions (design B on one GPU): the per-species conversion factors and the scaled
+    thresholds only need the query species' own rows plus the imported transposed best hits."""
+    g = Golden(name)
+    S = len(g.n_seqs)
+    whole = waterfall.GraphBuilder(0)
+    whole.set_option("scores_v2", 1)
+    _load(whole, g.n_seqs, g.lengths, g.hit_text)
+    whole.build()
+    want = whole.graph_text_body().tobytes()
+    want_md = whole.thresholds()
+    whole.close()
+    pb = waterfall.PipelinedGraphBuilder(0, n_parts)
+    pb.set_species(g.n_seqs, g.lengths)
+    pb.set_option("scores_v2", 1)
+    pb.load(lambda p, j: g.hit_text(p, j))
+    pb.build()
+    assert pb.graph_text_body().tobytes() == want
+    starts = np.concatenate(([0], np.cumsum(g.n_seqs)))
+    for c, owned in zip(pb.ctxs, pb.parts):
+        md = c.thresholds()
+        for p in owned:
+            assert np.array_equal(md[starts[p]:starts[p + 1]], want_md[starts[p]:starts[p + 1]])
+    pb.close()
+    text = waterfall.graph_header(sum(g.n_seqs)) + want + waterfall.GRAPH_FOOTER
+    if text != g.graph_v2:
+        edge_diff, dec_diff = graph_text_diff(text, g.graph_v2)
+        assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
+
+
 def test_mid_size_job_equals_oracle(gb):
     """8 species x 2000 genes x 50 hits/query/pair (7 M lines, bins of 1000, m ~ 5 k points per fit): the whole
     graph against the CPU oracle — edge set and indices exact, fits bit-equal, weights within 1e-9."""
