@@ -14,6 +14,7 @@ messages.  There is no CPU fallback.
 """
 import ctypes
 import gzip
+import zlib
 import os
 import sys
 from collections import namedtuple
@@ -390,6 +391,18 @@ def GetSequenceLengths(seqsInfo, fasta_dir_list):
     return out
 
 
+def _gunzip(data):
+    """All members of a gzip stream in one go.  zlib releases the GIL while it inflates, so the reader threads of
+    read_hit_files run in parallel (gzip.GzipFile.read loops in Python)."""
+    out = []
+    while data:
+        d = zlib.decompressobj(wbits=31)
+        out.append(d.decompress(data))
+        out.append(d.flush())
+        data = d.unused_data.lstrip(b"\0")
+    return b"".join(out) if len(out) != 2 else out[0] + out[1]
+
+
 def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
     """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted)."""
     fn = None
@@ -402,10 +415,36 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
             return None, fn
         raise FileNotFoundError(fn)
     if os.path.exists(fn + ".gz"):
-        with gzip.open(fn + ".gz", "rb") as f:
-            return f.read(), fn
+        with open(fn + ".gz", "rb") as f:
+            return _gunzip(f.read()), fn
     with open(fn, "rb") as f:
         return f.read(), fn
+
+
+def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None, window=None):
+    """Yields (request, data, filename) for every request (iSpecies, jSpecies) IN ORDER while a pool of threads reads
+    and inflates the files ahead of the consumer - DIAMOND writes its hit files gzip-compressed (config.json:51), and
+    inflating 16 files at once is what keeps the device fed.  At most `window` files are held in memory."""
+    from concurrent.futures import ThreadPoolExecutor
+    requests = list(requests)
+    n_readers = n_readers or max(1, min(16, os.cpu_count() or 1))
+    window = window or 2 * n_readers
+    if n_readers <= 1 or len(requests) <= 1:
+        for r in requests:
+            data, fn = _read_hit_file(blastDir_list, r[0], r[1], q_allow_empty)
+            yield r, data, fn
+        return
+    with ThreadPoolExecutor(max_workers=n_readers) as pool:
+        pending = []
+        nxt = 0
+        while nxt < len(requests) or pending:
+            while nxt < len(requests) and len(pending) < window:
+                r = requests[nxt]
+                pending.append((r, pool.submit(_read_hit_file, blastDir_list, r[0], r[1], q_allow_empty)))
+                nxt += 1
+            r, fut = pending.pop(0)
+            data, fn = fut.result()
+            yield r, data, fn
 
 
 class WaterfallMethod:
@@ -413,7 +452,7 @@ class WaterfallMethod:
 
     @staticmethod
     def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
-                   builder=None):
+                   builder=None, n_readers=None):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
         the device-resident graph.  Returns the GraphBuilder holding it."""
         gb = builder or GraphBuilder(device)
@@ -422,12 +461,14 @@ class WaterfallMethod:
         gb.set_species(n_seqs, Lengths)
         gb.set_option("allow_empty", int(q_allow_empty))
         gb.set_option("scores_v2", int(bool(v2_scores)))  # --scores-v2: gathering.py:157-174, :314-388
+        cells = []
         for p, kp in enumerate(sp):
             for j, kj in enumerate(sp):
                 swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54
-                data, fn = _read_hit_file(blastDir_list, kj if swap else kp, kp if swap else kj, q_allow_empty)
-                if data is not None:
-                    gb.add_hits(p, j, data, swap_cols=swap)
+                cells.append((kj if swap else kp, kp if swap else kj, p, j, swap))
+        for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers):
+            if data is not None:
+                gb.add_hits(p, j, data, swap_cols=swap)
         try:
             gb.build(_lib.STAGE_GRAPH)
         except OfgError as e:

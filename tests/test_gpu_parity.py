@@ -3,6 +3,7 @@ golden vectors of the live reference.  Integer / index work must be bit-exact; f
 relative (BASELINE.json north_star); curve_fit parameters are expected bit-equal because np.log10 and
 MINPACK's summation order are emulated exactly."""
 import ctypes
+import os
 import random
 
 import numpy as np
@@ -514,6 +515,28 @@ def test_pipelined_builder_with_v2_scores(name, n_parts):
     if text != g.graph_v2:
         edge_diff, dec_diff = graph_text_diff(text, g.graph_v2)
         assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
+
+
+def test_working_directory_entry_point_reads_plain_and_gzip_files(tmp_path):
+    """waterfall.DoOrthogroupsGraph: the stand-alone equivalent of `orthofinder -b <WorkingDirectory> -og` up to the graph
+    file - SpeciesIDs / SequenceIDs / Species*.fa for the index space and the lengths, Blast*.txt[.gz] read ahead by the
+    reader threads - must write the live reference's OrthoFinder_graph.txt."""
+    import gzip
+    wd = str(tmp_path) + "/"
+    synth.write_working_directory(wd, "C2_tiny")
+    g = Golden("synth_C2_tiny")
+    for k, fn in enumerate(sorted(f for f in os.listdir(wd) if f.startswith("Blast") and f.endswith(".txt"))):
+        if k % 2:  # DIAMOND's default output is compressed (config.json:51)
+            with open(wd + fn, "rb") as f:
+                data = f.read()
+            with open(wd + fn + ".gz", "wb") as f:
+                f.write(gzip.compress(data, 1))
+            os.remove(wd + fn)
+    graph_fn, gb, si = waterfall.DoOrthogroupsGraph(wd, graphFN=wd + "OrthoFinder_graph.txt")
+    with open(graph_fn, "rb") as f:
+        assert f.read() == g.graph
+    assert gb.counts()["edges"] == g.graph.count(b":")
+    gb.close()
 
 
 def test_mid_size_job_equals_oracle(gb):

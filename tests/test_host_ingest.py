@@ -1,0 +1,56 @@
+"""Host-side ingestion of the hit files (no GPU): file lookup, gzip members, ordered parallel read-ahead."""
+import gzip
+import os
+
+import pytest
+
+from orthofinder_b200 import waterfall as w
+
+
+def _line(i, j, k):
+    return b"%d_1\t%d_2\t1\t1\t1\t1\t1\t1\t1\t1\t1e-5\t%d\n" % (i, j, k)
+
+
+def test_read_hit_files_keeps_order_and_inflates_all_gzip_members(tmp_path):
+    d = str(tmp_path) + "/"
+    texts = {}
+    for i in range(3):
+        for j in range(3):
+            t = _line(i, j, 10 * i + j) * (500 * (i + j + 1))
+            texts[(i, j)] = t
+            if (i + j) % 2:  # two concatenated gzip members, as `cat a.gz b.gz` produces
+                with open(d + "Blast%d_%d.txt.gz" % (i, j), "wb") as f:
+                    f.write(gzip.compress(t[:len(t) // 2]) + gzip.compress(t[len(t) // 2:]))
+            else:
+                with open(d + "Blast%d_%d.txt" % (i, j), "wb") as f:
+                    f.write(t)
+    req = [(i, j, "tag%d%d" % (i, j)) for i in range(3) for j in range(3)]
+    for readers in (1, 4):
+        got = list(w.read_hit_files([d], req, n_readers=readers, window=3))
+        assert [g[0] for g in got] == req
+        assert all(g[1] == texts[(g[0][0], g[0][1])] for g in got)
+        assert all(os.path.basename(g[2]) == "Blast%d_%d.txt" % g[0][:2] for g in got)
+
+
+def test_missing_file_is_an_error_unless_allowed(tmp_path):
+    d = str(tmp_path) + "/"
+    with open(d + "Blast0_0.txt", "wb") as f:
+        f.write(_line(0, 0, 5))
+    with pytest.raises(FileNotFoundError):
+        list(w.read_hit_files([d], [(0, 0), (0, 1)], n_readers=2))
+    got = list(w.read_hit_files([d], [(0, 0), (0, 1)], q_allow_empty=True, n_readers=2))
+    assert got[0][1] == _line(0, 0, 5) and got[1][1] is None   # blast_file_processor.py:62-63
+
+
+def test_first_directory_holding_the_file_wins(tmp_path):
+    a, b = str(tmp_path / "a") + "/", str(tmp_path / "b") + "/"
+    os.mkdir(a)
+    os.mkdir(b)
+    with open(b + "Blast1_2.txt", "wb") as f:
+        f.write(b"from b\n")
+    with open(a + "Blast3_4.txt.gz", "wb") as f:
+        f.write(gzip.compress(b"from a\n"))
+    with open(b + "Blast3_4.txt", "wb") as f:
+        f.write(b"shadowed\n")
+    got = {g[0]: g[1] for g in w.read_hit_files([a, b], [(1, 2), (3, 4)], n_readers=2)}
+    assert got[(1, 2)] == b"from b\n" and got[(3, 4)] == b"from a\n"   # blast_file_processor.py:59-65
