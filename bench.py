@@ -277,7 +277,10 @@ def run_ours(args):
         if best:
             out["roofline"] = {"bound": "hbm", "kernel": best[0], "achieved": best[1], "peak": peak, "unit": "GB/s",
                                "frac": best[1] / peak, "traffic": traffic, "peak_source": how,
-                               "ms_per_launch": best[2], "alg_bytes_per_launch": best[3]}
+                               "ms_per_launch": best[2], "alg_bytes_per_launch": best[3],
+                               "note": "DRAM traffic equals the algorithmic bytes; the kernel is bound by the integer ALU pipe "
+                                       "(ncu --set full: pipe_alu 73 %, issue 74 %, no memory stalls), see "
+                                       "profiles/r01_top_kernels_C2_ncu_full.txt and DESIGN.md §4"}
         # whole-path figure of SURVEY.md §8(d): B_alg = T + 124 bytes per line
         T = text_bytes_all / max(c["lines"], 1)
         out["path_roofline"] = {"B_alg_bytes_per_line": T + 124, "achieved_GBps_per_gpu": value / world * (T + 124) / 1e9,
