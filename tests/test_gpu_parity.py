@@ -287,6 +287,72 @@ def test_streaming_parser_boundaries(gb):
     assert gb.counts()["lines"] == want
 
 
+def _fuzz_hit_text(rng, n_q, n_s, n_lines, p_bad):
+    """Random BLAST-6 text: mostly well-formed lines in odd shapes (long prefixes, extra columns, padded scores, blank
+    lines, CR / CRLF ends), now and then a malformed one.  Returns the bytes."""
+    out = []
+    for _ in range(n_lines):
+        q, t = rng.randrange(n_q), rng.randrange(n_s)
+        pre_q = ("sp" * rng.randrange(0, 40) if rng.random() < 0.1 else "0") + ("x" * rng.randrange(3000, 7000) if rng.random() < 0.003 else "")
+        score = rng.choice(["%d" % rng.randrange(1, 3000), "%d.%d" % (rng.randrange(0, 900), rng.randrange(0, 1000)),
+                            " %d.5 " % rng.randrange(1, 99), "%de-1" % rng.randrange(1, 999), "0", "-3.5", "1.25e2"])
+        fields = ["%s_%d" % (pre_q, q), "1_%d" % t, "55.1", "100", "3", "0", "1", "100", "1", "100", "1e-20", score]
+        if rng.random() < 0.05:
+            fields += ["extra" * rng.randrange(1, 60)] * rng.randrange(1, 4)   # more than 12 columns / long lines
+        if rng.random() < 0.05:
+            fields[rng.randrange(2, 11)] = "9" * rng.randrange(20, 200)        # a wide middle column
+        if rng.random() < p_bad:
+            kind = rng.randrange(4)
+            if kind == 0:
+                fields = fields[:rng.randrange(1, 12)]                          # missing columns
+            elif kind == 1:
+                fields[rng.randrange(2)] = rng.choice(["nounderscore", "0_", "0_x7", "_"])
+            elif kind == 2:
+                fields[11] = rng.choice(["abc", "", "1e", "--1", "1 2"])
+            else:
+                fields[11] = fields[11] + "z"
+        line = "\t".join(fields)
+        end = rng.choice(["\n"] * 8 + ["\r\n", "\r", "\n\n", "\n\r\n\n"])
+        out.append(line + end)
+    text = "".join(out).encode()
+    if rng.random() < 0.5:
+        text = text.rstrip(b"\r\n")
+    return text
+
+
+def test_parser_fuzz_against_the_oracle(gb):
+    """Random hit files through the streaming parser (segments, ring, queue, forced rounds, global re-parse) against the
+    oracle's record parser: identical raw matrices, or the same first offending line (kind and byte offset)."""
+    rng = random.Random(2024)
+    n_seqs = [50, 40]
+    L = [np.arange(100., 150.), np.arange(200., 240.)]
+    n_err = n_ok = 0
+    for trial in range(60):
+        n_lines = rng.choice([0, 1, 3, 40, 700, 2500, 6000])
+        text = _fuzz_hit_text(rng, 50, 40, n_lines, rng.choice([0.0, 0.0, 0.001, 0.02]))
+        try:
+            want = wo.get_blast6_scores(text, 50, 40, False)
+            err = None
+        except wo.HitFileError as e:
+            want, err = None, e
+        gb.set_species(n_seqs, L)
+        for p in range(2):
+            for j in range(2):
+                gb.add_hits(p, j, text if (p, j) == (0, 1) else b"")
+        if err is None:
+            gb.build(_lib.STAGE_RAW)
+            indptr, cols, vals = gb.pair_csr(0, 1)
+            assert np.array_equal(indptr, want[0]) and np.array_equal(cols, want[1]) and np.array_equal(vals, want[2]), trial
+            n_ok += 1
+        else:
+            with pytest.raises(waterfall.OfgError) as e:
+                gb.build(_lib.STAGE_RAW)
+            msg = e.value.message
+            assert "kind=%d " % err.kind in msg and "offset=%d " % err.offset in msg, (trial, msg[:200], err.kind, err.offset)
+            n_err += 1
+    assert n_ok >= 20 and n_err >= 10, (n_ok, n_err)
+
+
 def test_one_way_mode_reads_swapped_columns(gb):
     """-1 mode (blast_file_processor.py:41-54): for i > j the file Blast{j}_{i} is read with columns swapped."""
     g = Golden("synth_C2_tiny")
