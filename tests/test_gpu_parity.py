@@ -654,6 +654,46 @@ def test_many_species_pairs_equal_oracle(gb):
         assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
 
 
+@pytest.mark.parametrize("v2", [False, True])
+def test_random_small_jobs_equal_oracle(gb, v2):
+    """Ten random job shapes (2-7 species, 5-500 genes, sparse to dense hit lists, integer / tie-heavy scores, missing
+    and self-only queries, twin lengths): whole graph against the oracle, default and --scores-v2."""
+    rng = random.Random(77 + int(v2))
+    gb.set_option("scores_v2", int(v2))
+    try:
+        for trial in range(10):
+            S = rng.randrange(2, 8)
+            G = rng.choice([5, 17, 60, 150, 500])
+            tie = rng.random() < 0.5
+            P = synth.params(seed=100 + trial, hq=rng.choice([1, 3, 8, 20, 45]), integer_scores=int(tie),
+                             ident_levels=rng.choice([0, 4, 16]) if tie else 0, p_dup=rng.choice([0, 100, 400]),
+                             p_missing=rng.choice([0, 100, 500]), p_nohit=rng.choice([0, 50]), p_selfonly=rng.choice([0, 30]),
+                             p_twin=rng.choice([0, 80]))
+            L = synth.make_lengths(S, G, P.seed, twins=P.p_twin_permille > 0, n_distinct=12 if P.ident_levels else 0)
+            ids, n_seqs = list(range(S)), [G] * S
+            gb.set_species(n_seqs, L)
+            gb.synth_hits(P, ids)
+            gb.build()
+            texts = {(p, j): gb.hits_text(p, j) for p in range(S) for j in range(S)}
+            ref = wo.waterfall(n_seqs, L, lambda p, j: texts[(p, j)], v2_scores=v2)
+            rows, indptr, idx, dat = gb.graph_csr()
+            assert np.array_equal(indptr, ref["indptr"]) and np.array_equal(idx, ref["indices"]), (trial, S, G)
+            if dat.size:
+                assert np.max(np.abs(dat - ref["data"]) / ref["data"]) <= REL_TOL, (trial, S, G)
+            md = gb.thresholds()
+            want_md = np.concatenate(ref["most_distant"])
+            assert np.max(np.abs(md - want_md) / want_md) <= REL_TOL, (trial, S, G)
+            if not v2:
+                for (p, j), f in ref["fits"].items():
+                    g = gb.pair_fit(p, j)
+                    if f is None:
+                        assert not g["normalised"], (trial, p, j)
+                    else:
+                        assert g["normalised"] and g["a"] == f[0] and g["b"] == f[1] and g["m"] == f[2], (trial, p, j, g, f)
+    finally:
+        gb.set_option("scores_v2", 0)
+
+
 def test_rebuild_is_deterministic_and_sorted(gb):
     """Size-independent properties on a mid-size job (8 species x 2000 genes x 50 hits/query, 7 M lines):
     two builds give identical bytes; rows are strictly column-sorted; weights are positive and finite."""
