@@ -106,6 +106,13 @@ int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
  * GetMostDistant_s; what the reference passes as v2_scores to ProcessBlastHits / ConnectCognates (:177, :251). */
 int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
 
+/* Optional, only read with "scores_v2": the per-gene factors Lengths[p] ** -0.5 of NormalisedBitScore
+ * (gathering.py:171-172) as the caller's numpy computes them, laid out like lengths_concat.  numpy's pow is
+ * not correctly rounded (SVML), so handing its values over makes the v2 graph byte-identical to the
+ * reference's on the same host; without this call the device evaluates pow(L, -0.5) itself (within 2 ulp).
+ * Reset by ofg_set_species. */
+int ofg_set_length_factors(ofg_ctx* ctx, const double* factors_concat);
+
 /* Run the path up to and including `stop_after` (OFG_STAGE_*).  OFG_STAGE_THRESH stops before the
  * thresholds of other ranks are needed; call ofg_thresholds_get / _set around the exchange and then
  * ofg_build(ctx, OFG_STAGE_GRAPH) to finish.  Single GPU: ofg_build(ctx, OFG_STAGE_GRAPH).  A later stage

@@ -14,7 +14,7 @@ FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, FLAG_TBH, COL_MASK = 0x80000000, 0x40000000
 
 # every symbol include/ofg.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "ofg_set_partition", "ofg_add_hits_text",
-           "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_build",
+           "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_set_length_factors", "ofg_build",
            "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_export_flags",
            "ofg_import_flags", "ofg_counts", "ofg_pair_csr",
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
@@ -49,6 +49,7 @@ def load():
         "ofg_hits_text_size": [vp, i32, i32, ctypes.POINTER(sz)],
         "ofg_hits_text_copy": [vp, i32, i32, vp, sz],
         "ofg_set_option": [vp, ctypes.c_char_p, i64],
+        "ofg_set_length_factors": [vp, vp],
         "ofg_build": [vp, i32],
         "ofg_thresholds_dev": [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)],
         "ofg_thresholds_mark_complete": [vp],

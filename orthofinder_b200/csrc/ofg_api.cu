@@ -72,6 +72,7 @@ struct ofg_ctx {
     std::vector<FileInfo> files;
     // options
     int allow_empty = 0;
+    bool have_length_factors = false;  // ofg_set_length_factors was called for the current species
     bool layout_dirty = true;   // species / partition changed: per-gene constant vectors must be rebuilt on the device
     bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
@@ -87,7 +88,7 @@ struct ofg_ctx {
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
     DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
-    DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
+    DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, d_length_factors, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
     // results
@@ -588,6 +589,7 @@ int stage_norm(ofg_ctx* c)
         FactorArgs fa;
         fa.pairs = c->d_pairs.as<PairDesc>(); fa.P = P; fa.fit = c->fit.as<double>(); fa.lengths = c->d_lengths.as<double>();
         fa.rowfac = c->rowfac.as<double>(); fa.colfac = c->colfac.as<double>();
+        fa.given = (c->scores_v2 && c->have_length_factors) ? c->d_length_factors.as<double>() : nullptr;
         int64_t maxg = 1;
         for (int i = 0; i < P; i++) maxg = std::max<int64_t>(maxg, (int64_t)c->pairs[i].Gi + c->pairs[i].Gj);
         dim3 g((unsigned)P, (unsigned)std::min<int64_t>((maxg + 255) / 256, 64));
@@ -813,7 +815,7 @@ void ofg_destroy(ofg_ctx* c)
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
                       &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg, &c->most_init,
+                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg, &c->most_init, &c->d_length_factors,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
@@ -834,6 +836,7 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     cudaSetDevice(c->device);
     c->S = n_species;
     c->layout_dirty = true;
+    c->have_length_factors = false;
     c->n_seqs.assign(n_seqs, n_seqs + n_species);
     c->seq_start.assign(n_species, 0);
     c->len_off.assign(n_species, 0);
@@ -881,6 +884,17 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "sel_capacity_frac_inv")) c->sel_frac_inv = value;
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else return fail(c, OFG_ERR_ARG, "unknown option %s", name);
+    return OFG_OK;
+}
+
+int ofg_set_length_factors(ofg_ctx* c, const double* factors_concat)
+{
+    if (!c || !factors_concat) return OFG_ERR_ARG;
+    if (c->S <= 0) return fail(c, OFG_ERR_ARG, "call ofg_set_species first");
+    cudaSetDevice(c->device);
+    if (upload(c, c->d_length_factors, factors_concat, sizeof(double) * c->lengths.size())) return OFG_ERR_CUDA;
+    CK(cudaStreamSynchronize(c->stream));  // the caller's buffer may go away
+    c->have_length_factors = true;
     return OFG_OK;
 }
 

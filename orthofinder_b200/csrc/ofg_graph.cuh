@@ -65,6 +65,7 @@ struct FactorArgs {
     const double* lengths;
     double* rowfac;   // [total rows]
     double* colfac;   // [total cols]
+    const double* given;  // --scores-v2 with ofg_set_length_factors: L ** -0.5 per gene, indexed like lengths; else null
 };
 
 __global__ void __launch_bounds__(256) factors_kernel(FactorArgs a)
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(256) factors_kernel(FactorArgs a)
     const double ten_mb = pow(10.0, -pb);  // 10**(-params[1])
     const int64_t n = (int64_t)pd.Gi + pd.Gj;
     for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x) {
-        if (i < pd.Gi) a.rowfac[pd.row_base + i] = __dmul_rn(ten_mb, pow(a.lengths[pd.li_off + i], -pa));
-        else a.colfac[pd.col_base + (i - pd.Gi)] = pow(a.lengths[pd.lj_off + (i - pd.Gi)], -pa);
+        if (i < pd.Gi) a.rowfac[pd.row_base + i] = __dmul_rn(ten_mb, a.given ? a.given[pd.li_off + i] : pow(a.lengths[pd.li_off + i], -pa));
+        else a.colfac[pd.col_base + (i - pd.Gi)] = a.given ? a.given[pd.lj_off + (i - pd.Gi)] : pow(a.lengths[pd.lj_off + (i - pd.Gi)], -pa);
     }
 }
 

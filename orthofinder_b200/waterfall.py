@@ -78,6 +78,8 @@ class GraphBuilder:
         self._ck(self.lib.ofg_set_species(self.h, len(n), _vp(n), _vp(L)))
         self.S = len(n)
         self.n_seqs = [int(x) for x in n]
+        self._lengths = L
+        self._factors_sent = False
 
     def set_partition(self, owned_rows, with_columns):
         o = np.ascontiguousarray(owned_rows, dtype=np.int32)
@@ -85,6 +87,8 @@ class GraphBuilder:
 
     def set_option(self, name, value):
         self._ck(self.lib.ofg_set_option(self.h, name.encode(), int(value)))
+        if name == "scores_v2":
+            self._v2 = bool(value)
 
     def add_hits(self, p, j, data, swap_cols=False):
         """data: bytes-like / numpy uint8 host buffer, or (device_ptr, nbytes) tuple."""
@@ -127,6 +131,11 @@ class GraphBuilder:
 
     # ---- run
     def build(self, stop_after=_lib.STAGE_GRAPH):
+        if getattr(self, "_v2", False) and getattr(self, "_lengths", None) is not None and not self._factors_sent:
+            # gathering.py:171-172: li_vals = Lq**(-0.5) with the host's numpy, so the graph matches the reference's bytes
+            fac = np.ascontiguousarray(self._lengths ** (-0.5))
+            self._ck(self.lib.ofg_set_length_factors(self.h, _vp(fac)))
+            self._factors_sent = True
         self._ck(self.lib.ofg_build(self.h, int(stop_after)))
 
     # ---- outputs

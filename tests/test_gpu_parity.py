@@ -177,7 +177,11 @@ def test_graph_equals_reference_with_v2_scores(gb, name):
         assert md.shape == g.most_distant_v2.shape
         assert np.max(np.abs(md - g.most_distant_v2) / g.most_distant_v2) <= REL_TOL
         text = waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
-        if text != g.graph_v2:
+        if wo.numpy_uses_svml():
+            # the host mirror hands numpy's own L ** -0.5 to the device (ofg_set_length_factors): same bytes as the
+            # reference wherever numpy dispatches pow like the machine that produced the goldens
+            assert text == g.graph_v2
+        elif text != g.graph_v2:
             edge_diff, dec_diff = graph_text_diff(text, g.graph_v2)
             assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
     finally:
