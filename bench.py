@@ -306,6 +306,8 @@ def run_ours(args):
             # partition g+1 overlapped with the parse/normalise of partition g
             pb = waterfall.PipelinedGraphBuilder(local, args.e2e_parts)
             pb.set_species([G] * S, L, [sum(sizes[(p, j)] for j in range(S)) for p in range(S)])
+            if args.scores_v2:
+                pb.set_option("scores_v2", 1)
             for c_, owned_ in zip(pb.ctxs, pb.parts):
                 c_.set_option("reserve_text_bytes", sum(sizes[(p, j)] + 16 for p in owned_ for j in range(S)) + 4096)
 
