@@ -99,9 +99,13 @@ int ofg_synth_hits(ofg_ctx* ctx, const ofg_synth_params* params, const int32_t* 
 int ofg_hits_text_size(ofg_ctx* ctx, int p, int j, size_t* nbytes);
 int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
 
-/* Options: "allow_empty" (0/1), "max_bytes_per_line_inv" (capacity: records <= bytes/this, default 24),
+/* Options: "allow_empty" (0/1), "max_bytes_per_line_inv" (capacity: records <= bytes/this, default 24; after a
+ * complete build the context sizes the next one from the line density it saw),
  * "sel_capacity_frac_inv" (selection capacity = records/this, default 4), "reserve_text_bytes" (size the text arena
- * once), "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)
+ * once), "wave_species" (RAW + NORM run over this many query species at a time out of one set of scratch buffers -
+ * the reference's "one query species per task", gathering.py:484-485; 0 = the whole partition at once),
+ * "async" (0/1: ofg_build only enqueues; counts, errors and sizes are read back by ofg_sync or by the first accessor),
+ * "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)
  * instead of the length-bin fit and GetMostDistant_s_estimate_from_relative_rbhs (gathering.py:314-388) instead of
  * GetMostDistant_s; what the reference passes as v2_scores to ProcessBlastHits / ConnectCognates (:177, :251). */
 int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
@@ -118,6 +122,13 @@ int ofg_set_length_factors(ofg_ctx* ctx, const double* factors_concat);
  * ofg_build(ctx, OFG_STAGE_GRAPH) to finish.  Single GPU: ofg_build(ctx, OFG_STAGE_GRAPH).  A later stage
  * includes every earlier one that has not run yet. */
 int ofg_build(ofg_ctx* ctx, int stop_after);
+
+/* Waits for everything enqueued on the context's stream and reads the results of the build(s) back (one host
+ * synchronisation: line counts, parse errors, capacity flags, fit table, graph sizes).  Returns what a synchronous
+ * ofg_build would have returned.  Every accessor below calls it implicitly. */
+int ofg_sync(ofg_ctx* ctx);
+/* Orders the context's stream after everything enqueued so far on `other`'s stream (event wait, no host block). */
+int ofg_wait_for(ofg_ctx* ctx, ofg_ctx* other);
 
 /* Per-gene cut-off "mostDistant" (gathering.py:294-310), global gene indexing (seqStartingIndices).
  * _dev returns the device array of nSeqs doubles (entries of species not owned hold +inf until set);
@@ -137,6 +148,24 @@ int ofg_thresholds_copy(ofg_ctx* ctx, double* host_dst, int64_t n);
 int ofg_export_flags(ofg_ctx* ctx, int which, int n_ranks, const int32_t* species_rank, int my_rank, int64_t* counts,
                      int32_t** dev_list);
 int ofg_import_flags(ofg_ctx* ctx, int which, const int32_t* dev_list, int64_t n_entries);
+
+/* Peer variant of the same exchange, without host round trips: every context owns an INBOX of n_ranks segments of
+ * seg_bytes ([u64 count][count x (int32, int32)] per source rank).  ofg_export_flags_peer computes all offsets on
+ * the device and writes this context's lists straight into segment `my_rank` of each destination's inbox
+ * (inbox_ptrs[r]: device pointer valid on this GPU - another context of the same process, or a peer GPU's buffer
+ * opened with ofg_ipc_open_handle: the stores travel over NVLink while the kernel runs).  After all exporters are
+ * done (ofg_wait_for between contexts of a process, a barrier between ranks) ofg_import_flags_peer marks every
+ * received entry.  A segment that is too small sets OFG_ERR_CAPACITY at the next ofg_sync; enlarge and repeat. */
+int ofg_export_flags_peer(ofg_ctx* ctx, int which, int n_ranks, const int32_t* species_rank, int my_rank,
+                          void* const* inbox_ptrs, size_t seg_bytes);
+int ofg_import_flags_peer(ofg_ctx* ctx, int which, int n_ranks, int my_rank, const void* inbox, size_t seg_bytes);
+/* Plumbing for the inboxes: zeroed device allocations on the context's GPU and CUDA IPC handles (64 bytes) so that
+ * the ranks of one node can map each other's inbox. */
+int ofg_device_alloc(ofg_ctx* ctx, size_t bytes, void** dev_ptr_out);
+int ofg_device_free(ofg_ctx* ctx, void* dev_ptr);
+int ofg_ipc_get_handle(ofg_ctx* ctx, void* dev_ptr, void* handle_out64);
+int ofg_ipc_open_handle(ofg_ctx* ctx, const void* handle64, void** dev_ptr_out);
+int ofg_ipc_close_handle(ofg_ctx* ctx, void* dev_ptr);
 
 /* Totals after a build: lines = non-empty records seen, records = lines kept after the self-hit and
  * score > 0 filters, nnz = stored (q,s) after max-dedup, edges = entries of the final graph. */

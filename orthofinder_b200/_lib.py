@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libofg.so")
 OFG_OK = 0
 ERR_NAMES = {-1: "OFG_ERR_CUDA", -2: "OFG_ERR_ARG", -3: "OFG_ERR_PARSE", -4: "OFG_ERR_INCONSISTENT", -5: "OFG_ERR_FIT",
              -6: "OFG_ERR_CAPACITY", -7: "OFG_ERR_UNSUPPORTED", -8: "OFG_ERR_MISSING"}
-ERR_PARSE, ERR_INCONSISTENT, ERR_FIT, ERR_UNSUPPORTED, ERR_MISSING = -3, -4, -5, -7, -8
+ERR_PARSE, ERR_INCONSISTENT, ERR_FIT, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_MISSING = -3, -4, -5, -6, -7, -8
 STAGE_RAW, STAGE_NORM, STAGE_THRESH, STAGE_CONNECT, STAGE_GRAPH = 1, 2, 3, 4, 5
 FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, FLAG_TBH, COL_MASK = 0x80000000, 0x40000000, 0x20000000, 0x10000000, 0x0FFFFFFF
 
@@ -18,7 +18,9 @@ SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "of
            "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_export_flags",
            "ofg_import_flags", "ofg_counts", "ofg_pair_csr",
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
-           "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
+           "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_sync", "ofg_wait_for", "ofg_export_flags_peer",
+           "ofg_import_flags_peer", "ofg_device_alloc", "ofg_device_free", "ofg_ipc_get_handle", "ofg_ipc_open_handle",
+           "ofg_ipc_close_handle", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
 _lib = None
 
@@ -56,6 +58,15 @@ def load():
         "ofg_thresholds_copy": [vp, vp, i64],
         "ofg_export_flags": [vp, i32, i32, vp, i32, vp, ctypes.POINTER(vp)],
         "ofg_import_flags": [vp, i32, vp, i64],
+        "ofg_sync": [vp],
+        "ofg_wait_for": [vp, vp],
+        "ofg_export_flags_peer": [vp, i32, i32, vp, i32, vp, sz],
+        "ofg_import_flags_peer": [vp, i32, i32, i32, vp, sz],
+        "ofg_device_alloc": [vp, sz, ctypes.POINTER(vp)],
+        "ofg_device_free": [vp, vp],
+        "ofg_ipc_get_handle": [vp, vp, vp],
+        "ofg_ipc_open_handle": [vp, vp, ctypes.POINTER(vp)],
+        "ofg_ipc_close_handle": [vp, vp],
         "ofg_counts": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)],
         "ofg_pair_csr": [vp, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), vp, vp, vp],
         "ofg_pair_fit": [vp, i32, i32, vp],

@@ -52,6 +52,17 @@ struct FileInfo {
 
 }  // namespace
 
+// One wave = a contiguous range of species pairs (whole query species) whose RAW + NORM stages run together out of
+// one set of scratch buffers; only the slotted CSR and the per-row / per-gene vectors persist across waves (the
+// reference processes one query species at a time for the same reason: gathering.py:484-485).
+struct Wave {
+    int P0 = 0, P1 = 0;       // pairs [P0, P1)
+    int64_t R0 = 0, R1 = 0;   // rows  [R0, R1)
+    int64_t text_bytes = 0;   // padded text of the wave
+    int64_t n_segs = 0;       // parse segments
+    u64 cap = 0;              // record-slot capacity (upper bound from the text size)
+};
+
 struct ofg_ctx {
     int device = 0;
     int n_sm = 148;
@@ -64,6 +75,7 @@ struct ofg_ctx {
     int64_t N = 0;
     // partition
     std::vector<int32_t> owned;
+    bool has_partition = false;  // ofg_set_partition was called (an empty owned list then means "no rows", not "all rows")
     int with_columns = 0;
     std::vector<PairDesc> pairs;
     std::vector<int32_t> pair_of;
@@ -77,6 +89,9 @@ struct ofg_ctx {
     bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
+    int wave_species = 0;       // option wave_species: query species per wave (0: the whole partition in one wave)
+    bool async = false;         // option async: ofg_build returns after enqueueing; results are read back by ofg_sync
+    double bpl_learned = 0.0;   // bytes of text per record slot seen by the last complete build (sizes the next one)
     // text arena
     DevBuf text;
     int64_t text_used = 0;
@@ -84,26 +99,39 @@ struct ofg_ctx {
     int stage_done = 0;
     bool thresholds_complete = false;
     bool pairs_dirty = true;
+    bool pending = false;       // device results of the last build(s) have not been read back yet
+    bool graph_pending = false; // ... including the graph sizes
+    std::vector<Wave> waves;
+    std::vector<int64_t> seg_prefix_host;   // parse segments before each pair, per wave (kept alive for the async uploads)
+    std::vector<int32_t> diag_host;
+    bool raw_scratch_valid = false;         // the wave scratch still holds the RAW output of the (only) wave
     // device buffers
     DevBuf d_pairs, d_pair_row_base, d_pair_of, d_lengths, d_tile_prefix, d_small;
     DevBuf coo_row, coo_col, coo_val, rowcount, row_start, rowlen, cols, vals, key, keyval, key2, keyval2;
-    DevBuf long_rows, counters, scan_partial, sort_tile_prefix, pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, task_prefix;
+    DevBuf long_rows, counters, scan_partial, wave_tile_prefix, wave_pair_slot, bin_tasks, bin_cut, bin_cnt, sel_off, wave_task_prefix;
     DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, d_length_factors, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
-    DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff;
+    DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff, diag_pairs;
+    DevBuf x_flag, x_off, x_list, x_pair_dst, x_order, x_dst_first, x_inbox_ptrs;
+    // pinned read-back area: [small block][fit table]
+    u64* h_small = nullptr;
+    size_t h_small_cap = 0;
+    double* h_fit = nullptr;
+    size_t h_fit_cap = 0;
+    size_t small_words = 0, small_pair_base = 0;
     // results
     std::vector<u64> pair_lines, pair_valid, pair_nnz;
     std::vector<double> fit_host;
     int64_t tot_lines = 0, tot_records = 0, tot_nnz = 0, tot_edges = 0, tot_text = 0, n_owned_genes = 0;
-    u64 sel_cap = 0, sel_total = 0;
+    u64 sel_cap = 0;
     int key_bits = 32;
     float ms[10] = {0};
     int64_t launches = 0;
-    cudaEvent_t ev[12] = {nullptr};
-    cudaEvent_t tl_ev[192] = {nullptr};
-    const char* tl_name[192] = {nullptr};
+    std::vector<cudaEvent_t> tl_ev;
+    std::vector<const char*> tl_name;
     int tl_n = 0;
-    std::string kernel_report;
+    EmitArgs last_emit;
+    int last_emit_grid = 0;
 };
 
 namespace {
@@ -133,11 +161,16 @@ int fail(ofg_ctx* c, int code, const char* fmt, ...)
         if (e_ != cudaSuccess) return fail(c, OFG_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// per-kernel timeline: one event after every launch (cheap), resolved after the build
+// per-kernel timeline: one event after every launch (cheap), resolved when the results are read back
 void note_launch(ofg_ctx* c, const char* name)
 {
-    if (c->tl_n >= (int)(sizeof(c->tl_ev) / sizeof(c->tl_ev[0]))) return;
-    if (!c->tl_ev[c->tl_n]) cudaEventCreate(&c->tl_ev[c->tl_n]);
+    if (c->tl_n >= (int)c->tl_ev.size()) {
+        if (c->tl_ev.size() >= 8192) return;
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        c->tl_ev.push_back(e);
+        c->tl_name.push_back(nullptr);
+    }
     cudaEventRecord(c->tl_ev[c->tl_n], c->stream);
     c->tl_name[c->tl_n] = name;
     c->tl_n++;
@@ -159,6 +192,13 @@ __global__ void gather_u64_kernel(const u64* src, const u64* idx, int n, u64* ou
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = src[idx[i]];
+}
+
+// offsets of every pair's selected points: pair_sel_off[i] = sel_off[task_prefix[i]] (both on the device)
+__global__ void pair_sel_off_kernel(const u64* sel_off, const u64* task_prefix, int n, u64* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sel_off[task_prefix[i]];
 }
 
 // unit-test kernels (ofg_test_*)
@@ -184,29 +224,28 @@ __global__ void test_score_kernel(const uint8_t* text, int64_t nbytes, const int
         y[i] = v;
     }
 }
-__global__ void __launch_bounds__(FIT_THREADS) test_fit_kernel(const double* lx, const double* ly, long m, double* out)
-{
-    extern __shared__ __align__(16) unsigned char fit_smem_raw[];  // sizeof(FitShared) > 48 KB: dynamic, opt-in
-    FitShared& sh = *reinterpret_cast<FitShared*>(fit_smem_raw);
-    fit_loglinear(lx, ly, m, &sh, out);
-}
-
+// Exclusive scan of n u32 values.  n is a host-side bound; the real count may live on the device (n_dev / n_shift,
+// see scan_count).  base_dev (nullable): device value added to every output.  write_total: out[n] = total.
 template <typename TO>
-int device_scan(ofg_ctx* c, const u32* in, int64_t n, TO* out, int write_total)
+int device_scan(ofg_ctx* c, const u32* in, int64_t n, TO* out, int write_total, const int64_t* n_dev = nullptr, int n_shift = 0,
+                const TO* base_dev = nullptr)
 {
     if (n <= 0) {
-        if (write_total) CK(cudaMemsetAsync(out, 0, sizeof(TO), c->stream));
+        if (write_total) {
+            if (base_dev) CK(cudaMemcpyAsync(out, base_dev, sizeof(TO), cudaMemcpyDeviceToDevice, c->stream));
+            else CK(cudaMemsetAsync(out, 0, sizeof(TO), c->stream));
+        }
         return 0;
     }
     const int64_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CK(c->scan_partial.ensure((size_t)(n_chunks + 1) * sizeof(u64)));
     TO* part = c->scan_partial.as<TO>();
     const int g = grid_for(c, n_chunks, 1, 8);
-    scan_reduce_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part);
+    scan_reduce_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part, n_dev, n_shift);
     CKL("scan_reduce_kernel<TO>");
-    scan_partials_kernel<TO><<<1, 1024, 0, c->stream>>>(part, n_chunks, (TO*)nullptr);
+    scan_partials_kernel<TO><<<1, 1024, 0, c->stream>>>(part, n, (TO*)nullptr, n_dev, n_shift, base_dev);
     CKL("scan_partials_kernel<TO>");
-    scan_apply_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part, out, write_total);
+    scan_apply_kernel<TO><<<g, SCAN_THREADS, 0, c->stream>>>(in, n, part, out, write_total, n_dev, n_shift, base_dev);
     CKL("scan_apply_kernel<TO>");
     return 0;
 }
@@ -215,7 +254,7 @@ int rebuild_pairs(ofg_ctx* c)
 {
     if (c->S <= 0) return fail(c, OFG_ERR_ARG, "ofg_set_species has not been called");
     std::vector<int32_t> owned = c->owned;
-    if (owned.empty()) for (int p = 0; p < c->S; p++) owned.push_back(p);
+    if (owned.empty() && !c->has_partition) for (int p = 0; p < c->S; p++) owned.push_back(p);
     std::sort(owned.begin(), owned.end());
     std::vector<char> is_owned(c->S, 0);
     for (int p : owned) is_owned[p] = 1;
@@ -309,13 +348,28 @@ void describe_line(ofg_ctx* c, int pair, u64 errword, std::string* out)
     out->append(buf.data() + s, (size_t)(e - s));
 }
 
-// ------------------------------------------------------------------------------------------ stages
-int stage_raw(ofg_ctx* c)
+// ------------------------------------------------------------------------------------------ plan
+u64* small_ptr(ofg_ctx* c) { return c->d_small.as<u64>(); }
+u32* err_flags_ptr(ofg_ctx* c) { return (u32*)(small_ptr(c) + 2); }
+int64_t* n_tiles_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 3); }
+int64_t* n_tasks_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 4); }
+u64* wave_count_ptr(ofg_ctx* c, int w) { return small_ptr(c) + 8 + w; }
+u64* pair_lines_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base; }
+u64* pair_valid_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base + c->pairs.size(); }
+u64* pair_err_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base + 2 * c->pairs.size(); }
+u64* pair_nnz_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base + 3 * c->pairs.size(); }
+
+// bytes of text that one record slot is assumed to need at least (capacity planning)
+double bytes_per_slot(ofg_ctx* c)
 {
-    mark_timeline(c);
+    return std::max<double>((double)std::max<int64_t>(c->bytes_per_line_inv, 2), c->bpl_learned);
+}
+
+// Waves, text offsets and capacities; uploads the descriptors.  Everything here depends only on the host-side
+// description of the job (file sizes), never on device results.
+int plan_build(ofg_ctx* c)
+{
     const int P = (int)c->pairs.size();
-    // text offsets into the descriptors
-    int64_t total_padded = 0;
     for (int i = 0; i < P; i++) {
         FileInfo& f = c->files[i];
         PairDesc& d = c->pairs[i];
@@ -325,93 +379,68 @@ int stage_raw(ofg_ctx* c)
         } else {
             d.present = 1; d.text_off = f.off; d.text_len = f.padded; d.text_raw = f.raw; d.swap = f.swap;
         }
-        total_padded += d.text_len;
     }
-    std::vector<int64_t> tile_prefix(P + 1, 0);  // parse segments before each pair
-    for (int i = 0; i < P; i++) tile_prefix[i + 1] = tile_prefix[i] + (c->pairs[i].text_len + PS_SEG - 1) / PS_SEG;
-    const int64_t n_tiles = tile_prefix[P];
-    const int parse_grid = grid_for(c, (n_tiles + PS_WARPS - 1) / PS_WARPS, 1, 4);
+    // waves: whole query species (S consecutive pairs each), wave_species of them at a time
+    c->waves.clear();
+    const int S = c->S;
+    const int n_groups = S > 0 ? (P + S - 1) / S : 0;   // row groups: owned species, then (design A) the column pairs in chunks of S
+    const int per = c->wave_species > 0 ? c->wave_species : std::max(n_groups, 1);
+    c->seg_prefix_host.clear();
+    const double bps = bytes_per_slot(c);
+    for (int g0 = 0; g0 < n_groups; g0 += per) {
+        Wave w;
+        w.P0 = g0 * S;
+        w.P1 = std::min(P, (g0 + per) * S);
+        w.R0 = c->pair_row_base[w.P0];
+        w.R1 = c->pair_row_base[w.P1];
+        for (int i = w.P0; i < w.P1; i++) {
+            w.text_bytes += c->pairs[i].text_len;
+            w.n_segs += (c->pairs[i].text_len + PS_SEG - 1) / PS_SEG;
+        }
+        const int parse_grid = grid_for(c, (w.n_segs + PS_WARPS - 1) / PS_WARPS, 1, 4);
+        // every parse warp may leave up to PS_RESERVE - 1 reserved slots unused
+        w.cap = (u64)((double)w.text_bytes / bps) + 1024 + (u64)parse_grid * PS_WARPS * PS_RESERVE;
+        c->waves.push_back(w);
+    }
+    if (c->waves.empty()) c->waves.push_back(Wave());
+    u64 tot_cap = 0;
+    for (const Wave& w : c->waves) tot_cap += w.cap;
+    if (tot_cap >= 0xfffffff0ULL)
+        return fail(c, OFG_ERR_CAPACITY, "more than 2^32 record slots in one context (%llu); shard by query species or raise max_bytes_per_line_inv", (unsigned long long)tot_cap);
+    // parse segments before each pair, per wave, back to back: [wave 0: Pw + 1 entries][wave 1: ...]
+    for (const Wave& w : c->waves) {
+        int64_t acc = 0;
+        for (int i = w.P0; i < w.P1; i++) {
+            c->seg_prefix_host.push_back(acc);
+            acc += (c->pairs[i].text_len + PS_SEG - 1) / PS_SEG;
+        }
+        c->seg_prefix_host.push_back(acc);
+    }
     if (upload(c, c->d_pairs, c->pairs.data(), sizeof(PairDesc) * P)) return OFG_ERR_CUDA;
     if (upload(c, c->d_pair_row_base, c->pair_row_base.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
     if (upload(c, c->d_pair_of, c->pair_of.data(), sizeof(int32_t) * c->pair_of.size())) return OFG_ERR_CUDA;
     if (upload(c, c->d_lengths, c->lengths.data(), sizeof(double) * c->lengths.size())) return OFG_ERR_CUDA;
-    if (upload(c, c->d_tile_prefix, tile_prefix.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
+    if (upload(c, c->d_tile_prefix, c->seg_prefix_host.data(), sizeof(int64_t) * c->seg_prefix_host.size())) return OFG_ERR_CUDA;
     if (upload(c, c->d_seq_start, c->seq_start.data(), sizeof(int64_t) * c->S)) return OFG_ERR_CUDA;
-
-    // every parse warp may leave up to PS_RESERVE - 1 reserved slots unused
-    const u64 cap = (u64)(total_padded / std::max<int64_t>(c->bytes_per_line_inv, 2)) + 1024 + (u64)parse_grid * PS_WARPS * PS_RESERVE;
-    if (cap >= 0xfffffff0ULL) return fail(c, OFG_ERR_CAPACITY, "more than 2^32 records in one context (%llu); shard by query species", (unsigned long long)cap);
-    CK(c->coo_row.ensure(cap * 4));
-    CK(c->coo_col.ensure(cap * 4));
-    CK(c->coo_val.ensure(cap * 8));
+    // small counters block: [1] n_long, [2] err_flags, [3] n_tiles, [4] n_tasks, [8 + w] record slots reserved by wave w,
+    // then pair_lines[P], pair_valid[P], pair_err[P], pair_nnz[P]
+    c->small_pair_base = 8 + ((c->waves.size() + 7) & ~(size_t)7);
+    c->small_words = c->small_pair_base + 4 * (size_t)P;
+    CK(c->d_small.ensure(c->small_words * 8));
+    CK(cudaMemsetAsync(c->d_small.p, 0, c->small_words * 8, c->stream));
+    if (P > 0) CK(cudaMemsetAsync(pair_err_ptr(c), 0xff, sizeof(u64) * P, c->stream));
+    // persistent per-row / per-slot arrays
     CK(c->rowcount.ensure((size_t)(c->n_rows + 1) * 4));
     CK(c->rowlen.ensure((size_t)(c->n_rows + 1) * 4));
     CK(c->row_start.ensure((size_t)(c->n_rows + 2) * 4));
-    // small counters block: [0] coo_count, [1] n_long, [2] err_flags, then pair_lines[P], pair_valid[P], pair_err[P], pair_nnz[P]
-    const size_t small_words = 8 + 4 * (size_t)P;
-    CK(c->d_small.ensure(small_words * 8));
-    CK(cudaMemsetAsync(c->d_small.p, 0, small_words * 8, c->stream));
-    u64* sm = c->d_small.as<u64>();
-    u64* d_pair_lines = sm + 8;
-    u64* d_pair_valid = sm + 8 + P;
-    u64* d_pair_err = sm + 8 + 2 * (size_t)P;
-    u64* d_pair_nnz = sm + 8 + 3 * (size_t)P;
-    CK(cudaMemsetAsync(d_pair_err, 0xff, sizeof(u64) * P, c->stream));
+    CK(c->long_rows.ensure((size_t)(c->n_rows + 1) * 4));
     CK(cudaMemsetAsync(c->rowcount.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
     CK(cudaMemsetAsync(c->rowlen.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
-
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    if (n_tiles > 0) {
-        ParseArgs a;
-        a.text = c->text.as<uint8_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.P = P;
-        a.seg_prefix = c->d_tile_prefix.as<int64_t>(); a.n_segs = n_tiles;
-        a.coo_row = c->coo_row.as<u32>(); a.coo_col = c->coo_col.as<u32>(); a.coo_val = c->coo_val.as<double>();
-        a.cap = cap; a.coo_count = sm; a.rowcount = c->rowcount.as<u32>();
-        a.pair_lines = d_pair_lines; a.pair_valid = d_pair_valid; a.pair_err = d_pair_err; a.one = 1u;
-        const int parse_smem = (int)(sizeof(PsWarp) * PS_WARPS);
-        CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_smem));
-        parse_kernel<<<parse_grid, PARSE_THREADS, parse_smem, c->stream>>>(a);
-        CKL("parse_kernel");
-    }
-    CK(cudaEventRecord(c->ev[1], c->stream));
-    // host sync 1: line counts, errors
-    std::vector<u64> small(small_words);
-    CK(cudaMemcpyAsync(small.data(), sm, small_words * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);
-    c->pair_lines.assign(small.begin() + 8, small.begin() + 8 + P);
-    c->pair_valid.assign(small.begin() + 8 + P, small.begin() + 8 + 2 * P);
-    const u64 coo_count = small[0];
-    for (int i = 0; i < P; i++) {
-        const u64 e = small[8 + 2 * (size_t)P + i];
-        if (e != ~0ULL) {
-            std::string d;
-            describe_line(c, i, e, &d);
-            const int kind = (int)(e & 15);
-            const int code = (kind == OFG_LINE_RANGE_Q || kind == OFG_LINE_RANGE_S) ? OFG_ERR_INCONSISTENT
-                             : (kind == OFG_LINE_QUOTE || kind == OFG_LINE_SCORE_FORMAT) ? OFG_ERR_UNSUPPORTED : OFG_ERR_PARSE;
-            return fail(c, code, "%s", d.c_str());
-        }
-    }
-    if (coo_count > cap)
-        return fail(c, OFG_ERR_CAPACITY, "record capacity exceeded: %llu lines but room for %llu (lines shorter than %lld bytes on average); lower option max_bytes_per_line_inv",
-                    (unsigned long long)coo_count, (unsigned long long)cap, (long long)c->bytes_per_line_inv);
-    c->tot_lines = 0; c->tot_records = 0;
-    for (int i = 0; i < P; i++) { c->tot_lines += (int64_t)c->pair_lines[i]; c->tot_records += (int64_t)c->pair_valid[i]; }
-    const u64 n_slots = (u64)c->tot_records;
-    CK(c->cols.ensure((n_slots + 64) * 4));
-    CK(c->vals.ensure((n_slots + 64) * 8));
-    CK(c->key.ensure((n_slots + 64) * 4));
-    CK(c->keyval.ensure((n_slots + 64) * 8));
-    CK(c->long_rows.ensure((size_t)(c->n_rows + 1) * 4));
-
-    if (device_scan<u32>(c, c->rowcount.as<u32>(), c->n_rows, c->row_start.as<u32>(), 1)) return OFG_ERR_CUDA;
-    if (coo_count > 0) {
-        scatter_rows_kernel<<<grid_for(c, (int64_t)coo_count, 256 * 8, 8), 256, 0, c->stream>>>(
-            c->coo_row.as<u32>(), c->coo_col.as<u32>(), c->coo_val.as<double>(), coo_count, c->row_start.as<u32>(),
-            c->rowlen.as<u32>(), c->cols.as<u32>(), c->vals.as<double>());
-        CKL("scatter_rows_kernel");
-    }
+    CK(cudaMemsetAsync(c->row_start.p, 0, 4, c->stream));   // the first wave starts at slot 0
+    CK(c->cols.ensure((tot_cap + 64) * 4));
+    CK(c->vals.ensure((tot_cap + 64) * 8));
+    CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
+    CK(cudaMemsetAsync(c->fit.p, 0, (size_t)P * 8 * 8 + 64, c->stream));
     // sentinel key: one bit above the largest possible length product
     double maxL = 1.0;
     for (double v : c->lengths) maxL = std::max(maxL, v);
@@ -419,127 +448,154 @@ int stage_raw(ofg_ctx* c)
     if (max_lf >= 2147483648.0) return fail(c, OFG_ERR_UNSUPPORTED, "sequence length product %.0f does not fit 31 bits", max_lf);
     int bits = 1;
     while ((double)(1ULL << bits) <= max_lf) bits++;
-    const u32 key_sentinel = 1u << bits;
+    c->key_bits = bits + 1;  // including the sentinel bit
+    // pinned read-back area
+    if (c->h_small_cap < c->small_words) {
+        if (c->h_small) cudaFreeHost(c->h_small);
+        c->h_small = nullptr;
+        CK(cudaHostAlloc((void**)&c->h_small, (c->small_words + 64) * 8, cudaHostAllocDefault));
+        c->h_small_cap = c->small_words + 64;
+    }
+    if (c->h_fit_cap < (size_t)P * 8 + 16) {
+        if (c->h_fit) cudaFreeHost(c->h_fit);
+        c->h_fit = nullptr;
+        CK(cudaHostAlloc((void**)&c->h_fit, ((size_t)P * 8 + 16 + 64) * 8, cudaHostAllocDefault));
+        c->h_fit_cap = (size_t)P * 8 + 16 + 64;
+    }
+    c->tot_edges = 0; c->tot_text = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stages, per wave
+int wave_raw(ofg_ctx* c, int wi)
+{
+    const Wave& w = c->waves[wi];
+    const int Pw = w.P1 - w.P0;
+    const int64_t nr = w.R1 - w.R0;
+    if (Pw <= 0) return 0;
+    size_t seg_off = 0;  // position of this wave's segment prefix inside d_tile_prefix
+    for (int k = 0; k < wi; k++) seg_off += (size_t)(c->waves[k].P1 - c->waves[k].P0) + 1;
+    const u64 cap = w.cap;
+    CK(c->coo_row.ensure(cap * 4));
+    CK(c->coo_col.ensure(cap * 4));
+    CK(c->coo_val.ensure(cap * 8));
+    CK(c->key.ensure((cap + 64) * 4));
+    u64* d_count = wave_count_ptr(c, wi);
+    if (w.n_segs > 0) {
+        const int parse_grid = grid_for(c, (w.n_segs + PS_WARPS - 1) / PS_WARPS, 1, 4);
+        ParseArgs a;
+        a.text = c->text.as<uint8_t>(); a.pairs = c->d_pairs.as<PairDesc>() + w.P0; a.P = Pw;
+        a.seg_prefix = c->d_tile_prefix.as<int64_t>() + seg_off; a.n_segs = w.n_segs;
+        a.coo_row = c->coo_row.as<u32>(); a.coo_col = c->coo_col.as<u32>(); a.coo_val = c->coo_val.as<double>();
+        a.cap = cap; a.coo_count = d_count; a.rowcount = c->rowcount.as<u32>();
+        a.pair_lines = pair_lines_ptr(c) + w.P0; a.pair_valid = pair_valid_ptr(c) + w.P0; a.pair_err = pair_err_ptr(c) + w.P0; a.one = 1u;
+        const int parse_smem = (int)(sizeof(PsWarp) * PS_WARPS);
+        CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_smem));
+        parse_kernel<<<parse_grid, PARSE_THREADS, parse_smem, c->stream>>>(a);
+        CKL("parse_kernel");
+    }
+    // row_start of the wave's rows: exclusive scan of the row histogram, starting at the slot where the previous wave ended
+    u32* rs = c->row_start.as<u32>() + w.R0;
+    if (device_scan<u32>(c, c->rowcount.as<u32>() + w.R0, nr, rs, 1, nullptr, 0, rs)) return OFG_ERR_CUDA;
+    scatter_rows_kernel<<<grid_for(c, (int64_t)cap, 256 * 8, 8), 256, 0, c->stream>>>(
+        c->coo_row.as<u32>(), c->coo_col.as<u32>(), c->coo_val.as<double>(), d_count, cap, c->row_start.as<u32>(),
+        c->rowlen.as<u32>(), c->cols.as<u32>(), c->vals.as<double>());
+    CKL("scatter_rows_kernel");
+    CK(cudaMemsetAsync(small_ptr(c) + 1, 0, 8, c->stream));  // n_long of this wave
     RowSortArgs r;
-    r.n_rows = c->n_rows; r.row_start = c->row_start.as<u32>(); r.rowlen = c->rowlen.as<u32>();
+    r.row_begin = w.R0; r.n_rows = w.R1; r.row_start = c->row_start.as<u32>(); r.rowlen = c->rowlen.as<u32>();
     r.cols = c->cols.as<u32>(); r.vals = c->vals.as<double>(); r.pairs = c->d_pairs.as<PairDesc>();
-    r.pair_row_base = c->d_pair_row_base.as<int64_t>(); r.P = P; r.lengths = c->d_lengths.as<double>();
-    r.key = c->key.as<u32>(); r.keyval = c->keyval.as<double>(); r.key_sentinel = key_sentinel;
-    r.long_rows = c->long_rows.as<u32>(); r.n_long = (u32*)(sm + 1); r.pair_nnz = d_pair_nnz;
+    r.pair_row_base = c->d_pair_row_base.as<int64_t>(); r.P = (int)c->pairs.size(); r.lengths = c->d_lengths.as<double>();
+    r.key = c->key.as<u32>(); r.slot0 = rs; r.keyval = nullptr; r.key_sentinel = 1u << (c->key_bits - 1);
+    r.long_rows = c->long_rows.as<u32>(); r.n_long = (u32*)(small_ptr(c) + 1); r.pair_nnz = pair_nnz_ptr(c);
     r.scratch_cols = c->coo_col.as<u32>(); r.scratch_vals = c->coo_val.as<double>();
-    if (c->n_rows > 0) {
-        rowsort_kernel<<<grid_for(c, c->n_rows, ROWSORT_WARPS, 16), ROWSORT_WARPS * 32, 0, c->stream>>>(r);
+    if (nr > 0) {
+        rowsort_kernel<<<grid_for(c, nr, ROWSORT_WARPS, 16), ROWSORT_WARPS * 32, 0, c->stream>>>(r);
         CKL("rowsort_kernel");
         rowsort_long_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(r);
         CKL("rowsort_long_kernel");
     }
-    CK(cudaEventRecord(c->ev[2], c->stream));
-    // host sync 2: stored entries per pair
-    std::vector<u64> nnz(P);
-    CK(cudaMemcpyAsync(nnz.data(), d_pair_nnz, sizeof(u64) * P, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);
-    c->pair_nnz = nnz;
-    c->tot_nnz = 0;
-    for (int i = 0; i < P; i++) c->tot_nnz += (int64_t)nnz[i];
-    c->stage_done = OFG_STAGE_RAW;
-    // remember sort parameters
-    c->fit_host.assign((size_t)P * 8, 0.0);
-    c->key_bits = bits + 1;  // including the sentinel bit
     return 0;
 }
 
-int stage_norm(ofg_ctx* c)
+int wave_norm(ofg_ctx* c, int wi)
 {
-    mark_timeline(c);
+    const Wave& w = c->waves[wi];
+    const int Pw = w.P1 - w.P0;
+    const int64_t nr = w.R1 - w.R0;
+    if (Pw <= 0) return 0;
     const int P = (int)c->pairs.size();
-    u64* sm = c->d_small.as<u64>();
-    u32* err_flags = (u32*)(sm + 2);
+    u32* err_flags = err_flags_ptr(c);
     const int key_bits = c->key_bits;
-    const u64 n_slots = (u64)c->tot_records;
+    const u64 cap = w.cap;
+    const u32* slot0 = c->row_start.as<u32>() + w.R0;
+    double* fit_w = c->fit.as<double>() + (size_t)w.P0 * 8;
     if (c->scores_v2) {
         // --scores-v2 (gathering.py:157-174 NormalisedBitScore): B' = diag(Lq^-0.5) B diag(Lh^-0.5), no fit and no pair is
         // zeroed.  Expressed through the same factor kernels as a fit with a = 0.5, b = 0 (10^-0 = 1 exactly).
-        std::vector<double> fv((size_t)P * 8, 0.0);
-        for (int i = 0; i < P; i++) { fv[(size_t)i * 8 + 0] = 0.5; fv[(size_t)i * 8 + 3] = 1.0; fv[(size_t)i * 8 + 6] = 1.0; }
-        CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
-        if (P > 0 && upload(c, c->fit, fv.data(), fv.size() * 8)) return OFG_ERR_CUDA;
-        CK(cudaStreamSynchronize(c->stream));  // fv goes out of scope
-        CK(cudaEventRecord(c->ev[3], c->stream));
-        CK(cudaEventRecord(c->ev[4], c->stream));
-        CK(cudaEventRecord(c->ev[5], c->stream));
-    } else {
-        // ---- segmented stable radix sort by Lf
-        std::vector<int64_t> pair_slot(P + 1, 0), tile_prefix(P + 1, 0);
-        for (int i = 0; i < P; i++) {
-            pair_slot[i + 1] = pair_slot[i] + (int64_t)c->pair_valid[i];
-            tile_prefix[i + 1] = tile_prefix[i] + ((int64_t)c->pair_valid[i] + RS_TILE - 1) / RS_TILE;
+        double* fv = c->h_fit;  // pinned staging (also the read-back area; rewritten by the read-back later)
+        for (int i = 0; i < Pw; i++) {
+            double* f = fv + (size_t)(w.P0 + i) * 8;
+            for (int k = 0; k < 8; k++) f[k] = 0.0;
+            f[0] = 0.5; f[3] = 1.0; f[6] = 1.0;
         }
-        const int64_t n_tiles = tile_prefix[P];
-        if (upload(c, c->pair_slot, pair_slot.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
-        if (upload(c, c->sort_tile_prefix, tile_prefix.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
+        CK(cudaMemcpyAsync(fit_w, fv + (size_t)w.P0 * 8, (size_t)Pw * 8 * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // ---- layout of the wave on the device: slots, sort tiles and length bins of every pair
+        const int64_t max_tiles = (int64_t)(cap / RS_TILE) + Pw + 1;
+        const int64_t max_tasks = (int64_t)(cap / 20) + Pw + 1;
+        CK(c->wave_pair_slot.ensure((size_t)(Pw + 2) * 8));
+        CK(c->wave_tile_prefix.ensure((size_t)(Pw + 2) * 8));
+        CK(c->wave_task_prefix.ensure((size_t)(Pw + 2) * 8));
+        WaveLayoutArgs la;
+        la.row_start = c->row_start.as<u32>(); la.pair_row_base = c->d_pair_row_base.as<int64_t>(); la.P0 = w.P0; la.P1 = w.P1;
+        la.pair_nnz = pair_nnz_ptr(c); la.pair_slot = c->wave_pair_slot.as<int64_t>(); la.tile_prefix = c->wave_tile_prefix.as<int64_t>();
+        la.task_prefix = c->wave_task_prefix.as<u64>(); la.n_tiles = n_tiles_ptr(c); la.n_tasks = n_tasks_ptr(c);
+        la.max_tiles = max_tiles; la.max_tasks = max_tasks; la.err_flags = err_flags;
+        wave_layout_kernel<<<1, 1024, 0, c->stream>>>(la, 1);
+        CKL("wave_layout_kernel");
+        // ---- segmented stable radix sort by Lf
         const int n_pass = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
         const int pass_bits = (key_bits + n_pass - 1) / n_pass;
-        CK(c->key2.ensure((n_slots + 64) * 4));
-        CK(c->keyval2.ensure((n_slots + 64) * 8));
-        CK(c->counters.ensure(((size_t)n_tiles << pass_bits) * 4 + 64));
+        CK(c->keyval.ensure((cap + 64) * 8));
+        CK(c->key2.ensure((cap + 64) * 4));
+        CK(c->keyval2.ensure((cap + 64) * 8));
+        CK(c->counters.ensure(((size_t)max_tiles << pass_bits) * 4 + 64));
+        CK(c->sort_desc.ensure((size_t)max_tiles * sizeof(RsTileDesc)));
+        rs_desc_kernel<<<grid_for(c, max_tiles, 256, 4), 256, 0, c->stream>>>(c->wave_tile_prefix.as<int64_t>(), c->wave_pair_slot.as<int64_t>(), Pw,
+                                                                              n_tiles_ptr(c), pass_bits, c->sort_desc.as<RsTileDesc>());
+        CKL("rs_desc_kernel");
         // the first pass reads the scores straight from the CSR values (same slots as the keys), so the row sort does
         // not have to write a second copy; from then on the two sort buffers ping-pong
         u32* kin = c->key.as<u32>(); double* vin = c->vals.as<double>();
         u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
-        if (n_tiles > 0) {
-            CK(c->sort_desc.ensure((size_t)n_tiles * sizeof(RsTileDesc)));
-            for (int pass = 0; pass < n_pass; pass++) {
-                RadixArgs a;
-                a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
-                a.tile_prefix = c->sort_tile_prefix.as<int64_t>(); a.pair_slot = c->pair_slot.as<int64_t>();
-                a.P = P; a.n_tiles = n_tiles; a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
-                a.desc = c->sort_desc.as<RsTileDesc>();
-                if (pass == 0) {
-                    rs_desc_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(a, c->sort_desc.as<RsTileDesc>());
-                    CKL("rs_desc_kernel");
-                }
-                const int g = grid_for(c, n_tiles, 1, 2);  // scatter: two resident CTAs per SM (registers, shared memory)
-                radix_hist_kernel<<<grid_for(c, n_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
-                CKL("radix_hist_kernel");
-                if (device_scan<u32>(c, a.counters, n_tiles << pass_bits, a.counters, 0)) return OFG_ERR_CUDA;
-                CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
-                radix_scatter_kernel<<<g, RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);
-                CKL("radix_scatter_kernel");
-                std::swap(kin, kout);
-                if (pass == 0) { vin = vout; vout = c->keyval.as<double>(); } else std::swap(vin, vout);
-            }
+        CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
+        for (int pass = 0; pass < n_pass; pass++) {
+            RadixArgs a;
+            a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
+            a.n_tiles_dev = n_tiles_ptr(c); a.val_in_off_dev_valid = pass == 0 ? 1 : 0; a.slot0 = slot0;
+            a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
+            a.desc = c->sort_desc.as<RsTileDesc>();
+            radix_hist_kernel<<<grid_for(c, max_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
+            CKL("radix_hist_kernel");
+            if (device_scan<u32>(c, a.counters, max_tiles << pass_bits, a.counters, 0, n_tiles_ptr(c), pass_bits)) return OFG_ERR_CUDA;
+            radix_scatter_kernel<<<grid_for(c, max_tiles, 1, 2), RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);  // two resident CTAs per SM
+            CKL("radix_scatter_kernel");
+            std::swap(kin, kout);
+            if (pass == 0) { vin = vout; vout = c->keyval.as<double>(); } else std::swap(vin, vout);
         }
-        CK(cudaEventRecord(c->ev[3], c->stream));
         // ---- bins
-        std::vector<BinTask> tasks;
-        std::vector<int64_t> task_prefix(P + 1, 0);
-        for (int i = 0; i < P; i++) {
-            const u64 H = c->pair_nnz[i];
-            const u32 first = (u32)pair_slot[i];
-            if (H > 0 && H < 100) {
-                tasks.push_back(BinTask{first, (u32)H, i, 1});
-            } else if (H >= 100) {
-                const u32 n_in = H > 5000 ? 1000u : (H > 1000 ? 200u : 20u);
-                const u64 n_bins = H / n_in;
-                for (u64 b = 0; b < n_bins; b++) tasks.push_back(BinTask{(u32)(first + b * n_in), n_in, i, 0});
-            }
-            task_prefix[i + 1] = (int64_t)tasks.size();
-        }
-        const int64_t n_tasks = (int64_t)tasks.size();
-        if (upload(c, c->bin_tasks, tasks.data(), sizeof(BinTask) * tasks.size())) return OFG_ERR_CUDA;
-        std::vector<u64> tp64(task_prefix.begin(), task_prefix.end());
-        if (upload(c, c->task_prefix, tp64.data(), sizeof(u64) * (P + 1))) return OFG_ERR_CUDA;
-        CK(c->bin_cut.ensure((size_t)(n_tasks + 1) * 8));
-        CK(c->bin_cnt.ensure((size_t)(n_tasks + 1) * 4));
-        CK(c->sel_off.ensure((size_t)(n_tasks + 2) * 8));
-        c->sel_cap = std::max<u64>(n_slots / (u64)std::max<int64_t>(c->sel_frac_inv, 1), 1u << 16);
-        if (c->sel_cap > n_slots + 1) c->sel_cap = n_slots + 1;
+        CK(c->bin_tasks.ensure((size_t)(max_tasks + 1) * sizeof(BinTask)));
+        CK(c->bin_cut.ensure((size_t)(max_tasks + 1) * 8));
+        CK(c->bin_cnt.ensure((size_t)(max_tasks + 1) * 4));
+        CK(c->sel_off.ensure((size_t)(max_tasks + 2) * 8));
+        c->sel_cap = std::max<u64>(cap / (u64)std::max<int64_t>(c->sel_frac_inv, 1), 1u << 16);
         CK(c->lx.ensure(c->sel_cap * 8)); CK(c->ly.ensure(c->sel_cap * 8));
-        CK(c->fit.ensure((size_t)P * 8 * 8 + 64));
-        CK(cudaMemsetAsync(c->fit.p, 0, (size_t)P * 8 * 8, c->stream));
+        bin_tasks_kernel<<<grid_for(c, max_tasks, 256, 4), 256, 0, c->stream>>>(c->wave_task_prefix.as<u64>(), c->wave_pair_slot.as<int64_t>(), pair_nnz_ptr(c),
+                                                                                w.P0, Pw, n_tasks_ptr(c), c->bin_tasks.as<BinTask>());
+        CKL("bin_tasks_kernel");
         BinArgs b;
-        b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks = n_tasks; b.key = kin; b.val = vin;
+        b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks_dev = n_tasks_ptr(c); b.key = kin; b.val = vin;
         {
             // numpy: virtual index (n-1)*q with q = 95/100, gamma = vi - floor(vi)
             const double q = 95.0 / 100.0;
@@ -550,90 +606,111 @@ int stage_norm(ofg_ctx* c)
         }
         b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
         b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
-        // staging: two free fp64 arrays of at least n_slots entries - the parse output scores and the idle sort buffer
+        // staging: two free fp64 arrays of at least `cap` entries - the parse output scores and the idle sort buffer
         b.stage_lx = c->coo_val.as<double>(); b.stage_ly = vout;
-        if (n_tasks > 0) {
-            const int g = grid_for(c, n_tasks, BIN_WARPS, 6);
-            bin_cut_kernel<<<g, BIN_THREADS, 0, c->stream>>>(b);
-            CKL("bin_cut_kernel");
-            if (device_scan<u64>(c, b.cnt, n_tasks, c->sel_off.as<u64>(), 1)) return OFG_ERR_CUDA;
-            bin_select_kernel<<<grid_for(c, n_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
-            CKL("bin_select_kernel");
-        } else {
-            CK(cudaMemsetAsync(c->sel_off.p, 0, 16, c->stream));
-        }
-        CK(cudaEventRecord(c->ev[4], c->stream));
+        bin_cut_kernel<<<grid_for(c, max_tasks, BIN_WARPS, 6), BIN_THREADS, 0, c->stream>>>(b);
+        CKL("bin_cut_kernel");
+        if (device_scan<u64>(c, b.cnt, max_tasks, c->sel_off.as<u64>(), 1, n_tasks_ptr(c), 0)) return OFG_ERR_CUDA;
+        bin_select_kernel<<<grid_for(c, max_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
+        CKL("bin_select_kernel");
         // ---- fit
-        CK(c->pair_sel_off.ensure((size_t)(P + 2) * 8));
-        gather_u64_kernel<<<(P + 1 + 255) / 256, 256, 0, c->stream>>>(c->sel_off.as<u64>(), c->task_prefix.as<u64>(), P + 1,
-                                                                       c->pair_sel_off.as<u64>());
-        CKL("gather_u64_kernel");
+        CK(c->pair_sel_off.ensure((size_t)(Pw + 2) * 8));
+        pair_sel_off_kernel<<<(Pw + 1 + 255) / 256, 256, 0, c->stream>>>(c->sel_off.as<u64>(), c->wave_task_prefix.as<u64>(), Pw + 1,
+                                                                         c->pair_sel_off.as<u64>());
+        CKL("pair_sel_off_kernel");
         FitArgs f;
-        f.P = P; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
-        f.fit = c->fit.as<double>(); f.err_flags = err_flags;
-        if (P > 0) {
-            CK(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
-            fit_kernel<<<P, FIT_THREADS, sizeof(FitShared), c->stream>>>(f);
-            CKL("fit_kernel");
-        }
-        CK(cudaEventRecord(c->ev[5], c->stream));
+        f.P = Pw; f.pair_sel_off = c->pair_sel_off.as<u64>(); f.sel_cap = c->sel_cap; f.lx = b.lx; f.ly = b.ly;
+        f.fit = fit_w; f.err_flags = err_flags;
+        CK(ofg_launch_fit(f, Pw, c->stream));
+        CKL("fit_kernel");
     }
     // ---- factors, scale, best hits
+    if (nr > 0) {
+        FactorArgs fa;
+        fa.pairs = c->d_pairs.as<PairDesc>() + w.P0; fa.P = Pw; fa.fit = fit_w; fa.lengths = c->d_lengths.as<double>();
+        fa.rowfac = c->rowfac.as<double>(); fa.colfac = c->colfac.as<double>();
+        fa.given = (c->scores_v2 && c->have_length_factors) ? c->d_length_factors.as<double>() : nullptr;
+        int64_t maxg = 1;
+        for (int i = w.P0; i < w.P1; i++) maxg = std::max<int64_t>(maxg, (int64_t)c->pairs[i].Gi + c->pairs[i].Gj);
+        dim3 g((unsigned)Pw, (unsigned)std::min<int64_t>((maxg + 255) / 256, 64));
+        factors_kernel<<<g, 256, 0, c->stream>>>(fa);
+        CKL("factors_kernel");
+        ScaleArgs sa;
+        sa.row_begin = w.R0; sa.n_rows = w.R1; sa.row_start = c->row_start.as<u32>(); sa.rowlen = c->rowlen.as<u32>();
+        sa.cols = c->cols.as<u32>(); sa.vals = c->vals.as<double>(); sa.pairs = c->d_pairs.as<PairDesc>();
+        sa.pair_row_base = c->d_pair_row_base.as<int64_t>(); sa.P = P; sa.fit = c->fit.as<double>();
+        sa.rowfac = c->rowfac.as<double>(); sa.colfac = c->colfac.as<double>(); sa.rowmax = c->rowmax.as<double>();
+        sa.best = c->best.as<double>();
+        sa.row_flagcnt = c->row_flagcnt.as<u32>();
+        scale_bh_kernel<16><<<grid_for(c, nr, 16, 8), 256, 0, c->stream>>>(sa);
+        CKL("scale_bh_kernel");
+    }
+    return 0;
+}
+
+// buffers of the NORM stage that span all waves
+int norm_begin(ofg_ctx* c)
+{
     CK(c->rowfac.ensure((size_t)(c->n_rows + 1) * 8));
     CK(c->colfac.ensure((size_t)(c->n_cols + 1) * 8));
     CK(c->rowmax.ensure((size_t)(c->n_rows + 1) * 8));
     CK(c->best.ensure((size_t)(c->N + 1) * 8));
     CK(c->most.ensure((size_t)(c->N + 1) * 8));
     CK(cudaMemsetAsync(c->best.p, 0, (size_t)(c->N + 1) * 8, c->stream));
-    if (P > 0 && c->n_rows > 0) {
-        FactorArgs fa;
-        fa.pairs = c->d_pairs.as<PairDesc>(); fa.P = P; fa.fit = c->fit.as<double>(); fa.lengths = c->d_lengths.as<double>();
-        fa.rowfac = c->rowfac.as<double>(); fa.colfac = c->colfac.as<double>();
-        fa.given = (c->scores_v2 && c->have_length_factors) ? c->d_length_factors.as<double>() : nullptr;
-        int64_t maxg = 1;
-        for (int i = 0; i < P; i++) maxg = std::max<int64_t>(maxg, (int64_t)c->pairs[i].Gi + c->pairs[i].Gj);
-        dim3 g((unsigned)P, (unsigned)std::min<int64_t>((maxg + 255) / 256, 64));
-        factors_kernel<<<g, 256, 0, c->stream>>>(fa);
-        CKL("factors_kernel");
+    CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
+    CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
+    return 0;
+}
+
+// best hits of the within-species matrices: needs the per-gene best of every other species, i.e. all waves
+int norm_finish(ofg_ctx* c)
+{
+    const int P = (int)c->pairs.size();
+    c->diag_host.clear();
+    int64_t max_gi = 1;
+    for (int i = 0; i < P; i++) if (c->pairs[i].same) { c->diag_host.push_back(i); max_gi = std::max<int64_t>(max_gi, c->pairs[i].Gi); }
+    if (!c->diag_host.empty() && c->n_rows > 0) {
+        if (upload(c, c->diag_pairs, c->diag_host.data(), c->diag_host.size() * 4)) return OFG_ERR_CUDA;
         ScaleArgs sa;
-        sa.n_rows = c->n_rows; sa.row_start = c->row_start.as<u32>(); sa.rowlen = c->rowlen.as<u32>();
+        sa.row_begin = 0; sa.n_rows = c->n_rows; sa.row_start = c->row_start.as<u32>(); sa.rowlen = c->rowlen.as<u32>();
         sa.cols = c->cols.as<u32>(); sa.vals = c->vals.as<double>(); sa.pairs = c->d_pairs.as<PairDesc>();
         sa.pair_row_base = c->d_pair_row_base.as<int64_t>(); sa.P = P; sa.fit = c->fit.as<double>();
         sa.rowfac = c->rowfac.as<double>(); sa.colfac = c->colfac.as<double>(); sa.rowmax = c->rowmax.as<double>();
-        sa.best = c->best.as<double>();
-        CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
-        CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
-        sa.row_flagcnt = c->row_flagcnt.as<u32>();
-        const int g2 = grid_for(c, c->n_rows, 16, 8);
-        scale_bh_kernel<16><<<g2, 256, 0, c->stream>>>(sa);
-        CKL("scale_bh_kernel");
-        std::vector<int32_t> diag;
-        int64_t max_gi = 1;
-        for (int i = 0; i < P; i++) if (c->pairs[i].same) { diag.push_back(i); max_gi = std::max<int64_t>(max_gi, c->pairs[i].Gi); }
-        if (!diag.empty()) {
-            if (upload(c, c->file_off, diag.data(), diag.size() * 4)) return OFG_ERR_CUDA;  // small scratch buffer
-            dim3 gd((unsigned)std::min<int64_t>((max_gi + 7) / 8, 256), (unsigned)diag.size());
-            bh_self_kernel<<<gd, 256, 0, c->stream>>>(sa, c->file_off.as<int32_t>());
-            CKL("bh_self_kernel");
-        }
+        sa.best = c->best.as<double>(); sa.row_flagcnt = c->row_flagcnt.as<u32>();
+        dim3 gd((unsigned)std::min<int64_t>((max_gi + 7) / 8, 256), (unsigned)c->diag_host.size());
+        bh_self_kernel<<<gd, 256, 0, c->stream>>>(sa, c->diag_pairs.as<int32_t>());
+        CKL("bh_self_kernel");
     }
-    CK(cudaEventRecord(c->ev[6], c->stream));
-    // host sync 3: fit table, error flags
-    c->fit_host.assign((size_t)P * 8, 0.0);
-    u32 flags = 0;
-    if (P > 0) CK(cudaMemcpyAsync(c->fit_host.data(), c->fit.p, (size_t)P * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int stage_raw_norm(ofg_ctx* c, int stop_after)
+{
     mark_timeline(c);
-    if (flags & 2u)
-        return fail(c, OFG_ERR_CAPACITY, "selection capacity exceeded (%llu points); lower option sel_capacity_frac_inv", (unsigned long long)c->sel_cap);
-    if (flags & 1u) {
-        for (int i = 0; i < P; i++)
-            if (c->fit_host[(size_t)i * 8 + 2] > 1 && c->fit_host[(size_t)i * 8 + 6] == 0.0)
-                return fail(c, OFG_ERR_FIT, "Optimal parameters not found for pair (%d,%d): MINPACK info %d", c->pairs[i].p, c->pairs[i].j,
-                            (int)c->fit_host[(size_t)i * 8 + 3]);
+    if (int rc = plan_build(c)) return rc;
+    const bool norm = stop_after >= OFG_STAGE_NORM;
+    if (norm) if (int rc = norm_begin(c)) return rc;
+    for (int wi = 0; wi < (int)c->waves.size(); wi++) {
+        if (int rc = wave_raw(c, wi)) return rc;
+        if (norm) if (int rc = wave_norm(c, wi)) return rc;
     }
+    if (norm) if (int rc = norm_finish(c)) return rc;
+    c->raw_scratch_valid = !norm && c->waves.size() == 1;
+    c->stage_done = norm ? OFG_STAGE_NORM : OFG_STAGE_RAW;
+    c->pending = true;
+    return 0;
+}
+
+// NORM on top of a finished RAW stage (single wave only: the wave scratch still holds the sort keys)
+int stage_norm_only(ofg_ctx* c)
+{
+    mark_timeline(c);
+    if (int rc = norm_begin(c)) return rc;
+    if (int rc = wave_norm(c, 0)) return rc;
+    if (int rc = norm_finish(c)) return rc;
+    c->raw_scratch_valid = false;
     c->stage_done = OFG_STAGE_NORM;
+    c->pending = true;
     return 0;
 }
 
@@ -656,7 +733,7 @@ int stage_thresh(ofg_ctx* c)
             for (int64_t q = 0; q < c->n_seqs[p]; q++) { gene_of.push_back(c->seq_start[p] + q); sp_of.push_back(p); }
         if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
         if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
-        CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+        CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope (once per species / partition layout)
         c->layout_dirty = false;
     }
     CK(c->most.ensure((size_t)(c->N + 1) * 8));
@@ -699,9 +776,9 @@ int stage_thresh(ofg_ctx* c)
                                                                                c->owned_gene.as<uint8_t>(), c->N);
         CKL("thresh_final_kernel");
     }
-    CK(cudaEventRecord(c->ev[7], c->stream));
     c->thresholds_complete = ((int)c->owned.size() == c->S);
     c->stage_done = OFG_STAGE_THRESH;
+    c->pending = true;
     return 0;
 }
 
@@ -724,12 +801,24 @@ int stage_connect(ofg_ctx* c)
         CK(c->row_flagcnt.ensure((size_t)(c->n_rows + 1) * 4));
         CK(cudaMemsetAsync(c->row_flagcnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
         g.row_flagcnt = c->row_flagcnt.as<u32>();
-        g.gene_cnt = c->gene_cntg.as<u32>(); g.gene_bytes = c->gene_bytesg.as<u32>(); g.err_flags = (u32*)(c->d_small.as<u64>() + 2);
+        g.gene_cnt = c->gene_cntg.as<u32>(); g.gene_bytes = c->gene_bytesg.as<u32>(); g.err_flags = err_flags_ptr(c);
         connect_kernel<2><<<grid_for(c, c->n_rows, 128, 8), 256, 0, c->stream>>>(g);
         CKL("connect_kernel");
     }
-    CK(cudaEventRecord(c->ev[8], c->stream));
     c->stage_done = OFG_STAGE_CONNECT;
+    c->pending = true;
+    return 0;
+}
+
+int launch_emit(ofg_ctx* c)
+{
+    EmitArgs& e = c->last_emit;
+    e.out_indices = c->out_indices.as<int32_t>(); e.out_data = c->out_data.as<double>(); e.out_text = c->out_text.as<char>();
+    e.cap_edges = c->out_indices.cap / 4 > 16 ? c->out_indices.cap / 4 - 16 : 0;
+    e.cap_edges = std::min<u64>(e.cap_edges, c->out_data.cap / 8 > 16 ? c->out_data.cap / 8 - 16 : 0);
+    e.cap_text = c->out_text.cap > 64 ? c->out_text.cap - 64 : 0;
+    emit_kernel<true><<<c->last_emit_grid, EMIT_WARPS * 32, 0, c->stream>>>(e);
+    CKL("emit_kernel<true>");
     return 0;
 }
 
@@ -737,8 +826,7 @@ int stage_emit(ofg_ctx* c)
 {
     mark_timeline(c);
     const int P = (int)c->pairs.size();
-    u64* sm = c->d_small.as<u64>();
-    u32* err_flags = (u32*)(sm + 2);
+    u32* err_flags = err_flags_ptr(c);
     GraphArgs g;
     g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
     g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
@@ -756,33 +844,151 @@ int stage_emit(ofg_ctx* c)
     e.gene_cnt = c->unit_cnt.as<u32>(); e.gene_bytes = c->unit_bytes.as<u32>();
     e.cnt_off = c->cnt_off.as<u64>(); e.byte_off = c->byte_off.as<u64>();
     e.out_indices = nullptr; e.out_data = nullptr; e.out_text = nullptr; e.err_flags = err_flags;
+    e.cap_edges = 0; e.cap_text = 0;
+    c->last_emit = e;
+    c->last_emit_grid = 0;
     c->tot_edges = 0; c->tot_text = 0;
     if (n_units > 0) {
-        const int ge = grid_for(c, n_units, EMIT_WARPS, 6);
+        c->last_emit_grid = grid_for(c, n_units, EMIT_WARPS, 6);
         emit_sizes_kernel<<<grid_for(c, n_units, 256, 4), 256, 0, c->stream>>>(e, c->gene_cntg.as<u32>(), c->gene_bytesg.as<u32>());
         CKL("emit_sizes_kernel");
         if (device_scan<u64>(c, e.gene_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
         if (device_scan<u64>(c, e.gene_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
-        u64 tots[2] = {0, 0};
-        CK(cudaMemcpyAsync(&tots[0], c->cnt_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&tots[1], c->byte_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);  // host sync 4: output sizes
-        c->tot_edges = (int64_t)tots[0]; c->tot_text = (int64_t)tots[1];
-        CK(c->out_indices.ensure((size_t)(tots[0] + 16) * 4));
-        CK(c->out_data.ensure((size_t)(tots[0] + 16) * 8));
-        CK(c->out_text.ensure((size_t)tots[1] + 64));
-        e.out_indices = c->out_indices.as<int32_t>(); e.out_data = c->out_data.as<double>(); e.out_text = c->out_text.as<char>();
-        emit_kernel<true><<<ge, EMIT_WARPS * 32, 0, c->stream>>>(e);
-        CKL("emit_kernel<true>");
+        // the output sizes are known only on the device: emit into the buffers of the previous build and let the kernel
+        // check the capacity; the read-back grows them and emits again when they were too small (first build)
+        if (int rc = launch_emit(c)) return rc;
     }
-    CK(cudaEventRecord(c->ev[9], c->stream));
-    u32 flags = 0;
-    CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    mark_timeline(c);
-    if (flags & 4u) return fail(c, OFG_ERR_UNSUPPORTED, "a graph weight is too large for \"%%.3f\" formatting on the device");
     c->stage_done = OFG_STAGE_GRAPH;
+    c->pending = true;
+    c->graph_pending = true;
+    return 0;
+}
+
+const char* const STAGE_OF_KERNEL[][2] = {
+    {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
+    {"wave_layout_kernel", "2"}, {"rs_desc_kernel", "2"}, {"radix_hist_kernel", "2"}, {"radix_scatter_kernel", "2"},
+    {"bin_tasks_kernel", "3"}, {"bin_cut_kernel", "3"}, {"bin_select_kernel", "3"}, {"pair_sel_off_kernel", "4"}, {"fit_kernel", "4"},
+    {"factors_kernel", "5"}, {"scale_bh_kernel", "5"}, {"bh_self_kernel", "5"}, {"rbh_kernel", "6"}, {"v2_ratio_kernel", "6"},
+    {"thresh_final_kernel", "6"}, {"connect_kernel", "7"}, {"emit_sizes_kernel", "8"}, {"emit_kernel<true>", "8"}};
+
+// One host synchronisation for everything a build left on the device: line counts, parse errors, capacity flags,
+// fit table, graph sizes, kernel timeline.  Called at the end of ofg_build (unless option async) and by every accessor.
+int sync_results(ofg_ctx* c)
+{
+    if (!c->pending) return 0;
+    const int P = (int)c->pairs.size();
+    u64 tots[2] = {0, 0};
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CK(cudaMemcpyAsync(c->h_small, c->d_small.p, c->small_words * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (P > 0 && c->stage_done >= OFG_STAGE_NORM) CK(cudaMemcpyAsync(c->h_fit, c->fit.p, (size_t)P * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
+        const int64_t n_units = c->n_owned_genes;
+        if (c->graph_pending && n_units > 0) {
+            CK(cudaMemcpyAsync(c->h_fit + (size_t)P * 8, c->cnt_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(c->h_fit + (size_t)P * 8 + 1, c->byte_off.as<u64>() + n_units, 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        const u32 flags = (u32)c->h_small[2];
+        if (c->graph_pending && n_units > 0) {
+            memcpy(tots, c->h_fit + (size_t)P * 8, 16);
+            if (flags & 64u) {
+                // output buffers too small: grow and emit again
+                CK(c->out_indices.ensure((size_t)(tots[0] + 32) * 4));
+                CK(c->out_data.ensure((size_t)(tots[0] + 32) * 8));
+                CK(c->out_text.ensure((size_t)tots[1] + 128));
+                u32 cleared = flags & ~64u;
+                CK(cudaMemcpyAsync(err_flags_ptr(c), &cleared, 4, cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                if (int rc = launch_emit(c)) return rc;
+                continue;
+            }
+        }
+        break;
+    }
+    c->pending = false;
+    const u64* small = c->h_small;
+    const u32 flags = (u32)small[2];
+    const size_t pb = c->small_pair_base;
+    c->pair_lines.assign(small + pb, small + pb + P);
+    c->pair_valid.assign(small + pb + P, small + pb + 2 * (size_t)P);
+    c->pair_nnz.assign(small + pb + 3 * (size_t)P, small + pb + 4 * (size_t)P);
+    c->tot_lines = 0; c->tot_records = 0; c->tot_nnz = 0;
+    for (int i = 0; i < P; i++) { c->tot_lines += (int64_t)c->pair_lines[i]; c->tot_records += (int64_t)c->pair_valid[i]; c->tot_nnz += (int64_t)c->pair_nnz[i]; }
+    // resolve the timeline into the per-stage totals
+    for (int i = 0; i < 10; i++) c->ms[i] = 0.f;
+    for (int i = 1; i < c->tl_n; i++) {
+        if (!c->tl_name[i]) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->tl_ev[i - 1], c->tl_ev[i]) != cudaSuccess) continue;
+        int st = -1;
+        for (auto& m : STAGE_OF_KERNEL) if (!strcmp(m[0], c->tl_name[i])) { st = m[1][0] - '0'; break; }
+        if (st < 0 && strstr(c->tl_name[i], "scan_")) {
+            // scans belong to the stage of the next non-scan kernel
+            for (int k = i + 1; k < c->tl_n && st < 0; k++)
+                if (c->tl_name[k] && !strstr(c->tl_name[k], "scan_"))
+                    for (auto& m : STAGE_OF_KERNEL) if (!strcmp(m[0], c->tl_name[k])) { st = m[1][0] - '0'; break; }
+        }
+        if (st >= 0) c->ms[st] += t;
+        c->ms[9] += t;
+    }
+    // parse errors first (the reference fails on the first offending line of a file)
+    for (int i = 0; i < P; i++) {
+        const u64 e = small[pb + 2 * (size_t)P + i];
+        if (e != ~0ULL) {
+            std::string d;
+            describe_line(c, i, e, &d);
+            const int kind = (int)(e & 15);
+            const int code = (kind == OFG_LINE_RANGE_Q || kind == OFG_LINE_RANGE_S) ? OFG_ERR_INCONSISTENT
+                             : (kind == OFG_LINE_QUOTE || kind == OFG_LINE_SCORE_FORMAT) ? OFG_ERR_UNSUPPORTED : OFG_ERR_PARSE;
+            c->stage_done = 0;
+            return fail(c, code, "%s", d.c_str());
+        }
+    }
+    for (size_t w = 0; w < c->waves.size(); w++) {
+        const u64 used = small[8 + w];
+        if (used > c->waves[w].cap) {
+            const bool learned = c->bpl_learned > (double)c->bytes_per_line_inv;
+            c->bpl_learned = 0.0;
+            c->stage_done = 0;
+            return fail(c, OFG_ERR_CAPACITY, "record capacity exceeded: %llu lines but room for %llu (%s); %s",
+                        (unsigned long long)used, (unsigned long long)c->waves[w].cap,
+                        learned ? "sized from the previous build of this context" : "lines shorter than max_bytes_per_line_inv bytes on average",
+                        learned ? "build again" : "lower option max_bytes_per_line_inv");
+        }
+    }
+    if (flags & 16u) { c->stage_done = 0; return fail(c, OFG_ERR_CAPACITY, "sort tile / length bin capacity exceeded"); }
+    if (c->stage_done >= OFG_STAGE_NORM) {
+        c->fit_host.assign(c->h_fit, c->h_fit + (size_t)P * 8);
+        if (flags & 2u) {
+            c->stage_done = 0;
+            return fail(c, OFG_ERR_CAPACITY, "selection capacity exceeded (%llu points); lower option sel_capacity_frac_inv", (unsigned long long)c->sel_cap);
+        }
+        if (flags & 1u) {
+            for (int i = 0; i < P; i++)
+                if (c->fit_host[(size_t)i * 8 + 2] > 1 && c->fit_host[(size_t)i * 8 + 6] == 0.0) {
+                    c->stage_done = 0;
+                    return fail(c, OFG_ERR_FIT, "Optimal parameters not found for pair (%d,%d): MINPACK info %d", c->pairs[i].p, c->pairs[i].j,
+                                (int)c->fit_host[(size_t)i * 8 + 3]);
+                }
+        }
+    } else {
+        c->fit_host.assign((size_t)P * 8, 0.0);
+    }
+    if (flags & 8u) return fail(c, OFG_ERR_ARG, "imported list addresses a species pair this context does not hold");
+    if (flags & 32u) return fail(c, OFG_ERR_CAPACITY, "exchange inbox too small for the exported lists; enlarge it and repeat the step");
+    if (c->graph_pending) {
+        c->graph_pending = false;
+        c->tot_edges = (int64_t)tots[0]; c->tot_text = (int64_t)tots[1];
+        if (flags & 64u) return fail(c, OFG_ERR_CAPACITY, "graph output buffers could not be sized");
+        if (flags & 4u) return fail(c, OFG_ERR_UNSUPPORTED, "a graph weight is too large for \"%%.3f\" formatting on the device");
+    }
+    // size the next build of this context from what this one saw (with a margin)
+    if (c->tot_records > 0 && c->stage_done >= OFG_STAGE_RAW) {
+        int64_t text = 0;
+        u64 slots = 0;
+        for (const Wave& w : c->waves) text += w.text_bytes;
+        for (size_t w = 0; w < c->waves.size(); w++) slots += small[8 + w];
+        if (slots > 0) c->bpl_learned = 0.85 * (double)text / (double)slots;
+    }
     return 0;
 }
 
@@ -802,7 +1008,6 @@ int ofg_create(ofg_ctx** out, int device)
     c->device = device;
     cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return OFG_ERR_CUDA; }
-    for (auto& e : c->ev) cudaEventCreate(&e);
     *out = c;
     return OFG_OK;
 }
@@ -814,14 +1019,17 @@ void ofg_destroy(ofg_ctx* c)
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->text, &c->d_pairs, &c->d_pair_row_base, &c->d_pair_of, &c->d_lengths, &c->d_tile_prefix, &c->d_small,
                       &c->coo_row, &c->coo_col, &c->coo_val, &c->rowcount, &c->row_start, &c->rowlen, &c->cols, &c->vals, &c->key,
-                      &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->sort_tile_prefix,
-                      &c->pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg, &c->most_init, &c->d_length_factors,
+                      &c->keyval, &c->key2, &c->keyval2, &c->long_rows, &c->counters, &c->scan_partial, &c->wave_tile_prefix,
+                      &c->wave_pair_slot, &c->bin_tasks, &c->bin_cut, &c->bin_cnt, &c->sel_off, &c->wave_task_prefix, &c->lx, &c->ly, &c->sort_desc, &c->zrow, &c->pair_factor, &c->d_owned, &c->gene_cntg, &c->gene_bytesg, &c->most_init, &c->d_length_factors,
                       &c->fit, &c->rowfac, &c->colfac, &c->rowmax, &c->best, &c->most, &c->owned_gene,
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
-                      &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff};
+                      &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff, &c->diag_pairs,
+                      &c->x_flag, &c->x_off, &c->x_list, &c->x_pair_dst, &c->x_order, &c->x_dst_first, &c->x_inbox_ptrs};
     for (DevBuf* b : bufs) b->release();
-    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->tl_ev) if (e) cudaEventDestroy(e);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h_fit) cudaFreeHost(c->h_fit);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -842,7 +1050,7 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     c->len_off.assign(n_species, 0);
     int64_t acc = 0;
     for (int p = 0; p < n_species; p++) {
-        if (n_seqs[p] < 0 || n_seqs[p] > (int64_t)OFG_COL_MASK) return fail(c, OFG_ERR_UNSUPPORTED, "species %d has %lld sequences (limit 2^29-1)", p, (long long)n_seqs[p]);
+        if (n_seqs[p] < 0 || n_seqs[p] > (int64_t)OFG_COL_MASK) return fail(c, OFG_ERR_UNSUPPORTED, "species %d has %lld sequences (limit 2^28-1)", p, (long long)n_seqs[p]);
         c->seq_start[p] = acc;
         c->len_off[p] = acc;
         acc += n_seqs[p];
@@ -851,6 +1059,10 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     c->N = acc;
     c->lengths.assign(lengths_concat, lengths_concat + acc);
     c->owned.clear();
+    c->has_partition = false;
+    c->pending = false;
+    c->graph_pending = false;
+    c->bpl_learned = 0.0;
     c->pairs_dirty = true;
     c->files.clear();
     c->pairs.clear();
@@ -870,6 +1082,7 @@ int ofg_set_partition(ofg_ctx* c, int n_owned, const int32_t* owned_rows, int wi
         o.push_back(owned_rows[i]);
     }
     c->owned = o;
+    c->has_partition = true;
     c->with_columns = with_columns;
     c->pairs_dirty = true;
     return ensure_pairs(c);
@@ -882,6 +1095,8 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "scores_v2")) c->scores_v2 = value != 0;
     else if (!strcmp(name, "max_bytes_per_line_inv")) c->bytes_per_line_inv = value;
     else if (!strcmp(name, "sel_capacity_frac_inv")) c->sel_frac_inv = value;
+    else if (!strcmp(name, "wave_species")) { c->wave_species = (int)std::max<int64_t>(value, 0); c->stage_done = 0; }
+    else if (!strcmp(name, "async")) c->async = value != 0;
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else return fail(c, OFG_ERR_ARG, "unknown option %s", name);
     return OFG_OK;
@@ -1002,55 +1217,62 @@ int ofg_hits_text_copy(ofg_ctx* c, int p, int j, void* host_dst, size_t cap)
     return OFG_OK;
 }
 
+static int build_once(ofg_ctx* c, int stop_after)
+{
+    if (c->stage_done >= stop_after) c->stage_done = 0;  // asked for a stage that is already built: rebuild from the text
+    if (c->stage_done == OFG_STAGE_RAW && !(c->raw_scratch_valid && c->waves.size() == 1)) c->stage_done = 0;  // sort keys of the waves are gone
+    if (c->stage_done == 0) {
+        if (c->pending) { c->pending = false; c->graph_pending = false; CK(cudaStreamSynchronize(c->stream)); }
+        c->tl_n = 0;
+        c->launches = 0;
+    }
+    if (c->stage_done < OFG_STAGE_RAW) {
+        if (int rc = stage_raw_norm(c, stop_after)) { c->stage_done = 0; return rc; }
+    } else if (stop_after >= OFG_STAGE_NORM && c->stage_done < OFG_STAGE_NORM) {
+        if (int rc = stage_norm_only(c)) { c->stage_done = 0; return rc; }
+    }
+    if (stop_after >= OFG_STAGE_THRESH && c->stage_done < OFG_STAGE_THRESH)
+        if (int rc = stage_thresh(c)) { c->stage_done = 0; return rc; }
+    if (stop_after >= OFG_STAGE_CONNECT && c->stage_done < OFG_STAGE_CONNECT)
+        if (int rc = stage_connect(c)) return rc;
+    if (stop_after >= OFG_STAGE_GRAPH && c->stage_done < OFG_STAGE_GRAPH)
+        if (int rc = stage_emit(c)) return rc;
+    if (c->async) return OFG_OK;
+    return sync_results(c);
+}
+
 int ofg_build(ofg_ctx* c, int stop_after)
 {
     if (!c) return OFG_ERR_ARG;
     cudaSetDevice(c->device);
     if (int rc = ensure_pairs(c)) return rc;
     if (stop_after < OFG_STAGE_RAW || stop_after > OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "bad stage %d", stop_after);
-    if (c->stage_done >= stop_after) c->stage_done = 0;  // asked for a stage that is already built: rebuild from the text
-    const bool fresh = c->stage_done == 0;
-    if (fresh) {
-        c->tl_n = 0;
-        c->launches = 0;
-        for (int i = 0; i < 10; i++) c->ms[i] = 0.f;
-    }
-    int first_ev = -1, last_ev = -1;
-    if (c->stage_done < OFG_STAGE_RAW) {
-        if (int rc = stage_raw(c)) { c->stage_done = 0; return rc; }
-        first_ev = 0; last_ev = 2;
-    }
-    if (stop_after >= OFG_STAGE_NORM && c->stage_done < OFG_STAGE_NORM) {
-        if (first_ev < 0) { CK(cudaEventRecord(c->ev[2], c->stream)); first_ev = 2; }
-        if (int rc = stage_norm(c)) { c->stage_done = 0; return rc; }
-        last_ev = 6;
-    }
-    if (stop_after >= OFG_STAGE_THRESH && c->stage_done < OFG_STAGE_THRESH) {
-        if (first_ev < 0) { CK(cudaEventRecord(c->ev[6], c->stream)); first_ev = 6; }
-        if (int rc = stage_thresh(c)) { c->stage_done = 0; return rc; }
-        last_ev = 7;
-    }
-    if (stop_after >= OFG_STAGE_CONNECT && c->stage_done < OFG_STAGE_CONNECT) {
-        if (first_ev < 0) { CK(cudaEventRecord(c->ev[7], c->stream)); first_ev = 7; }
-        if (int rc = stage_connect(c)) return rc;
-        last_ev = 8;
-    }
-    if (stop_after >= OFG_STAGE_GRAPH && c->stage_done < OFG_STAGE_GRAPH) {
-        if (first_ev < 0) { CK(cudaEventRecord(c->ev[8], c->stream)); first_ev = 8; }
-        if (int rc = stage_emit(c)) return rc;
-        last_ev = 9;
-    }
-    CK(cudaStreamSynchronize(c->stream));
-    // group timings between consecutive events that were recorded in this call
-    if (first_ev >= 0) {
-        for (int k = first_ev; k < last_ev; k++) {
-            float t = 0.f;
-            if (cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]) == cudaSuccess) c->ms[k] = t;
-        }
-        float tot = 0.f;
-        for (int k = 0; k < 9; k++) tot += c->ms[k];
-        c->ms[9] = tot;
-    }
+    const bool sized_from_last = c->bpl_learned > (double)c->bytes_per_line_inv;
+    int rc = build_once(c, stop_after);
+    if (rc == OFG_ERR_CAPACITY && sized_from_last && c->bpl_learned == 0.0 && !c->async)
+        rc = build_once(c, stop_after);  // the capacities learned from the previous input were too small for this one: conservative sizes
+    return rc;
+}
+
+int ofg_sync(ofg_ctx* c)
+{
+    if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (!c->pending) { CK(cudaStreamSynchronize(c->stream)); return OFG_OK; }
+    return sync_results(c);
+}
+
+int ofg_wait_for(ofg_ctx* c, ofg_ctx* other)
+{
+    if (!c || !other) return OFG_ERR_ARG;
+    if (c == other) return OFG_OK;
+    cudaSetDevice(other->device);
+    cudaEvent_t e = nullptr;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventRecord(e, other->stream));
+    cudaSetDevice(c->device);
+    CK(cudaStreamWaitEvent(c->stream, e, 0));
+    CK(cudaEventDestroy(e));  // released once the recorded work has completed
     return OFG_OK;
 }
 
@@ -1058,6 +1280,7 @@ int ofg_kernel_report(ofg_ctx* c, char* buf, size_t cap)
 {
     if (!c || !buf || cap == 0) return OFG_ERR_ARG;
     cudaSetDevice(c->device);
+    if (int rc = sync_results(c)) return rc;
     cudaStreamSynchronize(c->stream);
     struct Agg { const char* name; int n; double ms; };
     std::vector<Agg> agg;
@@ -1080,6 +1303,8 @@ int ofg_kernel_report(ofg_ctx* c, char* buf, size_t cap)
 int ofg_last_timing(ofg_ctx* c, float ms[10], int64_t* n_launches)
 {
     if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = sync_results(c)) return rc;
     if (ms) memcpy(ms, c->ms, sizeof(float) * 10);
     if (n_launches) *n_launches = c->launches;
     return OFG_OK;
@@ -1105,6 +1330,8 @@ int ofg_thresholds_mark_complete(ofg_ctx* c)
 int ofg_thresholds_copy(ofg_ctx* c, double* host_dst, int64_t n)
 {
     if (!c || !host_dst) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_THRESH) return fail(c, OFG_ERR_ARG, "thresholds are not built yet");
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(host_dst, c->most.p, (size_t)std::min<int64_t>(n, c->N) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1112,20 +1339,32 @@ int ofg_thresholds_copy(ofg_ctx* c, double* host_dst, int64_t n)
     return OFG_OK;
 }
 
+// row_flagcnt is one buffer: scale_bh_kernel fills it with best-hit counts, connect_kernel overwrites it with connect
+// counts.  The best-hit lists can therefore only be exported between NORM and CONNECT, the connect lists from CONNECT on.
+static int check_exchange_stage(ofg_ctx* c, int which, const char* what)
+{
+    if (which != 0 && which != 1) return fail(c, OFG_ERR_ARG, "which must be 0 (best hits) or 1 (connect)");
+    if (which == 0 && !(c->stage_done == OFG_STAGE_NORM || c->stage_done == OFG_STAGE_THRESH))
+        return fail(c, OFG_ERR_ARG, "%s of best-hit lists is only possible right after stage NORM / THRESH (stage is %d)", what, c->stage_done);
+    if (which == 1 && c->stage_done != OFG_STAGE_CONNECT)
+        return fail(c, OFG_ERR_ARG, "%s of connect lists is only possible right after stage CONNECT (stage is %d)", what, c->stage_done);
+    return 0;
+}
+
 int ofg_export_flags(ofg_ctx* c, int which, int n_ranks, const int32_t* species_rank, int my_rank, int64_t* counts, int32_t** dev_list)
 {
     if (!c || !species_rank || !counts || !dev_list || n_ranks <= 0) return OFG_ERR_ARG;
     cudaSetDevice(c->device);
-    const int need = which == 0 ? OFG_STAGE_NORM : OFG_STAGE_CONNECT;
-    if (c->stage_done < need) return fail(c, OFG_ERR_ARG, "export of %s lists needs stage %d", which == 0 ? "best-hit" : "connect", need);
+    if (int rc = sync_results(c)) return rc;
+    if (int rc = check_exchange_stage(c, which, "export")) return rc;
     const int P = (int)c->pairs.size();
     std::vector<uint8_t> ex(P, 0);
     for (int i = 0; i < P; i++) {
         const PairDesc& d = c->pairs[i];
         ex[i] = d.owned_row && species_rank[d.j] != my_rank;  // (k, p): column species p lives elsewhere
     }
-    DevBuf& flagbuf = c->synth_bytes;  // scratch buffers of the generator are free at this point
-    DevBuf& offbuf = c->synth_off;
+    DevBuf& flagbuf = c->x_flag;
+    DevBuf& offbuf = c->x_off;
     for (int r = 0; r < n_ranks; r++) counts[r] = 0;
     *dev_list = nullptr;
     if (P == 0 || c->n_rows == 0) return OFG_OK;
@@ -1148,47 +1387,159 @@ int ofg_export_flags(ofg_ctx* c, int which, int n_ranks, const int32_t* species_
     for (int r = 0; r < n_ranks; r++)
         for (int i = 0; i < P; i++)
             if (ex[i] && species_rank[c->pairs[i].j] == r) { off[i] = total; total += pb[i + 1] - pb[i]; counts[r] += (int64_t)(pb[i + 1] - pb[i]); }
-    CK(c->unit_bytes.ensure((size_t)(total + 1) * 8));  // list buffer (free until the emit stage)
+    CK(c->x_list.ensure((size_t)(total + 1) * 8));
     CK(cudaMemcpyAsync(offbuf.p, off.data(), sizeof(u64) * P, cudaMemcpyHostToDevice, c->stream));
     ExportArgs a;
     a.n_rows = c->n_rows; a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>();
     a.pairs = c->d_pairs.as<PairDesc>(); a.pair_row_base = c->d_pair_row_base.as<int64_t>(); a.P = P;
     a.pair_export = flagbuf.as<uint8_t>(); a.flag = which == 0 ? OFG_FLAG_BH : OFG_FLAG_CONNECT;
-    a.row_off = c->row_flagoff.as<u64>(); a.pair_off = offbuf.as<u64>(); a.out = c->unit_bytes.as<int2>();
+    a.row_off = c->row_flagoff.as<u64>(); a.pair_off = offbuf.as<u64>(); a.out = c->x_list.as<int2>();
     if (total > 0) {
         export_flags_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(a);
         CKL("export_flags_kernel");
     }
     CK(cudaStreamSynchronize(c->stream));
-    *dev_list = c->unit_bytes.as<int32_t>();
+    *dev_list = c->x_list.as<int32_t>();
     return OFG_OK;
+}
+
+static void fill_import_args(ofg_ctx* c, int which, ImportArgs& a)
+{
+    a.list = nullptr; a.n = 0; a.seq_start = c->d_seq_start.as<int64_t>(); a.S = c->S;
+    a.pair_of = c->d_pair_of.as<int32_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.row_start = c->row_start.as<u32>();
+    a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>(); a.set_flag = which == 0 ? OFG_FLAG_TBH : OFG_FLAG_REVERSE;
+    a.err_flags = err_flags_ptr(c); a.vals = c->vals.as<double>(); a.gene_cnt = c->gene_cntg.as<u32>(); a.gene_bytes = c->gene_bytesg.as<u32>();
+    a.inbox = nullptr; a.seg_bytes = 0; a.my_rank = -1;
 }
 
 int ofg_import_flags(ofg_ctx* c, int which, const int32_t* dev_list, int64_t n_entries)
 {
     if (!c || n_entries < 0 || (n_entries > 0 && !dev_list)) return OFG_ERR_ARG;
     cudaSetDevice(c->device);
-    const int need = which == 0 ? OFG_STAGE_NORM : OFG_STAGE_CONNECT;
-    if (c->stage_done < need) return fail(c, OFG_ERR_ARG, "import of %s lists needs stage %d", which == 0 ? "best-hit" : "connect", need);
+    if (int rc = check_exchange_stage(c, which, "import")) return rc;
     if (n_entries == 0) return OFG_OK;
-    u32* err_flags = (u32*)(c->d_small.as<u64>() + 2);
     ImportArgs a;
-    a.list = reinterpret_cast<const int2*>(dev_list); a.n = n_entries; a.seq_start = c->d_seq_start.as<int64_t>(); a.S = c->S;
-    a.pair_of = c->d_pair_of.as<int32_t>(); a.pairs = c->d_pairs.as<PairDesc>(); a.row_start = c->row_start.as<u32>();
-    a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>(); a.set_flag = which == 0 ? OFG_FLAG_TBH : OFG_FLAG_REVERSE;
-    a.err_flags = err_flags; a.vals = c->vals.as<double>(); a.gene_cnt = c->gene_cntg.as<u32>(); a.gene_bytes = c->gene_bytesg.as<u32>();
+    fill_import_args(c, which, a);
+    a.list = reinterpret_cast<const int2*>(dev_list); a.n = n_entries;
     import_flags_kernel<<<grid_for(c, n_entries, 256, 8), 256, 0, c->stream>>>(a);
     CKL("import_flags_kernel");
-    u32 flags = 0;
-    CK(cudaMemcpyAsync(&flags, err_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (flags & 8u) return fail(c, OFG_ERR_ARG, "imported list addresses a species pair this context does not hold");
+    c->pending = true;
+    if (c->async) return OFG_OK;
+    return sync_results(c);
+}
+
+// ---- peer exchange: lists written straight into the destinations' inboxes, everything sized and placed on the device
+int ofg_export_flags_peer(ofg_ctx* c, int which, int n_ranks, const int32_t* species_rank, int my_rank, void* const* inbox_ptrs,
+                          size_t seg_bytes)
+{
+    if (!c || !species_rank || !inbox_ptrs || n_ranks <= 0 || n_ranks > 32 || my_rank < 0 || my_rank >= n_ranks || seg_bytes < 16 || (seg_bytes & 7))
+        return c ? fail(c, OFG_ERR_ARG, "bad arguments to ofg_export_flags_peer") : OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = check_exchange_stage(c, which, "export")) return rc;
+    const int P = (int)c->pairs.size();
+    // static part (depends on the partition only): destination of every pair, exported pairs grouped by destination
+    std::vector<int32_t> pair_dst(std::max(P, 1), -1), order, dst_first(n_ranks + 1, 0);
+    for (int i = 0; i < P; i++) {
+        const PairDesc& d = c->pairs[i];
+        const int r = species_rank[d.j];
+        if (r < 0 || r >= n_ranks) return fail(c, OFG_ERR_ARG, "species %d has no owner rank", d.j);
+        if (d.owned_row && r != my_rank) pair_dst[i] = r;
+    }
+    for (int r = 0; r < n_ranks; r++) {
+        dst_first[r] = (int32_t)order.size();
+        for (int i = 0; i < P; i++) if (pair_dst[i] == r) order.push_back(i);
+    }
+    dst_first[n_ranks] = (int32_t)order.size();
+    if (order.empty()) order.push_back(0);
+    if (upload(c, c->x_pair_dst, pair_dst.data(), pair_dst.size() * 4)) return OFG_ERR_CUDA;
+    if (upload(c, c->x_order, order.data(), order.size() * 4)) return OFG_ERR_CUDA;
+    if (upload(c, c->x_dst_first, dst_first.data(), dst_first.size() * 4)) return OFG_ERR_CUDA;
+    if (upload(c, c->x_inbox_ptrs, inbox_ptrs, sizeof(void*) * n_ranks)) return OFG_ERR_CUDA;
+    CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope (a few KB; the lists themselves never touch the host)
+    CK(c->row_flagoff.ensure((size_t)(c->n_rows + 2) * 8));
+    CK(c->x_off.ensure((size_t)(P + 4) * 8));
+    if (device_scan<u64>(c, c->row_flagcnt.as<u32>(), c->n_rows, c->row_flagoff.as<u64>(), 1)) return OFG_ERR_CUDA;
+    PeerExportArgs a;
+    a.n_rows = c->n_rows; a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>();
+    a.pairs = c->d_pairs.as<PairDesc>(); a.pair_row_base = c->d_pair_row_base.as<int64_t>(); a.P = P;
+    a.pair_dst = c->x_pair_dst.as<int32_t>(); a.flag = which == 0 ? OFG_FLAG_BH : OFG_FLAG_CONNECT;
+    a.row_off = c->row_flagoff.as<u64>(); a.pair_off = c->x_off.as<u64>(); a.order = c->x_order.as<int32_t>();
+    a.dst_first = c->x_dst_first.as<int32_t>(); a.inbox = reinterpret_cast<unsigned char* const*>(c->x_inbox_ptrs.p);
+    a.seg_bytes = (u64)seg_bytes; a.my_rank = my_rank; a.n_ranks = n_ranks; a.err_flags = err_flags_ptr(c);
+    export_layout_kernel<<<1, 32 * n_ranks, 0, c->stream>>>(a);
+    CKL("export_layout_kernel");
+    if (P > 0 && c->n_rows > 0 && dst_first[n_ranks] > 0) {
+        export_peer_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(a);
+        CKL("export_peer_kernel");
+    }
+    c->pending = true;
+    return OFG_OK;
+}
+
+int ofg_import_flags_peer(ofg_ctx* c, int which, int n_ranks, int my_rank, const void* inbox, size_t seg_bytes)
+{
+    if (!c || !inbox || n_ranks <= 0 || my_rank < 0 || my_rank >= n_ranks) return c ? fail(c, OFG_ERR_ARG, "bad arguments to ofg_import_flags_peer") : OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = check_exchange_stage(c, which, "import")) return rc;
+    ImportArgs a;
+    fill_import_args(c, which, a);
+    a.inbox = reinterpret_cast<const unsigned char*>(inbox); a.seg_bytes = (u64)seg_bytes; a.my_rank = my_rank;
+    dim3 g((unsigned)std::max(1, c->n_sm * 2 / std::max(n_ranks - 1, 1)), (unsigned)n_ranks);
+    import_flags_kernel<<<g, 256, 0, c->stream>>>(a);
+    CKL("import_flags_kernel");
+    c->pending = true;
+    return OFG_OK;
+}
+
+int ofg_ipc_get_handle(ofg_ctx* c, void* dev_ptr, void* handle_out64)
+{
+    if (!c || !dev_ptr || !handle_out64) return OFG_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaSetDevice(c->device);
+    CK(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle_out64), dev_ptr));
+    return OFG_OK;
+}
+
+int ofg_ipc_open_handle(ofg_ctx* c, const void* handle64, void** dev_ptr_out)
+{
+    if (!c || !handle64 || !dev_ptr_out) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    CK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return OFG_OK;
+}
+
+int ofg_ipc_close_handle(ofg_ctx* c, void* dev_ptr)
+{
+    if (!c || !dev_ptr) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return OFG_OK;
+}
+
+int ofg_device_alloc(ofg_ctx* c, size_t bytes, void** dev_ptr_out)
+{
+    if (!c || !dev_ptr_out) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMalloc(dev_ptr_out, bytes));
+    CK(cudaMemset(*dev_ptr_out, 0, bytes));
+    return OFG_OK;
+}
+
+int ofg_device_free(ofg_ctx* c, void* dev_ptr)
+{
+    if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (dev_ptr) CK(cudaFree(dev_ptr));
     return OFG_OK;
 }
 
 int ofg_counts(ofg_ctx* c, int64_t* lines, int64_t* records, int64_t* nnz, int64_t* edges)
 {
     if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (lines) *lines = c->tot_lines;
     if (records) *records = c->tot_records;
     if (nnz) *nnz = c->tot_nnz;
@@ -1199,6 +1550,8 @@ int ofg_counts(ofg_ctx* c, int64_t* lines, int64_t* records, int64_t* nnz, int64
 int ofg_pair_csr(ofg_ctx* c, int p, int j, int64_t* n_rows, int64_t* nnz, int32_t* row_len, uint32_t* cols, double* vals)
 {
     if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_RAW) return fail(c, OFG_ERR_ARG, "nothing built yet");
     if (p < 0 || j < 0 || p >= c->S || j >= c->S) return fail(c, OFG_ERR_ARG, "pair (%d,%d) out of range", p, j);
     const int pi = c->pair_of[(size_t)p * c->S + j];
@@ -1237,6 +1590,8 @@ int ofg_pair_csr(ofg_ctx* c, int p, int j, int64_t* n_rows, int64_t* nnz, int32_
 int ofg_pair_fit(ofg_ctx* c, int p, int j, double out[6])
 {
     if (!c || !out) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_NORM) return fail(c, OFG_ERR_ARG, "normalisation not built yet");
     if (p < 0 || j < 0 || p >= c->S || j >= c->S) return fail(c, OFG_ERR_ARG, "pair (%d,%d) out of range", p, j);
     const int pi = c->pair_of[(size_t)p * c->S + j];
@@ -1249,6 +1604,8 @@ int ofg_pair_fit(ofg_ctx* c, int p, int j, double out[6])
 int ofg_graph_csr_size(ofg_ctx* c, int64_t* n_rows, int64_t* nnz)
 {
     if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "graph not built yet");
     if (n_rows) *n_rows = c->n_owned_genes;
     if (nnz) *nnz = c->tot_edges;
@@ -1258,6 +1615,8 @@ int ofg_graph_csr_size(ofg_ctx* c, int64_t* n_rows, int64_t* nnz)
 int ofg_graph_csr_copy(ofg_ctx* c, int64_t* row_ids, int64_t* indptr, int32_t* indices, double* data)
 {
     if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "graph not built yet");
     cudaSetDevice(c->device);
     const int64_t n = c->n_owned_genes;
@@ -1281,6 +1640,8 @@ int ofg_graph_csr_copy(ofg_ctx* c, int64_t* row_ids, int64_t* indptr, int32_t* i
 int ofg_graph_text_size(ofg_ctx* c, size_t* nbytes)
 {
     if (!c || !nbytes) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "graph not built yet");
     *nbytes = (size_t)c->tot_text;
     return OFG_OK;
@@ -1289,6 +1650,8 @@ int ofg_graph_text_size(ofg_ctx* c, size_t* nbytes)
 int ofg_graph_text_copy(ofg_ctx* c, void* host_dst, size_t cap)
 {
     if (!c || !host_dst) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
     if (c->stage_done < OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "graph not built yet");
     if (cap < (size_t)c->tot_text) return fail(c, OFG_ERR_ARG, "destination too small");
     cudaSetDevice(c->device);
@@ -1358,8 +1721,7 @@ int ofg_test_lmfit(ofg_ctx* c, const double* host_lx, const double* host_ly, int
     CK(x.ensure((size_t)m * 8)); CK(y.ensure((size_t)m * 8)); CK(o.ensure(64));
     CK(cudaMemcpyAsync(x.p, host_lx, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(y.p, host_ly, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaFuncSetAttribute(test_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitShared)));
-    test_fit_kernel<<<1, FIT_THREADS, sizeof(FitShared), c->stream>>>(x.as<double>(), y.as<double>(), (long)m, o.as<double>());
+    CK(ofg_launch_test_fit(x.as<double>(), y.as<double>(), (long)m, o.as<double>(), c->stream));
     CKL("test_fit_kernel");
     double h[8];
     CK(cudaMemcpyAsync(h, o.p, 48, cudaMemcpyDeviceToHost, c->stream));

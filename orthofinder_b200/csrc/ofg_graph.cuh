@@ -16,46 +16,10 @@
 //                    glibc-exact "%d:%.3f " formatting (gathering.py:39-48); offsets from the booked sizes
 #pragma once
 #include "ofg_common.cuh"
-#include "ofg_fit_core.h"
 
 // ---------------------------------------------------------------- fit
-constexpr int FIT_THREADS = 256;
-
-struct FitArgs {
-    int P;
-    const u64* pair_sel_off;  // [P+1] offsets of each pair's selected points in lx / ly
-    u64 sel_cap;
-    const double* lx;
-    const double* ly;
-    double* fit;      // [P][8]: a, b, m, info, nfev, iterative, ok, pad
-    u32* err_flags;   // bit 0: a fit failed (curve_fit would raise); bit 1: selection overflowed sel_cap
-};
-
-__global__ void __launch_bounds__(FIT_THREADS) fit_kernel(FitArgs a)
-{
-    extern __shared__ __align__(16) unsigned char fit_smem_raw[];  // sizeof(FitShared) > 48 KB: dynamic, opt-in
-    FitShared& sh = *reinterpret_cast<FitShared*>(fit_smem_raw);
-    for (int pair = blockIdx.x; pair < a.P; pair += gridDim.x) {
-        const u64 o0 = a.pair_sel_off[pair], o1 = a.pair_sel_off[pair + 1];
-        const long m = (long)(o1 - o0);
-        double* out = a.fit + (size_t)pair * 8;
-        if (o1 > a.sel_cap) {
-            if (threadIdx.x == 0) { atomicOr(a.err_flags, 2u); out[6] = 0.0; out[2] = (double)m; out[3] = -1.0; }
-            continue;
-        }
-        if (m <= 1) {  // len(topScores) > 1 fails: the pair's hits are ignored (gathering.py:145,152-155)
-            if (threadIdx.x == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = (double)m; out[3] = 0.0; out[4] = 0.0; out[5] = 0.0; out[6] = 0.0; }
-            continue;
-        }
-        const int info = fit_loglinear(a.lx + o0, a.ly + o0, m, &sh, out);
-        if (threadIdx.x == 0) {
-            const bool ok = info >= 1 && info <= 4;
-            out[6] = ok ? 1.0 : 0.0;
-            if (!ok) atomicOr(a.err_flags, 1u);
-        }
-        __syncthreads();
-    }
-}
+// fit_kernel lives in its own translation unit (ofg_fit.cu): it is by far the slowest piece to compile.
+#include "ofg_fit_api.h"
 
 // ---------------------------------------------------------------- normalisation factors
 struct FactorArgs {
@@ -94,6 +58,7 @@ __device__ __forceinline__ int advance_pair(const int64_t* pair_row_base, int P,
 
 // ---------------------------------------------------------------- scale + best hits
 struct ScaleArgs {
+    int64_t row_begin;   // rows [row_begin, n_rows) are processed (one wave of query species)
     int64_t n_rows;
     const u32* row_start;
     u32* rowlen;
@@ -143,7 +108,7 @@ __global__ void __launch_bounds__(256) scale_bh_kernel(ScaleArgs a)
     const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
     const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     int pair = -1;
-    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+    for (int64_t row0 = a.row_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
         const int64_t row = row0 + sub;
         int n = row < a.n_rows ? (int)a.rowlen[row] : 0;
         u32 s0 = 0;
@@ -623,6 +588,90 @@ __global__ void __launch_bounds__(256) export_flags_kernel(ExportArgs a)
     }
 }
 
+// ---- peer variant: the lists go straight into the destination's inbox (peer memory over NVLink, or another
+// context of the same GPU), all offsets computed on the device - no host round trip, no collective for the payload.
+// Inbox of a destination: n_ranks segments of seg_bytes; segment `src` = [u64 count][count x int2 entries].
+struct PeerExportArgs {
+    int64_t n_rows;
+    const u32* row_start;
+    const u32* rowlen;
+    const u32* cols;
+    const PairDesc* pairs;
+    const int64_t* pair_row_base;
+    int P;
+    const int32_t* pair_dst;     // [P] destination rank of the pair's list, -1: not exported
+    u32 flag;
+    const u64* row_off;          // [n_rows + 1] exclusive scan of the per-row flag counts
+    u64* pair_off;               // [P] first entry of the pair inside its destination's segment (export_layout_kernel)
+    const int32_t* order;        // [n_exported] exported pairs grouped by destination
+    const int32_t* dst_first;    // [n_ranks + 1] group boundaries in order
+    unsigned char* const* inbox; // [n_ranks] base of every rank's inbox
+    u64 seg_bytes;
+    int my_rank, n_ranks;
+    u32* err_flags;              // bit 5: a segment overflowed
+};
+
+// one warp per destination rank: offsets of the exported pairs inside the segment, entry count into the remote header
+__global__ void __launch_bounds__(1024) export_layout_kernel(PeerExportArgs a)
+{
+    const int r = threadIdx.x >> 5, lane = lane_id();
+    if (r >= a.n_ranks) return;
+    const int g0 = a.dst_first[r], g1 = a.dst_first[r + 1];
+    u64 run = 0;
+    for (int b = g0; b < g1; b += 32) {
+        const int i = b + lane;
+        u64 cnt = 0;
+        int pair = -1;
+        if (i < g1) {
+            pair = a.order[i];
+            cnt = a.row_off[a.pair_row_base[pair + 1]] - a.row_off[a.pair_row_base[pair]];
+        }
+        u64 inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t = __shfl_up_sync(OFG_FULL, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (pair >= 0) a.pair_off[pair] = run + inc - cnt;
+        run += __shfl_sync(OFG_FULL, inc, 31);
+    }
+    if (lane == 0 && r != a.my_rank) {
+        const u64 cap = (a.seg_bytes - 8) / 8;
+        if (run > cap) { atomicOr(a.err_flags, 32u); run = 0; }
+        *reinterpret_cast<u64*>(a.inbox[r] + (u64)a.my_rank * a.seg_bytes) = run;
+    }
+}
+
+__global__ void __launch_bounds__(256) export_peer_kernel(PeerExportArgs a)
+{
+    const int lane = lane_id();
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const u64 cap = (a.seg_bytes - 8) / 8;
+    int pair = -1;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
+        const u64 o0 = a.row_off[row];
+        if (a.row_off[row + 1] == o0) continue;  // nothing flagged in this row
+        pair = advance_pair(a.pair_row_base, a.P, pair, row);
+        const int dst = a.pair_dst[pair];
+        if (dst < 0) continue;
+        const PairDesc& pd = a.pairs[pair];
+        const int n = (int)a.rowlen[row];
+        const u32 s0 = a.row_start[row];
+        const int r = (int)(row - pd.row_base);
+        u64 pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
+        int2* out = reinterpret_cast<int2*>(a.inbox[dst] + (u64)a.my_rank * a.seg_bytes + 8);
+        for (int k0 = 0; k0 < n; k0 += 32) {
+            const int k = k0 + lane;
+            const u32 cw = k < n ? a.cols[s0 + k] : 0u;
+            const bool on = (cw & a.flag) != 0;
+            const u32 bal = __ballot_sync(OFG_FULL, on);
+            const u64 o = pos + __popc(bal & lanemask_lt());
+            if (on && o < cap) out[o] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
+            pos += __popc(bal);
+        }
+    }
+}
+
 struct ImportArgs {
     const int2* list;
     int64_t n;
@@ -638,12 +687,24 @@ struct ImportArgs {
     const double* vals;        // REVERSE imports also keep the edge bookkeeping (edge_account)
     u32* gene_cnt;
     u32* gene_bytes;
+    const unsigned char* inbox;  // peer variant: this rank's inbox (n_ranks segments), else nullptr
+    u64 seg_bytes;
+    int my_rank;
 };
 
 __global__ void __launch_bounds__(256) import_flags_kernel(ImportArgs a)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int2 e = a.list[i];
+    // peer variant (inbox != nullptr): blockIdx.y = source rank, its segment holds [u64 count][entries]
+    const int2* list = a.list;
+    int64_t n = a.n;
+    if (a.inbox) {
+        if ((int)blockIdx.y == a.my_rank) return;
+        const unsigned char* seg = a.inbox + (u64)blockIdx.y * a.seg_bytes;
+        n = (int64_t)*reinterpret_cast<const u64*>(seg);
+        list = reinterpret_cast<const int2*>(seg + 8);
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 e = list[i];
         const int p = upper_bound_dev(a.seq_start, a.S, (int64_t)e.x) - 1;  // local (row) species
         const int k = upper_bound_dev(a.seq_start, a.S, (int64_t)e.y) - 1;  // species of the sender
         const int pair = a.pair_of[p * a.S + k];
@@ -676,7 +737,9 @@ struct EmitArgs {
     int32_t* out_indices;
     double* out_data;
     char* out_text;
-    u32* err_flags;           // bit 2: a weight could not be formatted
+    u32* err_flags;           // bit 2: a weight could not be formatted; bit 6: the output buffers are too small
+    u64 cap_edges, cap_text;  // capacity of out_indices / out_data and of out_text (checked on the device: the sizes are
+                              // known only there, the host reads them back once at the end of the build)
 };
 
 // Per graph row (owned gene, list order): number of edges and text bytes = "%d    " + entries + "$\n" (gathering.py:42-47),
@@ -707,6 +770,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(EmitArgs a)
     __shared__ double s_w[EMIT_WARPS][EMIT_LIST];
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const int S = a.g.S;
+    if (WRITE && (a.cnt_off[a.n_genes] > a.cap_edges || a.byte_off[a.n_genes] > a.cap_text)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.err_flags, 64u);  // the host grows the buffers and emits again
+        return;
+    }
     const int64_t n_warps = (int64_t)gridDim.x * EMIT_WARPS;
     for (int64_t lg = (int64_t)blockIdx.x * EMIT_WARPS + w; lg < a.n_genes; lg += n_warps) {
         const int p = a.species_of_local[lg];

@@ -29,14 +29,94 @@ struct RadixArgs {
     const double* val_in;
     u32* key_out;
     double* val_out;
-    const int64_t* tile_prefix;    // [P+1] sort tiles before each pair
-    const int64_t* pair_slot;      // [P+1] first slot of each pair
-    int P;
-    int64_t n_tiles;
+    const int64_t* n_tiles_dev;    // sort tiles of this wave (device-side: follows from the row scan)
+    int64_t val_in_off_dev_valid;  // != 0: val_in is the CSR value array (absolute slots): add *slot0 to the wave-relative slot
+    const u32* slot0;              // first CSR slot of the wave (device)
     int shift, bits;               // digit = (key >> shift) & ((1 << bits) - 1)
     u32* counters;                 // [n_tiles << bits], layout [pair][digit][tile in pair]
     const struct RsTileDesc* desc; // [n_tiles]
 };
+
+// Sort / bin layout of one wave of species pairs, derived on the device from the row scan (no host round trip):
+// the records of pair i occupy the CSR slots [row_start[first row of i], row_start[first row of i + 1]).
+struct WaveLayoutArgs {
+    const u32* row_start;          // absolute
+    const int64_t* pair_row_base;  // [P_all + 1] absolute
+    int P0, P1;                    // pairs of the wave
+    const u64* pair_nnz;           // [P_all] stored entries after dedup (rowsort)
+    int64_t* pair_slot;            // out [Pw + 1] wave-relative first slot of each pair
+    int64_t* tile_prefix;          // out [Pw + 1] sort tiles before each pair
+    u64* task_prefix;              // out [Pw + 1] length bins before each pair
+    int64_t* n_tiles;              // out
+    int64_t* n_tasks;              // out
+    int64_t max_tiles, max_tasks;  // capacity of the per-tile / per-bin arrays
+    u32* err_flags;                // bit 4: capacity exceeded
+};
+
+// bins of a pair with H stored hits (gathering.py:100-107): all hits when H < 100, else H // binSize bins
+__host__ __device__ __forceinline__ u64 ofg_bins_of(u64 H, u32* n_in)
+{
+    if (H == 0) { *n_in = 0; return 0; }
+    if (H < 100) { *n_in = (u32)H; return 1; }
+    *n_in = H > 5000 ? 1000u : (H > 1000 ? 200u : 20u);
+    return H / *n_in;
+}
+
+__global__ void __launch_bounds__(1024) wave_layout_kernel(WaveLayoutArgs a, int with_sort)
+{
+    // single CTA: two exclusive scans over the pairs of the wave
+    __shared__ u64 s_w[2][32];
+    __shared__ u64 s_carry[2];
+    const int Pw = a.P1 - a.P0;
+    const u32 s0 = a.row_start[a.pair_row_base[a.P0]];
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int b = 0; b < Pw; b += 1024) {
+        const int i = b + (int)threadIdx.x;
+        u64 v0 = 0, v1 = 0;
+        if (i < Pw) {
+            const u32 sa = a.row_start[a.pair_row_base[a.P0 + i]], sb = a.row_start[a.pair_row_base[a.P0 + i + 1]];
+            a.pair_slot[i] = (int64_t)(sa - s0);
+            if (i == Pw - 1) a.pair_slot[Pw] = (int64_t)(sb - s0);
+            v0 = with_sort ? ((u64)(sb - sa) + RS_TILE - 1) / RS_TILE : 0;
+            u32 n_in;
+            v1 = with_sort ? ofg_bins_of(a.pair_nnz[a.P0 + i], &n_in) : 0;
+        }
+        u64 i0 = v0, i1 = v1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u64 t0 = __shfl_up_sync(OFG_FULL, i0, d), t1 = __shfl_up_sync(OFG_FULL, i1, d);
+            if ((int)lane_id() >= d) { i0 += t0; i1 += t1; }
+        }
+        if (lane_id() == 31) { s_w[0][threadIdx.x >> 5] = i0; s_w[1][threadIdx.x >> 5] = i1; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const u64 a0 = s_w[0][threadIdx.x], a1 = s_w[1][threadIdx.x];
+            u64 c0 = a0, c1 = a1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 t0 = __shfl_up_sync(OFG_FULL, c0, d), t1 = __shfl_up_sync(OFG_FULL, c1, d);
+                if ((int)lane_id() >= d) { c0 += t0; c1 += t1; }
+            }
+            s_w[0][threadIdx.x] = c0 - a0;
+            s_w[1][threadIdx.x] = c1 - a1;
+        }
+        __syncthreads();
+        const u64 e0 = s_carry[0] + s_w[0][threadIdx.x >> 5] + i0 - v0, e1 = s_carry[1] + s_w[1][threadIdx.x >> 5] + i1 - v1;
+        if (i < Pw) { a.tile_prefix[i] = (int64_t)e0; a.task_prefix[i] = e1; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry[0] = e0 + v0; s_carry[1] = e1 + v1; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.tile_prefix[Pw] = (int64_t)s_carry[0];
+        a.task_prefix[Pw] = s_carry[1];
+        int64_t nt = (int64_t)s_carry[0], nk = (int64_t)s_carry[1];
+        if (nt > a.max_tiles || nk > a.max_tasks) { atomicOr(a.err_flags, 16u); nt = 0; nk = 0; }
+        *a.n_tiles = nt;
+        *a.n_tasks = nk;
+    }
+}
 
 // Per-tile constants, computed once per sort by rs_desc_kernel so that the per-tile path of the three passes
 // has no dependent global loads: every thread prefetches the next tile's descriptor while it works.
@@ -47,20 +127,21 @@ struct __align__(16) RsTileDesc {
     int ntp;        // tiles in the tile's pair
 };
 
-__global__ void rs_desc_kernel(RadixArgs a, RsTileDesc* desc)
+__global__ void rs_desc_kernel(const int64_t* tile_prefix, const int64_t* pair_slot, int Pw, const int64_t* n_tiles_dev, int bits, RsTileDesc* desc)
 {
-    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= a.n_tiles) return;
-    const int pair = upper_bound_dev(a.tile_prefix, a.P + 1, tile) - 1;
-    const int64_t tp0 = a.tile_prefix[pair], tp1 = a.tile_prefix[pair + 1];
-    const int64_t t = tile - tp0;
-    RsTileDesc d;
-    d.e0 = a.pair_slot[pair] + t * RS_TILE;
-    const int64_t rem = a.pair_slot[pair + 1] - d.e0;
-    d.cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
-    d.cidx0 = (tp0 << a.bits) + t;
-    d.ntp = (int)(tp1 - tp0);
-    desc[tile] = d;
+    const int64_t n_tiles = *n_tiles_dev;
+    for (int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tile < n_tiles; tile += (int64_t)gridDim.x * blockDim.x) {
+        const int pair = upper_bound_dev(tile_prefix, Pw + 1, tile) - 1;
+        const int64_t tp0 = tile_prefix[pair], tp1 = tile_prefix[pair + 1];
+        const int64_t t = tile - tp0;
+        RsTileDesc d;
+        d.e0 = pair_slot[pair] + t * RS_TILE;
+        const int64_t rem = pair_slot[pair + 1] - d.e0;
+        d.cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
+        d.cidx0 = (tp0 << bits) + t;
+        d.ntp = (int)(tp1 - tp0);
+        desc[tile] = d;
+    }
 }
 
 __device__ __forceinline__ RsTileDesc rs_load_desc(const RsTileDesc* desc, int64_t tile, int64_t n_tiles)
@@ -76,10 +157,11 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(RadixArgs a)
     __shared__ u32 s_hist[RS_MAX_DIGITS];
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
-    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, a.n_tiles);
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t n_tiles = *a.n_tiles_dev;
+    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, n_tiles);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const RsTileDesc td = next;
-        next = rs_load_desc(a.desc, tile + gridDim.x, a.n_tiles);
+        next = rs_load_desc(a.desc, tile + gridDim.x, n_tiles);
         const int cnt = td.cnt;
         const int64_t e0 = td.e0, cidx0 = td.cidx0, ntp = td.ntp;
         s_hist[threadIdx.x] = 0;
@@ -111,10 +193,12 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(RadixArgs 
     const int nd = 1 << a.bits;
     const u32 mask = (u32)nd - 1u;
     const int w = threadIdx.x >> 5, lane = lane_id();
-    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, a.n_tiles);
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int64_t n_tiles = *a.n_tiles_dev;
+    const int64_t voff = a.val_in_off_dev_valid ? (int64_t)*a.slot0 : 0;  // first pass: scores come from the CSR values
+    RsTileDesc next = rs_load_desc(a.desc, blockIdx.x, n_tiles);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const RsTileDesc td = next;
-        next = rs_load_desc(a.desc, tile + gridDim.x, a.n_tiles);
+        next = rs_load_desc(a.desc, tile + gridDim.x, n_tiles);
         const int cnt = td.cnt;
         const int64_t e0 = td.e0, cidx0 = td.cidx0, ntp = td.ntp;
 #pragma unroll
@@ -128,7 +212,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) radix_scatter_kernel(RadixArgs 
         for (int it = 0; it < RS_ITEMS; it++) {
             const int k = kbase + it * 32;
             key[it] = k < cnt ? a.key_in[e0 + k] : 0u;
-            val[it] = k < cnt ? a.val_in[e0 + k] : 0.0;
+            val[it] = k < cnt ? a.val_in[voff + e0 + k] : 0.0;
         }
         // all match operations first: they are independent and their latency overlaps
 #pragma unroll
@@ -207,9 +291,27 @@ struct BinTask {      // host-built, one per length bin (or one per pair with < 
     int32_t take_all; // nScores < 100 (gathering.py:100-102)
 };
 
+// Expands the per-pair bin counts (task_prefix of wave_layout_kernel) into one BinTask per length bin.
+__global__ void bin_tasks_kernel(const u64* task_prefix, const int64_t* pair_slot, const u64* pair_nnz, int P0, int Pw, const int64_t* n_tasks_dev,
+                                 BinTask* tasks)
+{
+    const int64_t n_tasks = *n_tasks_dev;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_tasks; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pair = upper_bound_dev(task_prefix, Pw + 1, (u64)t) - 1;
+        u32 n_in;
+        ofg_bins_of(pair_nnz[P0 + pair], &n_in);
+        BinTask bt;
+        bt.first = (u32)(pair_slot[pair] + (int64_t)(t - (int64_t)task_prefix[pair]) * n_in);
+        bt.n = n_in;
+        bt.pair = pair;            // wave-relative
+        bt.take_all = pair_nnz[P0 + pair] < 100 ? 1 : 0;
+        tasks[t] = bt;
+    }
+}
+
 struct BinArgs {
     const BinTask* tasks;
-    int64_t n_tasks;
+    const int64_t* n_tasks_dev;
     const u32* key;        // sorted Lf
     const double* val;     // scores in the same order
     // numpy percentile(…, 95) 'linear': k = floor((n-1)*0.95), g = (n-1)*0.95 - k, for n = 20, 200, 1000
@@ -317,7 +419,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
     u32* s_hist = s_hist_all[w];
     uint16_t* s_idx = s_idx_all[w];
     const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
-    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
+    const int64_t n_tasks = *a.n_tasks_dev;
+    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < n_tasks; t += n_warps) {
         const BinTask bt = a.tasks[t];
         const int n = (int)bt.n;
         u64 vmin = ~0ULL, vmax = 0ULL;
@@ -401,7 +504,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_select_kernel(BinArgs a)
 {
     const int w = threadIdx.x >> 5, lane = lane_id();
     const int64_t n_warps = (int64_t)gridDim.x * BIN_WARPS;
-    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < a.n_tasks; t += n_warps) {
+    const int64_t n_tasks = *a.n_tasks_dev;
+    for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < n_tasks; t += n_warps) {
         const u32 first = a.tasks[t].first;
         const u64 o0 = a.sel_off[t];
         const u32 cnt = (u32)(a.sel_off[t + 1] - o0);

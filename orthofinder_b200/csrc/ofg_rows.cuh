@@ -17,10 +17,20 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
 
+// The element count of a scan may live on the device (n_dev != nullptr: n = *n_dev << n_shift, clamped to the
+// host-side bound n): the sizes of later stages follow from earlier kernels without a host round trip.
+__device__ __forceinline__ int64_t scan_count(int64_t n, const int64_t* n_dev, int n_shift)
+{
+    if (!n_dev) return n;
+    const int64_t m = *n_dev << n_shift;
+    return m < n ? m : n;
+}
+
 template <typename TO>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const u32* in, int64_t n, TO* partial)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const u32* in, int64_t n, TO* partial, const int64_t* n_dev, int n_shift)
 {
     __shared__ TO s_w[SCAN_THREADS / 32];
+    n = scan_count(n, n_dev, n_shift);
     for (int64_t chunk = blockIdx.x; chunk * SCAN_CHUNK < n; chunk += gridDim.x) {
         const int64_t base = chunk * SCAN_CHUNK;
         TO s = 0;
@@ -43,12 +53,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const u32* in
 }
 
 template <typename TO>
-__global__ void __launch_bounds__(1024) scan_partials_kernel(TO* partial, int64_t n_chunks, TO* total_out)
+__global__ void __launch_bounds__(1024) scan_partials_kernel(TO* partial, int64_t n, TO* total_out, const int64_t* n_dev, int n_shift, const TO* base_dev)
 {
-    // single CTA: exclusive scan of the chunk sums, in place
+    // single CTA: exclusive scan of the chunk sums, in place (starting at *base_dev)
+    const TO base = base_dev ? *base_dev : (TO)0;
     __shared__ TO s_w[32];
     __shared__ TO s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    n = scan_count(n, n_dev, n_shift);
+    const int64_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (threadIdx.x == 0) s_carry = base;
     __syncthreads();
     for (int64_t b = 0; b < n_chunks; b += 1024) {
         int64_t i = b + threadIdx.x;
@@ -84,9 +97,14 @@ __global__ void __launch_bounds__(1024) scan_partials_kernel(TO* partial, int64_
 // out has n + 1 entries when write_total != 0 (out[n] = grand total)
 template <typename TO>
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const u32* in, int64_t n, const TO* partial, TO* out,
-                                                                  int write_total)
+                                                                  int write_total, const int64_t* n_dev, int n_shift, const TO* base_dev)
 {
     __shared__ u32 s_scan[SCAN_THREADS / 32 + 1];
+    n = scan_count(n, n_dev, n_shift);
+    if (n <= 0) {
+        if (write_total && blockIdx.x == 0 && threadIdx.x == 0) out[0] = base_dev ? *base_dev : (TO)0;
+        return;
+    }
     for (int64_t chunk = blockIdx.x; chunk * SCAN_CHUNK < n; chunk += gridDim.x) {
         const int64_t base = chunk * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
         u32 v[SCAN_ITEMS];
@@ -112,10 +130,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const u32* in,
 
 // ---------------------------------------------------------------- scatter (counting sort by row)
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const u32* __restrict__ coo_row, const u32* __restrict__ coo_col,
-                                                           const double* __restrict__ coo_val, u64 n,
+                                                           const double* __restrict__ coo_val, const u64* __restrict__ n_dev, u64 cap,
                                                            const u32* __restrict__ row_start, u32* rowfill, u32* cols,
                                                            double* vals)
 {
+    const u64 n = *n_dev < cap ? *n_dev : cap;  // record slots the parse reserved (clamped: the host checks the overflow)
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 n_round = (n + 31) & ~(u64)31;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -144,6 +163,7 @@ constexpr int ROWSORT_MAXN = 128;
 constexpr int ROWSORT_WARPS = 4;
 
 struct RowSortArgs {
+    int64_t row_begin;         // rows [row_begin, n_rows) are processed (one wave of query species)
     int64_t n_rows;
     const u32* row_start;      // [n_rows + 1]
     u32* rowlen;               // [n_rows] out: stored entries after dedup
@@ -153,7 +173,8 @@ struct RowSortArgs {
     const int64_t* pair_row_base;  // [P + 1]
     int P;
     const double* lengths;
-    u32* key;                  // out: Lf per slot (sentinel for unused slots)
+    u32* key;                  // out: Lf per slot of the wave (index: slot - *slot0; sentinel for unused slots)
+    const u32* slot0;          // first CSR slot of the wave (device)
     double* keyval;            // (unused: the first sort pass reads the scores from vals, which sits at the same slots)
     u32 key_sentinel;
     u32* long_rows;            // out: rows with more than ROWSORT_MAXN records
@@ -239,9 +260,10 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
     __shared__ __align__(16) RowSortWarp s_w[ROWSORT_WARPS];
     const int w = threadIdx.x >> 5, lane = (int)lane_id();
     RowSortWarp& sw = s_w[w];
+    u32* const key_rel = a.key - *a.slot0;  // the key array is wave scratch, indexed from the wave's first slot
     // every CTA owns a contiguous run of rows (the pair changes rarely), its warps interleave inside it
-    const int64_t rows_per_cta = (a.n_rows + gridDim.x - 1) / gridDim.x;
-    const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t rows_per_cta = (a.n_rows - a.row_begin + gridDim.x - 1) / gridDim.x;
+    const int64_t row_begin = a.row_begin + (int64_t)blockIdx.x * rows_per_cta;
     const int64_t row_end = row_begin + rows_per_cta < a.n_rows ? row_begin + rows_per_cta : a.n_rows;
     int64_t row = row_begin + w;
     if (row >= row_end) return;
@@ -377,9 +399,9 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
             const double val = __longlong_as_double((long long)sw.ov[k]);
             a.cols[pos] = sw.oc[k];
             a.vals[pos] = val;
-            a.key[pos] = sw.okey[k];
+            key_rel[pos] = sw.okey[k];
         }
-        for (int k = outn + lane; k < n; k += 32) a.key[s0 + k] = a.key_sentinel;
+        for (int k = outn + lane; k < n; k += 32) key_rel[s0 + k] = a.key_sentinel;
         if (lane == 0) {
             a.rowlen[cur_row] = (u32)outn;
             atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_nnz[cur_pair]), (unsigned long long)outn);
@@ -395,6 +417,7 @@ __global__ void __launch_bounds__(256) rowsort_long_kernel(RowSortArgs a)
     __shared__ u32 s_scan[256 / 32 + 1];
     __shared__ u32 s_outn;
     const u32 n_long = *a.n_long;
+    u32* const key_rel = a.key - *a.slot0;
     for (u32 li = blockIdx.x; li < n_long; li += gridDim.x) {
         const int64_t row = a.long_rows[li];
         const u32 s0 = a.row_start[row];
@@ -432,14 +455,14 @@ __global__ void __launch_bounds__(256) rowsort_long_kernel(RowSortArgs a)
                 const double val = a.scratch_vals[s0 + k];
                 a.cols[pos] = col;
                 a.vals[pos] = val;
-                a.key[pos] = (u32)(Lq * Lh[col]);
+                key_rel[pos] = (u32)(Lq * Lh[col]);
                 }
             __syncthreads();
             if (threadIdx.x == 0) s_outn = base + tot;
             __syncthreads();
         }
         const int outn = (int)s_outn;
-        for (int k = outn + threadIdx.x; k < n; k += blockDim.x) a.key[s0 + k] = a.key_sentinel;
+        for (int k = outn + threadIdx.x; k < n; k += blockDim.x) key_rel[s0 + k] = a.key_sentinel;
         if (threadIdx.x == 0) {
             a.rowlen[row] = (u32)outn;
             atomicAdd(&a.pair_nnz[pair], (u64)outn);

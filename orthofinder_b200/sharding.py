@@ -1,20 +1,29 @@
-"""Sharding of the pair grid by query species (design A).
+"""Sharding of the pair grid by query species.
 
 Rank r owns a set of query species p ("rows" of the S x S pair grid), exactly the unit the reference
 parallelises over (gathering.py:484-485).  Everything that is reduced per gene (row maxima, best hit in
-another species, the "most distant" threshold) stays local to the owner.  The two places where the
-reference reads the transposed direction from pickles (BH_jp at gathering.py:254, connect_jp at :30) are
-served by also ingesting the column pairs Blast{j}_{p}: their fit, normalisation and best hits depend
-only on that file and the two length vectors, so they are recomputed locally and bit-identically, and the
-only data exchanged is the per-gene threshold vector (8 bytes per gene): one all-reduce(MIN) over a
-vector that holds +inf for genes a rank does not own, which is an all-gather in one NCCL call.
+another species, the "most distant" threshold) stays local to the owner.  The reference reads the
+transposed direction from pickles in two places: BH_jp (gathering.py:254) and connect_jp (:30).
+
+Design B (default): a rank ingests only its rows; the two transposed matrices travel as sparse index lists
+(8 bytes per flagged entry).  `PeerExchange` (one process per GPU) and `LocalExchange` (row partitions in
+several contexts of one GPU) let the export kernel write the lists straight into the destinations' inboxes -
+peer memory over NVLink, mapped with CUDA IPC - with all offsets computed on the device; the only collective
+is a 4-byte all-reduce that orders "every exporter is done" before the imports.  `exchange_lists` is the
+older variant that ships the same lists with two NCCL all-to-all calls (host-sized).
+
+Design A (north-star wording): a rank also ingests the column pairs Blast{j}_{p}; their fit, normalisation
+and best hits depend only on that file and the two length vectors, so they are recomputed locally and
+bit-identically, and the only data exchanged is the per-gene threshold vector (8 bytes per gene): one
+all-reduce(MIN) over a vector that holds +inf for genes a rank does not own (`exchange_thresholds`).
 """
 import numpy as np
 
 
 def partition_rows(n_species, world, weights=None):
     """Greedy longest-first assignment of query species to ranks, balanced by `weights` (e.g. hit-file
-    bytes per query species; default: equal).  Returns a list of sorted species lists, one per rank."""
+    bytes per query species; default: equal).  Returns a list of sorted species lists, one per rank
+    (ranks beyond the number of species own nothing)."""
     w = np.ones(n_species) if weights is None else np.asarray(weights, dtype=np.float64)
     load = [0.0] * world
     owned = [[] for _ in range(world)]
@@ -46,7 +55,7 @@ def exchange_lists_local(ctxs, which, owner):
     destinations import them straight from the exporter's device buffer (no collective, no host copy)."""
     outbox = []
     for r, c in enumerate(ctxs):
-        ptr, counts = c.export_flags(which, owner, r)   # synchronises c's stream: the lists are complete
+        ptr, counts = c.export_flags(which, owner, r, len(ctxs))   # synchronises c's stream: the lists are complete
         outbox.append((ptr, counts))
     total = 0
     for src, (ptr, counts) in enumerate(outbox):
@@ -58,6 +67,118 @@ def exchange_lists_local(ctxs, which, owner):
             off += n
             total += n
     return total
+
+
+def _inbox_segment_bytes(owner, n_seqs, n_ranks, factor=4):
+    """Initial size of one inbox segment: `factor` entries per matrix row of the largest (source, destination) block
+    of species pairs; best-hit lists hold ~1 entry per row, connect lists a few (grown on demand)."""
+    n_seqs = np.asarray(n_seqs, dtype=np.int64)
+    owner = np.asarray(owner)
+    rows = 0
+    for src in range(n_ranks):
+        g_src = int(n_seqs[owner == src].sum())
+        for dst in range(n_ranks):
+            if dst != src:
+                rows = max(rows, g_src * int((owner == dst).sum()))
+    return int(8 + 8 * (factor * rows + 4096))
+
+
+class LocalExchange:
+    """Design B exchange between row partitions held by several contexts of ONE process / GPU: every context exports
+    straight into the other contexts' inboxes and the imports are ordered by stream events - nothing touches the host."""
+
+    def __init__(self, ctxs, owner, n_seqs):
+        self.ctxs, self.owner, self.n = ctxs, np.asarray(owner, dtype=np.int32), len(ctxs)
+        self.seg = _inbox_segment_bytes(owner, n_seqs, self.n)
+        self.inbox = None
+        self._alloc()
+
+    def _alloc(self):
+        self.close()
+        # two inboxes per context (best-hit lists, connect lists): a context may still be importing one while the next
+        # export already arrives
+        self.inbox = [[c.device_alloc(self.seg * self.n) for c in self.ctxs] for _ in range(2)]
+
+    def grow(self):
+        self.seg = 8 + 2 * (self.seg - 8)
+        self._alloc()
+
+    def close(self):
+        if self.inbox:
+            for boxes in self.inbox:
+                for c, p in zip(self.ctxs, boxes):
+                    if getattr(c, "h", None):
+                        c.device_free(p)
+        self.inbox = None
+
+    def exchange(self, which):
+        boxes = self.inbox[which]
+        for r, c in enumerate(self.ctxs):
+            c.export_flags_peer(which, self.owner, r, boxes, self.seg)
+        for r, c in enumerate(self.ctxs):
+            for src, other in enumerate(self.ctxs):
+                if src != r:
+                    c.wait_for(other)
+            c.import_flags_peer(which, self.n, r, boxes[r], self.seg)
+
+
+class PeerExchange:
+    """Design B exchange between the ranks of one node (one process per GPU): every rank maps the other ranks' inboxes
+    with CUDA IPC, the export kernel stores the lists into them over NVLink, and a 4-byte NCCL all-reduce on the
+    builder's stream is the only collective (it orders "all exporters are done" before the imports)."""
+
+    def __init__(self, gb, species_rank, rank, world, device_index, n_seqs):
+        import torch
+        import torch.distributed as dist
+        self.gb, self.rank, self.world = gb, rank, world
+        self.owner = np.asarray(species_rank, dtype=np.int32)
+        self.dev = torch.device("cuda", device_index)
+        self.stream = torch.cuda.ExternalStream(gb.lib.ofg_stream(gb.h), device=self.dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.seg = _inbox_segment_bytes(species_rank, n_seqs, world)
+        self.mine, self.ptrs = None, None
+        self._alloc()
+
+    def _alloc(self):
+        import torch.distributed as dist
+        self._release()
+        self.mine = [self.gb.device_alloc(self.seg * self.world) for _ in range(2)]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, [self.gb.ipc_handle(p) for p in self.mine])
+        self.ptrs = []
+        for which in range(2):
+            self.ptrs.append([self.mine[which] if r == self.rank else self.gb.ipc_open(handles[r][which])
+                              for r in range(self.world)])
+
+    def _release(self):
+        import torch
+        import torch.distributed as dist
+        if self.ptrs:
+            torch.cuda.synchronize()
+            dist.barrier()
+            for which in range(2):
+                for r, p in enumerate(self.ptrs[which]):
+                    if r != self.rank:
+                        self.gb.ipc_close(p)
+            dist.barrier()
+            for p in self.mine:
+                self.gb.device_free(p)
+        self.mine, self.ptrs = None, None
+
+    def grow(self):
+        self.seg = 8 + 2 * (self.seg - 8)
+        self._alloc()
+
+    def close(self):
+        self._release()
+
+    def exchange(self, which):
+        import torch
+        import torch.distributed as dist
+        self.gb.export_flags_peer(which, self.owner, self.rank, self.ptrs[which], self.seg)
+        with torch.cuda.stream(self.stream):
+            dist.all_reduce(self.token)   # stream-ordered: starts after this rank's export, ends after every rank's
+        self.gb.import_flags_peer(which, self.world, self.rank, self.mine[which], self.seg)
 
 
 def rank_pairs(owned, n_species):
@@ -100,7 +221,7 @@ def exchange_lists(gb, which, species_rank, rank, world, device_index):
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", device_index)
-    ptr, counts = gb.export_flags(which, species_rank, rank)
+    ptr, counts = gb.export_flags(which, species_rank, rank, world)
     send_counts = torch.from_numpy(np.ascontiguousarray(counts[:world], dtype=np.int64)).to(dev)
     recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
     dist.all_to_all_single(recv_counts, send_counts)

@@ -194,11 +194,51 @@ class GraphBuilder:
     def thresholds_mark_complete(self):
         self._ck(self.lib.ofg_thresholds_mark_complete(self.h))
 
-    def export_flags(self, which, species_rank, my_rank):
+    def sync(self):
+        """Wait for the enqueued work and read its results back (option "async"); raises what the build would have."""
+        self._ck(self.lib.ofg_sync(self.h))
+
+    def wait_for(self, other):
+        """Order this context's stream after everything enqueued on `other`'s (no host block)."""
+        self._ck(self.lib.ofg_wait_for(self.h, other.h))
+
+    def device_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._ck(self.lib.ofg_device_alloc(self.h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        self._ck(self.lib.ofg_device_free(self.h, ctypes.c_void_p(ptr)))
+
+    def ipc_handle(self, ptr):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.lib.ofg_ipc_get_handle(self.h, ctypes.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        self._ck(self.lib.ofg_ipc_open_handle(self.h, ctypes.c_char_p(handle), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        self._ck(self.lib.ofg_ipc_close_handle(self.h, ctypes.c_void_p(ptr)))
+
+    def export_flags_peer(self, which, species_rank, my_rank, inbox_ptrs, seg_bytes):
+        """Design B exchange without host round trips: this context's best-hit (which=0) / connect (which=1) lists go
+        straight into segment `my_rank` of every destination's inbox (device pointers valid on this GPU)."""
+        sr = np.ascontiguousarray(species_rank, dtype=np.int32)
+        ptrs = (ctypes.c_void_p * len(inbox_ptrs))(*[ctypes.c_void_p(x) for x in inbox_ptrs])
+        self._ck(self.lib.ofg_export_flags_peer(self.h, int(which), len(inbox_ptrs), _vp(sr), int(my_rank), ptrs, int(seg_bytes)))
+
+    def import_flags_peer(self, which, n_ranks, my_rank, inbox_ptr, seg_bytes):
+        self._ck(self.lib.ofg_import_flags_peer(self.h, int(which), int(n_ranks), int(my_rank), ctypes.c_void_p(inbox_ptr), int(seg_bytes)))
+
+    def export_flags(self, which, species_rank, my_rank, n_ranks=None):
         """Design B exchange: (device pointer, counts per destination rank) of the best-hit (which=0) or
         connect (which=1) index lists for species pairs whose column species another rank owns."""
         sr = np.ascontiguousarray(species_rank, dtype=np.int32)
-        n_ranks = int(sr.max()) + 1 if sr.size else 1
+        if n_ranks is None:
+            n_ranks = int(sr.max()) + 1 if sr.size else 1
         counts = np.zeros(n_ranks, np.int64)
         ptr = ctypes.c_void_p()
         self._ck(self.lib.ofg_export_flags(self.h, int(which), n_ranks, _vp(sr), int(my_rank), _vp(counts), ctypes.byref(ptr)))
@@ -246,8 +286,12 @@ class PipelinedGraphBuilder:
         self.n_parts_req = n_parts
         self.ctxs = []
         self.parts = []
+        self.xchg = None
 
     def close(self):
+        if self.xchg is not None:
+            self.xchg.close()
+            self.xchg = None
         for c in self.ctxs:
             c.close()
         self.ctxs = []
@@ -265,6 +309,10 @@ class PipelinedGraphBuilder:
         for c, owned in zip(self.ctxs, parts):
             c.set_species(n_seqs, lengths)
             c.set_partition(owned, False)
+            c.set_option("async", 1)   # the contexts only enqueue: their streams overlap with each other and with the copies
+        if self.xchg is not None:
+            self.xchg.close()
+        self.xchg = sharding.LocalExchange(self.ctxs, self.owner, n_seqs) if len(self.ctxs) > 1 else None
 
     def set_option(self, name, value):
         for c in self.ctxs:
@@ -291,17 +339,33 @@ class PipelinedGraphBuilder:
             prev.record(st)
 
     def build(self):
-        from . import sharding
-        for c in self.ctxs:
-            c.build(_lib.STAGE_NORM)
-        if len(self.ctxs) > 1:
-            sharding.exchange_lists_local(self.ctxs, 0, self.owner)
-        for c in self.ctxs:
-            c.build(_lib.STAGE_CONNECT)
-        if len(self.ctxs) > 1:
-            sharding.exchange_lists_local(self.ctxs, 1, self.owner)
-        for c in self.ctxs:
-            c.build(_lib.STAGE_GRAPH)
+        """Enqueues the whole job on the contexts' streams (no host synchronisation in between: the transposed lists go
+        from context to context on the device) and then reads every context's results back."""
+        for attempt in range(4):
+            for c in self.ctxs:
+                c.build(_lib.STAGE_NORM)
+            if self.xchg is not None:
+                self.xchg.exchange(0)
+            for c in self.ctxs:
+                c.build(_lib.STAGE_CONNECT)
+            if self.xchg is not None:
+                self.xchg.exchange(1)
+            for c in self.ctxs:
+                c.build(_lib.STAGE_GRAPH)
+            try:
+                for c in self.ctxs:
+                    c.sync()
+                return
+            except OfgError as e:
+                if e.code == _lib.ERR_CAPACITY and "inbox" in e.message and self.xchg is not None and attempt < 3:
+                    for c in self.ctxs:     # drain the other contexts, then repeat the job with larger inboxes
+                        try:
+                            c.sync()
+                        except OfgError:
+                            pass
+                    self.xchg.grow()
+                    continue
+                raise
 
     def counts(self):
         out = dict(lines=0, records=0, nnz=0, edges=0)
@@ -339,8 +403,8 @@ GRAPH_FOOTER = b")\n"  # gathering.py:48, written after the last species
 # Reference-facing interface
 # --------------------------------------------------------------------------------------------------
 def GetSpeciesToUse(speciesIDsFN):
-    """util.py:178-192 (host; not part of the device path)."""
-    use, skipped = [], 0
+    """util.py:178-192 (host; not part of the device path): (speciesToUse, nSpAll, speciesToUse_names)."""
+    use, names, skipped = [], [], 0
     with open(speciesIDsFN) as f:
         for line in f:
             line = line.rstrip()
@@ -349,8 +413,10 @@ def GetSpeciesToUse(speciesIDsFN):
             if line.startswith("#"):
                 skipped += 1
             else:
-                use.append(int(line.split(": ")[0]))
-    return use, len(use) + skipped
+                iSp, spName = line.split(": ")
+                use.append(int(iSp))
+                names.append(spName)
+    return use, len(use) + skipped, names
 
 
 def GetSeqsInfo(inputDirectory_list, speciesToUse, nSpAll):
@@ -408,6 +474,10 @@ def _gunzip(data):
         d = zlib.decompressobj(wbits=31)
         out.append(d.decompress(data))
         out.append(d.flush())
+        if not d.eof:  # what gzip.open (blast_file_processor.py:63) raises on a truncated member
+            e = EOFError("Compressed file ended before the end-of-stream marker was reached")
+            e.partial = b"".join(out)
+            raise e
         data = d.unused_data.lstrip(b"\0")
     return b"".join(out) if len(out) != 2 else out[0] + out[1]
 
@@ -425,7 +495,11 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
         raise FileNotFoundError(fn)
     if os.path.exists(fn + ".gz"):
         with open(fn + ".gz", "rb") as f:
-            return _gunzip(f.read()), fn
+            try:
+                return _gunzip(f.read()), fn
+            except (EOFError, zlib.error) as e:
+                e.hit_file = (iSpecies, jSpecies, d)
+                raise
     with open(fn, "rb") as f:
         return f.read(), fn
 
@@ -475,9 +549,21 @@ class WaterfallMethod:
             for j, kj in enumerate(sp):
                 swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54
                 cells.append((kj if swap else kp, kp if swap else kj, p, j, swap))
-        for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers):
-            if data is not None:
-                gb.add_hits(p, j, data, swap_cols=swap)
+        try:
+            for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers):
+                if data is not None:
+                    gb.add_hits(p, j, data, swap_cols=swap)
+        except (EOFError, zlib.error) as e:
+            # a truncated / damaged .gz ends the reference's csv loop with an exception: same report (blast_file_processor.py:99-103)
+            if hasattr(e, "hit_file"):
+                i_sp, j_sp, d = e.hit_file
+                lines = getattr(e, "partial", b"").split(b"\n")
+                last = lines[-2] if len(lines) > 1 else b""   # the last complete row the csv reader had returned
+                print("ERROR: Blast%d_%d.txt is corrupted" % (i_sp, j_sp))
+                sys.stderr.write("Malformatted line in %sBlast%d_%d.txt\nOffending line was:\n" % (d, i_sp, j_sp))
+                sys.stderr.write(last.decode(errors="replace") + "\n")
+                print("ERROR: Error processing files Blast%d_*" % i_sp)
+            raise
         try:
             gb.build(_lib.STAGE_GRAPH)
         except OfgError as e:
@@ -532,7 +618,7 @@ def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empt
     SpeciesIDs.txt / Species*.fa / Blast*_*.txt from workingDir and writes OrthoFinder_graph.txt."""
     if not workingDir.endswith(os.sep):
         workingDir += os.sep
-    sp, n_all = GetSpeciesToUse(workingDir + "SpeciesIDs.txt")
+    sp, n_all, _ = GetSpeciesToUse(workingDir + "SpeciesIDs.txt")
     si = GetSeqsInfo([workingDir], sp, n_all)
     L = GetSequenceLengths(si, [workingDir])
     gb = WaterfallMethod.BuildGraph(si, [workingDir], L, qDoubleBlast=qDoubleBlast, q_allow_empty=q_allow_empty,

@@ -54,3 +54,20 @@ def test_first_directory_holding_the_file_wins(tmp_path):
         f.write(b"shadowed\n")
     got = {g[0]: g[1] for g in w.read_hit_files([a, b], [(1, 2), (3, 4)], n_readers=2)}
     assert got[(1, 2)] == b"from b\n" and got[(3, 4)] == b"from a\n"   # blast_file_processor.py:59-65
+
+
+def test_truncated_gzip_raises_like_gzip_open(tmp_path):
+    """blast_file_processor.py:63 reads .gz files through gzip.open, which raises EOFError when the stream ends before its
+    end-of-stream marker (interrupted DIAMOND run, full disk); the host mirror must not hand the partial text to the parser."""
+    d = str(tmp_path) + "/"
+    data = b"".join(_line(0, 1, k) for k in range(2000))
+    z = gzip.compress(data)
+    with open(d + "Blast0_1.txt.gz", "wb") as f:
+        f.write(z[:len(z) // 2])
+    with pytest.raises(EOFError):
+        gzip.decompress(z[:len(z) // 2])   # what the reference's reader does with this file
+    with pytest.raises(EOFError) as ei:
+        list(w.read_hit_files([d], [(0, 1)], n_readers=1))
+    assert ei.value.hit_file[:2] == (0, 1) and 0 < len(ei.value.partial) < len(data)
+    with pytest.raises(EOFError):
+        list(w.read_hit_files([d], [(0, 1), (0, 1)], n_readers=2))
