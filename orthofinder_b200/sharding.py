@@ -100,7 +100,7 @@ class LocalExchange:
         self.inbox = [[c.device_alloc(self.seg * self.n) for c in self.ctxs] for _ in range(2)]
 
     def grow(self):
-        self.seg = 8 + 2 * (self.seg - 8)
+        self.seg = 8 + 4 * (self.seg - 8)
         self._alloc()
 
     def close(self):
@@ -166,7 +166,7 @@ class PeerExchange:
         self.mine, self.ptrs = None, None
 
     def grow(self):
-        self.seg = 8 + 2 * (self.seg - 8)
+        self.seg = 8 + 4 * (self.seg - 8)
         self._alloc()
 
     def close(self):

@@ -341,7 +341,7 @@ class PipelinedGraphBuilder:
     def build(self):
         """Enqueues the whole job on the contexts' streams (no host synchronisation in between: the transposed lists go
         from context to context on the device) and then reads every context's results back."""
-        for attempt in range(4):
+        for attempt in range(8):
             for c in self.ctxs:
                 c.build(_lib.STAGE_NORM)
             if self.xchg is not None:
@@ -357,7 +357,7 @@ class PipelinedGraphBuilder:
                     c.sync()
                 return
             except OfgError as e:
-                if e.code == _lib.ERR_CAPACITY and "inbox" in e.message and self.xchg is not None and attempt < 3:
+                if e.code == _lib.ERR_CAPACITY and "inbox" in e.message and self.xchg is not None and attempt < 7:
                     for c in self.ctxs:     # drain the other contexts, then repeat the job with larger inboxes
                         try:
                             c.sync()

@@ -719,3 +719,136 @@ def test_rebuild_is_deterministic_and_sorted(gb):
     assert np.all(np.isfinite(dat)) and np.all(dat > 0)
     c = gb.counts()
     assert c["lines"] > 6_000_000 and c["records"] < c["lines"] and c["nnz"] < c["records"]
+
+
+def _check_against_oracle(gb, n_seqs, L, v2=False, procs=None):
+    S = len(n_seqs)
+    texts = {(p, j): gb.hits_text(p, j) for p in range(S) for j in range(S)}
+    if v2:
+        ref = wo.waterfall(n_seqs, L, lambda p, j: texts[(p, j)], v2_scores=True)
+        ref["graph"] = wo.graph_text(ref["indptr"], ref["indices"], ref["data"], sum(n_seqs))
+    else:
+        from oracle import parallel
+        ref = parallel.waterfall_parallel(n_seqs, L, texts, procs, want_text=True)
+    rows, indptr, idx, dat = gb.graph_csr()
+    assert np.array_equal(indptr, ref["indptr"]) and np.array_equal(idx, ref["indices"])
+    if dat.size:
+        assert np.max(np.abs(dat - ref["data"]) / ref["data"]) <= REL_TOL
+    n_fit = 0
+    for (p, j), f in ref["fits"].items():
+        if v2:
+            break
+        g = gb.pair_fit(p, j)
+        if f is None:
+            assert not g["normalised"], (p, j)
+        else:
+            assert g["normalised"] and g["a"] == f[0] and g["b"] == f[1] and g["m"] == f[2], (p, j, g, f)
+            n_fit += 1
+    text = waterfall.graph_header(sum(n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+    if text != ref["graph"]:
+        edge_diff, dec_diff = graph_text_diff(text, ref["graph"])
+        assert edge_diff == 0 and dec_diff <= 3, (edge_diff, dec_diff)
+    return ref, n_fit
+
+
+def test_full_C5_stress_config_equals_oracle(gb):
+    """BASELINE.json configs[4] at its full size (synth.CONFIGS["C5"]: 6 species x 5000 genes, integer scores on 16 identity
+    levels, 12 distinct lengths, 30 % missing reciprocals, zero-hit and self-only genes, near-tie twins, one pair with too
+    few hits): bit-exact edge set, bit-equal fits, byte-identical text against the CPU oracle."""
+    ids, n_seqs, L, P = synth.config_inputs("C5")
+    gb.set_species(n_seqs, L)
+    gb.synth_hits(P, ids)
+    gb.build()
+    ref, n_fit = _check_against_oracle(gb, n_seqs, L)
+    assert n_fit == 35 and not gb.pair_fit(5, 4)["normalised"]   # the "too few hits" pair is zeroed (gathering.py:152-155)
+    assert gb.counts()["edges"] > 100_000
+
+
+@pytest.mark.parametrize("name,wave", [("ref_AddTwoSpecies", 1), ("ref_AddTwoSpecies", 2), ("synth_C5_small", 3)])
+def test_waves_of_query_species_give_the_single_wave_graph(gb, name, wave):
+    """RAW + NORM over `wave_species` query species at a time (one set of scratch buffers reused, only the CSR kept -
+    the reference's one-query-species-per-task, gathering.py:484-485): byte-identical graph, same fits."""
+    g = Golden(name)
+    _load(gb, g.n_seqs, g.lengths, g.hit_text)
+    gb.set_option("wave_species", wave)
+    try:
+        gb.build()
+        text = waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+        assert text == g.graph
+        S = len(g.n_seqs)
+        for p in range(S):
+            for j in range(S):
+                f = gb.pair_fit(p, j)
+                if np.isnan(g.fits[p, j, 0]):
+                    assert not f["normalised"]
+                else:
+                    assert f["a"] == g.fits[p, j, 0] and f["b"] == g.fits[p, j, 1] and f["m"] == int(g.fits[p, j, 2])
+        # stage by stage with waves: RAW alone, then the rest (the wave scratch is gone: RAW + NORM run again)
+        gb.build(_lib.STAGE_RAW)
+        ip, cols, vals = gb.pair_csr(S - 1, 0)
+        want = wo.get_blast6_scores(g.hit_text(S - 1, 0), g.n_seqs[S - 1], g.n_seqs[0], False)
+        assert np.array_equal(ip, want[0]) and np.array_equal(cols & _lib.COL_MASK, want[1]) and np.array_equal(vals, want[2])
+        gb.build()
+        assert waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER == g.graph
+    finally:
+        gb.set_option("wave_species", 0)
+
+
+def test_waves_on_a_mid_size_job_equal_oracle(gb):
+    """8 species x 2000 genes in waves of 3 query species (the last wave is short), device-generated text."""
+    ids, n_seqs, L, P = synth.config_inputs("C2_small")
+    ids, n_seqs, L = ids[:8], n_seqs[:8], L[:8]
+    gb.set_species(n_seqs, L)
+    gb.synth_hits(P, ids)
+    gb.set_option("wave_species", 3)
+    try:
+        gb.build()
+        _check_against_oracle(gb, n_seqs, L)
+    finally:
+        gb.set_option("wave_species", 0)
+
+
+def test_async_build_reports_errors_at_sync(gb):
+    """Option async: ofg_build only enqueues; a malformed line surfaces at ofg_sync with the same code and text."""
+    n_seqs, L = [3, 3], [np.array([100.0, 200.0, 300.0]), np.array([150.0, 250.0, 350.0])]
+    good = _mk(0, 1, b"50") + _mk(1, 2, b"60")
+    gb.set_species(n_seqs, L)
+    gb.set_option("async", 1)
+    try:
+        for p in range(2):
+            for j in range(2):
+                gb.add_hits(p, j, good if (p, j) != (1, 0) else good + b"1_0\t0_x\t1\t1\t1\t1\t1\t1\t1\t1\t1e-5\t50\n")
+        gb.build()
+        with pytest.raises(waterfall.OfgError) as ei:
+            gb.sync()
+        assert ei.value.code == _lib.ERR_PARSE and "0_x" in ei.value.message
+        gb.clear_hits()
+        for p in range(2):
+            for j in range(2):
+                gb.add_hits(p, j, good)
+        gb.build()
+        gb.sync()
+        assert gb.counts()["lines"] == 8
+    finally:
+        gb.set_option("async", 0)
+
+
+def test_peer_exchange_grows_inboxes_that_are_too_small():
+    """The inbox segments are sized from a guess (entries per matrix row); a segment that overflows is reported by the
+    export kernel at the next read-back and the pipelined builder repeats the job with larger inboxes."""
+    g = Golden("synth_C5_small")
+    S = len(g.n_seqs)
+    whole = waterfall.GraphBuilder(0)
+    _load(whole, g.n_seqs, g.lengths, g.hit_text)
+    whole.build()
+    want = whole.graph_text_body().tobytes()
+    whole.close()
+    pb = waterfall.PipelinedGraphBuilder(0, 3)
+    pb.set_species(g.n_seqs, g.lengths)
+    pb.xchg.seg = 8 + 8 * 32        # room for 32 entries per (source, destination)
+    pb.xchg._alloc()
+    pb.load(lambda p, j: g.hit_text(p, j))
+    pb.build()
+    assert pb.xchg.seg > 8 + 8 * 32
+    assert pb.graph_text_body().tobytes() == want
+    pb.close()
