@@ -85,6 +85,22 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
             fits[(norm_probe.p, j)] = (cur.get("pars"), cur.get("m", 0), B.nnz)
             return r
 
+        most = {}
+        orig_md = gathering.WaterfallMethod.GetMostDistant_s
+        orig_md2 = gathering.WaterfallMethod.GetMostDistant_s_estimate_from_relative_rbhs
+
+        def md_probe(RBH, B, seqsInfo, iSpec):
+            m = orig_md(RBH, B, seqsInfo, iSpec)
+            most[iSpec] = np.array(m, dtype=np.float64, copy=True)
+            return m
+
+        def md2_probe(RBH, B, seqsInfo, iSpec):
+            m = orig_md2(RBH, B, seqsInfo, iSpec)
+            most[iSpec] = np.array(m, dtype=np.float64, copy=True)
+            return m
+
+        gathering.WaterfallMethod.GetMostDistant_s = staticmethod(md_probe)
+        gathering.WaterfallMethod.GetMostDistant_s_estimate_from_relative_rbhs = staticmethod(md2_probe)
         if capture_fit:
             gathering.scnorm.CalculateFittingParameters = staticmethod(fit_probe)
             gathering.WaterfallMethod.NormaliseScores = staticmethod(norm_probe)
@@ -115,12 +131,15 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
         finally:
             gathering.scnorm.CalculateFittingParameters = staticmethod(orig_fit)
             gathering.WaterfallMethod.NormaliseScores = staticmethod(orig_norm)
+            gathering.WaterfallMethod.GetMostDistant_s = staticmethod(orig_md)
+            gathering.WaterfallMethod.GetMostDistant_s_estimate_from_relative_rbhs = staticmethod(orig_md2)
         with open(graph_fn, "rb") as g:
             res["graph"] = g.read()
         res.update(nSeqs=si.nSeqs, nSpecies=si.nSpecies, speciesToUse=list(si.speciesToUse),
                    seqStartingIndices=list(si.seqStartingIndices),
                    nSeqsPerSpecies=dict(si.nSeqsPerSpecies), lengths=[np.asarray(x) for x in L],
-                   mats=mats, fits=fits, stdout=buf.getvalue())
+                   mats=mats, fits=fits, stdout=buf.getvalue(),
+                   most_distant=[most[p] for p in range(si.nSpecies)])
     finally:
         fh.wd_base, fh.wd_current = saved
         shutil.rmtree(out, ignore_errors=True)

@@ -4,11 +4,11 @@ TEST INFRASTRUCTURE ONLY.  Nothing under orthofinder_b200/ imports this module; 
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it, and only
 as the checker / the timed CPU baseline.
 
-Parity status: PINNED.  tests/test_oracle_vs_reference.py runs the unmodified live reference
-(oracle/ref_harness.py) in the build container and requires this restatement to reproduce its
-OrthoFinder_graph.txt byte for byte and its curve_fit parameters bit for bit; the resulting
-golden vectors are committed under tests/golden/ (tools/make_golden.py) so the same check runs
-where /root/reference is absent.
+Parity status: PINNED.  tests/test_reference_pin.py (marker `reference`) runs the unmodified live reference
+(oracle/ref_harness.py) in the build container on the ten usable fixtures of SURVEY.md section 8(c) and requires
+this restatement to reproduce its OrthoFinder_graph.txt byte for byte, its curve_fit parameters bit for bit and its
+per-gene thresholds exactly; the golden vectors committed under tests/golden/ (tools/make_golden.py, same check)
+carry the live reference's outputs to where /root/reference is absent (tests/test_oracle_golden.py).
 
 Each function cites the reference lines it follows (paths relative to /root/reference/scripts_of).
 Flat CSR arrays per species pair are used instead of scipy.sparse; the arithmetic that decides

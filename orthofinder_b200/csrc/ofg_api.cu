@@ -132,6 +132,8 @@ struct ofg_ctx {
     int tl_n = 0;
     EmitArgs last_emit;
     int last_emit_grid = 0;
+    std::vector<int64_t> x_sig;             // what the exchange tables on the device were built from
+    std::vector<unsigned char> plan_sig;    // what the descriptor tables on the device were built from
 };
 
 namespace {
@@ -416,12 +418,24 @@ int plan_build(ofg_ctx* c)
         }
         c->seg_prefix_host.push_back(acc);
     }
-    if (upload(c, c->d_pairs, c->pairs.data(), sizeof(PairDesc) * P)) return OFG_ERR_CUDA;
-    if (upload(c, c->d_pair_row_base, c->pair_row_base.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
-    if (upload(c, c->d_pair_of, c->pair_of.data(), sizeof(int32_t) * c->pair_of.size())) return OFG_ERR_CUDA;
-    if (upload(c, c->d_lengths, c->lengths.data(), sizeof(double) * c->lengths.size())) return OFG_ERR_CUDA;
-    if (upload(c, c->d_tile_prefix, c->seg_prefix_host.data(), sizeof(int64_t) * c->seg_prefix_host.size())) return OFG_ERR_CUDA;
-    if (upload(c, c->d_seq_start, c->seq_start.data(), sizeof(int64_t) * c->S)) return OFG_ERR_CUDA;
+    {
+        // descriptor tables: uploaded only when they changed (a job that is built repeatedly enqueues without host stalls)
+        std::vector<unsigned char> sig;
+        auto put = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; sig.insert(sig.end(), b, b + n); };
+        put(c->pairs.data(), sizeof(PairDesc) * P);
+        put(c->pair_of.data(), sizeof(int32_t) * c->pair_of.size());
+        put(c->seg_prefix_host.data(), sizeof(int64_t) * c->seg_prefix_host.size());
+        put(c->seq_start.data(), sizeof(int64_t) * c->S);
+        if (sig != c->plan_sig || c->layout_dirty) {
+            if (upload(c, c->d_pairs, c->pairs.data(), sizeof(PairDesc) * P)) return OFG_ERR_CUDA;
+            if (upload(c, c->d_pair_row_base, c->pair_row_base.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
+            if (upload(c, c->d_pair_of, c->pair_of.data(), sizeof(int32_t) * c->pair_of.size())) return OFG_ERR_CUDA;
+            if (upload(c, c->d_lengths, c->lengths.data(), sizeof(double) * c->lengths.size())) return OFG_ERR_CUDA;
+            if (upload(c, c->d_tile_prefix, c->seg_prefix_host.data(), sizeof(int64_t) * c->seg_prefix_host.size())) return OFG_ERR_CUDA;
+            if (upload(c, c->d_seq_start, c->seq_start.data(), sizeof(int64_t) * c->S)) return OFG_ERR_CUDA;
+            c->plan_sig.swap(sig);
+        }
+    }
     // small counters block: [1] n_long, [2] err_flags, [3] n_tiles, [4] n_tasks, [8 + w] record slots reserved by wave w,
     // then pair_lines[P], pair_valid[P], pair_err[P], pair_nnz[P]
     c->small_pair_base = 8 + ((c->waves.size() + 7) & ~(size_t)7);
@@ -1060,6 +1074,8 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     c->lengths.assign(lengths_concat, lengths_concat + acc);
     c->owned.clear();
     c->has_partition = false;
+    c->plan_sig.clear();
+    c->x_sig.clear();
     c->pending = false;
     c->graph_pending = false;
     c->bpl_learned = 0.0;
@@ -1151,6 +1167,7 @@ int ofg_synth_hits(ofg_ctx* c, const ofg_synth_params* params, const int32_t* sp
     const int P = (int)c->pairs.size();
     for (auto& f : c->files) f = FileInfo();
     c->text_used = 0;
+    c->plan_sig.clear();   // the descriptor table on the device is rewritten here
     if (upload(c, c->d_pairs, c->pairs.data(), sizeof(PairDesc) * P)) return OFG_ERR_CUDA;
     if (upload(c, c->d_pair_row_base, c->pair_row_base.data(), sizeof(int64_t) * (P + 1))) return OFG_ERR_CUDA;
     if (upload(c, c->d_lengths, c->lengths.data(), sizeof(double) * c->lengths.size())) return OFG_ERR_CUDA;
@@ -1451,11 +1468,19 @@ int ofg_export_flags_peer(ofg_ctx* c, int which, int n_ranks, const int32_t* spe
     }
     dst_first[n_ranks] = (int32_t)order.size();
     if (order.empty()) order.push_back(0);
-    if (upload(c, c->x_pair_dst, pair_dst.data(), pair_dst.size() * 4)) return OFG_ERR_CUDA;
-    if (upload(c, c->x_order, order.data(), order.size() * 4)) return OFG_ERR_CUDA;
-    if (upload(c, c->x_dst_first, dst_first.data(), dst_first.size() * 4)) return OFG_ERR_CUDA;
-    if (upload(c, c->x_inbox_ptrs, inbox_ptrs, sizeof(void*) * n_ranks)) return OFG_ERR_CUDA;
-    CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope (a few KB; the lists themselves never touch the host)
+    // uploaded once per (partition, owner map, inbox set): the steady state of a job enqueues the exchange without a host stall
+    std::vector<int64_t> sig;
+    sig.push_back(n_ranks); sig.push_back(my_rank); sig.push_back(P);
+    for (int i = 0; i < P; i++) sig.push_back(pair_dst[i]);
+    for (int r = 0; r < n_ranks; r++) sig.push_back((int64_t)(uintptr_t)inbox_ptrs[r]);
+    if (sig != c->x_sig) {
+        if (upload(c, c->x_pair_dst, pair_dst.data(), pair_dst.size() * 4)) return OFG_ERR_CUDA;
+        if (upload(c, c->x_order, order.data(), order.size() * 4)) return OFG_ERR_CUDA;
+        if (upload(c, c->x_dst_first, dst_first.data(), dst_first.size() * 4)) return OFG_ERR_CUDA;
+        if (upload(c, c->x_inbox_ptrs, inbox_ptrs, sizeof(void*) * n_ranks)) return OFG_ERR_CUDA;
+        CK(cudaStreamSynchronize(c->stream));  // host vectors go out of scope (a few KB; the lists themselves never touch the host)
+        c->x_sig = sig;
+    }
     CK(c->row_flagoff.ensure((size_t)(c->n_rows + 2) * 8));
     CK(c->x_off.ensure((size_t)(P + 4) * 8));
     if (device_scan<u64>(c, c->row_flagcnt.as<u32>(), c->n_rows, c->row_flagoff.as<u64>(), 1)) return OFG_ERR_CUDA;
@@ -1469,7 +1494,7 @@ int ofg_export_flags_peer(ofg_ctx* c, int which, int n_ranks, const int32_t* spe
     export_layout_kernel<<<1, 32 * n_ranks, 0, c->stream>>>(a);
     CKL("export_layout_kernel");
     if (P > 0 && c->n_rows > 0 && dst_first[n_ranks] > 0) {
-        export_peer_kernel<<<grid_for(c, c->n_rows, 8, 8), 256, 0, c->stream>>>(a);
+        export_peer_kernel<4><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(a);
         CKL("export_peer_kernel");
     }
     c->pending = true;

@@ -10,7 +10,7 @@
 //
 // One source, two builds: nvcc compiles it as the body of fit_kernel (one CTA per species pair);
 // g++ compiles it with a one-thread "CTA" so the exact same control flow can be checked on the CPU
-// against scipy and the oracle (tests/test_fit_core_host.py).
+// against scipy and the oracle (tests/test_host_shared_code.py).
 #pragma once
 #include <math.h>
 #include <float.h>

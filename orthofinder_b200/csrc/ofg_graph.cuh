@@ -642,31 +642,47 @@ __global__ void __launch_bounds__(1024) export_layout_kernel(PeerExportArgs a)
     }
 }
 
+// ROW_G lanes per matrix row (several rows in flight per warp: the work per row is a short chain of dependent loads)
+template <int ROW_G>
 __global__ void __launch_bounds__(256) export_peer_kernel(PeerExportArgs a)
 {
-    const int lane = lane_id();
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
     const u64 cap = (a.seg_bytes - 8) / 8;
+    const u32 gmask = (ROW_G == 32) ? 0xffffffffu : (((1u << ROW_G) - 1u) << (sub * ROW_G));
     int pair = -1;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.n_rows; row += n_warps) {
-        const u64 o0 = a.row_off[row];
-        if (a.row_off[row + 1] == o0) continue;  // nothing flagged in this row
-        pair = advance_pair(a.pair_row_base, a.P, pair, row);
-        const int dst = a.pair_dst[pair];
-        if (dst < 0) continue;
-        const PairDesc& pd = a.pairs[pair];
-        const int n = (int)a.rowlen[row];
-        const u32 s0 = a.row_start[row];
-        const int r = (int)(row - pd.row_base);
-        u64 pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
-        int2* out = reinterpret_cast<int2*>(a.inbox[dst] + (u64)a.my_rank * a.seg_bytes + 8);
-        for (int k0 = 0; k0 < n; k0 += 32) {
-            const int k = k0 + lane;
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        int n = 0;
+        u64 pos = 0;
+        u32 s0 = 0;
+        int r = 0;
+        int2* out = nullptr;
+        int64_t gi = 0, gj = 0;
+        if (row < a.n_rows) {
+            const u64 o0 = a.row_off[row];
+            if (a.row_off[row + 1] != o0) {   // something is flagged in this row
+                pair = advance_pair(a.pair_row_base, a.P, pair, row);
+                const int dst = a.pair_dst[pair];
+                if (dst >= 0) {
+                    const PairDesc& pd = a.pairs[pair];
+                    n = (int)a.rowlen[row];
+                    s0 = a.row_start[row];
+                    r = (int)(row - pd.row_base);
+                    gi = pd.gi_start; gj = pd.gj_start;
+                    pos = a.pair_off[pair] + (o0 - a.row_off[pd.row_base]);
+                    out = reinterpret_cast<int2*>(a.inbox[dst] + (u64)a.my_rank * a.seg_bytes + 8);
+                }
+            }
+        }
+        const int nmax = warp_max_over_groups<ROW_G>(n);
+        for (int k0 = 0; k0 < nmax; k0 += ROW_G) {
+            const int k = k0 + gl;
             const u32 cw = k < n ? a.cols[s0 + k] : 0u;
             const bool on = (cw & a.flag) != 0;
-            const u32 bal = __ballot_sync(OFG_FULL, on);
+            const u32 bal = __ballot_sync(OFG_FULL, on) & gmask;
             const u64 o = pos + __popc(bal & lanemask_lt());
-            if (on && o < cap) out[o] = make_int2((int)(pd.gj_start + (cw & OFG_COL_MASK)), (int)(pd.gi_start + r));
+            if (on && o < cap) out[o] = make_int2((int)(gj + (cw & OFG_COL_MASK)), (int)(gi + r));
             pos += __popc(bal);
         }
     }

@@ -613,17 +613,35 @@ class WaterfallMethod:
         return graphFN
 
 
-def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empty=False, device=0):
-    """The part of gathering.DoOrthogroups between :476 and :512 for a `-b <dir> -og` run: reads
-    SpeciesIDs.txt / Species*.fa / Blast*_*.txt from workingDir and writes OrthoFinder_graph.txt."""
+def GetGraphFilename(wd_current, i_unassigned=None, fileIdentifierString="OrthoFinder"):
+    """files.py:324-327 FileHandler.GetGraphFilename."""
+    identifier = fileIdentifierString + ("" if i_unassigned is None else "_unassigned_clade_%d" % i_unassigned)
+    return wd_current + "%s_graph.txt" % identifier
+
+
+def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empty=None, device=0, blastDir_list=None,
+                       v2_scores=False, i_unassigned=None, wd_current=None, n_readers=None):
+    """The part of gathering.DoOrthogroups between :476 and :512 for a `-b <dir> -og` run: reads SpeciesIDs.txt /
+    Species*.fa from workingDir and Blast*_*.txt[.gz] from blastDir_list (default [workingDir]; the first directory
+    holding a file wins, files.py:313-322) and writes the graph file.
+
+    i_unassigned: the clade-specific run of `--assign` (gathering.py:469-483, __main__.py:1083-1093): only the latest
+    blast directory is searched, missing hit files are empty (q_allow_empty), the caller passes v2_scores=True and the
+    graph goes to OrthoFinder_unassigned_clade_<i>_graph.txt (files.py:324-327)."""
     if not workingDir.endswith(os.sep):
         workingDir += os.sep
+    q_unassigned = i_unassigned is not None
     sp, n_all, _ = GetSpeciesToUse(workingDir + "SpeciesIDs.txt")
     si = GetSeqsInfo([workingDir], sp, n_all)
     L = GetSequenceLengths(si, [workingDir])
-    gb = WaterfallMethod.BuildGraph(si, [workingDir], L, qDoubleBlast=qDoubleBlast, q_allow_empty=q_allow_empty,
-                                    device=device)
+    dirs = [d if d.endswith(os.sep) else d + os.sep for d in (blastDir_list or [workingDir])]
+    if q_unassigned:
+        dirs = dirs[:1]   # gathering.py:482-483: only the latest directory holds the unassigned-gene searches
+    if q_allow_empty is None:
+        q_allow_empty = q_unassigned   # gathering.py:492 passes q_unassigned as q_allow_empty
+    gb = WaterfallMethod.BuildGraph(si, dirs, L, qDoubleBlast=qDoubleBlast, v2_scores=v2_scores, q_allow_empty=q_allow_empty,
+                                    device=device, n_readers=n_readers)
     if graphFN is None:
-        graphFN = workingDir + "OrthoFinder_graph.txt"  # files.py:324-327 GetGraphFilename
+        graphFN = GetGraphFilename(wd_current or workingDir, i_unassigned)
     WaterfallMethod.WriteGraphParallel(gb, si, graphFN)
     return graphFN, gb, si

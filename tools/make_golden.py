@@ -41,6 +41,7 @@ def run_one(name, wd, store_inputs):
     ref = rh.run_reference(wd)
     mine = wo.waterfall_from_directory(wd)
     assert ref["graph"] == mine["graph"], "%s: oracle graph differs from the reference" % name
+    assert np.array_equal(np.concatenate(ref["most_distant"]), np.concatenate(mine["most_distant"])), "%s: thresholds differ" % name
     S = ref["nSpecies"]
     fits = np.full((S, S, 3), np.nan)
     nnz = np.zeros((S, S, 3), np.int64)
@@ -55,7 +56,7 @@ def run_one(name, wd, store_inputs):
         nnz[p, j] = [ref["mats"][(k, p, j)].nnz for k in ("B", "BH", "connect")]
     out = dict(graph_z=np.frombuffer(zlib.compress(ref["graph"], 9), np.uint8), fits=fits, nnz=nnz,
                n_seqs=np.array([ref["nSeqsPerSpecies"][k] for k in ref["speciesToUse"]], np.int64),
-               species=np.array(ref["speciesToUse"], np.int64), most_distant=np.concatenate(mine["most_distant"]),
+               species=np.array(ref["speciesToUse"], np.int64), most_distant=np.concatenate(ref["most_distant"]),
                provenance=np.array(provenance()))
     if store_inputs:
         out["lengths"] = np.concatenate(ref["lengths"])
@@ -73,7 +74,8 @@ def run_one(name, wd, store_inputs):
     mine2 = wo.waterfall_from_directory(wd, v2_scores=True)
     assert ref2["graph"] == mine2["graph"], "%s: oracle v2 graph differs from the reference" % name
     out["graph_v2_z"] = np.frombuffer(zlib.compress(ref2["graph"], 9), np.uint8)
-    out["most_distant_v2"] = np.concatenate(mine2["most_distant"])
+    assert np.array_equal(np.concatenate(ref2["most_distant"]), np.concatenate(mine2["most_distant"])), "%s: v2 thresholds differ" % name
+    out["most_distant_v2"] = np.concatenate(ref2["most_distant"])
     fn = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez(fn, **out)
     print("%-20s S=%d genes=%d graph=%d B  entries=%d  -> %s (%d KB)" % (
