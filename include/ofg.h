@@ -104,6 +104,7 @@ int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
  * "sel_capacity_frac_inv" (selection capacity = records/this, default 4), "reserve_text_bytes" (size the text arena
  * once), "wave_species" (RAW + NORM run over this many query species at a time out of one set of scratch buffers -
  * the reference's "one query species per task", gathering.py:484-485; 0 = the whole partition at once),
+ * "length_sort_radix" (0/1: build the length bins with the segmented LSD radix sort only - the fallback of the bucket path),
  * "async" (0/1: ofg_build only enqueues; counts, errors and sizes are read back by ofg_sync or by the first accessor),
  * "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)
  * instead of the length-bin fit and GetMostDistant_s_estimate_from_relative_rbhs (gathering.py:314-388) instead of
@@ -127,6 +128,9 @@ int ofg_build(ofg_ctx* ctx, int stop_after);
  * synchronisation: line counts, parse errors, capacity flags, fit table, graph sizes).  Returns what a synchronous
  * ofg_build would have returned.  Every accessor below calls it implicitly. */
 int ofg_sync(ofg_ctx* ctx);
+/* Statistics of the last build: "radix_fallback_waves" (waves whose length bins were built by the LSD radix sort because
+ * the bucket path could not take them), "waves", "record_slot_capacity". */
+int ofg_get_stat(ofg_ctx* ctx, const char* name, int64_t* value);
 /* Orders the context's stream after everything enqueued so far on `other`'s stream (event wait, no host block). */
 int ofg_wait_for(ofg_ctx* ctx, ofg_ctx* other);
 

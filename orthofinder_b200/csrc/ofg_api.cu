@@ -15,6 +15,7 @@
 #include "ofg_parse.cuh"
 #include "ofg_rows.cuh"
 #include "ofg_norm.cuh"
+#include "ofg_bins.cuh"
 #include "ofg_graph.cuh"
 #include "ofg_synth.cuh"
 
@@ -89,6 +90,8 @@ struct ofg_ctx {
     bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
+    bool radix_only = false;    // option length_sort_radix: always take the LSD radix path (the fallback of the bucket path)
+    int64_t fallback_waves = 0; // waves of the last build that took the radix path
     int wave_species = 0;       // option wave_species: query species per wave (0: the whole partition in one wave)
     bool async = false;         // option async: ofg_build returns after enqueueing; results are read back by ofg_sync
     double bpl_learned = 0.0;   // bytes of text per record slot seen by the last complete build (sizes the next one)
@@ -112,6 +115,7 @@ struct ofg_ctx {
     DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, d_length_factors, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff, diag_pairs;
+    DevBuf bk_hist, bk_rec, bk_bbidx, bk_shist, bk_thr, bk_below, bk_bin16, bk_bb, bk_bbfill, bk_split, bk_gcursor, bin_val;
     DevBuf x_flag, x_off, x_list, x_pair_dst, x_order, x_dst_first, x_inbox_ptrs;
     // pinned read-back area: [small block][fit table]
     u64* h_small = nullptr;
@@ -355,7 +359,15 @@ u64* small_ptr(ofg_ctx* c) { return c->d_small.as<u64>(); }
 u32* err_flags_ptr(ofg_ctx* c) { return (u32*)(small_ptr(c) + 2); }
 int64_t* n_tiles_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 3); }
 int64_t* n_tasks_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 4); }
-u64* wave_count_ptr(ofg_ctx* c, int w) { return small_ptr(c) + 8 + w; }
+u32* bk_flags_ptr(ofg_ctx* c) { return (u32*)(small_ptr(c) + 5); }
+int64_t* n_tiles_fb_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 6); }
+int64_t* n_tasks_fb_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 7); }
+int64_t* n_tiles_nw_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 8); }
+int64_t* n_tasks_nw_ptr(ofg_ctx* c) { return (int64_t*)(small_ptr(c) + 9); }
+u32* n_bb_ptr(ofg_ctx* c) { return (u32*)(small_ptr(c) + 10); }
+unsigned long long* list_used_ptr(ofg_ctx* c) { return (unsigned long long*)(small_ptr(c) + 11); }
+u64* fallback_waves_ptr(ofg_ctx* c) { return small_ptr(c) + 12; }   // waves that took the radix path (statistics)
+u64* wave_count_ptr(ofg_ctx* c, int w) { return small_ptr(c) + 16 + w; }
 u64* pair_lines_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base; }
 u64* pair_valid_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base + c->pairs.size(); }
 u64* pair_err_ptr(ofg_ctx* c) { return small_ptr(c) + c->small_pair_base + 2 * c->pairs.size(); }
@@ -436,9 +448,9 @@ int plan_build(ofg_ctx* c)
             c->plan_sig.swap(sig);
         }
     }
-    // small counters block: [1] n_long, [2] err_flags, [3] n_tiles, [4] n_tasks, [8 + w] record slots reserved by wave w,
-    // then pair_lines[P], pair_valid[P], pair_err[P], pair_nnz[P]
-    c->small_pair_base = 8 + ((c->waves.size() + 7) & ~(size_t)7);
+    // small counters block: [1] n_long, [2] err_flags, [3] n_tiles, [4] n_tasks, [5..12] bucket-path routing, [16 + w] record
+    // slots reserved by wave w, then pair_lines[P], pair_valid[P], pair_err[P], pair_nnz[P]
+    c->small_pair_base = 16 + ((c->waves.size() + 7) & ~(size_t)7);
     c->small_words = c->small_pair_base + 4 * (size_t)P;
     CK(c->d_small.ensure(c->small_words * 8));
     CK(cudaMemsetAsync(c->d_small.p, 0, c->small_words * 8, c->stream));
@@ -557,7 +569,8 @@ int wave_norm(ofg_ctx* c, int wi)
     } else {
         // ---- layout of the wave on the device: slots, sort tiles and length bins of every pair
         const int64_t max_tiles = (int64_t)(cap / RS_TILE) + Pw + 1;
-        const int64_t max_tasks = (int64_t)(cap / 20) + Pw + 1;
+        // bins: H / 1000 for H > 5000; at most 25 (H <= 5000, bins of 200) or 50 (H <= 1000, bins of 20) or 1 per smaller pair
+        const int64_t max_tasks = (int64_t)(cap / 1000) + 76 * (int64_t)Pw + 16;
         CK(c->wave_pair_slot.ensure((size_t)(Pw + 2) * 8));
         CK(c->wave_tile_prefix.ensure((size_t)(Pw + 2) * 8));
         CK(c->wave_task_prefix.ensure((size_t)(Pw + 2) * 8));
@@ -568,37 +581,16 @@ int wave_norm(ofg_ctx* c, int wi)
         la.max_tiles = max_tiles; la.max_tasks = max_tasks; la.err_flags = err_flags;
         wave_layout_kernel<<<1, 1024, 0, c->stream>>>(la, 1);
         CKL("wave_layout_kernel");
-        // ---- segmented stable radix sort by Lf
-        const int n_pass = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;
+        const int n_pass = (key_bits + RS_MAX_BITS - 1) / RS_MAX_BITS;     // of the radix path
         const int pass_bits = (key_bits + n_pass - 1) / n_pass;
-        CK(c->keyval.ensure((cap + 64) * 8));
-        CK(c->key2.ensure((cap + 64) * 4));
-        CK(c->keyval2.ensure((cap + 64) * 8));
-        CK(c->counters.ensure(((size_t)max_tiles << pass_bits) * 4 + 64));
         CK(c->sort_desc.ensure((size_t)max_tiles * sizeof(RsTileDesc)));
         rs_desc_kernel<<<grid_for(c, max_tiles, 256, 4), 256, 0, c->stream>>>(c->wave_tile_prefix.as<int64_t>(), c->wave_pair_slot.as<int64_t>(), Pw,
                                                                               n_tiles_ptr(c), pass_bits, c->sort_desc.as<RsTileDesc>());
         CKL("rs_desc_kernel");
-        // the first pass reads the scores straight from the CSR values (same slots as the keys), so the row sort does
-        // not have to write a second copy; from then on the two sort buffers ping-pong
-        u32* kin = c->key.as<u32>(); double* vin = c->vals.as<double>();
-        u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
-        CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
-        for (int pass = 0; pass < n_pass; pass++) {
-            RadixArgs a;
-            a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
-            a.n_tiles_dev = n_tiles_ptr(c); a.val_in_off_dev_valid = pass == 0 ? 1 : 0; a.slot0 = slot0;
-            a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
-            a.desc = c->sort_desc.as<RsTileDesc>();
-            radix_hist_kernel<<<grid_for(c, max_tiles, 1, 4), RS_THREADS, 0, c->stream>>>(a);
-            CKL("radix_hist_kernel");
-            if (device_scan<u32>(c, a.counters, max_tiles << pass_bits, a.counters, 0, n_tiles_ptr(c), pass_bits)) return OFG_ERR_CUDA;
-            radix_scatter_kernel<<<grid_for(c, max_tiles, 1, 2), RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);  // two resident CTAs per SM
-            CKL("radix_scatter_kernel");
-            std::swap(kin, kout);
-            if (pass == 0) { vin = vout; vout = c->keyval.as<double>(); } else std::swap(vin, vout);
-        }
-        // ---- bins
+        CK(c->keyval.ensure((cap + 64) * 8));
+        CK(c->key2.ensure((cap + 64) * 4));
+        CK(c->keyval2.ensure((cap + 64) * 8));
+        CK(c->bin_val.ensure((cap + 64) * 8));
         CK(c->bin_tasks.ensure((size_t)(max_tasks + 1) * sizeof(BinTask)));
         CK(c->bin_cut.ensure((size_t)(max_tasks + 1) * 8));
         CK(c->bin_cnt.ensure((size_t)(max_tasks + 1) * 4));
@@ -609,7 +601,7 @@ int wave_norm(ofg_ctx* c, int wi)
                                                                                 w.P0, Pw, n_tasks_ptr(c), c->bin_tasks.as<BinTask>());
         CKL("bin_tasks_kernel");
         BinArgs b;
-        b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks_dev = n_tasks_ptr(c); b.key = kin; b.val = vin;
+        b.tasks = c->bin_tasks.as<BinTask>(); b.n_tasks_dev = n_tasks_ptr(c); b.key = nullptr; b.val = nullptr; b.rec = nullptr; b.cand_cnt = nullptr; b.below = nullptr;
         {
             // numpy: virtual index (n-1)*q with q = 95/100, gamma = vi - floor(vi)
             const double q = 95.0 / 100.0;
@@ -620,10 +612,99 @@ int wave_norm(ofg_ctx* c, int wi)
         }
         b.cut = c->bin_cut.as<double>(); b.cnt = c->bin_cnt.as<u32>(); b.sel_off = c->sel_off.as<u64>();
         b.lx = c->lx.as<double>(); b.ly = c->ly.as<double>(); b.sel_cap = c->sel_cap;
-        // staging: two free fp64 arrays of at least `cap` entries - the parse output scores and the idle sort buffer
-        b.stage_lx = c->coo_val.as<double>(); b.stage_ly = vout;
-        bin_cut_kernel<<<grid_for(c, max_tasks, BIN_WARPS, 6), BIN_THREADS, 0, c->stream>>>(b);
-        CKL("bin_cut_kernel");
+        // staging of the selected hits of every bin (bin_cut -> bin_select): two fp64 arrays of at least `cap` entries
+        b.stage_lx = c->coo_val.as<double>(); b.stage_ly = c->bin_val.as<double>();
+        // ---- bucket path (ofg_bins.cuh): bins without a full sort; routes itself to the radix path on the device
+        CK(cudaMemsetAsync(small_ptr(c) + 5, 0, 7 * 8, c->stream));   // routing words of this wave
+        if (c->radix_only) {
+            const u32 one = BK_FALLBACK;
+            CK(cudaMemcpyAsync(bk_flags_ptr(c), &one, 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        const size_t tab = (size_t)Pw * BK_NB * 4;
+        CK(c->bk_hist.ensure(tab)); CK(c->bk_bbidx.ensure(tab));
+        CK(c->bk_rec.ensure((cap + 64) * 16));
+        CK(c->bk_bb.ensure((size_t)(max_tasks + 1) * sizeof(BbDesc)));
+        CK(c->bk_bbfill.ensure((size_t)(max_tasks + 1) * 4));
+        CK(c->bk_split.ensure((size_t)(max_tasks + 1) * 8));
+        CK(c->bk_gcursor.ensure((size_t)(max_tasks + 1) * 4));
+        CK(c->bk_shist.ensure((size_t)(max_tasks + 1) * (BK_SB / 2) * 4));
+        CK(c->bk_thr.ensure((size_t)(max_tasks + 1) * 2));
+        CK(c->bk_below.ensure((size_t)(max_tasks + 1) * 2));
+        CK(c->bk_bin16.ensure((cap + 64) * 2));
+        BkArgs k;
+        k.key = c->key.as<u32>(); k.key_sentinel = 1u << (key_bits - 1); k.vals = c->vals.as<double>(); k.slot0 = slot0;
+        k.desc = c->sort_desc.as<RsTileDesc>(); k.n_tiles_all = n_tiles_ptr(c); k.n_tiles_nw = n_tiles_nw_ptr(c);
+        k.pair_slot = c->wave_pair_slot.as<int64_t>(); k.task_prefix = c->wave_task_prefix.as<u64>(); k.pair_nnz = pair_nnz_ptr(c) + w.P0; k.Pw = Pw;
+        k.hist = c->bk_hist.as<u32>(); k.binof = c->bk_bbidx.as<u32>();
+        k.bb = c->bk_bb.as<BbDesc>(); k.bb_cap = (u32)std::min<int64_t>(max_tasks, 0x7fffffff); k.n_bb = n_bb_ptr(c); k.list_used = list_used_ptr(c);
+        k.list_cap = cap; k.list = c->keyval.as<u64>(); k.bbfill = c->bk_bbfill.as<u32>(); k.split = c->bk_split.as<u64>();
+        k.gcursor = c->bk_gcursor.as<u32>(); k.rec_b = c->bk_rec.as<uint4>(); k.flags = bk_flags_ptr(c);
+        if (!c->radix_only) {
+            CK(cudaMemsetAsync(c->bk_hist.p, 0, tab, c->stream));
+            CK(cudaMemsetAsync(c->bk_bbidx.p, 0, tab, c->stream));
+            CK(cudaMemsetAsync(c->bk_bbfill.p, 0, (size_t)(max_tasks + 1) * 4, c->stream));
+            CK(cudaMemsetAsync(c->bk_gcursor.p, 0, (size_t)(max_tasks + 1) * 4, c->stream));
+            CK(cudaMemsetAsync(c->bk_shist.p, 0, (size_t)(max_tasks + 1) * (BK_SB / 2) * 4, c->stream));
+            CK(cudaFuncSetAttribute(bk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_NB * 2));
+            bk_hist_kernel<<<grid_for(c, max_tiles, BKH_TILES, 1), BKH_THREADS, BK_NB * 2, c->stream>>>(k);
+            CKL("bk_hist_kernel");
+            bk_scan_kernel<<<Pw, 1024, 0, c->stream>>>(k);
+            CKL("bk_scan_kernel");
+        }
+        bk_route_kernel<<<1, 1, 0, c->stream>>>(bk_flags_ptr(c), n_tiles_ptr(c), n_tasks_ptr(c), n_bb_ptr(c), k.bb_cap, n_tiles_fb_ptr(c), n_tasks_fb_ptr(c),
+                                                n_tiles_nw_ptr(c), n_tasks_nw_ptr(c), fallback_waves_ptr(c));
+        CKL("bk_route_kernel");
+        if (!c->radix_only) {
+            bk_gather_kernel<<<grid_for(c, max_tiles, 1, 4), 512, 0, c->stream>>>(k);
+            CKL("bk_gather_kernel");
+            bk_split_kernel<<<grid_for(c, max_tasks, BKS_WARPS, 8), BKS_WARPS * 32, 0, c->stream>>>(k);
+            CKL("bk_split_kernel");
+            BkCandArgs kc;
+            kc.bin16 = c->bk_bin16.as<unsigned short>(); kc.shist = c->bk_shist.as<u32>(); kc.thr = c->bk_thr.as<unsigned short>();
+            kc.below = c->bk_below.as<unsigned short>(); kc.n_tasks_nw = n_tasks_nw_ptr(c); kc.tasks = c->bin_tasks.as<BinTask>();
+            kc.k20 = b.k20; kc.k200 = b.k200; kc.k1000 = b.k1000;
+            bk_binhist_kernel<<<grid_for(c, max_tiles, 1, 4), 512, 0, c->stream>>>(k, kc);
+            CKL("bk_binhist_kernel");
+            bk_thr_kernel<<<grid_for(c, max_tasks, 8, 8), 256, 0, c->stream>>>(kc);
+            CKL("bk_thr_kernel");
+            bk_cand_kernel<<<grid_for(c, max_tiles, 1, 4), 512, 0, c->stream>>>(k, kc);
+            CKL("bk_cand_kernel");
+            BinArgs bu = b;
+            bu.n_tasks_dev = n_tasks_nw_ptr(c); bu.key = nullptr; bu.val = nullptr; bu.rec = c->bk_rec.as<uint4>();
+            bu.cand_cnt = c->bk_gcursor.as<u32>(); bu.below = c->bk_below.as<unsigned short>();
+            bin_cut_kernel<true><<<grid_for(c, max_tasks, BIN_WARPS, 6), BIN_THREADS, 0, c->stream>>>(bu);
+            CKL("bin_cut_kernel");
+        }
+        // ---- radix path (fallback): segmented stable LSD radix sort by Lf, then the bins of the sorted order.  Its tile and
+        // task counts are zero unless the bucket path routed the wave here.
+        {
+            CK(c->counters.ensure(((size_t)max_tiles << pass_bits) * 4 + 64));
+            // the first pass reads the scores straight from the CSR values (same slots as the keys), so the row sort does
+            // not have to write a second copy; from then on the two sort buffers ping-pong
+            u32* kin = c->key.as<u32>(); double* vin = c->vals.as<double>();
+            u32* kout = c->key2.as<u32>(); double* vout = c->keyval2.as<double>();
+            CK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RadixSmem)));
+            // a wave that stays on the bucket path only pays for the (empty) launches; keep their grids small unless forced
+            const int gh = c->radix_only ? grid_for(c, max_tiles, 1, 4) : std::min(grid_for(c, max_tiles, 1, 4), c->n_sm * 4);
+            for (int pass = 0; pass < n_pass; pass++) {
+                RadixArgs a;
+                a.key_in = kin; a.val_in = vin; a.key_out = kout; a.val_out = vout;
+                a.n_tiles_dev = n_tiles_fb_ptr(c); a.val_in_off_dev_valid = pass == 0 ? 1 : 0; a.slot0 = slot0;
+                a.shift = pass * pass_bits; a.bits = pass_bits; a.counters = c->counters.as<u32>();
+                a.desc = c->sort_desc.as<RsTileDesc>();
+                radix_hist_kernel<<<gh, RS_THREADS, 0, c->stream>>>(a);
+                CKL("radix_hist_kernel");
+                if (device_scan<u32>(c, a.counters, max_tiles << pass_bits, a.counters, 0, n_tiles_fb_ptr(c), pass_bits)) return OFG_ERR_CUDA;
+                radix_scatter_kernel<<<grid_for(c, max_tiles, 1, 2), RS_THREADS, sizeof(RadixSmem), c->stream>>>(a);  // two resident CTAs per SM
+                CKL("radix_scatter_kernel");
+                std::swap(kin, kout);
+                if (pass == 0) { vin = vout; vout = c->keyval.as<double>(); } else std::swap(vin, vout);
+            }
+            BinArgs bs = b;
+            bs.n_tasks_dev = n_tasks_fb_ptr(c); bs.key = kin; bs.val = vin; bs.rec = nullptr;
+            bin_cut_kernel<false><<<grid_for(c, max_tasks, BIN_WARPS, 6), BIN_THREADS, 0, c->stream>>>(bs);
+            CKL("bin_cut_kernel");
+        }
         if (device_scan<u64>(c, b.cnt, max_tasks, c->sel_off.as<u64>(), 1, n_tasks_ptr(c), 0)) return OFG_ERR_CUDA;
         bin_select_kernel<<<grid_for(c, max_tasks, BIN_WARPS, 16), BIN_THREADS, 0, c->stream>>>(b);
         CKL("bin_select_kernel");
@@ -881,6 +962,7 @@ int stage_emit(ofg_ctx* c)
 const char* const STAGE_OF_KERNEL[][2] = {
     {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
     {"wave_layout_kernel", "2"}, {"rs_desc_kernel", "2"}, {"radix_hist_kernel", "2"}, {"radix_scatter_kernel", "2"},
+    {"bk_hist_kernel", "2"}, {"bk_scan_kernel", "2"}, {"bk_route_kernel", "2"}, {"bk_gather_kernel", "2"}, {"bk_split_kernel", "2"}, {"bk_binhist_kernel", "2"}, {"bk_thr_kernel", "3"}, {"bk_cand_kernel", "3"},
     {"bin_tasks_kernel", "3"}, {"bin_cut_kernel", "3"}, {"bin_select_kernel", "3"}, {"pair_sel_off_kernel", "4"}, {"fit_kernel", "4"},
     {"factors_kernel", "5"}, {"scale_bh_kernel", "5"}, {"bh_self_kernel", "5"}, {"rbh_kernel", "6"}, {"v2_ratio_kernel", "6"},
     {"thresh_final_kernel", "6"}, {"connect_kernel", "7"}, {"emit_sizes_kernel", "8"}, {"emit_kernel<true>", "8"}};
@@ -921,6 +1003,7 @@ int sync_results(ofg_ctx* c)
     c->pending = false;
     const u64* small = c->h_small;
     const u32 flags = (u32)small[2];
+    c->fallback_waves = (int64_t)small[12];
     const size_t pb = c->small_pair_base;
     c->pair_lines.assign(small + pb, small + pb + P);
     c->pair_valid.assign(small + pb + P, small + pb + 2 * (size_t)P);
@@ -958,7 +1041,7 @@ int sync_results(ofg_ctx* c)
         }
     }
     for (size_t w = 0; w < c->waves.size(); w++) {
-        const u64 used = small[8 + w];
+        const u64 used = small[16 + w];
         if (used > c->waves[w].cap) {
             const bool learned = c->bpl_learned > (double)c->bytes_per_line_inv;
             c->bpl_learned = 0.0;
@@ -1000,7 +1083,7 @@ int sync_results(ofg_ctx* c)
         int64_t text = 0;
         u64 slots = 0;
         for (const Wave& w : c->waves) text += w.text_bytes;
-        for (size_t w = 0; w < c->waves.size(); w++) slots += small[8 + w];
+        for (size_t w = 0; w < c->waves.size(); w++) slots += small[16 + w];
         if (slots > 0) c->bpl_learned = 0.85 * (double)text / (double)slots;
     }
     return 0;
@@ -1039,6 +1122,7 @@ void ofg_destroy(ofg_ctx* c)
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
                       &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff, &c->diag_pairs,
+                      &c->bk_hist, &c->bk_rec, &c->bk_bbidx, &c->bk_shist, &c->bk_thr, &c->bk_below, &c->bk_bin16, &c->bk_bb, &c->bk_bbfill, &c->bk_split, &c->bk_gcursor, &c->bin_val,
                       &c->x_flag, &c->x_off, &c->x_list, &c->x_pair_dst, &c->x_order, &c->x_dst_first, &c->x_inbox_ptrs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->tl_ev) if (e) cudaEventDestroy(e);
@@ -1113,6 +1197,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "sel_capacity_frac_inv")) c->sel_frac_inv = value;
     else if (!strcmp(name, "wave_species")) { c->wave_species = (int)std::max<int64_t>(value, 0); c->stage_done = 0; }
     else if (!strcmp(name, "async")) c->async = value != 0;
+    else if (!strcmp(name, "length_sort_radix")) c->radix_only = value != 0;
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else return fail(c, OFG_ERR_ARG, "unknown option %s", name);
     return OFG_OK;
@@ -1277,6 +1362,18 @@ int ofg_sync(ofg_ctx* c)
     cudaSetDevice(c->device);
     if (!c->pending) { CK(cudaStreamSynchronize(c->stream)); return OFG_OK; }
     return sync_results(c);
+}
+
+int ofg_get_stat(ofg_ctx* c, const char* name, int64_t* value)
+{
+    if (!c || !name || !value) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = sync_results(c)) return rc;
+    if (!strcmp(name, "radix_fallback_waves")) *value = c->fallback_waves;
+    else if (!strcmp(name, "waves")) *value = (int64_t)c->waves.size();
+    else if (!strcmp(name, "record_slot_capacity")) { int64_t t = 0; for (const Wave& w : c->waves) t += (int64_t)w.cap; *value = t; }
+    else return fail(c, OFG_ERR_ARG, "unknown statistic %s", name);
+    return OFG_OK;
 }
 
 int ofg_wait_for(ofg_ctx* c, ofg_ctx* other)

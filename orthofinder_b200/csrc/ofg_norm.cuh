@@ -125,6 +125,8 @@ struct __align__(16) RsTileDesc {
     int64_t cidx0;  // counter index of (digit 0, this tile);  + digit * ntp
     int cnt;        // records in the tile
     int ntp;        // tiles in the tile's pair
+    int pair;       // wave-relative pair of the tile
+    int pad;
 };
 
 __global__ void rs_desc_kernel(const int64_t* tile_prefix, const int64_t* pair_slot, int Pw, const int64_t* n_tiles_dev, int bits, RsTileDesc* desc)
@@ -140,6 +142,8 @@ __global__ void rs_desc_kernel(const int64_t* tile_prefix, const int64_t* pair_s
         d.cnt = (int)(rem < RS_TILE ? rem : RS_TILE);
         d.cidx0 = (tp0 << bits) + t;
         d.ntp = (int)(tp1 - tp0);
+        d.pair = pair;
+        d.pad = 0;
         desc[tile] = d;
     }
 }
@@ -147,7 +151,7 @@ __global__ void rs_desc_kernel(const int64_t* tile_prefix, const int64_t* pair_s
 __device__ __forceinline__ RsTileDesc rs_load_desc(const RsTileDesc* desc, int64_t tile, int64_t n_tiles)
 {
     RsTileDesc d;
-    d.e0 = 0; d.cidx0 = 0; d.cnt = 0; d.ntp = 0;
+    d.e0 = 0; d.cidx0 = 0; d.cnt = 0; d.ntp = 0; d.pair = 0; d.pad = 0;
     if (tile < n_tiles) d = desc[tile];
     return d;
 }
@@ -325,6 +329,9 @@ struct BinArgs {
     u64 sel_cap;
     double* stage_lx;      // [n_slots] per-bin staging of the selected hits (bin_cut -> bin_select)
     double* stage_ly;
+    const uint4* rec;      // UNORDERED only: candidate hits of every bin (slot, Lf, score lo, score hi) at the bin's slots
+    const u32* cand_cnt;   // UNORDERED only: [n_tasks] candidates per bin
+    const unsigned short* below;  // UNORDERED only: [n_tasks] hits of the bin below the candidates (shifts the order statistic)
 };
 
 // One WARP per length bin (no CTA barriers).  k-th smallest (0-based) of n positive doubles held in this warp's
@@ -409,6 +416,9 @@ static_assert(BIN_WARPS * 32 == BIN_THREADS, "one warp per bin");
 // Per bin: the 95th-percentile cut-off (numpy 'linear'), the number of hits >= cut-off, and those hits themselves
 // - log10(Lf), log10(score) in sorted order - staged at the bin's own slot range (stage_lx / stage_ly [first ..]).
 // The selected hits are first compacted in shared memory so that the two log10 evaluations run on full lanes.
+// UNORDERED (the bucket path of ofg_bins.cuh): the bin's hits arrive in arbitrary order; the selected ones are put into
+// the reference's order by ranking their (Lf, original index) words among each other.
+template <bool UNORDERED>
 __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
 {
     __shared__ u64 s_bits_all[BIN_WARPS][BIN_MAXN];
@@ -422,14 +432,22 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
     const int64_t n_tasks = *a.n_tasks_dev;
     for (int64_t t = (int64_t)blockIdx.x * BIN_WARPS + w; t < n_tasks; t += n_warps) {
         const BinTask bt = a.tasks[t];
-        const int n = (int)bt.n;
+        const int n_bin = (int)bt.n;                                    // hits of the bin (fixes numpy's virtual index)
+        const int n = UNORDERED ? (int)a.cand_cnt[t] : n_bin;           // hits looked at: all of them, or the top candidates
+        const int n_below = UNORDERED ? (int)a.below[t] : 0;
         u64 vmin = ~0ULL, vmax = 0ULL;
         for (int i0 = 0; i0 < n; i0 += 256) {  // eight independent loads in flight per lane
             u64 tb[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int i = i0 + u * 32 + lane;
-                tb[u] = i < n ? (u64)__double_as_longlong(a.val[bt.first + i]) : 0ULL;
+                if (UNORDERED) {
+                    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < n) r = a.rec[bt.first + i];
+                    tb[u] = (u64)r.z | ((u64)r.w << 32);
+                } else {
+                    tb[u] = i < n ? (u64)__double_as_longlong(a.val[bt.first + i]) : 0ULL;
+                }
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
@@ -450,8 +468,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
                 vmax = o2 > vmax ? o2 : vmax;
             }
             __syncwarp();
-            const int k = n == 1000 ? a.k1000 : (n == 200 ? a.k200 : a.k20);
-            const double g = n == 1000 ? a.g1000 : (n == 200 ? a.g200 : a.g20);
+            const int k = (n_bin == 1000 ? a.k1000 : (n_bin == 200 ? a.k200 : a.k20)) - n_below;   // a[k] and a[k + 1] are candidates
+            const double g = n_bin == 1000 ? a.g1000 : (n_bin == 200 ? a.g200 : a.g20);
             int n_le;
             const u64 ak = warp_kth(s_bits, n, k, vmin, vmax, s_hist, &n_le);
             u64 ak1 = ak;
@@ -490,10 +508,29 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_cut_kernel(BinArgs a)
             __syncwarp();
         }
         if (lane == 0) { a.cut[t] = cut; a.cnt[t] = (u32)cnt; }
-        for (int r = lane; r < cnt; r += 32) {
-            const u32 i = s_idx[r];
-            a.stage_lx[bt.first + r] = ofg_log10_svml((double)a.key[bt.first + i]);
-            a.stage_ly[bt.first + r] = ofg_log10_svml(__longlong_as_double((long long)s_bits[r]));
+        if (UNORDERED) {
+            constexpr int SC = 128;                       // words kept in shared memory (the select histogram is free now)
+            u64* s_word = reinterpret_cast<u64*>(s_hist);
+            const uint2* rec2 = reinterpret_cast<const uint2*>(a.rec);   // (slot, Lf) = the low half of a record
+            auto word_of = [&](int r) { const uint2 q = rec2[2 * (size_t)(bt.first + s_idx[r])]; return (u64)q.x | ((u64)q.y << 32); };
+            for (int r = lane; r < cnt && r < SC; r += 32) s_word[r] = word_of(r);
+            __syncwarp();
+            for (int r = lane; r < cnt; r += 32) {
+                const u64 wr = r < SC ? s_word[r] : word_of(r);
+                int rank = 0;
+                for (int j = 0; j < cnt; j++) {
+                    const u64 wj = j < SC ? s_word[j] : word_of(j);
+                    rank += wj < wr;
+                }
+                a.stage_lx[bt.first + rank] = ofg_log10_svml((double)(u32)(wr >> 32));
+                a.stage_ly[bt.first + rank] = ofg_log10_svml(__longlong_as_double((long long)s_bits[r]));
+            }
+        } else {
+            for (int r = lane; r < cnt; r += 32) {
+                const u32 i = s_idx[r];
+                a.stage_lx[bt.first + r] = ofg_log10_svml((double)a.key[bt.first + i]);
+                a.stage_ly[bt.first + r] = ofg_log10_svml(__longlong_as_double((long long)s_bits[r]));
+            }
         }
         __syncwarp();
     }

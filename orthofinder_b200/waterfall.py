@@ -198,6 +198,11 @@ class GraphBuilder:
         """Wait for the enqueued work and read its results back (option "async"); raises what the build would have."""
         self._ck(self.lib.ofg_sync(self.h))
 
+    def stat(self, name):
+        v = ctypes.c_int64(0)
+        self._ck(self.lib.ofg_get_stat(self.h, name.encode(), ctypes.byref(v)))
+        return v.value
+
     def wait_for(self, other):
         """Order this context's stream after everything enqueued on `other`'s (no host block)."""
         self._ck(self.lib.ofg_wait_for(self.h, other.h))

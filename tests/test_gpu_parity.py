@@ -852,3 +852,56 @@ def test_peer_exchange_grows_inboxes_that_are_too_small():
     assert pb.xchg.seg > 8 + 8 * 32
     assert pb.graph_text_body().tobytes() == want
     pb.close()
+
+
+@pytest.mark.parametrize("name", ["ref_AddTwoSpecies", "synth_C2_tiny", "synth_C5_small"])
+def test_bucket_path_and_radix_path_build_the_same_bins(gb, name):
+    """The length bins are built without a full sort (ofg_bins.cuh); the segmented LSD radix sort is its fallback.  Both
+    must give the reference's fits bit for bit and the same graph bytes."""
+    g = Golden(name)
+    _load(gb, g.n_seqs, g.lengths, g.hit_text)
+    gb.build()
+    assert gb.stat("radix_fallback_waves") == 0
+    a = gb.graph_text_body().tobytes()
+    fits_a = [gb.pair_fit(p, j) for p in range(len(g.n_seqs)) for j in range(len(g.n_seqs))]
+    gb.set_option("length_sort_radix", 1)
+    try:
+        gb.build()
+        assert gb.stat("radix_fallback_waves") == 1
+        assert gb.graph_text_body().tobytes() == a
+        assert [gb.pair_fit(p, j) for p in range(len(g.n_seqs)) for j in range(len(g.n_seqs))] == fits_a
+    finally:
+        gb.set_option("length_sort_radix", 0)
+    assert waterfall.graph_header(sum(g.n_seqs)) + a + waterfall.GRAPH_FOOTER == g.graph
+
+
+def test_degenerate_lengths_route_to_the_radix_path(gb):
+    """Two or three distinct protein lengths: a pair's hits fall into a handful of huge tie groups (one bucket each, tens
+    of thousands of hits, many bin boundaries inside) - the bucket path raises its device-side flag and the wave is
+    sorted by the radix path, where equal keys keep their original order."""
+    for trial, lens in enumerate([(120.0, 450.0), (100.0, 200.0, 400.0)]):
+        S, G = 3, 1500
+        P = synth.params(seed=40 + trial, hq=30)
+        rng = np.random.default_rng(trial)
+        L = [rng.choice(np.array(lens), G) for _ in range(S)]
+        gb.set_species([G] * S, L)
+        gb.synth_hits(P, list(range(S)))
+        gb.build()
+        assert gb.stat("radix_fallback_waves") == 1, trial
+        _check_against_oracle(gb, [G] * S, L, procs=1)
+
+
+def test_bucket_path_on_a_mid_size_job_with_small_and_large_bins(gb):
+    """Pairs of very different sizes in one job (bins of 20, 200 and 1000 hits, pairs below 100 hits taken whole, an empty
+    pair): 6 species with 40 ... 3000 genes, against the oracle."""
+    n_seqs = [40, 150, 700, 3000, 1200, 9]
+    S = len(n_seqs)
+    P = synth.params(seed=77, hq=40, p_dup=150, p_missing=100)
+    L = []
+    for k, G in enumerate(n_seqs):
+        L.append(synth.make_lengths(1, G, 500 + k)[0])
+    gb.set_species(n_seqs, L)
+    gb.synth_hits(P, list(range(S)))
+    gb.build()
+    assert gb.stat("radix_fallback_waves") == 0
+    _check_against_oracle(gb, n_seqs, L, procs=1)
