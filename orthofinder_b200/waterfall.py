@@ -650,3 +650,144 @@ def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empt
         graphFN = GetGraphFilename(wd_current or workingDir, i_unassigned)
     WaterfallMethod.WriteGraphParallel(gb, si, graphFN)
     return graphFN, gb, si
+
+
+def BuildGraphDistributed(seqsInfo, blastDir_list, Lengths, graphFN, qDoubleBlast=True, v2_scores=False, q_allow_empty=False,
+                          device=None, n_readers=None):
+    """The graph stage of DoOrthogroups (gathering.py:480-512) over the GPUs of one node, one process per GPU
+    (torch.distributed must be initialised, backend nccl).  What the reference does with a queue of query species and
+    pickles on disk (gathering.py:484-509, matrices.py:37-57):
+
+      * the query species are dealt to the ranks greedily by the size of their hit files (partition_rows);
+      * every rank reads, inflates and uploads only the Blast{p}_{j} files of its own query species and runs
+        ProcessBlastHits for them (design B of SURVEY.md 8e: rows only);
+      * the two reads of the transposed direction - BH_jp at gathering.py:254, connect_jp at :30 - are index lists that
+        the export kernel stores straight into the owning rank's inbox over NVLink (sharding.PeerExchange);
+      * every rank writes the part files <graphFN>_<iSpec> of its species, exactly the files WriteGraph_perSpecies writes
+        (gathering.py:26), and rank 0 assembles header + parts in species order + ")" like WriteGraphParallel (:279-290).
+
+    Every rank returns graphFN once the file is complete."""
+    import torch
+    import torch.distributed as dist
+    from . import sharding
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if device is None:
+        device = torch.cuda.current_device()
+    sp = list(seqsInfo.speciesToUse)
+    S = len(sp)
+    n_seqs = [seqsInfo.nSeqsPerSpecies[k] for k in sp]
+
+    def file_of(kp, kj):
+        for d in blastDir_list:
+            fn = os.path.join(d, "Blast%d_%d.txt" % (kp, kj))
+            if os.path.exists(fn):
+                return fn
+            if os.path.exists(fn + ".gz"):
+                return fn + ".gz"
+        return None
+
+    # weights: bytes on disk of every query species' files (a .gz counts a few times its size: it inflates)
+    weights = np.zeros(S)
+    for p, kp in enumerate(sp):
+        for j, kj in enumerate(sp):
+            swap = (not qDoubleBlast) and kp > kj
+            fn = file_of(kj, kp) if swap else file_of(kp, kj)
+            if fn is not None:
+                weights[p] += os.path.getsize(fn) * (4 if fn.endswith(".gz") else 1)
+    parts = sharding.partition_rows(S, world, weights)
+    owner = sharding.species_owner(parts, S)
+    owned = parts[rank]
+    gb = GraphBuilder(device)
+    try:
+        gb.set_species(n_seqs, Lengths)
+        gb.set_partition(owned, False)
+        gb.set_option("allow_empty", int(q_allow_empty))
+        gb.set_option("scores_v2", int(bool(v2_scores)))
+        gb.set_option("async", 1)
+        cells = []
+        for p in owned:
+            kp = sp[p]
+            for j, kj in enumerate(sp):
+                swap = (not qDoubleBlast) and kp > kj
+                cells.append((kj if swap else kp, kp if swap else kj, p, j, swap))
+        for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers):
+            if data is not None:
+                gb.add_hits(p, j, data, swap_cols=swap)
+        px = sharding.PeerExchange(gb, owner, rank, world, device, n_seqs) if world > 1 else None
+        err = None
+        try:
+            for attempt in range(6):
+                gb.build(_lib.STAGE_NORM)
+                if px is not None:
+                    px.exchange(0)
+                gb.build(_lib.STAGE_CONNECT)
+                if px is not None:
+                    px.exchange(1)
+                gb.build(_lib.STAGE_GRAPH)
+                status = 0
+                try:
+                    gb.sync()
+                except OfgError as e:
+                    err = e
+                    status = 2 if (e.code == _lib.ERR_CAPACITY and "inbox" in e.message) else 1
+                # every rank must take the same decision: an inbox that was too small anywhere repeats the job everywhere
+                st = torch.tensor([status], dtype=torch.int32, device=torch.device("cuda", device))
+                if world > 1:
+                    dist.all_reduce(st, op=dist.ReduceOp.MAX)
+                worst = int(st.item())
+                if worst == 0:
+                    err = None
+                    break
+                if worst == 2 and px is not None and attempt < 5:
+                    px.grow()
+                    err = None
+                    continue
+                break
+            if err is not None:
+                WaterfallMethod._report(err, sp, blastDir_list)
+                raise err
+            if worst != 0:
+                raise OfgError(_lib.ERR_ARG, "another rank failed while building the graph")
+        finally:
+            if px is not None:
+                px.close()
+        for p in owned:
+            for j in range(S):
+                f = gb.pair_fit(p, j)
+                if not f["normalised"]:
+                    if p == j and f["m"] == 0:
+                        print("WARNING: THIS IS UNCOMMON, there are zero hits when searching the genes in species %d "
+                              "against itself. Check the input proteome contains all the genes from that species and "
+                              "check the search program is working (default is diamond)." % p)
+                    else:
+                        print("WARNING: Too few hits between species %d and species %d to normalise the scores, "
+                              "these hits will be ignored" % (p, j))
+        # part files per owned species (rows of a species are one contiguous run of lines of the rank's block)
+        body = gb.graph_text_body()
+        ends = np.flatnonzero(body == 10)
+        line0 = 0
+        for p in owned:
+            lo = 0 if line0 == 0 else int(ends[line0 - 1]) + 1
+            hi = int(ends[line0 + n_seqs[p] - 1]) + 1 if n_seqs[p] else lo
+            with open(graphFN + "_%d" % p, "wb") as f:
+                f.write(body[lo:hi].tobytes())
+            line0 += n_seqs[p]
+    finally:
+        gb.close()
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        with open(graphFN, "wb") as out:
+            out.write(graph_header(seqsInfo.nSeqs))
+            for p in range(S):
+                with open(graphFN + "_%d" % p, "rb") as part:
+                    while True:
+                        chunk = part.read(1 << 24)
+                        if not chunk:
+                            break
+                        out.write(chunk)
+                os.remove(graphFN + "_%d" % p)
+            out.write(GRAPH_FOOTER)
+    if world > 1:
+        dist.barrier()
+    return graphFN
