@@ -25,7 +25,7 @@ constexpr int PS_STEP = 1024;            // bytes per refill: 32 chunks of 32 by
 constexpr int PS_SEG = 65536;            // lines starting in a 64 KB segment of one file are one warp's unit of work
 constexpr int PS_WARPS = 8;
 constexpr int PARSE_THREADS = PS_WARPS * 32;
-constexpr int PS_QCAP = 32 + PS_STEP / 2;  // pending (< 32) + the most line starts one step can add
+constexpr int PS_QCAP = 36 + PS_STEP / 2;  // pending (<= 33: 32 complete lines + the open one) + the most line starts one step can add
 constexpr int PS_RESERVE = 256;          // record slots reserved per atomicAdd
 constexpr u32 PS_RMASK = PS_RING - 1;
 constexpr u32 PS_WMASK = PS_RING / 32 - 1;
@@ -137,8 +137,9 @@ __device__ __forceinline__ void chunk_masks_exact(const u32 (&xs)[8], u32* term,
 // the plain shapes BLAST / DIAMOND / MMseqs2 write ("<species>_<digits>", "<digits>[.<digits>]", <= 9 digits,
 // 12+ fields within 128 bytes) is handed to the generic parser afterwards.
 
-// 128-bit window of a ring bitmap starting at stream offset st (bit i = byte st + i)
-__device__ __forceinline__ void rel_mask128(const u32* m, u32 st, u64* lo, u64* hi)
+// Offset of the first line terminator at or after stream offset st, searched in a 128-byte window (128 if none).  Only
+// the last line of a segment needs it: every other line ends right before the next queued line start.
+__device__ __forceinline__ u32 find_line_end(const u32* m, u32 st)
 {
     const u32 w0 = st >> 5;
     const int sh = (int)(st & 31u);
@@ -146,32 +147,51 @@ __device__ __forceinline__ void rel_mask128(const u32* m, u32 st, u64* lo, u64* 
               a4 = m[(w0 + 4) & PS_WMASK];
     const u32 r0 = __funnelshift_r(a0, a1, sh), r1 = __funnelshift_r(a1, a2, sh);
     const u32 r2 = __funnelshift_r(a2, a3, sh), r3 = __funnelshift_r(a3, a4, sh);
-    *lo = (u64)r0 | ((u64)r1 << 32);
-    *hi = (u64)r2 | ((u64)r3 << 32);
+    if (r0) return (u32)__ffs(r0) - 1u;
+    if (r1) return 32u + (u32)__ffs(r1) - 1u;
+    if (r2) return 64u + (u32)__ffs(r2) - 1u;
+    if (r3) return 96u + (u32)__ffs(r3) - 1u;
+    return 128u;
 }
-__device__ __forceinline__ int ctz128(u64 lo, u64 hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
 
-// Field boundaries relative to the record start for a record with EXACTLY 12 fields inside a 128-byte
-// window: first and second tab, the last (11th) tab and the line end.  Anything else is left to the
-// generic parser.
-__device__ __forceinline__ bool locate_fields_conv(const u32* s_tab, const u32* s_term, u32 st, bool act, int* tab1, int* tab2,
-                                                   int* tab11, int* line_end)
+// Field boundaries of a record with EXACTLY 12 fields, relative to the record start `st`.  The caller knows where the
+// NEXT line starts (lines are queued in order), so the line end is the byte before it - provided the two lines are
+// separated by exactly one terminator (no "\r\n", no blank lines; otherwise the generic parser takes the record).
+// The tabs of a line of up to 96 bytes are all inside two windows of the tab bitmap: the 64 bits from the record start
+// (which also give the first two tabs) and the 32 bits before the line end (which also give the last tab).  Anything
+// else is left to the generic parser.
+__device__ __forceinline__ bool locate_fields_conv(const PsWarp& sw, u32 st, u32 nx, bool act, int* tab1, int* tab2, int* tab11, int* line_end)
 {
-    u64 ea, eb, ta, tb;
-    rel_mask128(s_term, st, &ea, &eb);
-    rel_mask128(s_tab, st, &ta, &tb);
-    const int le = (ea | eb) ? ctz128(ea, eb) : 128;
-    bool ok = act && le < 128;  // the caller only hands over complete lines: every bit up to the terminator is valid
-    // tabs of this record only
-    if (le < 64) { ta &= (1ULL << le) - 1ULL; tb = 0; }
-    else if (le < 128) { tb &= (1ULL << (le - 64)) - 1ULL; }
-    ok = ok && (__popcll(ta) + __popcll(tb) == 11);
-    const u64 t2m = ta & (ta - 1ULL);
-    ok = ok && t2m != 0;  // the two id fields end inside the first 64 bytes
-    *tab1 = __ffsll((long long)ta) - 1;
-    *tab2 = __ffsll((long long)t2m) - 1;
-    *tab11 = tb ? 127 - __clzll((long long)tb) : 63 - __clzll((long long)ta);
-    *line_end = le;
+    const u32 end = nx - 1u;                       // stream offset of the terminator
+    const u32 le = end - st;
+    // exactly one terminator between the two lines: the byte before it belongs to this line
+    const u32 pb = nx - 2u;
+    const bool single = ((sw.term[(pb >> 5) & PS_WMASK] >> (pb & 31u)) & 1u) == 0u;
+    bool ok = act && single && le <= 96u;
+    // 64-bit window starting at st, restricted to the line
+    const u32 ws = (st >> 5) & PS_WMASK;
+    const int sh = (int)(st & 31u);
+    const u32 a0 = sw.tab[ws], a1 = sw.tab[(ws + 1) & PS_WMASK], a2 = sw.tab[(ws + 2) & PS_WMASK];
+    u32 lo = __funnelshift_r(a0, a1, sh), hi = __funnelshift_r(a1, a2, sh);
+    lo &= le >= 32u ? 0xffffffffu : ((1u << le) - 1u);
+    hi &= le >= 64u ? 0xffffffffu : (le > 32u ? ((1u << (le - 32u)) - 1u) : 0u);
+    // 32 bits before the line end: bit i = byte end - 32 + i; the part beyond the first 64 bytes of the line is counted from here
+    const u32 wb = end - 32u;
+    const u32 b0 = sw.tab[(wb >> 5) & PS_WMASK], b1 = sw.tab[((wb >> 5) + 1u) & PS_WMASK];
+    const u32 last32 = __funnelshift_r(b0, b1, (int)(wb & 31u));
+    const u32 tail = le > 64u ? (last32 & (0xffffffffu << (96u - le))) : 0u;
+    ok = ok && (__popc(lo) + __popc(hi) + __popc(tail)) == 11;
+    const int f1 = lo ? __ffs(lo) - 1 : 32 + __ffs(hi) - 1;
+    const u32 lo2 = lo & (lo - 1u), hi2 = lo ? hi : (hi & (hi - 1u));
+    const int f2 = lo2 ? __ffs(lo2) - 1 : 32 + __ffs(hi2) - 1;
+    ok = ok && (lo2 | hi2) != 0u;                   // the two id fields end inside the first 64 bytes
+    // last tab: highest tab bit among the 32 bytes before the line end (bytes before st may be another line's: rejected by t11 > f2)
+    const int t11 = (int)le - 1 - __clz((int)last32);
+    ok = ok && last32 != 0u && t11 > f2;
+    *tab1 = f1;
+    *tab2 = f2;
+    *tab11 = t11;
+    *line_end = (int)le;
     return ok;
 }
 
@@ -211,21 +231,20 @@ __device__ __forceinline__ bool swar_digits8(u64 X, u32* out)
 }
 
 // "<anything>_<1..7 digits>" of length 2..8 with exactly one underscore, ending at byte `end` (the tab).
+// The digits are the bytes above the underscore: everything at or below it is replaced by '0' with one mask, no shifts.
 __device__ __forceinline__ bool swar_id(const uint8_t* s_text, u32 end, int len, bool act, u32* out)
 {
     act = act && len >= 2 && len <= 8;
     const int l = act ? len : 8;
     const u32 e = act ? end : 8u;
     const u64 w = load8_ending_at(s_text, e);
-    const u64 vm = ~0ULL << (8 * (8 - l));
-    const u64 us = zero_bytes64(w ^ 0x5f5f5f5f5f5f5f5fULL) & vm;
-    const bool one = us != 0 && (us & (us - 1ULL)) == 0;
-    const int u = one ? (__ffsll((long long)us) - 1) >> 3 : 0;  // byte index of the underscore
-    const int nd = 7 - u;
-    const bool shape = one && nd >= 1;
-    const int ndc = shape ? nd : 1;
-    const u64 D = w >> (8 * (8 - ndc));                       // digits, first digit in the lowest byte
-    const u64 X = (D << (8 * (8 - ndc))) | (0x3030303030303030ULL >> (8 * ndc));
+    const u64 vm = ~0ULL << (8 * (8 - l));                       // bytes of the field
+    const u64 us = zero_bytes64(w ^ 0x5f5f5f5f5f5f5f5fULL) & vm; // 0x80 in the underscore bytes
+    const u64 um1 = us - 1ULL;
+    const bool one = us != 0 && (us & um1) == 0;                 // exactly one underscore
+    const u64 M = ~(us | um1);                                    // the bytes above it (the flag sits in the top bit of its byte)
+    const bool shape = one && M != 0;                             // at least one digit
+    const u64 X = (w & M) | (0x3030303030303030ULL & ~M);
     u32 v;
     const bool dig = swar_digits8(X, &v);
     *out = v;
@@ -242,17 +261,17 @@ __device__ __forceinline__ bool swar_score(const uint8_t* s_text, u32 end, int l
     const u64 vm = ~0ULL << (8 * (8 - l));
     const u64 dots = zero_bytes64(w ^ 0x2e2e2e2e2e2e2e2eULL) & vm;
     const bool has_dot = dots != 0;
-    const bool one = (dots & (dots - 1ULL)) == 0;  // zero or one dot
-    const int u = has_dot ? (__ffsll((long long)dots) - 1) >> 3 : 7;
-    const int frac = has_dot ? 7 - u : 0;
+    const u64 dm1 = dots - 1ULL;
+    const bool one = (dots & dm1) == 0;                          // zero or one dot
     // remove the dot: everything below it moves up one byte
-    const u64 lower = w & ((1ULL << (8 * u)) - 1ULL);
-    const u64 upper = (u == 7) ? 0ULL : ((w >> (8 * (u + 1))) << (8 * (u + 1)));
-    const u64 Y = has_dot ? (upper | (lower << 8)) : w;
+    const u64 above = ~(dots | dm1);                              // bytes above the dot
+    const u64 below = (dots >> 7) - 1ULL;                         // bytes below the dot
+    const u64 Y = has_dot ? ((w & above) | ((w & below) << 8)) : w;
+    const u64 dmask = has_dot ? (vm << 8) : vm;                   // bytes that hold digits now
+    const int frac = has_dot ? (__popcll((long long)above) >> 3) : 0;
     const int ndig = has_dot ? l - 1 : l;
     const bool shape = one && ndig >= 1;
-    const int nc = shape ? ndig : 1;
-    const u64 X = (nc == 8) ? Y : ((Y & (~0ULL << (8 * (8 - nc)))) | (0x3030303030303030ULL >> (8 * nc)));
+    const u64 X = (Y & dmask) | (0x3030303030303030ULL & ~dmask);
     u32 m;
     const bool dig = swar_digits8(X, &m);
     const double v = (double)m;
@@ -283,7 +302,7 @@ struct PsOut {  // record slots of this warp (warp-uniform)
 // Parses up to 32 queued lines in lock step: lane l takes queue entry first + l (n entries are live).
 // open_last: the newest entry has not been terminated inside the ring (it is being evicted): parse it from
 // global memory.  loaded_end: stream offset one past the staged text.
-__device__ __forceinline__ void ps_round(const ParseArgs& a, PsWarp& sw, const PsFile& f, PsOut& out, int first, int n, bool open_last,
+__device__ __forceinline__ void ps_round(const ParseArgs& a, PsWarp& sw, const PsFile& f, PsOut& out, int first, int n, int q_total, bool open_last,
                                          u32 loaded_end, u32& n_valid)
 {
     const int lane = (int)lane_id();
@@ -296,11 +315,21 @@ __device__ __forceinline__ void ps_round(const ParseArgs& a, PsWarp& sw, const P
     const bool act = lane < n;
     const u32 st = act ? (u32)sw.q[first + lane] : 0u;
     const bool from_global = open_last && lane == n - 1;
+    // start of the next queued line (lines are queued in order): gives this line's end without a search
+    bool has_next = act && first + lane + 1 < q_total;
+    u32 nx = has_next ? (u32)sw.q[first + lane + 1] : st + 2u;
+    if (__any_sync(OFG_FULL, act && !has_next && !(open_last && lane == n - 1))) {
+        // the last queued line (end of a segment): its terminator is staged, find it in the bitmap
+        if (act && !has_next && !(open_last && lane == n - 1)) {
+            const u32 le = find_line_end(sw.term, st);
+            if (le < 128u) { nx = st + le + 1u; has_next = true; }
+        }
+    }
     u32 row = OFG_ROW_SENTINEL, col = 0;
     double score = 0.0;
     u32 f0 = 0, f1 = 0;
     int tab1, tab2, tab11, lend;
-    bool fast = locate_fields_conv(sw.tab, sw.term, st, act && !from_global, &tab1, &tab2, &tab11, &lend);
+    bool fast = locate_fields_conv(sw, st, nx, has_next && !from_global, &tab1, &tab2, &tab11, &lend);
     const bool ok0 = swar_id(sw.text, st + (u32)tab1, tab1, fast, &f0);
     const bool ok1 = swar_id(sw.text, st + (u32)tab2, tab2 - tab1 - 1, fast, &f1);
     const bool ok2 = swar_score(sw.text, st + (u32)lend, lend - tab11 - 1, fast, &score);
@@ -414,7 +443,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
                 if (qn > 0 && (int)sw.q[0] < (int)step_so - 2 * PS_STEP) {
                     for (int r0 = 0; r0 < qn; r0 += 32) {
                         const int n = qn - r0 < 32 ? qn - r0 : 32;
-                        ps_round(a, sw, f, out, r0, n, tail_open && r0 + n == qn, step_so, n_valid);
+                        ps_round(a, sw, f, out, r0, n, qn, tail_open && r0 + n == qn, step_so, n_valid);
                         n_lines += (u32)n;
                     }
                     qn = 0;
@@ -500,23 +529,27 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
                 }
             }
             __syncwarp();
-            // ---- parse complete lines, 32 at a time
+            // ---- parse complete lines, 32 at a time.  A round needs the start of the line after its last one (that is where
+            // the last line ends), so 33 queued starts make a round; the final flush of a segment hands its very last line to
+            // the generic parser.
             const bool seg_done = loaded_end >= b_rel && !tail_open;
             const int ready = tail_open ? qn - 1 : qn;
             int done = 0;
-            while (ready - done >= 32 || (seg_done && done < qn)) {
+            while (qn - done >= 33 && ready - done >= 32 || (seg_done && done < qn)) {
                 const int n = qn - done < 32 ? qn - done : 32;
-                ps_round(a, sw, f, out, done, n, false, loaded_end, n_valid);
+                ps_round(a, sw, f, out, done, n, qn, false, loaded_end, n_valid);
                 done += n;
                 n_lines += (u32)n;
             }
             if (seg_done) break;
-            if (done > 0) {  // keep the < 32 (+ the open one) leftovers at the front of the queue
+            if (done > 0) {  // keep the leftovers (at most 32 complete lines and the open one) at the front of the queue
                 const int left = qn - done;
-                uint16_t v = 0;  // left <= 32: at most 31 complete lines and the open one
+                uint16_t v = 0, v2 = 0;
                 if (lane < left) v = sw.q[done + lane];
+                if (lane == 0 && left > 32) v2 = sw.q[done + 32];
                 __syncwarp();
                 if (lane < left) sw.q[lane] = v;
+                if (lane == 0 && left > 32) sw.q[32] = v2;
                 qn = left;
             }
             __syncwarp();
