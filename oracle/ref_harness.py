@@ -45,7 +45,7 @@ def _import_reference_real():
     return gathering, util, files, matrices
 
 
-def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True, v2_scores=False):
+def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True, v2_scores=False, homology=False):
     """Run the reference hot path on WorkingDirectory ``wd`` (must end with '/').
 
     Returns dict with: graph (bytes), seqsInfo fields, lengths, per-pair CSR of B (normalised),
@@ -109,10 +109,11 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
                 for p in range(si.nSpecies):
                     norm_probe.p = p
                     gathering.WaterfallMethod.ProcessBlastHits(si, [wd], L, p, pic, q_double_blast, v2_scores)
-                for p in range(si.nSpecies):
-                    gathering.WaterfallMethod.ConnectCognates(si, p, pic, v2_scores)
+                if not homology:   # gathering_version (3, 2) (--c-homologs) skips ConnectCognates (gathering.py:498,520)
+                    for p in range(si.nSpecies):
+                        gathering.WaterfallMethod.ConnectCognates(si, p, pic, v2_scores)
                 mats = {}
-                if keep_matrices:
+                if keep_matrices and not homology:
                     for p in range(si.nSpecies):
                         for j in range(si.nSpecies):
                             for name in ("B", "BH", "connect"):
@@ -123,7 +124,10 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
                     g.write("(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (si.nSeqs, si.nSeqs))
                     g.write("\n(mclmatrix\nbegin\n\n")
                 for p in range(si.nSpecies):
-                    gathering.WriteGraph_perSpecies((si, graph_fn, p, pic))
+                    if homology:
+                        gathering.WriteGraph_perSpecies_homology((si, graph_fn, p, pic))   # gathering.py:51-73
+                    else:
+                        gathering.WriteGraph_perSpecies((si, graph_fn, p, pic))
                 with open(graph_fn, "ab") as g:
                     for p in range(si.nSpecies):
                         with open(graph_fn + "_%d" % p, "rb") as part:
@@ -139,7 +143,7 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
                    seqStartingIndices=list(si.seqStartingIndices),
                    nSeqsPerSpecies=dict(si.nSeqsPerSpecies), lengths=[np.asarray(x) for x in L],
                    mats=mats, fits=fits, stdout=buf.getvalue(),
-                   most_distant=[most[p] for p in range(si.nSpecies)])
+                   most_distant=[most[p] for p in range(si.nSpecies)] if not homology else None)
     finally:
         fh.wd_base, fh.wd_current = saved
         shutil.rmtree(out, ignore_errors=True)

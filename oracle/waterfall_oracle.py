@@ -415,6 +415,31 @@ def assemble_graph(B, conn, si_starts, n_seqs):
     return np.cumsum(indptr), C.astype(np.int32), V
 
 
+def assemble_homology_graph(B, si_starts, n_seqs):
+    """gathering.py:51-73 WriteGraph_perSpecies_homology (`--c-homologs`, gathering_version (3, 2)): per query species the
+    structural union W_pj = (B_pj + B_jp^T > 0) of the normalised matrices, every entry written with weight 1.0."""
+    S = len(B)
+    N = int(sum(n_seqs))
+    R, C = [], []
+    for p in range(S):
+        for j in range(S):
+            indptr, cols, vals = B[p][j]
+            rows, keys = _entry_keys(indptr, cols, n_seqs[j])
+            indptr2, cols2, vals2 = B[j][p]
+            rows2, _ = _entry_keys(indptr2, cols2, n_seqs[p])
+            tkeys = cols2.astype(np.int64) * n_seqs[j] + rows2      # entry (x, y) of B_jp is entry (y, x) of its transpose
+            u = np.union1d(keys[vals > 0], tkeys[vals2 > 0])
+            R.append(u // n_seqs[j] + si_starts[p])
+            C.append(u % n_seqs[j] + si_starts[j])
+    R = np.concatenate(R) if R else np.zeros(0, np.int64)
+    C = np.concatenate(C) if C else np.zeros(0, np.int64)
+    order = np.lexsort((C, R))
+    R, C = R[order], C[order]
+    indptr = np.zeros(N + 1, np.int64)
+    np.add.at(indptr, R + 1, 1)
+    return np.cumsum(indptr), C.astype(np.int32), np.ones(C.size)
+
+
 def graph_text(indptr, indices, data, n_total):
     """gathering.py:273-291 header + :39-48 rows + ')' after the last species."""
     head = ("(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (n_total, n_total)).encode()
@@ -434,7 +459,7 @@ def graph_text(indptr, indices, data, n_total):
 # ----------------------------------------------------------------------------------------------
 # whole path
 # ----------------------------------------------------------------------------------------------
-def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False, v2_scores=False):
+def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False, v2_scores=False, homology=False):
     """WaterfallMethod end to end (gathering.py:476-512 of DoOrthogroups; v2_scores = `--scores-v2`, A18).
 
     n_seqs[p], lengths[p] per used species (list order); hit_text(p, j) -> bytes of Blast{p}_{j}
@@ -457,6 +482,9 @@ def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False
             B[p][j], fits[(p, j)] = normalise_scores(raw, lengths[p], lengths[j])
             if fits[(p, j)] is None:
                 warns.append((p, j, int(raw[0][-1])))
+    if homology:   # gathering.py:520-521: no best hits, no thresholds - the symmetrised structure of B
+        indptr, indices, data = assemble_homology_graph(B, starts, n_seqs)
+        return dict(indptr=indptr, indices=indices, data=data, fits=fits, warnings=warns, most_distant=None)
     BH = [get_bh(B[p], p) for p in range(S)]
     conn, most = [], []
     for p in range(S):
@@ -470,7 +498,7 @@ def waterfall(n_seqs, lengths, hit_text, q_double_blast=True, return_parts=False
     return out
 
 
-def waterfall_from_directory(wd, q_double_blast=True, return_parts=False, v2_scores=False):
+def waterfall_from_directory(wd, q_double_blast=True, return_parts=False, v2_scores=False, homology=False):
     """Entry used by tests: reads SpeciesIDs.txt / Species*.fa / Blast*_*.txt like the reference."""
     import gzip
     use, n_all = get_species_to_use(os.path.join(wd, "SpeciesIDs.txt"))
@@ -486,7 +514,7 @@ def waterfall_from_directory(wd, q_double_blast=True, return_parts=False, v2_sco
         with open(fn, "rb") as f:
             return f.read()
 
-    res = waterfall(n_seqs, L, hit_text, q_double_blast, return_parts, v2_scores)
+    res = waterfall(n_seqs, L, hit_text, q_double_blast, return_parts, v2_scores, homology)
     res["seqsInfo"] = si
     res["lengths"] = L
     res["graph"] = graph_text(res["indptr"], res["indices"], res["data"], si.nSeqs)

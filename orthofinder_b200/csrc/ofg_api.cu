@@ -90,6 +90,7 @@ struct ofg_ctx {
     bool scores_v2 = false;     // option scores_v2: NormalisedBitScore + percentile-ratio thresholds (gathering.py:157-174,314-388)
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
+    bool homology = false;      // option homology_graph: `--c-homologs` (gathering.py:51-73, 520-521) instead of the connect / RBH graph
     bool radix_only = false;    // option length_sort_radix: always take the LSD radix path (the fallback of the bucket path)
     int64_t fallback_waves = 0; // waves of the last build that took the radix path
     int wave_species = 0;       // option wave_species: query species per wave (0: the whole partition in one wave)
@@ -115,6 +116,7 @@ struct ofg_ctx {
     DevBuf sort_desc, zrow, pair_factor, d_owned, gene_cntg, gene_bytesg, most_init, d_length_factors, lx, ly, fit, rowfac, colfac, rowmax, best, most, owned_gene;
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff, diag_pairs;
+    DevBuf hom_cnt, hom_off, hom_fill, hom_col;
     DevBuf bk_hist, bk_rec, bk_bbidx, bk_shist, bk_thr, bk_below, bk_bin16, bk_bb, bk_bbfill, bk_split, bk_gcursor, bin_val;
     DevBuf x_flag, x_off, x_list, x_pair_dst, x_order, x_dst_first, x_inbox_ptrs;
     // pinned read-back area: [small block][fit table]
@@ -136,6 +138,8 @@ struct ofg_ctx {
     int tl_n = 0;
     EmitArgs last_emit;
     int last_emit_grid = 0;
+    HomEmitArgs last_hom;
+    bool last_is_hom = false;
     std::vector<int64_t> x_sig;             // what the exchange tables on the device were built from
     std::vector<unsigned char> plan_sig;    // what the descriptor tables on the device were built from
 };
@@ -907,6 +911,16 @@ int stage_connect(ofg_ctx* c)
 
 int launch_emit(ofg_ctx* c)
 {
+    if (c->last_is_hom) {
+        HomEmitArgs& h = c->last_hom;
+        h.out_indices = c->out_indices.as<int32_t>(); h.out_data = c->out_data.as<double>(); h.out_text = c->out_text.as<char>();
+        h.cap_edges = c->out_indices.cap / 4 > 16 ? c->out_indices.cap / 4 - 16 : 0;
+        h.cap_edges = std::min<u64>(h.cap_edges, c->out_data.cap / 8 > 16 ? c->out_data.cap / 8 - 16 : 0);
+        h.cap_text = c->out_text.cap > 64 ? c->out_text.cap - 64 : 0;
+        hom_emit_kernel<true><<<c->last_emit_grid, HOM_WARPS * 32, 0, c->stream>>>(h);
+        CKL("hom_emit_kernel<true>");
+        return 0;
+    }
     EmitArgs& e = c->last_emit;
     e.out_indices = c->out_indices.as<int32_t>(); e.out_data = c->out_data.as<double>(); e.out_text = c->out_text.as<char>();
     e.cap_edges = c->out_indices.cap / 4 > 16 ? c->out_indices.cap / 4 - 16 : 0;
@@ -941,6 +955,7 @@ int stage_emit(ofg_ctx* c)
     e.out_indices = nullptr; e.out_data = nullptr; e.out_text = nullptr; e.err_flags = err_flags;
     e.cap_edges = 0; e.cap_text = 0;
     c->last_emit = e;
+    c->last_is_hom = false;
     c->last_emit_grid = 0;
     c->tot_edges = 0; c->tot_text = 0;
     if (n_units > 0) {
@@ -959,13 +974,78 @@ int stage_emit(ofg_ctx* c)
     return 0;
 }
 
+// `--c-homologs` (gathering.py:51-73, :520-524): the graph is the symmetrised structure of the normalised matrices; replaces
+// the THRESH / CONNECT / GRAPH stages.  Needs the whole pair grid in this context.
+int stage_homology(ofg_ctx* c)
+{
+    mark_timeline(c);
+    const int P = (int)c->pairs.size();
+    if ((int)c->owned.size() != c->S) return fail(c, OFG_ERR_UNSUPPORTED, "the homology graph needs every query species in one context");
+    if (c->layout_dirty) {
+        std::vector<int64_t> gene_of;
+        std::vector<int32_t> sp_of;
+        for (int p : c->owned)
+            for (int64_t q = 0; q < c->n_seqs[p]; q++) { gene_of.push_back(c->seq_start[p] + q); sp_of.push_back(p); }
+        if (upload(c, c->gene_of_local, gene_of.data(), gene_of.size() * 8)) return OFG_ERR_CUDA;
+        if (upload(c, c->species_of_local, sp_of.data(), sp_of.size() * 4)) return OFG_ERR_CUDA;
+        CK(cudaStreamSynchronize(c->stream));
+        // (layout_dirty stays set: stage_thresh builds the rest of the layout vectors when the default graph is asked for)
+    }
+    GraphArgs g;
+    g.n_rows = c->n_rows; g.row_start = c->row_start.as<u32>(); g.rowlen = c->rowlen.as<u32>(); g.cols = c->cols.as<u32>();
+    g.vals = c->vals.as<double>(); g.pairs = c->d_pairs.as<PairDesc>(); g.pair_row_base = c->d_pair_row_base.as<int64_t>();
+    g.P = P; g.pair_of = c->d_pair_of.as<int32_t>(); g.S = c->S; g.most = nullptr; g.best = nullptr; g.row_flagcnt = nullptr; g.zrow = nullptr; g.pair_factor = nullptr; g.gene_cnt = nullptr; g.gene_bytes = nullptr; g.err_flags = nullptr;
+    CK(c->hom_cnt.ensure((size_t)(c->n_rows + 1) * 4));
+    CK(c->hom_off.ensure((size_t)(c->n_rows + 2) * 4));
+    CK(c->hom_fill.ensure((size_t)(c->n_rows + 1) * 4));
+    CK(cudaMemsetAsync(c->hom_cnt.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
+    CK(cudaMemsetAsync(c->hom_fill.p, 0, (size_t)(c->n_rows + 1) * 4, c->stream));
+    // extras are entries of the transposed direction: never more than the stored entries
+    u64 tot_cap = 0;
+    for (const Wave& w : c->waves) tot_cap += w.cap;
+    CK(c->hom_col.ensure((size_t)(tot_cap + 64) * 4));
+    HomArgs h;
+    h.g = g; h.extra_cnt = c->hom_cnt.as<u32>(); h.extra_off = c->hom_off.as<u32>(); h.extra_fill = c->hom_fill.as<u32>(); h.extra_col = c->hom_col.as<u32>();
+    const int64_t n_units = c->n_owned_genes;
+    CK(c->unit_cnt.ensure((size_t)(n_units + 1) * 4));
+    CK(c->unit_bytes.ensure((size_t)(n_units + 1) * 4));
+    CK(c->cnt_off.ensure((size_t)(n_units + 2) * 8));
+    CK(c->byte_off.ensure((size_t)(n_units + 2) * 8));
+    c->tot_edges = 0; c->tot_text = 0;
+    c->last_emit_grid = 0;
+    c->last_is_hom = true;
+    if (P > 0 && c->n_rows > 0 && n_units > 0) {
+        hom_extras_kernel<false><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(h);
+        CKL("hom_extras_kernel");
+        if (device_scan<u32>(c, h.extra_cnt, c->n_rows, c->hom_off.as<u32>(), 1)) return OFG_ERR_CUDA;
+        hom_extras_kernel<true><<<grid_for(c, c->n_rows, 64, 8), 256, 0, c->stream>>>(h);
+        CKL("hom_extras_kernel");
+        HomEmitArgs e;
+        e.g = g; e.extra_off = c->hom_off.as<u32>(); e.extra_col = c->hom_col.as<u32>(); e.n_genes = n_units;
+        e.gene_of_local = c->gene_of_local.as<int64_t>(); e.species_of_local = c->species_of_local.as<int32_t>(); e.seq_start = c->d_seq_start.as<int64_t>();
+        e.gene_cnt = c->unit_cnt.as<u32>(); e.gene_bytes = c->unit_bytes.as<u32>(); e.cnt_off = c->cnt_off.as<u64>(); e.byte_off = c->byte_off.as<u64>();
+        e.out_indices = nullptr; e.out_data = nullptr; e.out_text = nullptr; e.err_flags = err_flags_ptr(c); e.cap_edges = 0; e.cap_text = 0;
+        c->last_emit_grid = grid_for(c, n_units, HOM_WARPS, 8);
+        hom_emit_kernel<false><<<c->last_emit_grid, HOM_WARPS * 32, 0, c->stream>>>(e);
+        CKL("hom_emit_kernel<false>");
+        if (device_scan<u64>(c, e.gene_cnt, n_units, c->cnt_off.as<u64>(), 1)) return OFG_ERR_CUDA;
+        if (device_scan<u64>(c, e.gene_bytes, n_units, c->byte_off.as<u64>(), 1)) return OFG_ERR_CUDA;
+        c->last_hom = e;
+        if (int rc = launch_emit(c)) return rc;
+    }
+    c->stage_done = OFG_STAGE_GRAPH;
+    c->pending = true;
+    c->graph_pending = true;
+    return 0;
+}
+
 const char* const STAGE_OF_KERNEL[][2] = {
     {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
     {"wave_layout_kernel", "2"}, {"rs_desc_kernel", "2"}, {"radix_hist_kernel", "2"}, {"radix_scatter_kernel", "2"},
     {"bk_hist_kernel", "2"}, {"bk_scan_kernel", "2"}, {"bk_route_kernel", "2"}, {"bk_gather_kernel", "2"}, {"bk_split_kernel", "2"}, {"bk_binhist_kernel", "2"}, {"bk_thr_kernel", "3"}, {"bk_cand_kernel", "3"},
     {"bin_tasks_kernel", "3"}, {"bin_cut_kernel", "3"}, {"bin_select_kernel", "3"}, {"pair_sel_off_kernel", "4"}, {"fit_kernel", "4"},
     {"factors_kernel", "5"}, {"scale_bh_kernel", "5"}, {"bh_self_kernel", "5"}, {"rbh_kernel", "6"}, {"v2_ratio_kernel", "6"},
-    {"thresh_final_kernel", "6"}, {"connect_kernel", "7"}, {"emit_sizes_kernel", "8"}, {"emit_kernel<true>", "8"}};
+    {"thresh_final_kernel", "6"}, {"connect_kernel", "7"}, {"emit_sizes_kernel", "8"}, {"emit_kernel<true>", "8"}, {"hom_extras_kernel", "7"}, {"hom_emit_kernel<false>", "8"}, {"hom_emit_kernel<true>", "8"}};
 
 // One host synchronisation for everything a build left on the device: line counts, parse errors, capacity flags,
 // fit table, graph sizes, kernel timeline.  Called at the end of ofg_build (unless option async) and by every accessor.
@@ -1122,6 +1202,7 @@ void ofg_destroy(ofg_ctx* c)
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
                       &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff, &c->diag_pairs,
+                      &c->hom_cnt, &c->hom_off, &c->hom_fill, &c->hom_col,
                       &c->bk_hist, &c->bk_rec, &c->bk_bbidx, &c->bk_shist, &c->bk_thr, &c->bk_below, &c->bk_bin16, &c->bk_bb, &c->bk_bbfill, &c->bk_split, &c->bk_gcursor, &c->bin_val,
                       &c->x_flag, &c->x_off, &c->x_list, &c->x_pair_dst, &c->x_order, &c->x_dst_first, &c->x_inbox_ptrs};
     for (DevBuf* b : bufs) b->release();
@@ -1198,6 +1279,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "wave_species")) { c->wave_species = (int)std::max<int64_t>(value, 0); c->stage_done = 0; }
     else if (!strcmp(name, "async")) c->async = value != 0;
     else if (!strcmp(name, "length_sort_radix")) c->radix_only = value != 0;
+    else if (!strcmp(name, "homology_graph")) { c->homology = value != 0; c->stage_done = std::min(c->stage_done, (int)OFG_STAGE_NORM); }
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else return fail(c, OFG_ERR_ARG, "unknown option %s", name);
     return OFG_OK;
@@ -1332,6 +1414,11 @@ static int build_once(ofg_ctx* c, int stop_after)
         if (int rc = stage_raw_norm(c, stop_after)) { c->stage_done = 0; return rc; }
     } else if (stop_after >= OFG_STAGE_NORM && c->stage_done < OFG_STAGE_NORM) {
         if (int rc = stage_norm_only(c)) { c->stage_done = 0; return rc; }
+    }
+    if (c->homology && stop_after > OFG_STAGE_NORM) {
+        if (c->stage_done < OFG_STAGE_GRAPH) if (int rc = stage_homology(c)) return rc;
+        if (c->async) return OFG_OK;
+        return sync_results(c);
     }
     if (stop_after >= OFG_STAGE_THRESH && c->stage_done < OFG_STAGE_THRESH)
         if (int rc = stage_thresh(c)) { c->stage_done = 0; return rc; }

@@ -900,3 +900,189 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) emit_kernel(EmitArgs a)
         if (!WRITE && lane == 0) { a.gene_cnt[lg] = cnt; a.gene_bytes[lg] = bytes; }
     }
 }
+
+// ---------------------------------------------------------------- homology graph (`--c-homologs`)
+// gathering.py:51-73 WriteGraph_perSpecies_homology (gathering_version (3, 2), dispatched at :520-521): no best hits, no
+// thresholds - for query species p the graph row of gene q holds, per target species j, the structural union of row q of
+// B_pj and column q of B_jp, every entry with weight 1.0.  The entries that exist only in the transposed direction
+// ("extras") are collected per matrix row with a counting pass, a scan and a fill pass, then merged with the row's own
+// (sorted) columns while the text is written.
+struct HomArgs {
+    GraphArgs g;
+    u32* extra_cnt;      // [n_rows] extras of every matrix row
+    const u32* extra_off;  // [n_rows + 1] exclusive scan
+    u32* extra_fill;     // [n_rows]
+    u32* extra_col;      // [total extras]
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) hom_extras_kernel(HomArgs a)
+{
+    // ROW_G = 4 lanes per matrix row (x of pair (j, p)); every entry (x, y) looks for (y, x) in pair (p, j)
+    constexpr int ROW_G = 4;
+    const int lane = lane_id(), sub = lane / ROW_G, gl = lane % ROW_G;
+    const int64_t n_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * (32 / ROW_G);
+    int pair = -1;
+    for (int64_t row0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / ROW_G); row0 < a.g.n_rows; row0 += n_groups) {
+        const int64_t row = row0 + sub;
+        const int n = row < a.g.n_rows ? (int)a.g.rowlen[row] : 0;
+        if (n > 0) {
+            pair = advance_pair(a.g.pair_row_base, a.g.P, pair, row);
+            const PairDesc& pd = a.g.pairs[pair];
+            const int tp = a.g.pair_of[pd.j * a.g.S + pd.p];
+            if (tp >= 0) {
+                const PairDesc& td = a.g.pairs[tp];
+                const u32 s0 = a.g.row_start[row];
+                const u32 x = (u32)(row - pd.row_base);
+                for (int k = gl; k < n; k += ROW_G) {
+                    if (!(a.g.vals[s0 + k] > 0.0)) continue;            // (w1 + w2tr > 0): stored normalised scores are positive
+                    const u32 y = a.g.cols[s0 + k] & OFG_COL_MASK;
+                    const int64_t trow = td.row_base + y;
+                    const int64_t e = find_col(a.g.cols, a.g.row_start[trow], (int)a.g.rowlen[trow], x);
+                    if (e < 0 || !(a.g.vals[e] > 0.0)) {
+                        if (FILL) a.extra_col[a.extra_off[trow] + atomicAdd(&a.extra_fill[trow], 1u)] = x;
+                        else atomicAdd(&a.extra_cnt[trow], 1u);
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct HomEmitArgs {
+    GraphArgs g;
+    const u32* extra_off;
+    const u32* extra_col;
+    int64_t n_genes;
+    const int64_t* gene_of_local;
+    const int32_t* species_of_local;
+    const int64_t* seq_start;
+    u32* gene_cnt;            // [n_genes] edges of the graph row
+    u32* gene_bytes;          // [n_genes] text bytes of the graph row
+    const u64* cnt_off;
+    const u64* byte_off;
+    int32_t* out_indices;
+    double* out_data;
+    char* out_text;
+    u32* err_flags;           // bit 6: the output buffers are too small
+    u64 cap_edges, cap_text;
+};
+
+constexpr int HOM_WARPS = 4;
+constexpr int HOM_LIST = 256;   // merged entries staged per warp and pass
+
+// One warp per graph row.  WRITE = false only counts edges and text bytes.
+template <bool WRITE>
+__global__ void __launch_bounds__(HOM_WARPS * 32) hom_emit_kernel(HomEmitArgs a)
+{
+    __shared__ u32 s_list[HOM_WARPS][HOM_LIST];
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const int S = a.g.S;
+    if (WRITE && (a.cnt_off[a.n_genes] > a.cap_edges || a.byte_off[a.n_genes] > a.cap_text)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.err_flags, 64u);
+        return;
+    }
+    const int64_t n_warps = (int64_t)gridDim.x * HOM_WARPS;
+    for (int64_t lg = (int64_t)blockIdx.x * HOM_WARPS + w; lg < a.n_genes; lg += n_warps) {
+        const int p = a.species_of_local[lg];
+        const int64_t gene = a.gene_of_local[lg];
+        u64 ocnt = 0, obyte = 0;
+        u32 cnt = 0, bytes = 0;
+        if (WRITE) { ocnt = a.cnt_off[lg]; obyte = a.byte_off[lg]; }
+        {
+            const int nd = ofg_ndigits((unsigned long long)gene);
+            if (WRITE && lane == 0) {
+                char* o = a.out_text + obyte;
+                const int n = ofg_put_u64(o, (unsigned long long)gene);
+                o[n] = ' '; o[n + 1] = ' '; o[n + 2] = ' '; o[n + 3] = ' ';
+            }
+            bytes += nd + 4;
+            obyte += nd + 4;
+        }
+        for (int j = 0; j < S; j++) {
+            const int pair = a.g.pair_of[p * S + j];
+            if (pair < 0) continue;
+            const PairDesc& pd = a.g.pairs[pair];
+            const int64_t row = pd.row_base + (gene - pd.gi_start);
+            const u32 s0 = a.g.row_start[row];
+            const int n = (int)a.g.rowlen[row];
+            const u32 x0 = a.extra_off[row];
+            const int ne = (int)(a.extra_off[row + 1] - x0);
+            const u64 goff = (u64)a.seq_start[j];
+            const int total = n + ne;
+            if (!WRITE) {
+                // sizes need no merge: "%d:%.3f " of weight 1.0 is the column's digits + ":1.000 "
+                u32 b = 0, c = 0;
+                for (int k = lane; k < total; k += 32) {
+                    u32 col;
+                    bool on = true;
+                    if (k < n) { col = a.g.cols[s0 + k] & OFG_COL_MASK; on = a.g.vals[s0 + k] > 0.0; }
+                    else col = a.extra_col[x0 + (k - n)];
+                    if (on) { b += (u32)ofg_ndigits(goff + col) + 7u; c++; }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { b += __shfl_xor_sync(OFG_FULL, b, d); c += __shfl_xor_sync(OFG_FULL, c, d); }
+                bytes += b;
+                cnt += c;
+                continue;
+            }
+            // merged order: rank of a column = its index among the kept columns + extras below it; rank of an extra = columns below it
+            // + extras below it (the two sets are disjoint).  Passes of HOM_LIST ranks are staged in shared memory and formatted.
+            int kept = 0;   // kept columns (positive values) - all of them in practice
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                const int k = k0 + lane;
+                kept += __popc(__ballot_sync(OFG_FULL, k < n && a.g.vals[s0 + k] > 0.0));
+            }
+            const int tot = kept + ne;
+            for (int r0 = 0; r0 < tot; r0 += HOM_LIST) {
+                for (int k = lane; k < total; k += 32) {
+                    u32 col;
+                    int rank;
+                    if (k < n) {
+                        if (!(a.g.vals[s0 + k] > 0.0)) continue;
+                        col = a.g.cols[s0 + k] & OFG_COL_MASK;
+                        rank = k;
+                        if (kept != n) { rank = 0; for (int q = 0; q < k; q++) rank += a.g.vals[s0 + q] > 0.0; }
+                        for (int q = 0; q < ne; q++) rank += a.extra_col[x0 + q] < col;
+                    } else {
+                        col = a.extra_col[x0 + (k - n)];
+                        int lo = 0, hi = n;   // columns below col (sorted)
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((a.g.cols[s0 + mid] & OFG_COL_MASK) < col) lo = mid + 1; else hi = mid;
+                        }
+                        rank = lo;
+                        if (kept != n) { rank = 0; for (int q = 0; q < lo; q++) rank += a.g.vals[s0 + q] > 0.0; }
+                        for (int q = 0; q < ne; q++) rank += a.extra_col[x0 + q] < col;
+                    }
+                    if (rank >= r0 && rank < r0 + HOM_LIST) s_list[w][rank - r0] = col;
+                }
+                __syncwarp();
+                const int m = tot - r0 < HOM_LIST ? tot - r0 : HOM_LIST;
+                for (int b0 = 0; b0 < m; b0 += 32) {
+                    const int i = b0 + lane;
+                    const bool on = i < m;
+                    u64 gc = 0;
+                    int len = 0;
+                    if (on) { gc = goff + s_list[w][i]; len = ofg_ndigits(gc) + 7; }
+                    const u32 binc = warp_incl_scan((u32)len);
+                    const u32 btot = __shfl_sync(OFG_FULL, binc, 31);
+                    if (on) {
+                        a.out_indices[ocnt + i - b0] = (int32_t)gc;
+                        a.out_data[ocnt + i - b0] = 1.0;
+                        char* o = a.out_text + obyte + (binc - (u32)len);
+                        const int nd = ofg_put_u64(o, gc);
+                        o[nd] = ':'; o[nd + 1] = '1'; o[nd + 2] = '.'; o[nd + 3] = '0'; o[nd + 4] = '0'; o[nd + 5] = '0'; o[nd + 6] = ' ';
+                    }
+                    const int nb = m - b0 < 32 ? m - b0 : 32;
+                    ocnt += nb;
+                    obyte += btot;
+                }
+                __syncwarp();
+            }
+        }
+        if (WRITE && lane == 0) { a.out_text[obyte] = '$'; a.out_text[obyte + 1] = '\n'; }
+        bytes += 2;
+        if (!WRITE && lane == 0) { a.gene_cnt[lg] = cnt; a.gene_bytes[lg] = bytes; }
+    }
+}

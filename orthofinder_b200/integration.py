@@ -22,8 +22,8 @@ def patch_gathering(gathering, device=0, build_graph=None, write_graph=None):
     reference_DoOrthogroups = gathering.DoOrthogroups
 
     def DoOrthogroups(options, speciesInfoObj, seqsInfo, speciesNamesDict, speciesXML=None, i_unassigned=None):
-        if not options.gathering_version < (3, 0):
-            # --c-homologs (gathering_version (3, 2), gathering.py:520-524) and newer variants: the reference's own path
+        homology = options.gathering_version == (3, 2)       # --c-homologs (__main__.py:520-521, gathering.py:520-524)
+        if not (options.gathering_version < (3, 0) or homology):
             return reference_DoOrthogroups(options, speciesInfoObj, seqsInfo, speciesNamesDict, speciesXML, i_unassigned)
         q_unassigned = i_unassigned is not None
         util.PrintUnderline("Running OrthoFinder algorithm" + (" for clade-specific genes" if q_unassigned else ""))
@@ -33,12 +33,14 @@ def patch_gathering(gathering, device=0, build_graph=None, write_graph=None):
         if q_unassigned:
             blastDir_list = blastDir_list[:1]                                # :482-483
         try:
+            kw = dict(homology=True) if homology else {}
             gb = build_graph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=options.qDoubleBlast, v2_scores=options.v2_scores,
-                             q_allow_empty=q_unassigned, device=device)      # :484-509 (q_allow_empty: :492)
+                             q_allow_empty=q_unassigned, device=device, **kw)   # :484-509 (q_allow_empty: :492)
         except waterfall.OfgError:
             util.Fail()                                                      # what ManageQueue does when a worker dies
             raise
-        util.PrintTime("Connected putative homologues")                      # :511
+        if not homology:
+            util.PrintTime("Connected putative homologues")                  # :511
         graphFilename = write_graph(gb, seqsInfo, files.FileHandler.GetGraphFilename(i_unassigned))   # :512, files.py:324-327
         if hasattr(gb, "close"):
             gb.close()

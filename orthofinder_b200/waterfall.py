@@ -540,15 +540,17 @@ class WaterfallMethod:
 
     @staticmethod
     def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
-                   builder=None, n_readers=None):
+                   builder=None, n_readers=None, homology=False):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
-        the device-resident graph.  Returns the GraphBuilder holding it."""
+        the device-resident graph.  Returns the GraphBuilder holding it.
+        homology=True: the `--c-homologs` graph of gathering_version (3, 2) instead (gathering.py:51-73, 520-521)."""
         gb = builder or GraphBuilder(device)
         sp = list(seqsInfo.speciesToUse)
         n_seqs = [seqsInfo.nSeqsPerSpecies[k] for k in sp]
         gb.set_species(n_seqs, Lengths)
         gb.set_option("allow_empty", int(q_allow_empty))
         gb.set_option("scores_v2", int(bool(v2_scores)))  # --scores-v2: gathering.py:157-174, :314-388
+        gb.set_option("homology_graph", int(bool(homology)))
         cells = []
         for p, kp in enumerate(sp):
             for j, kj in enumerate(sp):

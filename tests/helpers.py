@@ -18,6 +18,7 @@ class Golden:
         self.graph = zlib.decompress(z["graph_z"].tobytes())
         self.graph_v2 = zlib.decompress(z["graph_v2_z"].tobytes()) if "graph_v2_z" in z.files else None
         self.most_distant_v2 = z["most_distant_v2"] if "most_distant_v2" in z.files else None
+        self.graph_hom = zlib.decompress(z["graph_hom_z"].tobytes()) if "graph_hom_z" in z.files else None
         self.fits = z["fits"]
         self.nnz = z["nnz"]
         self.n_seqs = [int(x) for x in z["n_seqs"]]

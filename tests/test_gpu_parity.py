@@ -905,3 +905,43 @@ def test_bucket_path_on_a_mid_size_job_with_small_and_large_bins(gb):
     gb.build()
     assert gb.stat("radix_fallback_waves") == 0
     _check_against_oracle(gb, n_seqs, L, procs=1)
+
+
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_homology_graph_equals_reference(gb, name):
+    """`--c-homologs` (gathering.py:51-73, :520-521): the symmetrised structure of the normalised matrices with weight 1.0;
+    golden text from the live reference's WriteGraph_perSpecies_homology."""
+    g = Golden(name)
+    _load(gb, g.n_seqs, g.lengths, g.hit_text)
+    gb.set_option("homology_graph", 1)
+    try:
+        gb.build()
+        text = waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+        assert text == g.graph_hom
+        rows, indptr, idx, dat = gb.graph_csr()
+        assert idx.size == g.graph_hom.count(b":") == gb.counts()["edges"] and np.all(dat == 1.0)
+        gb.build()                      # again: buffers sized by the first build
+        assert gb.graph_text_body().tobytes() == text[len(waterfall.graph_header(sum(g.n_seqs))):-2]
+    finally:
+        gb.set_option("homology_graph", 0)
+    gb.build()                          # and back to the default graph from the same normalised matrices
+    assert waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER == g.graph
+
+
+def test_homology_graph_on_a_mid_size_job_equals_oracle(gb):
+    ids, n_seqs, L, P = synth.config_inputs("C2_small")
+    ids, n_seqs, L = ids[:6], n_seqs[:6], L[:6]
+    P2 = synth.params(seed=9, hq=30, p_missing=250, p_dup=100)   # missing reciprocals: many transposed-only entries
+    gb.set_species(n_seqs, L)
+    gb.synth_hits(P2, ids)
+    gb.set_option("homology_graph", 1)
+    try:
+        gb.build()
+        texts = {(p, j): gb.hits_text(p, j) for p in range(6) for j in range(6)}
+        ref = wo.waterfall(n_seqs, L, lambda p, j: texts[(p, j)], homology=True)
+        rows, indptr, idx, dat = gb.graph_csr()
+        assert np.array_equal(indptr, ref["indptr"]) and np.array_equal(idx, ref["indices"]) and np.all(dat == 1.0)
+        text = waterfall.graph_header(sum(n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER
+        assert text == wo.graph_text(ref["indptr"], ref["indices"], ref["data"], sum(n_seqs))
+    finally:
+        gb.set_option("homology_graph", 0)

@@ -92,3 +92,14 @@ def test_empty_and_ragged_inputs():
     assert list(raw[2]) == [70.5]  # max over duplicate HSPs
     raw = wo.get_blast6_scores(texts[(1, 1)], 2, 2, True)
     assert raw[0][-1] == 0  # self hit dropped
+
+
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_oracle_reproduces_reference_homology_graph(name):
+    """`--c-homologs` (gathering_version (3, 2), gathering.py:51-73, dispatched at :520-521; the rest of SURVEY N1): the golden
+    comes from the live reference's WriteGraph_perSpecies_homology (tools/make_golden.py)."""
+    g = Golden(name)
+    res = wo.waterfall(g.n_seqs, g.lengths, g.hit_text, homology=True)
+    text = wo.graph_text(res["indptr"], res["indices"], res["data"], sum(g.n_seqs))
+    assert text == g.graph_hom, "oracle homology graph differs from the live reference's (%s)" % g.provenance
+    assert np.all(res["data"] == 1.0) and res["indices"].size > g.graph.count(b":")

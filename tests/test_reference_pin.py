@@ -87,8 +87,8 @@ class _Options:
         self.__dict__.update(kw)
 
 
-@pytest.mark.parametrize("i_unassigned,double,v2", [(None, True, False), (3, False, True)])
-def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2):
+@pytest.mark.parametrize("i_unassigned,double,v2,version", [(None, True, False, (1, 0)), (3, False, True, (1, 0)), (None, True, False, (3, 2))])
+def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2, version):
     """INTEGRATION.md section 1 executed against the live gathering module, with a stub in place of the CUDA builder."""
     gathering, util, files, matrices = rh._import_reference_real()
     from orthofinder_b200 import integration, waterfall
@@ -105,9 +105,9 @@ def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2):
     fh.wd_current = out
     calls = {}
 
-    def build_graph(seqsInfo, blastDir_list, Lengths, qDoubleBlast, v2_scores, q_allow_empty, device):
+    def build_graph(seqsInfo, blastDir_list, Lengths, qDoubleBlast, v2_scores, q_allow_empty, device, homology=False):
         calls["build"] = dict(seqsInfo=seqsInfo, blastDir_list=list(blastDir_list), n_len=[len(x) for x in Lengths],
-                              qDoubleBlast=qDoubleBlast, v2_scores=v2_scores, q_allow_empty=q_allow_empty)
+                              qDoubleBlast=qDoubleBlast, v2_scores=v2_scores, q_allow_empty=q_allow_empty, homology=homology)
         return object()
 
     def write_graph(gb, seqsInfo, graphFN):
@@ -122,7 +122,7 @@ def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2):
     gathering.post_clustering_orthogroups = lambda *a, **k: mcl_calls.append(("post",))
     try:
         integration.patch_gathering(gathering, build_graph=build_graph, write_graph=write_graph)
-        opts = _Options(qDoubleBlast=double, v2_scores=v2)
+        opts = _Options(qDoubleBlast=double, v2_scores=v2, gathering_version=version)
         gathering.DoOrthogroups(opts, None, si, {}, None, i_unassigned)
     finally:
         integration.unpatch_gathering(gathering)
@@ -130,6 +130,7 @@ def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2):
         fh.wd_base, fh.wd_current = saved
     b = calls["build"]
     assert b["seqsInfo"] is si and b["qDoubleBlast"] == double and b["v2_scores"] == v2
+    assert b["homology"] == (version == (3, 2))      # --c-homologs: gathering.py:520-521
     assert b["n_len"] == [si.nSeqsPerSpecies[k] for k in si.speciesToUse]
     if i_unassigned is None:
         assert b["blastDir_list"] == [wd, out] and b["q_allow_empty"] is False

@@ -76,6 +76,11 @@ def run_one(name, wd, store_inputs):
     out["graph_v2_z"] = np.frombuffer(zlib.compress(ref2["graph"], 9), np.uint8)
     assert np.array_equal(np.concatenate(ref2["most_distant"]), np.concatenate(mine2["most_distant"])), "%s: v2 thresholds differ" % name
     out["most_distant_v2"] = np.concatenate(ref2["most_distant"])
+    # the `--c-homologs` graph (gathering_version (3, 2), gathering.py:51-73): symmetrised structure of the normalised matrices
+    ref3 = rh.run_reference(wd, capture_fit=False, keep_matrices=False, homology=True)
+    mine3 = wo.waterfall_from_directory(wd, homology=True)
+    assert ref3["graph"] == mine3["graph"], "%s: oracle homology graph differs from the reference" % name
+    out["graph_hom_z"] = np.frombuffer(zlib.compress(ref3["graph"], 9), np.uint8)
     fn = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez(fn, **out)
     print("%-20s S=%d genes=%d graph=%d B  entries=%d  -> %s (%d KB)" % (
