@@ -89,6 +89,15 @@ int ofg_set_partition(ofg_ctx* ctx, int n_owned, const int32_t* owned_rows, int 
  * with ofg_set_option; otherwise ofg_build fails with OFG_ERR_MISSING. */
 int ofg_add_hits_text(ofg_ctx* ctx, int p, int j, const void* ptr, size_t nbytes, int swap_cols, int is_device);
 
+/* The same for a compressed file: `host_ptr` holds the bytes of Blast{p}_{j}.txt.gz as they are on disk (what the reference
+ * opens with gzip.open, blast_file_processor.py:63; DIAMOND writes its hit files compressed, config.json:48-52).  Only the
+ * compressed bytes are copied to the device; ofg_build inflates them there, one warp per gzip member.  Files whose members
+ * carry their compressed size in an extra field (bgzip / BGZF "BC", or the 32-bit "OF" field of this repo's writer) are
+ * inflated by as many warps as they have members; a plain single-member file is one warp's work.  Several members without
+ * size hints are OFG_ERR_UNSUPPORTED (inflate on the host and use ofg_add_hits_text).  A corrupt stream or a wrong ISIZE
+ * fails the build with OFG_ERR_PARSE; the CRC-32 is not verified. */
+int ofg_add_hits_gz(ofg_ctx* ctx, int p, int j, const void* host_ptr, size_t nbytes, int swap_cols);
+
 /* Drop all hit text (keeps species / partition). */
 int ofg_clear_hits(ofg_ctx* ctx);
 
@@ -102,7 +111,7 @@ int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
 /* Options: "allow_empty" (0/1), "max_bytes_per_line_inv" (capacity: records <= bytes/this, default 24; after a
  * complete build the context sizes the next one from the line density it saw),
  * "sel_capacity_frac_inv" (selection capacity = records/this, default 4), "reserve_text_bytes" (size the text arena
- * once), "wave_species" (RAW + NORM run over this many query species at a time out of one set of scratch buffers -
+ * once), "reserve_gz_bytes" (the same for the compressed arena of ofg_add_hits_gz), "wave_species" (RAW + NORM run over this many query species at a time out of one set of scratch buffers -
  * the reference's "one query species per task", gathering.py:484-485; 0 = the whole partition at once),
  * "length_sort_radix" (0/1: build the length bins with the segmented LSD radix sort only - the fallback of the bucket path),
  * "async" (0/1: ofg_build only enqueues; counts, errors and sizes are read back by ofg_sync or by the first accessor),

@@ -13,7 +13,7 @@ STAGE_RAW, STAGE_NORM, STAGE_THRESH, STAGE_CONNECT, STAGE_GRAPH = 1, 2, 3, 4, 5
 FLAG_BH, FLAG_CONNECT, FLAG_REVERSE, FLAG_TBH, COL_MASK = 0x80000000, 0x40000000, 0x20000000, 0x10000000, 0x0FFFFFFF
 
 # every symbol include/ofg.h declares (tests/test_abi.py checks the library exports all of them)
-SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "ofg_set_partition", "ofg_add_hits_text",
+SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "ofg_set_partition", "ofg_add_hits_text", "ofg_add_hits_gz",
            "ofg_clear_hits", "ofg_synth_hits", "ofg_hits_text_size", "ofg_hits_text_copy", "ofg_set_option", "ofg_set_length_factors", "ofg_build",
            "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_export_flags",
            "ofg_import_flags", "ofg_counts", "ofg_pair_csr",
@@ -46,6 +46,7 @@ def load():
         "ofg_set_species": [vp, i32, vp, vp],
         "ofg_set_partition": [vp, i32, vp, i32],
         "ofg_add_hits_text": [vp, i32, i32, vp, sz, i32, i32],
+        "ofg_add_hits_gz": [vp, i32, i32, vp, sz, i32],
         "ofg_clear_hits": [vp],
         "ofg_synth_hits": [vp, vp, vp],
         "ofg_hits_text_size": [vp, i32, i32, ctypes.POINTER(sz)],

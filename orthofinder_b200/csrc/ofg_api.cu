@@ -18,6 +18,7 @@
 #include "ofg_bins.cuh"
 #include "ofg_graph.cuh"
 #include "ofg_synth.cuh"
+#include "ofg_inflate.cuh"
 
 static_assert(sizeof(ofg_synth_params) == sizeof(OfgSynthParams), "synth parameter layouts must match");
 
@@ -117,6 +118,12 @@ struct ofg_ctx {
     DevBuf gene_of_local, species_of_local, d_seq_start, unit_cnt, unit_bytes, cnt_off, byte_off, out_indices, out_data, out_text;
     DevBuf species_ids, synth_bytes, synth_off, file_off, pair_sel_off, row_flagcnt, row_flagoff, diag_pairs;
     DevBuf hom_cnt, hom_off, hom_fill, hom_col;
+    // gzip input: compressed bytes of the hit files and their member table; inflated on the device at the start of a build
+    DevBuf gz_comp, gz_members_dev, gz_err;
+    int64_t gz_used = 0;
+    std::vector<GzMember> gz_members;
+    bool gz_pending = false;      // members were added since the last inflate
+    unsigned long long* h_gz_err = nullptr;
     DevBuf bk_hist, bk_rec, bk_bbidx, bk_shist, bk_thr, bk_below, bk_bin16, bk_bb, bk_bbfill, bk_split, bk_gcursor, bin_val;
     DevBuf x_flag, x_off, x_list, x_pair_dst, x_order, x_dst_first, x_inbox_ptrs;
     // pinned read-back area: [small block][fit table]
@@ -488,6 +495,7 @@ int plan_build(ofg_ctx* c)
     }
     if (c->h_fit_cap < (size_t)P * 8 + 16) {
         if (c->h_fit) cudaFreeHost(c->h_fit);
+    if (c->h_gz_err) cudaFreeHost(c->h_gz_err);
         c->h_fit = nullptr;
         CK(cudaHostAlloc((void**)&c->h_fit, ((size_t)P * 8 + 16 + 64) * 8, cudaHostAllocDefault));
         c->h_fit_cap = (size_t)P * 8 + 16 + 64;
@@ -783,9 +791,27 @@ int norm_finish(ofg_ctx* c)
     return 0;
 }
 
+// gzip members added since the last build: inflated into the text arena, one warp per member
+int inflate_pending(ofg_ctx* c)
+{
+    if (!c->gz_pending) return 0;
+    const int64_t n = (int64_t)c->gz_members.size();
+    CK(c->gz_err.ensure(16));
+    CK(cudaMemsetAsync(c->gz_err.p, 0xff, 8, c->stream));
+    if (n > 0) {
+        if (upload(c, c->gz_members_dev, c->gz_members.data(), sizeof(GzMember) * (size_t)n)) return OFG_ERR_CUDA;
+        inflate_kernel<<<grid_for(c, n, GZ_WARPS, 5), GZ_WARPS * 32, 0, c->stream>>>(c->gz_comp.as<uint8_t>(), c->gz_members_dev.as<GzMember>(), n,
+                                                                                     c->text.as<uint8_t>(), c->gz_err.as<unsigned long long>());
+        CKL("inflate_kernel");
+    }
+    c->gz_pending = false;
+    return 0;
+}
+
 int stage_raw_norm(ofg_ctx* c, int stop_after)
 {
     mark_timeline(c);
+    if (int rc = inflate_pending(c)) return rc;
     if (int rc = plan_build(c)) return rc;
     const bool norm = stop_after >= OFG_STAGE_NORM;
     if (norm) if (int rc = norm_begin(c)) return rc;
@@ -1040,7 +1066,7 @@ int stage_homology(ofg_ctx* c)
 }
 
 const char* const STAGE_OF_KERNEL[][2] = {
-    {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
+    {"inflate_kernel", "0"}, {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
     {"wave_layout_kernel", "2"}, {"rs_desc_kernel", "2"}, {"radix_hist_kernel", "2"}, {"radix_scatter_kernel", "2"},
     {"bk_hist_kernel", "2"}, {"bk_scan_kernel", "2"}, {"bk_route_kernel", "2"}, {"bk_gather_kernel", "2"}, {"bk_split_kernel", "2"}, {"bk_binhist_kernel", "2"}, {"bk_thr_kernel", "3"}, {"bk_cand_kernel", "3"},
     {"bin_tasks_kernel", "3"}, {"bin_cut_kernel", "3"}, {"bin_select_kernel", "3"}, {"pair_sel_off_kernel", "4"}, {"fit_kernel", "4"},
@@ -1056,6 +1082,10 @@ int sync_results(ofg_ctx* c)
     u64 tots[2] = {0, 0};
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(cudaMemcpyAsync(c->h_small, c->d_small.p, c->small_words * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (c->gz_err.p) {
+            if (!c->h_gz_err) CK(cudaHostAlloc((void**)&c->h_gz_err, 16, cudaHostAllocDefault));
+            CK(cudaMemcpyAsync(c->h_gz_err, c->gz_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        }
         if (P > 0 && c->stage_done >= OFG_STAGE_NORM) CK(cudaMemcpyAsync(c->h_fit, c->fit.p, (size_t)P * 8 * 8, cudaMemcpyDeviceToHost, c->stream));
         const int64_t n_units = c->n_owned_genes;
         if (c->graph_pending && n_units > 0) {
@@ -1106,6 +1136,18 @@ int sync_results(ofg_ctx* c)
         }
         if (st >= 0) c->ms[st] += t;
         c->ms[9] += t;
+    }
+    // a corrupt .gz: gzip.open raises inside the reference's reader (blast_file_processor.py:63-66)
+    if (c->gz_err.p && c->h_gz_err && *c->h_gz_err != ~0ULL && !c->gz_members.empty()) {
+        const unsigned long long e = *c->h_gz_err;
+        const size_t mi = (size_t)(e >> 8);
+        const int kind = (int)(e & 255);
+        c->stage_done = 0;
+        if (mi < c->gz_members.size()) {
+            const PairDesc& pd = c->pairs[c->gz_members[mi].file];
+            return fail(c, OFG_ERR_PARSE, "pair=%d,%d gzip: compressed hit file is corrupt (member %zu, error kind %d)", pd.p, pd.j, mi, kind);
+        }
+        return fail(c, OFG_ERR_PARSE, "gzip: compressed hit file is corrupt");
     }
     // parse errors first (the reference fails on the first offending line of a file)
     for (int i = 0; i < P; i++) {
@@ -1202,13 +1244,14 @@ void ofg_destroy(ofg_ctx* c)
                       &c->gene_of_local, &c->species_of_local, &c->d_seq_start, &c->unit_cnt, &c->unit_bytes, &c->cnt_off,
                       &c->byte_off, &c->out_indices, &c->out_data, &c->out_text, &c->species_ids, &c->synth_bytes, &c->synth_off,
                       &c->file_off, &c->pair_sel_off, &c->row_flagcnt, &c->row_flagoff, &c->diag_pairs,
-                      &c->hom_cnt, &c->hom_off, &c->hom_fill, &c->hom_col,
+                      &c->hom_cnt, &c->hom_off, &c->hom_fill, &c->hom_col, &c->gz_comp, &c->gz_members_dev, &c->gz_err,
                       &c->bk_hist, &c->bk_rec, &c->bk_bbidx, &c->bk_shist, &c->bk_thr, &c->bk_below, &c->bk_bin16, &c->bk_bb, &c->bk_bbfill, &c->bk_split, &c->bk_gcursor, &c->bin_val,
                       &c->x_flag, &c->x_off, &c->x_list, &c->x_pair_dst, &c->x_order, &c->x_dst_first, &c->x_inbox_ptrs};
     for (DevBuf* b : bufs) b->release();
     for (auto& e : c->tl_ev) if (e) cudaEventDestroy(e);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_fit) cudaFreeHost(c->h_fit);
+    if (c->h_gz_err) cudaFreeHost(c->h_gz_err);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1248,6 +1291,9 @@ int ofg_set_species(ofg_ctx* c, int n_species, const int64_t* n_seqs, const doub
     c->files.clear();
     c->pairs.clear();
     c->text_used = 0;
+    c->gz_used = 0;
+    c->gz_members.clear();
+    c->gz_pending = false;
     c->stage_done = 0;
     return OFG_OK;
 }
@@ -1281,6 +1327,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "length_sort_radix")) c->radix_only = value != 0;
     else if (!strcmp(name, "homology_graph")) { c->homology = value != 0; c->stage_done = std::min(c->stage_done, (int)OFG_STAGE_NORM); }
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
+    else if (!strcmp(name, "reserve_gz_bytes")) { cudaSetDevice(c->device); CK(c->gz_comp.ensure((size_t)value + 64)); }
     else return fail(c, OFG_ERR_ARG, "unknown option %s", name);
     return OFG_OK;
 }
@@ -1301,6 +1348,99 @@ int ofg_clear_hits(ofg_ctx* c)
     if (!c) return OFG_ERR_ARG;
     for (auto& f : c->files) f = FileInfo();
     c->text_used = 0;
+    c->gz_used = 0;
+    c->gz_members.clear();
+    c->gz_pending = false;
+    c->stage_done = 0;
+    return OFG_OK;
+}
+
+// One gzip member starting at data[o]: header fields (RFC 1952), the "BC" extra subfield of BGZF-style writers gives the
+// member's total size.  Returns false if it is not a gzip member.
+static bool gz_parse_member(const uint8_t* d, size_t n, size_t o, size_t* deflate_start, size_t* member_size)
+{
+    if (o + 18 > n || d[o] != 0x1f || d[o + 1] != 0x8b || d[o + 2] != 8) return false;
+    const int flg = d[o + 3];
+    size_t q = o + 10;
+    *member_size = 0;
+    if (flg & 4) {
+        if (q + 2 > n) return false;
+        const size_t xlen = d[q] | ((size_t)d[q + 1] << 8);
+        q += 2;
+        if (q + xlen > n) return false;
+        size_t x = q;
+        while (x + 4 <= q + xlen) {
+            const size_t slen = d[x + 2] | ((size_t)d[x + 3] << 8);
+            if (d[x] == 'B' && d[x + 1] == 'C' && slen == 2 && x + 6 <= q + xlen) *member_size = (size_t)(d[x + 4] | ((size_t)d[x + 5] << 8)) + 1;
+            else if (d[x] == 'O' && d[x + 1] == 'F' && slen == 4 && x + 8 <= q + xlen)   // this repo's writer: 32-bit member size
+                *member_size = (size_t)d[x + 4] | ((size_t)d[x + 5] << 8) | ((size_t)d[x + 6] << 16) | ((size_t)d[x + 7] << 24);
+            x += 4 + slen;
+        }
+        q += xlen;
+    }
+    if (flg & 8) { while (q < n && d[q]) q++; q++; }
+    if (flg & 16) { while (q < n && d[q]) q++; q++; }
+    if (flg & 2) q += 2;
+    if (q + 8 > n) return false;
+    *deflate_start = q;
+    return true;
+}
+
+int ofg_add_hits_gz(ofg_ctx* c, int p, int j, const void* host_ptr, size_t nbytes, int swap_cols)
+{
+    if (!c || (!host_ptr && nbytes)) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc = ensure_pairs(c)) return rc;
+    if (p < 0 || j < 0 || p >= c->S || j >= c->S) return fail(c, OFG_ERR_ARG, "pair (%d,%d) out of range", p, j);
+    const int pi = c->pair_of[(size_t)p * c->S + j];
+    if (pi < 0) return fail(c, OFG_ERR_ARG, "pair (%d,%d) is not part of this context's partition", p, j);
+    const uint8_t* d = (const uint8_t*)host_ptr;
+    // walk the members: with a size hint in every header the walk never inflates; a file without hints is taken as ONE member
+    std::vector<GzMember> ms;
+    const int64_t cbase = (c->gz_used + 15) & ~15LL;
+    size_t o = 0;
+    u64 raw_total = 0;
+    while (o < nbytes) {
+        if (d[o] == 0) { o++; continue; }   // zero padding between members is legal (gzip.py skips it)
+        size_t ds = 0, msz = 0;
+        if (!gz_parse_member(d, nbytes, o, &ds, &msz)) return fail(c, OFG_ERR_UNSUPPORTED, "Blast file of pair (%d,%d): not a gzip stream at byte %zu", p, j, o);
+        size_t end;
+        if (msz) {
+            end = o + msz;
+            if (end > nbytes || end < ds + 8) return fail(c, OFG_ERR_PARSE, "Blast file of pair (%d,%d): gzip member at byte %zu is truncated", p, j, o);
+        } else {
+            if (!ms.empty()) return fail(c, OFG_ERR_UNSUPPORTED, "Blast file of pair (%d,%d): several gzip members without size hints", p, j);
+            end = nbytes;   // a classic single-member file
+        }
+        GzMember m;
+        m.in_off = (u64)cbase + ds; m.in_len = end - ds - 8; m.out_off = raw_total; m.file = pi; m.pad = 0;
+        m.out_len = (u64)d[end - 4] | ((u64)d[end - 3] << 8) | ((u64)d[end - 2] << 16) | ((u64)d[end - 1] << 24);
+        raw_total += m.out_len;
+        ms.push_back(m);
+        o = end;
+    }
+    // text arena range of the inflated file
+    const int64_t off = (c->text_used + 15) & ~15LL;
+    const int64_t padded = ((int64_t)raw_total + 16) & ~15LL;
+    if (int rc = text_reserve(c, off + padded)) return rc;
+    // compressed arena (kept until the build: the members are inflated together)
+    const int64_t cneed = cbase + (int64_t)nbytes + 64;
+    if ((size_t)cneed > c->gz_comp.cap) {
+        DevBuf nb;
+        CK(nb.ensure((size_t)std::max<int64_t>(cneed, (int64_t)(c->gz_comp.cap + c->gz_comp.cap / 2))));
+        if (c->gz_comp.p && c->gz_used > 0) CK(cudaMemcpyAsync(nb.p, c->gz_comp.p, (size_t)c->gz_used, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->gz_comp.release();
+        c->gz_comp = nb;
+    }
+    if (nbytes) CK(cudaMemcpyAsync(c->gz_comp.as<uint8_t>() + cbase, host_ptr, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->text.as<uint8_t>() + off + raw_total, '\n', (size_t)(padded - (int64_t)raw_total), c->stream));
+    for (auto& m : ms) { m.out_off += (u64)off; c->gz_members.push_back(m); }
+    FileInfo& f = c->files[pi];
+    f.off = off; f.raw = (int64_t)raw_total; f.padded = padded; f.swap = swap_cols;
+    c->text_used = off + padded;
+    c->gz_used = cbase + (int64_t)nbytes;
+    c->gz_pending = true;
     c->stage_done = 0;
     return OFG_OK;
 }
@@ -1395,6 +1535,17 @@ int ofg_hits_text_copy(ofg_ctx* c, int p, int j, void* host_dst, size_t cap)
     if (int rc = ofg_hits_text_size(c, p, j, &n)) return rc;
     if (cap < n) return fail(c, OFG_ERR_ARG, "destination too small");
     cudaSetDevice(c->device);
+    if (c->gz_pending) {   // compressed files are inflated on demand
+        if (int rc = inflate_pending(c)) return rc;
+        unsigned long long e = ~0ULL;
+        CK(cudaMemcpyAsync(&e, c->gz_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (e != ~0ULL) {
+            const size_t mi = (size_t)(e >> 8);
+            const PairDesc& pd = c->pairs[c->gz_members[std::min(mi, c->gz_members.size() - 1)].file];
+            return fail(c, OFG_ERR_PARSE, "pair=%d,%d gzip: compressed hit file is corrupt (member %zu, error kind %d)", pd.p, pd.j, mi, (int)(e & 255));
+        }
+    }
     const int pi = c->pair_of[(size_t)p * c->S + j];
     CK(cudaMemcpyAsync(host_dst, c->text.as<uint8_t>() + c->files[pi].off, n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

@@ -104,6 +104,19 @@ class GraphBuilder:
         self._ck(self.lib.ofg_add_hits_text(self.h, p, j, ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), len(b),
                                             int(swap_cols), 0))
 
+    def add_hits_gz(self, p, j, data, swap_cols=False):
+        """data: the bytes of Blast{p}_{j}.txt.gz as on disk (bytes / numpy uint8) or a (host pointer, nbytes) tuple; inflated
+        on the device by ofg_build (one warp per gzip member)."""
+        if isinstance(data, tuple):
+            self._ck(self.lib.ofg_add_hits_gz(self.h, p, j, ctypes.c_void_p(data[0]), int(data[1]), int(swap_cols)))
+            return
+        if isinstance(data, np.ndarray):
+            buf = np.ascontiguousarray(data, dtype=np.uint8)
+            self._ck(self.lib.ofg_add_hits_gz(self.h, p, j, _vp(buf), buf.size, int(swap_cols)))
+            return
+        b = bytes(data)
+        self._ck(self.lib.ofg_add_hits_gz(self.h, p, j, ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p), len(b), int(swap_cols)))
+
     def add_hits_ptr(self, p, j, host_ptr, nbytes, swap_cols=False):
         self._ck(self.lib.ofg_add_hits_text(self.h, p, j, ctypes.c_void_p(host_ptr), nbytes, int(swap_cols), 0))
 
@@ -471,6 +484,28 @@ def GetSequenceLengths(seqsInfo, fasta_dir_list):
     return out
 
 
+BGZF_CHUNK = 65280   # text bytes per member, as bgzip: every member stays below 64 KB compressed
+
+
+def gzip_members(data, level=1, chunk=BGZF_CHUNK):
+    """Writes `data` as a gzip file of independent members of `chunk` text bytes each, BGZF style: every member's header
+    carries its compressed size in a "BC" extra field (readable by gzip.open / zcat / bgzip like any multi-member gzip
+    file).  This is the layout the device-side inflate parallelises over: one warp per member."""
+    import struct
+    out = []
+    mv = memoryview(data)
+    for o in range(0, max(len(mv), 1), chunk):
+        part = bytes(mv[o:o + chunk])
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        body = co.compress(part) + co.flush()
+        total = 18 + len(body) + 8
+        assert total <= 65536
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", total - 1))
+        out.append(body)
+        out.append(struct.pack("<II", zlib.crc32(part) & 0xffffffff, len(part) & 0xffffffff))
+    return b"".join(out)
+
+
 def _gunzip(data):
     """All members of a gzip stream in one go.  zlib releases the GIL while it inflates, so the reader threads of
     read_hit_files run in parallel (gzip.GzipFile.read loops in Python)."""
@@ -487,8 +522,13 @@ def _gunzip(data):
     return b"".join(out) if len(out) != 2 else out[0] + out[1]
 
 
-def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
-    """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted)."""
+class GzBytes(bytes):
+    """The raw bytes of a .gz hit file (to be inflated on the device)."""
+
+
+def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty, raw_gz=False):
+    """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted).
+    raw_gz: hand .gz files over compressed (GzBytes) instead of inflating them with zlib on the host."""
     fn = None
     for d in blastDir_list:
         fn = os.path.join(d, "Blast%d_%d.txt" % (iSpecies, jSpecies))
@@ -500,6 +540,8 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
         raise FileNotFoundError(fn)
     if os.path.exists(fn + ".gz"):
         with open(fn + ".gz", "rb") as f:
+            if raw_gz:
+                return GzBytes(f.read()), fn
             try:
                 return _gunzip(f.read()), fn
             except (EOFError, zlib.error) as e:
@@ -509,7 +551,7 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty):
         return f.read(), fn
 
 
-def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None, window=None):
+def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None, window=None, raw_gz=False):
     """Yields (request, data, filename) for every request (iSpecies, jSpecies) IN ORDER while a pool of threads reads
     and inflates the files ahead of the consumer - DIAMOND writes its hit files gzip-compressed (config.json:51), and
     inflating 16 files at once is what keeps the device fed.  At most `window` files are held in memory."""
@@ -519,7 +561,7 @@ def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None,
     window = window or 2 * n_readers
     if n_readers <= 1 or len(requests) <= 1:
         for r in requests:
-            data, fn = _read_hit_file(blastDir_list, r[0], r[1], q_allow_empty)
+            data, fn = _read_hit_file(blastDir_list, r[0], r[1], q_allow_empty, raw_gz)
             yield r, data, fn
         return
     with ThreadPoolExecutor(max_workers=n_readers) as pool:
@@ -528,7 +570,7 @@ def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None,
         while nxt < len(requests) or pending:
             while nxt < len(requests) and len(pending) < window:
                 r = requests[nxt]
-                pending.append((r, pool.submit(_read_hit_file, blastDir_list, r[0], r[1], q_allow_empty)))
+                pending.append((r, pool.submit(_read_hit_file, blastDir_list, r[0], r[1], q_allow_empty, raw_gz)))
                 nxt += 1
             r, fut = pending.pop(0)
             data, fn = fut.result()
@@ -540,7 +582,7 @@ class WaterfallMethod:
 
     @staticmethod
     def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
-                   builder=None, n_readers=None, homology=False):
+                   builder=None, n_readers=None, homology=False, device_gunzip=True):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
         the device-resident graph.  Returns the GraphBuilder holding it.
         homology=True: the `--c-homologs` graph of gathering_version (3, 2) instead (gathering.py:51-73, 520-521)."""
@@ -557,9 +599,24 @@ class WaterfallMethod:
                 swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54
                 cells.append((kj if swap else kp, kp if swap else kj, p, j, swap))
         try:
-            for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers):
-                if data is not None:
-                    gb.add_hits(p, j, data, swap_cols=swap)
+            for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers, raw_gz=device_gunzip):
+                if data is None:
+                    continue
+                if isinstance(data, GzBytes):
+                    # the compressed bytes go to the device as they are (ofg_add_hits_gz); layouts the device cannot split
+                    # into members are inflated here instead
+                    try:
+                        gb.add_hits_gz(p, j, data, swap_cols=swap)
+                        continue
+                    except OfgError as e:
+                        if e.code != _lib.ERR_UNSUPPORTED:
+                            raise
+                        try:
+                            data = _gunzip(data)
+                        except (EOFError, zlib.error) as e2:
+                            e2.hit_file = (cells[0][0], cells[0][1], blastDir_list[0])
+                            raise
+                gb.add_hits(p, j, data, swap_cols=swap)
         except (EOFError, zlib.error) as e:
             # a truncated / damaged .gz ends the reference's csv loop with an exception: same report (blast_file_processor.py:99-103)
             if hasattr(e, "hit_file"):
@@ -574,6 +631,11 @@ class WaterfallMethod:
         try:
             gb.build(_lib.STAGE_GRAPH)
         except OfgError as e:
+            if device_gunzip and e.code == _lib.ERR_PARSE and " gzip: " in e.message:
+                # a .gz the device could not inflate (e.g. concatenated members without size hints, which look like one member
+                # with a wrong length): let zlib decide - it either inflates the file or raises what gzip.open raises
+                return WaterfallMethod.BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast, v2_scores, q_allow_empty, device,
+                                                  gb, n_readers, homology, device_gunzip=False)
             WaterfallMethod._report(e, sp, blastDir_list)
             raise
         for p in range(len(sp)):
@@ -594,6 +656,13 @@ class WaterfallMethod:
     def _report(e, sp, blastDir_list):
         """Reproduce the reference's messages (blast_file_processor.py:74-103, gathering.py:209)."""
         msg = e.message
+        if e.code == _lib.ERR_PARSE and msg.startswith("pair=") and " gzip: " in msg:
+            # a damaged .gz: the reference's reader raises inside gzip.open and reports the file (blast_file_processor.py:99-103)
+            p, j = [int(x) for x in msg.split()[0][5:].split(",")]
+            print("ERROR: Blast%d_%d.txt is corrupted" % (sp[p], sp[j]))
+            sys.stderr.write("Malformatted line in %sBlast%d_%d.txt\nOffending line was:\n\n" % (blastDir_list[0], sp[p], sp[j]))
+            print("ERROR: Error processing files Blast%d_*" % sp[p])
+            return
         if e.code in (_lib.ERR_PARSE, _lib.ERR_INCONSISTENT, _lib.ERR_UNSUPPORTED) and msg.startswith("pair="):
             head, line = msg.split(" line=", 1)
             p, j = [int(x) for x in head.split()[0][5:].split(",")]

@@ -945,3 +945,100 @@ def test_homology_graph_on_a_mid_size_job_equals_oracle(gb):
         assert text == wo.graph_text(ref["indptr"], ref["indices"], ref["data"], sum(n_seqs))
     finally:
         gb.set_option("homology_graph", 0)
+
+
+# ------------------------------------------------------------------------------------------ device gunzip
+def _inflate_on_device(gb, blob):
+    """bytes of a .gz file -> text as the device inflates it (read back from the text arena)."""
+    gb.set_species([4, 4], [np.full(4, 100.0), np.full(4, 100.0)])
+    gb.add_hits_gz(0, 1, blob)
+    return gb.hits_text(0, 1)
+
+
+def test_device_inflate_equals_gzip_decompress(gb):
+    """blast_file_processor.py:63 opens .gz hit files with gzip.open; the device inflate must give the same bytes for every
+    DEFLATE block type and member layout: dynamic and fixed Huffman blocks, stored blocks, zlib levels 1/6/9, single
+    member, BGZF-style members with size hints (one warp each), empty input, long matches with distance < length."""
+    import gzip
+    import zlib as _z
+    rng = np.random.default_rng(3)
+    g = Golden("ref_AddTwoSpecies")
+    text = b"".join(g.hit_text(p, j) for p in range(3) for j in range(3))
+    payloads = {
+        "hits": text,
+        "tiny": b"0_1\t1_2\t50\n",                      # fixed Huffman block
+        "empty": b"",
+        "run": b"A" * 100000 + b"\n",                   # distance 1, length 258 matches
+        "period": (b"abcdefg" * 40000)[:250001],       # distance < length, not a divisor of 32
+        "random": rng.integers(0, 256, 200000, dtype=np.uint8).tobytes(),   # stored blocks
+        "mixed": text[:50000] + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + text[50000:120000],
+    }
+    for name, data in payloads.items():
+        blobs = {"bgzf": waterfall.gzip_members(data), "bgzf_small": waterfall.gzip_members(data, level=6, chunk=4000)}
+        for lvl in (0, 1, 6, 9):
+            blobs["single_l%d" % lvl] = gzip.compress(data, lvl)
+        co = _z.compressobj(6, _z.DEFLATED, 31, 9, _z.Z_FIXED)   # fixed Huffman codes throughout
+        blobs["fixed"] = co.compress(data) + co.flush()
+        for kind, blob in blobs.items():
+            assert gzip.decompress(blob) == data
+            got = _inflate_on_device(gb, blob)
+            assert got == data, (name, kind, len(got), len(data))
+
+
+def test_device_inflate_reports_corrupt_streams(gb):
+    g = Golden("ref_AddTwoSpecies")
+    data = g.hit_text(0, 1)
+    blob = bytearray(waterfall.gzip_members(data, chunk=8000))
+    blob[len(blob) // 2] ^= 0x55                       # damage one member's deflate stream
+    gb.set_species([4, 4], [np.full(4, 100.0), np.full(4, 100.0)])
+    gb.add_hits_gz(0, 1, bytes(blob))
+    with pytest.raises(waterfall.OfgError) as ei:
+        gb.hits_text(0, 1)
+    assert ei.value.code == _lib.ERR_PARSE and "gzip" in ei.value.message
+    with pytest.raises(waterfall.OfgError):           # a truncated member is caught while the members are walked
+        gb.add_hits_gz(0, 1, bytes(waterfall.gzip_members(data, chunk=8000))[:-100])
+    import gzip
+    # concatenated plain members carry no size hints: the file is taken for one member and the ISIZE check fails when it is
+    # inflated (BuildGraph then inflates such files on the host)
+    gb.set_species([4, 4], [np.full(4, 100.0), np.full(4, 100.0)])
+    gb.add_hits_gz(0, 1, gzip.compress(data[:1000]) + gzip.compress(data[1000:]))
+    with pytest.raises(waterfall.OfgError) as ei:
+        gb.hits_text(0, 1)
+    assert ei.value.code == _lib.ERR_PARSE and "gzip" in ei.value.message
+
+
+@pytest.mark.parametrize("layout", ["bgzf", "single", "concatenated"])
+def test_working_directory_with_compressed_hit_files_inflated_on_the_device(tmp_path, layout):
+    """-b <dir> -og on a directory whose Blast*.txt.gz files are inflated by the device (BGZF-style members, classic single
+    member) or, for member layouts the device cannot split, by the host: same graph bytes as the live reference."""
+    import gzip
+    g = Golden("ref_FromTrees")
+    wd = str(tmp_path) + "/"
+    synth_like = _write_wd_plain(g, wd)
+    for fn in [f for f in os.listdir(wd) if f.startswith("Blast")]:
+        data = open(wd + fn, "rb").read()
+        if layout == "bgzf":
+            z = waterfall.gzip_members(data, chunk=20000)
+        elif layout == "single":
+            z = gzip.compress(data, 6)
+        else:
+            z = gzip.compress(data[:len(data) // 2], 1) + gzip.compress(data[len(data) // 2:], 1)
+        open(wd + fn + ".gz", "wb").write(z)
+        os.remove(wd + fn)
+    graph_fn, gb2, si = waterfall.DoOrthogroupsGraph(wd, graphFN=wd + "OrthoFinder_graph.txt")
+    assert open(graph_fn, "rb").read() == g.graph
+    gb2.close()
+
+
+def _write_wd_plain(g, wd):
+    with open(wd + "SpeciesIDs.txt", "w") as f:
+        for k in g.species:
+            f.write("%d: sp%d.fa\n" % (k, k))
+    for p, k in enumerate(g.species):
+        with open(wd + "Species%d.fa" % k, "w") as f:
+            for q, L in enumerate(g.lengths[p]):
+                f.write(">%d_%d\n%s\n" % (k, q, "A" * int(L)))
+    for p, kp in enumerate(g.species):
+        for j, kj in enumerate(g.species):
+            with open(wd + "Blast%d_%d.txt" % (kp, kj), "wb") as f:
+                f.write(g.hit_text(p, j))
