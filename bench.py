@@ -474,6 +474,33 @@ def run_e2e(args, gb, world, rank, local, S, G, P, L, parts, sizes, step, make_s
     step()
     gb.sync()
     lines_e2e = gb.counts()["lines"]
+    use_gz = args.e2e_input == "gz"
+    gz_total, gz_offs, gz_sizes, gz_pinned, gz_base, t_comp = 0, {}, {}, None, 0, 0.0
+    if use_gz:
+        # the hit files as DIAMOND leaves them on disk: gzip (config.json:48-52), written as independent 64 KB members with a
+        # size hint in every header (BGZF layout, readable by gzip.open) so that the device can inflate the members in parallel
+        from concurrent.futures import ThreadPoolExecutor
+        pn = pinned.numpy()
+        t0c = time.perf_counter()
+
+        def comp(k):
+            return k, waterfall.gzip_members(pn[offs[k]:offs[k] + sizes[k]], level=1)
+        with ThreadPoolExecutor(max_workers=min(32, (os.cpu_count() or 1) * 2)) as pool:
+            blobs = dict(pool.map(comp, list(sizes.keys())))
+        t_comp = time.perf_counter() - t0c
+        gz_total = sum(len(b) for b in blobs.values())
+        gz_pinned = torch.empty(gz_total + 64 * len(blobs) + 64, dtype=torch.uint8).pin_memory()
+        gz_base = gz_pinned.data_ptr()
+        gn = gz_pinned.numpy()
+        o = 0
+        for k in sizes:
+            b = blobs[k]
+            gn[o:o + len(b)] = np.frombuffer(b, np.uint8)
+            gz_offs[k], gz_sizes[k] = o, len(b)
+            o += (len(b) + 63) & ~63
+        del blobs
+        log("[rank %d] compressed %.2f GB of hit text to %.2f GB (zlib level 1, %d-byte members) in %.1fs" % (
+            rank, total / 1e9, gz_total / 1e9, waterfall.BGZF_CHUNK, t_comp))
     out_pinned = torch.empty(gb.graph_text_size() + (1 << 20), dtype=torch.uint8).pin_memory()
     out_np = out_pinned.numpy()
     want_text = gb.graph_text_body().tobytes() if args.e2e_check else None
@@ -489,18 +516,28 @@ def run_e2e(args, gb, world, rank, local, S, G, P, L, parts, sizes, step, make_s
         pb.set_option("max_bytes_per_line_inv", 40)
         for c_, owned_ in zip(pb.ctxs, pb.parts):
             c_.set_option("reserve_text_bytes", sum(sizes[(p, j)] + 16 for p in owned_ for j in range(S)) + 4096)
+            if use_gz:
+                c_.set_option("reserve_gz_bytes", sum(gz_sizes[(p, j)] + 80 for p in owned_ for j in range(S)) + 4096)
 
         def e2e_step():
-            pb.load(lambda p, j: (base + offs[(p, j)], sizes[(p, j)]))
+            if use_gz:
+                pb.load(lambda p, j: (gz_base + gz_offs[(p, j)], gz_sizes[(p, j)]), gz=True)
+            else:
+                pb.load(lambda p, j: (base + offs[(p, j)], sizes[(p, j)]))
             pb.build()
             return pb.graph_text_body(out_np).size
     else:
         gb.set_option("reserve_text_bytes", total + 16 * len(sizes) + 4096)
+        if use_gz:
+            gb.set_option("reserve_gz_bytes", gz_total + 80 * len(sizes) + 4096)
 
         def e2e_step():
             gb.clear_hits()
             for k, n in sizes.items():
-                gb.add_hits_ptr(k[0], k[1], base + offs[k], n)
+                if use_gz:
+                    gb.add_hits_gz(k[0], k[1], (gz_base + gz_offs[k], gz_sizes[k]))
+                else:
+                    gb.add_hits_ptr(k[0], k[1], base + offs[k], n)
             step()
             return gb.graph_text_body(out_np).size
 
@@ -513,7 +550,7 @@ def run_e2e(args, gb, world, rank, local, S, G, P, L, parts, sizes, step, make_s
         d2h = e2e_step()
     barrier()
     dt = (time.perf_counter() - t0) / n_e2e
-    tt = torch.tensor([dt, float(lines_e2e), float(total), float(d2h)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dt, float(lines_e2e), float(gz_total if use_gz else total), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = tt.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -523,9 +560,24 @@ def run_e2e(args, gb, world, rank, local, S, G, P, L, parts, sizes, step, make_s
         lines_tot, h2d, d2h_all = float(lines_e2e), float(total), float(d2h)
     res = {"value": lines_tot / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_all),
            "ms_per_step": dt * 1e3, "steps": n_e2e, "lines": int(lines_tot),
+           "input": ("gzip: the hit files as multi-member .gz in pinned host memory (%d-byte members with BGZF size hints, zlib level 1, "
+                     "%.2f GB for %.2f GB of text on this rank); only the compressed bytes cross PCIe, the device inflates one member per warp"
+                     % (waterfall.BGZF_CHUNK, gz_total / 1e9, total / 1e9)) if use_gz else "plain text of the hit files in pinned host memory",
            "note": ("pinned host text -> PipelinedGraphBuilder (%d row partitions in asynchronous contexts of the GPU: the H2D copies, "
                     "the builds and the on-device list hand-over of the partitions overlap) -> graph text D2H" % len(pb.parts)) if pipelined else
                    "pinned host text -> ofg_add_hits_text (H2D) -> ofg_build -> graph text D2H, per rank"}
+    if use_gz and world == 1:
+        # the same leg with plain text in the host buffers (what round 1 measured): PCIe carries every text byte
+        use_gz = False
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt2 = (time.perf_counter() - t0) / 2
+        res["plain_text_input"] = {"value": lines_tot / dt2, "unit": UNIT, "ms_per_step": dt2 * 1e3, "h2d_bytes_per_step": int(total)}
+        use_gz = True
     if e2e_world_note:
         res["workload"] = e2e_world_note
     if want_text is not None:
@@ -629,6 +681,8 @@ def main():
     ap.add_argument("--scores-v2", action="store_true", help="measure the --scores-v2 variant of the path instead of the default scores")
     ap.add_argument("--e2e-parts", type=int, default=4, help="row partitions of the pipelined e2e run (1 = single context)")
     ap.add_argument("--e2e-check", action="store_true", help="compare the e2e graph text with the device-resident run's")
+    ap.add_argument("--e2e-input", default="text", choices=["gz", "text"],
+                    help="what the pinned host buffers of the e2e leg hold: the .gz files (inflated on the device) or plain text")
     ap.add_argument("--e2e-host-gb", type=float, default=110.0, help="N > 1: host memory all ranks together may pin for the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-species", type=int, default=4, help="species in the cpu_baseline sample")

@@ -800,7 +800,7 @@ int inflate_pending(ofg_ctx* c)
     CK(cudaMemsetAsync(c->gz_err.p, 0xff, 8, c->stream));
     if (n > 0) {
         if (upload(c, c->gz_members_dev, c->gz_members.data(), sizeof(GzMember) * (size_t)n)) return OFG_ERR_CUDA;
-        inflate_kernel<<<grid_for(c, n, GZ_WARPS, 5), GZ_WARPS * 32, 0, c->stream>>>(c->gz_comp.as<uint8_t>(), c->gz_members_dev.as<GzMember>(), n,
+        inflate_kernel<<<grid_for(c, n, GZ_WARPS, 8), GZ_WARPS * 32, 0, c->stream>>>(c->gz_comp.as<uint8_t>(), c->gz_members_dev.as<GzMember>(), n,
                                                                                      c->text.as<uint8_t>(), c->gz_err.as<unsigned long long>());
         CKL("inflate_kernel");
     }

@@ -24,14 +24,16 @@ struct GzMember {
 
 constexpr int GZ_TB = 10;                 // bits of the primary literal/length table
 constexpr int GZ_TD = 9;                  // bits of the primary distance table
-constexpr int GZ_WARPS = 8;
+constexpr int GZ_WARPS = 4;
+constexpr int GZ_RING = 2048;             // output ring per warp: matches up to GZ_RING - 258 bytes back never touch global memory
+constexpr int GZ_FLUSH = 512;             // bytes written back per flush (coalesced)
 #ifdef OFG_HOST_SHIM
 constexpr int GZ_LANES = 1;
 #else
 constexpr int GZ_LANES = 32;
 #endif
 
-struct GzWarp {                           // shared memory of one warp (about 4.2 KB)
+struct GzWarp {                           // shared memory of one warp (about 6.3 KB)
     unsigned short lit[1 << GZ_TB];       // (symbol << 4) | code length; 0: code longer than GZ_TB bits
     unsigned short dist[1 << GZ_TD];
     unsigned short lsym[288], dsym[32];   // symbols ordered by (code length, symbol): canonical decode of long codes
@@ -40,6 +42,7 @@ struct GzWarp {                           // shared memory of one warp (about 4.
     unsigned short offs[16];              // scratch of gz_build
     u32 next[16];
     int ok;
+    u32 win[GZ_RING / 4];                 // the last GZ_RING bytes of the member's output (ring by output position)
 };
 
 struct GzBits {
@@ -132,21 +135,29 @@ __device__ __constant__ unsigned char GZ_CLORD[19] = {16, 17, 18, 0, 8, 7, 9, 6,
 
 // err: min over failing members of (member index << 8 | kind); kinds: 1 bad block type / header, 2 bad code, 3 distance too far,
 // 4 output overrun, 5 output short of ISIZE, 6 stored block length check
+//
+// Output path: every byte goes into a shared-memory ring indexed by its output position; whole GZ_FLUSH-byte pieces are
+// written back to global memory with coalesced word stores.  A match whose distance is below GZ_RING - 258 reads the
+// ring (a few shared-memory cycles instead of a global round trip per symbol); longer distances read bytes that were
+// written back long ago.
 __global__ void __launch_bounds__(GZ_WARPS * 32) inflate_kernel(const uint8_t* comp, const GzMember* members, int64_t n_members, uint8_t* text,
                                                                  unsigned long long* err)
 {
     __shared__ GzWarp s_all[GZ_WARPS];
     GzWarp& sw = s_all[threadIdx.x >> 5];
+    uint8_t* const ring = reinterpret_cast<uint8_t*>(sw.win);
     const int lane = (int)lane_id();
     const int64_t n_warps = (int64_t)gridDim.x * GZ_WARPS;
     for (int64_t mi = (int64_t)blockIdx.x * GZ_WARPS + (threadIdx.x >> 5); mi < n_members; mi += n_warps) {
         const GzMember m = members[mi];
         GzBits b;
         b.in = comp + m.in_off; b.n = m.in_len; b.pos = 0; b.buf = 0; b.cnt = 0;
-        uint8_t* out = text + m.out_off;
-        u64 op = 0;
+        uint8_t* out = text + m.out_off;   // 4-byte aligned: members start at multiples of 16 of the arena or at BGZF chunk ends
+        const u64 head = (u64)((4 - ((uintptr_t)out & 3)) & 3);   // bytes before the first aligned word are stored one by one
+        u64 op = 0, flushed = 0;
         int kind = 0;
         bool last = false;
+        // ring position = output position + head, so that ring words line up with aligned words of the output
         while (!last && !kind) {
             b.refill();
             last = b.get(1) != 0;
@@ -159,11 +170,18 @@ __global__ void __launch_bounds__(GZ_WARPS * 32) inflate_kernel(const uint8_t* c
                 b.refill();
                 const u32 nl = b.get(16);
                 if ((ln ^ nl) != 0xffffu) { kind = 6; break; }
-                // bytes still in the bit buffer belong to the block
-                const u64 src = b.pos - (u64)(b.cnt >> 3);
+                const u64 src = b.pos - (u64)(b.cnt >> 3);   // bytes still in the bit buffer belong to the block
                 if (src + ln > m.in_len || op + ln > m.out_len) { kind = 4; break; }
+                // bytes of the ring that were not written back yet go out one by one, then the block is copied directly and the
+                // ring is reloaded with the last bytes of the output
+                __syncwarp();
+                for (u64 q = flushed + (u64)lane; q < op; q += GZ_LANES) out[q] = ring[(q + head) & (GZ_RING - 1)];
                 for (u32 i = lane; i < ln; i += GZ_LANES) out[op + i] = b.in[src + i];
                 op += ln;
+                __syncwarp();
+                const u64 lo = op > (u64)GZ_RING ? op - GZ_RING : 0;
+                for (u64 q = lo + (u64)lane; q < op; q += GZ_LANES) ring[(q + head) & (GZ_RING - 1)] = out[q];
+                flushed = op;
                 b.pos = src + ln; b.buf = 0; b.cnt = 0;
                 __syncwarp();
                 continue;
@@ -220,12 +238,33 @@ __global__ void __launch_bounds__(GZ_WARPS * 32) inflate_kernel(const uint8_t* c
             }
             // ---- symbols of the block
             for (;;) {
+                // write whole pieces of the ring back while they are at least a maximal match away from being overwritten
+                {
+                    // aligned window [fa, fb): fa = first unflushed aligned position, in ring coordinates (output position + head)
+                    const u64 done = flushed;   // output positions below `done` are in global memory
+                    if (op - done >= (u64)(GZ_FLUSH + 8)) {
+                        // bytes [done, done + head') one by one until aligned, then words
+                        u64 a0 = done;
+                        if (((a0 + head) & 3) != 0) {
+                            const u64 a1 = a0 + (4 - ((a0 + head) & 3));
+                            __syncwarp();
+                            for (u64 q = a0 + (u64)lane; q < a1; q += GZ_LANES) out[q] = ring[(q + head) & (GZ_RING - 1)];
+                            a0 = a1;
+                        }
+                        const u64 a2 = a0 + GZ_FLUSH;
+                        __syncwarp();
+                        for (u64 q = a0 + 4 * (u64)lane; q < a2; q += 4 * GZ_LANES)
+                            *reinterpret_cast<u32*>(out + q) = sw.win[((q + head) & (GZ_RING - 1)) >> 2];
+                        flushed = a2;
+                        __syncwarp();
+                    }
+                }
                 b.refill();
                 int s = gz_decode(b, sw.lit, GZ_TB, sw.lsym, sw.lcnt);
                 if (s < 256) {
                     if (s < 0) { kind = 2; break; }
                     if (op >= m.out_len) { kind = 4; break; }
-                    if (lane == 0) out[op] = (uint8_t)s;
+                    if (lane == 0) ring[(op + head) & (GZ_RING - 1)] = (uint8_t)s;
                     op++;
                     continue;
                 }
@@ -240,16 +279,35 @@ __global__ void __launch_bounds__(GZ_WARPS * 32) inflate_kernel(const uint8_t* c
                 if (dist > op) { kind = 3; break; }
                 if (op + (u64)ln > m.out_len) { kind = 4; break; }
                 __syncwarp();   // earlier stores of this warp are visible to the loads below
-                const uint8_t* src = out + op - dist;
-                if (dist >= (u64)ln) {
-                    for (int i = lane; i < ln; i += GZ_LANES) out[op + i] = src[i];
+                if (dist <= (u64)(GZ_RING - 264)) {
+                    // source bytes are still in the ring (period-dist pattern when the match overlaps itself)
+                    const u32 sb = (u32)(op + head - dist);
+                    if (dist >= (u64)ln) {
+                        for (int i = lane; i < ln; i += GZ_LANES) ring[(u32)(op + head + i) & (GZ_RING - 1)] = ring[(sb + (u32)i) & (GZ_RING - 1)];
+                    } else {
+                        const u32 d32 = (u32)dist;
+                        uint8_t v[9];   // read everything first: with GZ_LANES lanes a source byte may be a destination of this very match
+#pragma unroll
+                        for (int k = 0; k < 9; k++) { const int i = lane + k * GZ_LANES; v[k] = (GZ_LANES > 1 && i < ln) ? ring[(sb + (u32)i % d32) & (GZ_RING - 1)] : 0; }
+                        if (GZ_LANES > 1) {
+#pragma unroll
+                            for (int k = 0; k < 9; k++) { const int i = lane + k * GZ_LANES; if (i < ln) ring[(u32)(op + head + i) & (GZ_RING - 1)] = v[k]; }
+                        } else {
+                            for (int i = 0; i < ln; i++) ring[(u32)(op + head + i) & (GZ_RING - 1)] = ring[(sb + (u32)i % d32) & (GZ_RING - 1)];
+                        }
+                    }
                 } else {
-                    for (int i = lane; i < ln; i += GZ_LANES) out[op + i] = src[(u64)i % dist];
+                    // far back: those bytes were written to global memory long ago (flushed > op - GZ_FLUSH - 270 > op - dist + ln)
+                    const uint8_t* src = out + op - dist;
+                    for (int i = lane; i < ln; i += GZ_LANES) ring[(u32)(op + head + i) & (GZ_RING - 1)] = src[i];
                 }
                 op += (u64)ln;
                 __syncwarp();
             }
         }
+        // the rest of the ring
+        __syncwarp();
+        if (!kind) for (u64 q = flushed + (u64)lane; q < op; q += GZ_LANES) out[q] = ring[(q + head) & (GZ_RING - 1)];
         if (!kind && op != m.out_len) kind = 5;
         if (kind && lane == 0) atomicMin(err, ((unsigned long long)mi << 8) | (unsigned long long)kind);
         __syncwarp();

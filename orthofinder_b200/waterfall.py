@@ -336,9 +336,10 @@ class PipelinedGraphBuilder:
         for c in self.ctxs:
             c.set_option(name, value)
 
-    def load(self, host_buffer_of):
+    def load(self, host_buffer_of, gz=False):
         """host_buffer_of(p, j) -> (host pointer, nbytes) (pinned memory for an asynchronous copy) or a
-        bytes-like object.  Queues every copy; returns immediately."""
+        bytes-like object.  Queues every copy; returns immediately.  gz: the buffers hold the .gz files as they are on
+        disk; only the compressed bytes are copied and every context inflates its files on the device."""
         import torch
         prev = None
         for c, owned in zip(self.ctxs, self.parts):
@@ -349,7 +350,9 @@ class PipelinedGraphBuilder:
             for p in owned:
                 for j in range(self.S):
                     d = host_buffer_of(p, j)
-                    if isinstance(d, tuple):
+                    if gz:
+                        c.add_hits_gz(p, j, d)
+                    elif isinstance(d, tuple):
                         c.add_hits_ptr(p, j, d[0], d[1])
                     else:
                         c.add_hits(p, j, d)

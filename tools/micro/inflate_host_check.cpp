@@ -38,14 +38,16 @@ int main(int argc, char** argv)
     GzMember m;
     m.in_off = 10; m.in_len = n - 18; m.out_off = 0; m.file = 0; m.pad = 0;
     m.out_len = z[n - 4] | (z[n - 3] << 8) | (z[n - 2] << 16) | ((u64)z[n - 1] << 24);
-    std::vector<uint8_t> out(m.out_len + 64);
+    int shift = argc > 3 ? atoi(argv[3]) : 0;   // misalign the output by 0..3 bytes
+    m.out_off = shift;
+    std::vector<uint8_t> out(m.out_len + 64 + 16);
     unsigned long long err = ~0ULL;
     // 4-byte aligned copy of the stream (the kernel reads aligned words)
     uint8_t* zz = (uint8_t*)aligned_alloc(16, n + 64);
     memcpy(zz, z.data(), n);
     memset(zz + n, 0, 64);
     inflate_kernel(zz, &m, 1, out.data(), &err);
-    printf("isize %llu raw %zu err %llx equal %d\n", m.out_len, nr, err, (int)(m.out_len == nr && !memcmp(out.data(), raw.data(), nr)));
-    if (err == ~0ULL && m.out_len == nr) for (size_t i = 0; i < nr; i++) if (out[i] != raw[i]) { printf("first diff at %zu\n", i); break; }
+    printf("isize %llu raw %zu err %llx equal %d\n", m.out_len, nr, err, (int)(m.out_len == nr && !memcmp(out.data() + shift, raw.data(), nr)));
+    if (err == ~0ULL && m.out_len == nr) for (size_t i = 0; i < nr; i++) if (out[i + shift] != raw[i]) { printf("first diff at %zu\n", i); break; }
     return 0;
 }
