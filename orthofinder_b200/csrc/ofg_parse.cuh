@@ -56,6 +56,7 @@ struct __align__(16) PsWarp {
     u32 term[PS_RING / 32];   // bit i of word w: byte 32 w + i is '\n' or '\r'
     u32 tab[PS_RING / 32];
     uint16_t q[PS_QCAP];      // stream offsets of the line starts not parsed yet, ascending
+    u64 bar;                  // mbarrier of the bulk refills (byte count of one step)
 };
 
 struct RingSrc {  // generic parser over the ring
@@ -76,6 +77,35 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 1-D bulk copy (TMA engine) global -> shared with an mbarrier that counts the bytes: one lane arms the barrier and issues the
+// copy of a whole 1 KB step, every lane of the warp then waits on the barrier's phase.  No per-lane addresses, no LDGSTS.
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load_step(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OFG_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra OFG_MBAR_WAIT;\n"
+        "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 // 0x80 in every byte of w that equals the pattern byte (exact, no cross-byte carries)
 __device__ __forceinline__ u32 bytes_eq_hi(u32 w, u32 pattern)
@@ -392,6 +422,9 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
     const int lane = (int)lane_id();
     const int64_t n_warps = (int64_t)gridDim.x * PS_WARPS;
     PsOut out{0, 0};
+    u32 bar_phase = 0;   // parity of the next bulk refill of this warp
+    if (lane == 0) { mbar_init(&sw.bar, 1u); mbar_fence_init(); }
+    __syncwarp();
     for (int64_t seg = (int64_t)blockIdx.x * PS_WARPS + (threadIdx.x >> 5); seg < a.n_segs; seg += n_warps) {
         PsFile f;
         {
@@ -415,13 +448,16 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
         bool tail_open = false;             // the newest queued line has not seen its terminator yet
         bool foreign_open = prev_term == 0; // the line running into the staged text is not in the queue
         u32 n_lines = 0, n_valid = 0;
+        bool bulk_pending = false;          // a bulk refill is in flight (its barrier phase has not been consumed)
         const uint8_t* glane = f.gfile + f.seg_a + lane * 16;  // this lane's first 16-byte piece of step 0
-        auto issue_step = [&](u32 k) {  // two 16-byte pieces per lane; pieces past the end of the file become '\n'
+        auto issue_step = [&](u32 k) {  // whole steps: one bulk copy per warp; the last, partial step: 16-byte pieces per lane, '\n' past the end of the file
             uint8_t* dst = sw.text + ((k * PS_STEP) & PS_RMASK) + lane * 16;
             const uint8_t* src = glane + (size_t)k * PS_STEP;
             if (k < full_steps) {
-                cp_async16(dst, src);
-                cp_async16(dst + 512, src + 512);
+                // the ring slot was read by the whole warp before (generic proxy): every lane is past those reads here
+                __syncwarp();
+                if (lane == 0) bulk_load_step(sw.text + ((k * PS_STEP) & PS_RMASK), f.gfile + f.seg_a + (size_t)k * PS_STEP, PS_STEP, &sw.bar);
+                bulk_pending = true;
             } else {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -433,7 +469,8 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
         };
         issue_step(0);
         for (u32 k = 0;; k++) {
-            cp_async_wait_all();
+            if (k < full_steps) { mbar_wait(&sw.bar, bar_phase); bar_phase ^= 1u; bulk_pending = false; }   // the bulk copy of step k has landed
+            else cp_async_wait_all();
             __syncwarp();
             const u32 step_so = k * PS_STEP;
             const u32 loaded_end = step_so + PS_STEP;   // bytes past the file end are staged as '\n'
@@ -541,7 +578,11 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
                 done += n;
                 n_lines += (u32)n;
             }
-            if (seg_done) break;
+            if (seg_done) {
+                // a refill that was issued ahead and is not needed any more must still land before the barrier is armed again
+                if (bulk_pending) { mbar_wait(&sw.bar, bar_phase); bar_phase ^= 1u; bulk_pending = false; }
+                break;
+            }
             if (done > 0) {  // keep the leftovers (at most 32 complete lines and the open one) at the front of the queue
                 const int left = qn - done;
                 uint16_t v = 0, v2 = 0;
