@@ -35,9 +35,19 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
     sl = sass_lines(sass_fn, sym)
     rows = list(csv.reader(open(csv_fn)))
+    # a report with several kernels lists them one after the other ("Kernel Name", <name>): take the one that matches
+    want = sys.argv[5] if len(sys.argv) > 5 else None
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] or [0]
+    pick = starts[0]
+    for i in starts:
+        if want and want in rows[i][1]:
+            pick = i
+            break
+    end = next((i for i in starts if i > pick), len(rows))
+    rows = rows[pick:end]
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
-    body = rows[hdr_i + 1:]
+    body = [r for r in rows[hdr_i + 1:] if r and r[0].startswith("0x")]
     ci = hdr.index("Instructions Executed")
     cs = hdr.index("# Samples")
     base = int(body[0][0], 16)
