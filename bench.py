@@ -352,7 +352,7 @@ def run_ours(args):
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "%s: %d species x %d genes, hq=%d (%d pairs, %d hit lines, %.2f GB text%s)" % (
-               ("C3" if (world == 8 and S == 64 and not args.species) else args.config), S, G, P.hq, S * S, int(lines_all),
+               ("C3" if (args.config == "C2" and S == 64 and G == 20000 and P.hq == 50) else args.config), S, G, P.hq, S * S, int(lines_all),
                text_bytes_all * (world if world > 1 else 1) / 1e9,
                ", per-rank text incl. column pairs" if (world > 1 and mode == "thresholds") else ""),
                "scores": "v2 (NormalisedBitScore, percentile-ratio thresholds)" if args.scores_v2 else "default (length-normalised fit)",

@@ -148,3 +148,61 @@ def run_reference(wd, q_double_blast=True, capture_fit=True, keep_matrices=True,
         fh.wd_base, fh.wd_current = saved
         shutil.rmtree(out, ignore_errors=True)
     return res
+
+
+def run_reference_dendroblast(wd, ogs, q_double_blast=True):
+    """The live reference's DendroBLAST distance matrices (orthologues.py:264-291 worker, :396-411 completion, :413-431
+    Phylip text) for WorkingDirectory ``wd``.  ogs: list of orthogroups, each a list of (species ID, iSeq), sizes
+    non-increasing and >= 4 like GetOGMatrices_FullParallel :327-337 guarantees.
+    Returns dict(M=[n x n arrays before completion], D=[after], phylip=[bytes per orthogroup])."""
+    import queue
+    _import_reference_real()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from scripts_of import orthologues, util, files
+    if not wd.endswith("/"):
+        wd += "/"
+    out = tempfile.mkdtemp(prefix="ofg_refd_") + "/"
+    sp, n_all, _ = util.GetSpeciesToUse(wd + "SpeciesIDs.txt")
+    si = util.GetSeqsInfo([wd], sp, n_all)
+    og_seqs = [[orthologues.Seq((int(a), int(b))) for a, b in og] for og in ogs]
+    # orthologues.py:338-341
+    ogsPerSpecies = [[[(g, i) for i, g in enumerate(og) if g.iSp == iSp] for iSp in si.speciesToUse] for og in og_seqs]
+    nGenes = [len(og) for og in og_seqs]
+    ogMatrices = [[np.zeros(n) for _ in range(n)] for n in nGenes]
+
+    class _Cmds:
+        def __init__(self, items):
+            self.items = list(items)
+
+        def get(self, *_a):
+            if not self.items:
+                raise queue.Empty
+            return self.items.pop(0)
+
+    class _Status:
+        def put(self, _x):
+            pass
+
+    cmds = _Cmds((iiSp, sp1, si.nSeqsPerSpecies[sp1]) for iiSp, sp1 in enumerate(si.speciesToUse))   # :344-345
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orthologues.Worker_OGMatrices_ReadBLASTAndUpdateDistances(cmds, _Status(), 0, ogMatrices, nGenes, si, [wd], ogsPerSpecies,
+                                                                  q_double_blast)
+        M = [np.array([np.array(r) for r in m]) for m in ogMatrices]
+        fh = files.FileHandler
+        saved = getattr(fh, "GetOGsDistMatFN", None)
+        fh.GetOGsDistMatFN = staticmethod(lambda iog: out + "OG%07d.phy" % iog)
+        try:
+            inst = orthologues.DendroBLASTTrees.__new__(orthologues.DendroBLASTTrees)
+            orthologues.DendroBLASTTrees.CompleteAndWriteOGMatrices(inst, og_seqs, ogMatrices)
+        finally:
+            if saved is not None:
+                fh.GetOGsDistMatFN = saved
+    D = [np.array([np.array(r) for r in m]) for m in ogMatrices]
+    phy = []
+    for iog in range(len(ogs)):
+        with open(out + "OG%07d.phy" % iog, "rb") as f:
+            phy.append(f.read())
+    shutil.rmtree(out, ignore_errors=True)
+    return dict(M=M, D=D, phylip=phy, seqsInfo=si)
