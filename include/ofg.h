@@ -117,7 +117,10 @@ int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
  * "async" (0/1: ofg_build only enqueues; counts, errors and sizes are read back by ofg_sync or by the first accessor),
  * "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)
  * instead of the length-bin fit and GetMostDistant_s_estimate_from_relative_rbhs (gathering.py:314-388) instead of
- * GetMostDistant_s; what the reference passes as v2_scores to ProcessBlastHits / ConnectCognates (:177, :251). */
+ * GetMostDistant_s; what the reference passes as v2_scores to ProcessBlastHits / ConnectCognates (:177, :251),
+ * "homology_graph" (0/1): the `--c-homologs` graph of gathering.py:51-73 instead of the connect graph,
+ * "keep_self_hits" (0/1): GetBLAST6Scores(..., qExcludeSelfHits=False) - the raw matrices of DendroBLAST
+ * (orthologues.py:272-274); only OFG_STAGE_RAW can be built with it (see ofg_dendro_matrices). */
 int ofg_set_option(ofg_ctx* ctx, const char* name, int64_t value);
 
 /* Optional, only read with "scores_v2": the per-gene factors Lengths[p] ** -0.5 of NormalisedBitScore
@@ -140,6 +143,21 @@ int ofg_sync(ofg_ctx* ctx);
 /* Statistics of the last build: "radix_fallback_waves" (waves whose length bins were built by the LSD radix sort because
  * the bucket path could not take them), "waves", "record_slot_capacity". */
 int ofg_get_stat(ofg_ctx* ctx, const char* name, int64_t* value);
+
+/* DendroBLAST distance matrices of orthogroups (replaces the worker
+ * orthologues.py:264-291 `Worker_OGMatrices_ReadBLASTAndUpdateDistances` and, with complete != 0, the completion loop of
+ * `DendroBLASTTrees.CompleteAndWriteOGMatrices` :396-410).  The context must be built to OFG_STAGE_RAW and no further, with
+ * option "keep_self_hits" = 1 (GetBLAST6Scores(..., qExcludeSelfHits=False), orthologues.py:272-274), every species pair in
+ * one context.
+ *   og_off[n_ogs + 1]  first member of every orthogroup in species[] / iseq[] (og_off[0] = 0)
+ *   species[k], iseq[k] member k: species list position and sequence index (util.py:54-61)
+ *   complete == 0:     M_ij = 0.5 * max(B_ij, Bmin_i) * (1 / Bmax_i), bit-identical to the reference
+ *   complete != 0:     D_ij = D_ji = -log(M_ij + M_ji) for i != j (CUDA log, <= 1 ulp from numpy's), D_ii = M_ii;
+ *                      host_max_og[g] (may be NULL) = max over j < i of D_ij, -9e99 if there is none
+ *   host_out           sum over orthogroups of n^2 doubles, orthogroup after orthogroup, row-major; out_len = its capacity
+ * Errors: OFG_ERR_ARG for a gene that does not exist, a wrong stage, a partitioned context or a short output. */
+int ofg_dendro_matrices(ofg_ctx* ctx, int64_t n_ogs, const int64_t* og_off, const int32_t* species, const int32_t* iseq,
+                        int complete, double* host_out, int64_t out_len, double* host_max_og);
 /* Orders the context's stream after everything enqueued so far on `other`'s stream (event wait, no host block). */
 int ofg_wait_for(ofg_ctx* ctx, ofg_ctx* other);
 

@@ -18,7 +18,7 @@ SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "of
            "ofg_thresholds_dev", "ofg_thresholds_mark_complete", "ofg_thresholds_copy", "ofg_export_flags",
            "ofg_import_flags", "ofg_counts", "ofg_pair_csr",
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
-           "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_sync", "ofg_get_stat", "ofg_wait_for", "ofg_export_flags_peer",
+           "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_sync", "ofg_get_stat", "ofg_dendro_matrices", "ofg_wait_for", "ofg_export_flags_peer",
            "ofg_import_flags_peer", "ofg_device_alloc", "ofg_device_free", "ofg_ipc_get_handle", "ofg_ipc_open_handle",
            "ofg_ipc_close_handle", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
@@ -61,6 +61,7 @@ def load():
         "ofg_import_flags": [vp, i32, vp, i64],
         "ofg_sync": [vp],
         "ofg_get_stat": [vp, ctypes.c_char_p, ctypes.POINTER(i64)],
+        "ofg_dendro_matrices": [vp, i64, vp, vp, vp, i32, vp, i64, vp],
         "ofg_wait_for": [vp, vp],
         "ofg_export_flags_peer": [vp, i32, i32, vp, i32, vp, sz],
         "ofg_import_flags_peer": [vp, i32, i32, i32, vp, sz],

@@ -19,6 +19,7 @@
 #include "ofg_graph.cuh"
 #include "ofg_synth.cuh"
 #include "ofg_inflate.cuh"
+#include "ofg_dendro.cuh"
 
 static_assert(sizeof(ofg_synth_params) == sizeof(OfgSynthParams), "synth parameter layouts must match");
 
@@ -92,6 +93,7 @@ struct ofg_ctx {
     int64_t bytes_per_line_inv = 24;
     int64_t sel_frac_inv = 4;
     bool homology = false;      // option homology_graph: `--c-homologs` (gathering.py:51-73, 520-521) instead of the connect / RBH graph
+    bool keep_self = false;     // option keep_self_hits: qExcludeSelfHits=False of GetBLAST6Scores (DendroBLAST, orthologues.py:272-274); RAW stage only
     bool radix_only = false;    // option length_sort_radix: always take the LSD radix path (the fallback of the bucket path)
     int64_t fallback_waves = 0; // waves of the last build that took the radix path
     int wave_species = 0;       // option wave_species: query species per wave (0: the whole partition in one wave)
@@ -526,7 +528,7 @@ int wave_raw(ofg_ctx* c, int wi)
         a.seg_prefix = c->d_tile_prefix.as<int64_t>() + seg_off; a.n_segs = w.n_segs;
         a.coo_row = c->coo_row.as<u32>(); a.coo_col = c->coo_col.as<u32>(); a.coo_val = c->coo_val.as<double>();
         a.cap = cap; a.coo_count = d_count; a.rowcount = c->rowcount.as<u32>();
-        a.pair_lines = pair_lines_ptr(c) + w.P0; a.pair_valid = pair_valid_ptr(c) + w.P0; a.pair_err = pair_err_ptr(c) + w.P0; a.one = 1u;
+        a.pair_lines = pair_lines_ptr(c) + w.P0; a.pair_valid = pair_valid_ptr(c) + w.P0; a.pair_err = pair_err_ptr(c) + w.P0; a.one = 1u; a.keep_self = c->keep_self ? 1 : 0;
         const int parse_smem = (int)(sizeof(PsWarp) * PS_WARPS);
         CK(cudaFuncSetAttribute(parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, parse_smem));
         parse_kernel<<<parse_grid, PARSE_THREADS, parse_smem, c->stream>>>(a);
@@ -1325,6 +1327,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "wave_species")) { c->wave_species = (int)std::max<int64_t>(value, 0); c->stage_done = 0; }
     else if (!strcmp(name, "async")) c->async = value != 0;
     else if (!strcmp(name, "length_sort_radix")) c->radix_only = value != 0;
+    else if (!strcmp(name, "keep_self_hits")) { c->keep_self = value != 0; c->stage_done = 0; }
     else if (!strcmp(name, "homology_graph")) { c->homology = value != 0; c->stage_done = std::min(c->stage_done, (int)OFG_STAGE_NORM); }
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else if (!strcmp(name, "reserve_gz_bytes")) { cudaSetDevice(c->device); CK(c->gz_comp.ensure((size_t)value + 64)); }
@@ -1587,6 +1590,8 @@ int ofg_build(ofg_ctx* c, int stop_after)
     cudaSetDevice(c->device);
     if (int rc = ensure_pairs(c)) return rc;
     if (stop_after < OFG_STAGE_RAW || stop_after > OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "bad stage %d", stop_after);
+    if (c->keep_self && stop_after > OFG_STAGE_RAW)
+        return fail(c, OFG_ERR_ARG, "option keep_self_hits is for the raw matrices only (OFG_STAGE_RAW, DendroBLAST): the graph path drops self hits");
     const bool sized_from_last = c->bpl_learned > (double)c->bytes_per_line_inv;
     int rc = build_once(c, stop_after);
     if (rc == OFG_ERR_CAPACITY && sized_from_last && c->bpl_learned == 0.0 && !c->async)
@@ -1945,6 +1950,75 @@ int ofg_pair_csr(ofg_ctx* c, int p, int j, int64_t* n_rows, int64_t* nnz, int32_
             }
     }
     return OFG_OK;
+}
+
+// DendroBLAST distance matrices of orthogroups on the raw matrices (orthologues.py:264-291, 396-410).
+int ofg_dendro_matrices(ofg_ctx* c, int64_t n_ogs, const int64_t* og_off, const int32_t* species, const int32_t* iseq, int complete,
+                        double* host_out, int64_t out_len, double* host_max_og)
+{
+    if (!c || !og_off || n_ogs < 0 || (n_ogs > 0 && (!species || !iseq || !host_out))) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
+    if (c->stage_done != OFG_STAGE_RAW)
+        return fail(c, OFG_ERR_ARG, "the distance matrices need the raw scores: build to OFG_STAGE_RAW and no further (stage is %d)", c->stage_done);
+    if (c->has_partition) return fail(c, OFG_ERR_ARG, "the distance matrices need every species pair in one context");
+    if (og_off[0] != 0) return fail(c, OFG_ERR_ARG, "og_off[0] must be 0");
+    const int64_t K = og_off[n_ogs];
+    std::vector<int32_t> mem_og((size_t)K);
+    std::vector<int64_t> out_off((size_t)n_ogs + 1, 0);
+    for (int64_t g = 0; g < n_ogs; g++) {
+        const int64_t n = og_off[g + 1] - og_off[g];
+        if (n < 0) return fail(c, OFG_ERR_ARG, "og_off must not decrease (orthogroup %lld)", (long long)g);
+        out_off[(size_t)g + 1] = out_off[(size_t)g] + n * n;
+        for (int64_t k = og_off[g]; k < og_off[g + 1]; k++) {
+            if (species[k] < 0 || species[k] >= c->S || iseq[k] < 0 || iseq[k] >= c->n_seqs[species[k]])
+                return fail(c, OFG_ERR_ARG, "orthogroup %lld member %lld: gene %d_%d does not exist", (long long)g, (long long)(k - og_off[g]), species[k], iseq[k]);
+            mem_og[(size_t)k] = (int32_t)g;
+        }
+    }
+    if (out_len < out_off[(size_t)n_ogs]) return fail(c, OFG_ERR_ARG, "output holds %lld values, %lld needed", (long long)out_len, (long long)out_off[(size_t)n_ogs]);
+    if (n_ogs == 0 || K == 0) return OFG_OK;
+    DevBuf gmin, gmaxinv, d_mem_og, d_og_off, d_out_off, d_sp, d_seq, dM, dD, d_max;
+    DevBuf* tmp[] = {&gmin, &gmaxinv, &d_mem_og, &d_og_off, &d_out_off, &d_sp, &d_seq, &dM, &dD, &d_max};
+    auto done = [&](int rc) { for (DevBuf* b : tmp) b->release(); return rc; };
+    const int64_t E = out_off[(size_t)n_ogs];
+    std::vector<unsigned long long> max_init((size_t)n_ogs, 0ull);
+    {
+        const double lo = -9e99;   // max_og starts at -9e99 (:401)
+        unsigned long long b; memcpy(&b, &lo, 8);
+        b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        std::fill(max_init.begin(), max_init.end(), b);
+    }
+    if (gmin.ensure((size_t)c->N * 8) != cudaSuccess || gmaxinv.ensure((size_t)c->N * 8) != cudaSuccess || dM.ensure((size_t)E * 8) != cudaSuccess ||
+        (complete && dD.ensure((size_t)E * 8) != cudaSuccess))
+        return done(fail(c, OFG_ERR_CUDA, "out of device memory for %lld matrix elements", (long long)E));
+    if (upload(c, d_mem_og, mem_og.data(), (size_t)K * 4) || upload(c, d_og_off, og_off, (size_t)(n_ogs + 1) * 8) ||
+        upload(c, d_out_off, out_off.data(), (size_t)(n_ogs + 1) * 8) || upload(c, d_sp, species, (size_t)K * 4) ||
+        upload(c, d_seq, iseq, (size_t)K * 4) || upload(c, d_max, max_init.data(), (size_t)n_ogs * 8))
+        return done(OFG_ERR_CUDA);
+    DendroArgs a;
+    a.pairs = c->d_pairs.as<PairDesc>(); a.pair_of = c->d_pair_of.as<int32_t>(); a.S = c->S; a.seq_start = c->d_seq_start.as<int64_t>();
+    a.row_start = c->row_start.as<u32>(); a.rowlen = c->rowlen.as<u32>(); a.cols = c->cols.as<u32>(); a.vals = c->vals.as<double>();
+    a.gmin = gmin.as<double>(); a.gmaxinv = gmaxinv.as<double>(); a.N = c->N;
+    a.n_members = K; a.mem_og = d_mem_og.as<int32_t>(); a.og_off = d_og_off.as<int64_t>(); a.out_off = d_out_off.as<int64_t>();
+    a.mem_sp = d_sp.as<int32_t>(); a.mem_seq = d_seq.as<int32_t>(); a.M = dM.as<double>(); a.D = dD.as<double>();
+    a.og_max = d_max.as<unsigned long long>();
+    dendro_minmax_kernel<<<(unsigned)((c->N + 7) / 8), 256, 0, c->stream>>>(a);
+    dendro_rows_kernel<<<(unsigned)((K + 7) / 8), 256, 0, c->stream>>>(a);
+    if (complete) dendro_complete_kernel<<<(unsigned)((K + 7) / 8), 256, 0, c->stream>>>(a);
+    if (cudaGetLastError() != cudaSuccess) return done(fail(c, OFG_ERR_CUDA, "distance matrix kernels failed to launch"));
+    cudaError_t e = cudaMemcpyAsync(host_out, complete ? dD.p : dM.p, (size_t)E * 8, cudaMemcpyDeviceToHost, c->stream);
+    std::vector<unsigned long long> mx((size_t)n_ogs);
+    if (e == cudaSuccess && host_max_og && complete) e = cudaMemcpyAsync(mx.data(), d_max.p, (size_t)n_ogs * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return done(fail(c, OFG_ERR_CUDA, "distance matrices: %s", cudaGetErrorString(e)));
+    if (host_max_og)
+        for (int64_t g = 0; g < n_ogs; g++) {
+            unsigned long long b = complete ? mx[(size_t)g] : max_init[0];
+            b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+            memcpy(&host_max_og[g], &b, 8);
+        }
+    return done(OFG_OK);
 }
 
 int ofg_pair_fit(ofg_ctx* c, int p, int j, double out[6])

@@ -47,6 +47,7 @@ struct ParseArgs {
     u64* pair_valid;  // [P]
     u64* pair_err;    // [P] min over offending lines of (byte offset << 4 | kind), ~0 if none
     u32 one;          // 1 (opaque to the compiler: see chunk_masks_fast)
+    int keep_self;    // qExcludeSelfHits = False (DendroBLAST's raw matrices, orthologues.py:272-274)
 };
 
 // One warp's staging area.  Positions are "stream offsets": bytes from the start of the segment; the ring index
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 4) parse_kernel(ParseArgs a)
             f.text_len = d.text_len;
             f.seg_a = (seg - a.seg_prefix[pair]) * (int64_t)PS_SEG;
             f.row_base = (u32)d.row_base; f.Gi = (u32)d.Gi; f.Gj = (u32)d.Gj;
-            f.same = d.same != 0; f.swap = d.swap != 0;
+            f.same = d.same != 0 && !a.keep_self; f.swap = d.swap != 0;
         }
         const int64_t len_rel64 = f.text_len - f.seg_a;  // bytes of the file from the segment start on (multiple of 16)
         const u32 b_rel = (u32)(len_rel64 < (int64_t)PS_SEG ? len_rel64 : (int64_t)PS_SEG);  // starts below this offset are ours

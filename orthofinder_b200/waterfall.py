@@ -216,6 +216,19 @@ class GraphBuilder:
         self._ck(self.lib.ofg_get_stat(self.h, name.encode(), ctypes.byref(v)))
         return v.value
 
+    def dendro_matrices(self, og_off, species, iseq, complete=False):
+        """DendroBLAST matrices of orthogroups on the raw scores (ofg_dendro_matrices; orthologues.py:264-291, 396-410).
+        Returns (flat float64 array of sum n^2 values, max_og per orthogroup)."""
+        og_off = np.ascontiguousarray(og_off, np.int64)
+        species = np.ascontiguousarray(species, np.int32)
+        iseq = np.ascontiguousarray(iseq, np.int32)
+        n_ogs = og_off.size - 1
+        sizes = np.diff(og_off)
+        out = np.empty(int((sizes * sizes).sum()), np.float64)
+        mx = np.empty(max(n_ogs, 1), np.float64)
+        self._ck(self.lib.ofg_dendro_matrices(self.h, n_ogs, _vp(og_off), _vp(species), _vp(iseq), int(bool(complete)), _vp(out), out.size, _vp(mx)))
+        return out, mx[:n_ogs]
+
     def wait_for(self, other):
         """Order this context's stream after everything enqueued on `other`'s (no host block)."""
         self._ck(self.lib.ofg_wait_for(self.h, other.h))
@@ -585,10 +598,13 @@ class WaterfallMethod:
 
     @staticmethod
     def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
-                   builder=None, n_readers=None, homology=False, device_gunzip=True):
+                   builder=None, n_readers=None, homology=False, device_gunzip=True, stage=None, keep_self_hits=False):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
         the device-resident graph.  Returns the GraphBuilder holding it.
-        homology=True: the `--c-homologs` graph of gathering_version (3, 2) instead (gathering.py:51-73, 520-521)."""
+        homology=True: the `--c-homologs` graph of gathering_version (3, 2) instead (gathering.py:51-73, 520-521).
+        stage=_lib.STAGE_RAW with keep_self_hits=True: only the raw matrices of GetBLAST6Scores(qExcludeSelfHits=False), what
+        DendroBLAST reads (orthologues.py:272-274; orthofinder_b200/dendroblast.py)."""
+        stage = _lib.STAGE_GRAPH if stage is None else stage
         gb = builder or GraphBuilder(device)
         sp = list(seqsInfo.speciesToUse)
         n_seqs = [seqsInfo.nSeqsPerSpecies[k] for k in sp]
@@ -596,6 +612,7 @@ class WaterfallMethod:
         gb.set_option("allow_empty", int(q_allow_empty))
         gb.set_option("scores_v2", int(bool(v2_scores)))  # --scores-v2: gathering.py:157-174, :314-388
         gb.set_option("homology_graph", int(bool(homology)))
+        gb.set_option("keep_self_hits", int(bool(keep_self_hits)))
         cells = []
         for p, kp in enumerate(sp):
             for j, kj in enumerate(sp):
@@ -632,15 +649,18 @@ class WaterfallMethod:
                 print("ERROR: Error processing files Blast%d_*" % i_sp)
             raise
         try:
-            gb.build(_lib.STAGE_GRAPH)
+            gb.build(stage)
         except OfgError as e:
             if device_gunzip and e.code == _lib.ERR_PARSE and " gzip: " in e.message:
                 # a .gz the device could not inflate (e.g. concatenated members without size hints, which look like one member
                 # with a wrong length): let zlib decide - it either inflates the file or raises what gzip.open raises
                 return WaterfallMethod.BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast, v2_scores, q_allow_empty, device,
-                                                  gb, n_readers, homology, device_gunzip=False)
+                                                  gb, n_readers, homology, device_gunzip=False, stage=stage,
+                                                  keep_self_hits=keep_self_hits)
             WaterfallMethod._report(e, sp, blastDir_list)
             raise
+        if stage < _lib.STAGE_NORM:
+            return gb
         for p in range(len(sp)):
             for j in range(len(sp)):
                 f = gb.pair_fit(p, j)

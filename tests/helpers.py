@@ -51,6 +51,27 @@ class Golden:
         return self.texts[(p, j)]
 
 
+class DendroGolden:
+    """Orthogroups and the live reference's DendroBLAST matrices / Phylip files for one dataset
+    (tools/make_golden_dendro.py; orthologues.py:264-291, 396-431)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, "dendro_" + name + ".npz"))
+        self.og_off = z["og_off"]
+        self.og_sp = z["og_sp"]          # species list positions
+        self.og_seq = z["og_seq"]
+        self.ogs = [[(int(self.og_sp[k]), int(self.og_seq[k])) for k in range(self.og_off[g], self.og_off[g + 1])]
+                    for g in range(self.og_off.size - 1)]
+        n = np.diff(self.og_off)
+        eo = np.concatenate(([0], np.cumsum(n * n)))
+        self.M = [z["M"][eo[g]:eo[g + 1]].reshape(n[g], n[g]) for g in range(n.size)]
+        self.D = [z["D"][eo[g]:eo[g + 1]].reshape(n[g], n[g]) for g in range(n.size)]
+        blob = zlib.decompress(z["phy_z"].tobytes())
+        po = np.concatenate(([0], np.cumsum(z["phy_sizes"])))
+        self.phylip = [blob[po[g]:po[g + 1]] for g in range(n.size)]
+        self.provenance = str(z["provenance"])
+
+
 def parse_graph_text(graph):
     """OrthoFinder_graph.txt -> (n, list of (row, [(col, 'w.www')...]))."""
     lines = graph.split(b"\n")

@@ -1042,3 +1042,133 @@ def _write_wd_plain(g, wd):
         for j, kj in enumerate(g.species):
             with open(wd + "Blast%d_%d.txt" % (kp, kj), "wb") as f:
                 f.write(g.hit_text(p, j))
+
+
+# ------------------------------------------------------------------------------------------ DendroBLAST matrices
+def _dendro_check(flatM, flatD, mx, g, dg):
+    from orthofinder_b200 import dendroblast
+    assert np.array_equal(flatM, np.concatenate([m.ravel() for m in dg.M]))      # every operation is IEEE-exact: bit-equal
+    want = np.concatenate([d.ravel() for d in dg.D])
+    fin = np.isfinite(want)
+    assert np.array_equal(flatD[~fin], want[~fin])
+    assert np.all(np.abs(flatD[fin] - want[fin]) <= 1e-12 * np.maximum(np.abs(want[fin]), 1e-3))   # CUDA log vs numpy's: <= 1 ulp
+    o = 0
+    for iog, og in enumerate(dg.ogs):
+        n = len(og)
+        d = flatD[o:o + n * n].reshape(n, n)
+        o += n * n
+        low = dg.D[iog][np.tril_indices(n, -1)]
+        assert abs(mx[iog] - max(-9e99, low.max())) <= 1e-12 * abs(mx[iog])
+        text = dendroblast.phylip_text(d, ["%d_%d" % (g.species[p], q) for p, q in og], mx[iog])
+        assert text == dg.phylip[iog], (iog, "Phylip text differs from the live reference's")
+
+
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_dendroblast_matrices_equal_reference(gb, name):
+    """orthologues.py:264-291 (raw scores with self hits, per-gene min / max, M), :396-410 (completion) and :413-431 (Phylip
+    text) against the live reference's goldens (tools/make_golden_dendro.py)."""
+    from tests.helpers import DendroGolden
+    g, dg = Golden(name), DendroGolden(name)
+    gb.set_option("keep_self_hits", 1)
+    try:
+        _load(gb, g.n_seqs, g.lengths, g.hit_text)
+        gb.build(_lib.STAGE_RAW)
+        indptr, cols, vals = gb.pair_csr(0, 0)
+        e = wo.get_blast6_scores(g.hit_text(0, 0), g.n_seqs[0], g.n_seqs[0], False)   # qExcludeSelfHits=False
+        assert np.array_equal(indptr, e[0]) and np.array_equal(cols, e[1].astype(np.uint32)) and np.array_equal(vals, e[2])
+        flatM, _ = gb.dendro_matrices(dg.og_off, dg.og_sp, dg.og_seq, complete=False)
+        flatD, mx = gb.dendro_matrices(dg.og_off, dg.og_sp, dg.og_seq, complete=True)
+        _dendro_check(flatM, flatD, mx, g, dg)
+        with pytest.raises(waterfall.OfgError, match="keep_self_hits"):
+            gb.build(_lib.STAGE_GRAPH)
+        bad = dg.og_seq.copy()
+        bad[3] = g.n_seqs[dg.og_sp[3]]
+        with pytest.raises(waterfall.OfgError, match="does not exist"):
+            gb.dendro_matrices(dg.og_off, dg.og_sp, bad)
+    finally:
+        gb.set_option("keep_self_hits", 0)
+    gb.build(_lib.STAGE_NORM)
+    with pytest.raises(waterfall.OfgError, match="raw scores"):
+        gb.dendro_matrices(dg.og_off, dg.og_sp, dg.og_seq)
+
+
+@pytest.mark.parametrize("double", [True, False])
+def test_dendroblast_working_directory_entry_point(tmp_path, double):
+    """dendroblast.DendroBLASTTrees on a working directory (hit files partly .gz, two-way and one-way searches) against the
+    oracle, and the Phylip files it writes against the live reference's (two-way)."""
+    import gzip
+    from oracle import dendroblast_oracle as do
+    from orthofinder_b200 import dendroblast
+    from tests.helpers import DendroGolden
+    g, dg = Golden("ref_AddTwoSpecies"), DendroGolden("ref_AddTwoSpecies")
+    wd = str(tmp_path) + "/"
+    _write_wd_plain(g, wd)
+    for k, fn in enumerate(sorted(f for f in os.listdir(wd) if f.startswith("Blast"))):
+        if k % 3 == 0:
+            with open(wd + fn, "rb") as f:
+                data = f.read()
+            with open(wd + fn + ".gz", "wb") as f:
+                f.write(gzip.compress(data, 1))
+            os.remove(wd + fn)
+    sp, n_all, _ = waterfall.GetSpeciesToUse(wd + "SpeciesIDs.txt")
+    si = waterfall.GetSeqsInfo([wd], sp, n_all)
+    ogs = [[(g.species[p], q) for p, q in og] for og in dg.ogs] + [[(g.species[0], 0), (g.species[1], 1), (g.species[2], 2)]]   # the last one has < 4 genes
+    t = dendroblast.DendroBLASTTrees(si, [wd], qDoubleBlast=double)
+    try:
+        kept, M = t.GetOGMatrices_FullParallel(ogs)
+        assert len(kept) == len(dg.ogs)                     # orthologues.py:334-337
+        want = do.og_matrices(g.n_seqs, g.hit_text, dg.ogs, q_double_blast=double)
+        for a, b in zip(M, want):
+            assert np.array_equal(a, b)
+        os.mkdir(wd + "Distances")
+        t.CompleteAndWriteOGMatrices(kept, lambda iog: wd + "Distances/OG%07d.phy" % iog)
+        for iog in range(len(kept)):
+            with open(wd + "Distances/OG%07d.phy" % iog, "rb") as f:
+                text = f.read()
+            if double:
+                assert text == dg.phylip[iog], iog
+            else:
+                d, mx = do.complete(want[iog])
+                assert text == do.phylip_text(d, ["%d_%d" % x for x in kept[iog]], mx), iog
+    finally:
+        t.close()
+
+
+def test_dendroblast_large_orthogroups_equal_oracle(gb):
+    """Orthogroups of several hundred genes (rows longer than a warp, members of every species) on a 6 x 2000 job."""
+    from oracle import dendroblast_oracle as do
+    P = synth.params(seed=99, hq=12, p_missing=200, p_nohit=30)
+    S, G = 6, 2000
+    ids, n_seqs, L = list(range(S)), [G] * S, synth.make_lengths(S, G, 99)
+    rng = np.random.default_rng(5)
+    sizes = [700, 260, 33, 32, 5, 4]
+    ogs = [[(int(p), int(q)) for p, q in zip(rng.integers(0, S, n), rng.choice(G, n, replace=False))] for n in sizes]
+    og_off = np.cumsum([0] + sizes)
+    sp = np.array([p for og in ogs for p, _ in og], np.int32)
+    sq = np.array([q for og in ogs for _, q in og], np.int32)
+    lib = synth.host_lib()
+    texts = {(p, j): synth.pair_text(lib, P, p, j, ids[p], ids[j], L[p], L[j])[0] for p in range(S) for j in range(S)}
+    gb.set_option("keep_self_hits", 1)
+    try:
+        _load(gb, n_seqs, L, lambda p, j: texts[(p, j)])
+        gb.build(_lib.STAGE_RAW)
+        flatM, _ = gb.dendro_matrices(og_off, sp, sq, complete=False)
+        flatD, mx = gb.dendro_matrices(og_off, sp, sq, complete=True)
+    finally:
+        gb.set_option("keep_self_hits", 0)
+    want = do.og_matrices(n_seqs, lambda p, j: texts[(p, j)], ogs)
+    assert np.array_equal(flatM, np.concatenate([m.ravel() for m in want]))
+    o = 0
+    for iog, m in enumerate(want):
+        n = m.shape[0]
+        with np.errstate(divide="ignore"):
+            d = -np.log(m + m.T)
+        got = flatD[o:o + n * n].reshape(n, n)
+        o += n * n
+        off = ~np.eye(n, dtype=bool)
+        fin = np.isfinite(d) & off
+        assert np.array_equal(got[off & ~fin], d[off & ~fin])
+        assert np.all(np.abs(got[fin] - d[fin]) <= 1e-12 * np.maximum(np.abs(d[fin]), 1e-3))
+        assert np.array_equal(np.diag(got), np.diag(m))
+        low = d[np.tril_indices(n, -1)]
+        assert abs(mx[iog] - max(-9e99, low.max())) <= 1e-12 * abs(mx[iog])

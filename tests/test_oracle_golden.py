@@ -103,3 +103,19 @@ def test_oracle_reproduces_reference_homology_graph(name):
     text = wo.graph_text(res["indptr"], res["indices"], res["data"], sum(g.n_seqs))
     assert text == g.graph_hom, "oracle homology graph differs from the live reference's (%s)" % g.provenance
     assert np.all(res["data"] == 1.0) and res["indices"].size > g.graph.count(b":")
+
+
+@pytest.mark.parametrize("name", REF_GOLDENS + SYNTH_GOLDENS)
+def test_oracle_reproduces_reference_dendroblast_matrices(name):
+    """DendroBLAST distance matrices (orthologues.py:264-291 worker on raw scores with self hits, :396-410 completion,
+    :413-431 Phylip text); goldens from the live reference's own functions (tools/make_golden_dendro.py)."""
+    from oracle import dendroblast_oracle as do
+    from tests.helpers import DendroGolden
+    g, dg = Golden(name), DendroGolden(name)
+    M = do.og_matrices(g.n_seqs, g.hit_text, dg.ogs)
+    assert len(M) == len(dg.M) > 0
+    for iog, (og, m) in enumerate(zip(dg.ogs, M)):
+        assert np.array_equal(m, dg.M[iog]), (name, iog)
+        d, max_og = do.complete(m)
+        assert np.array_equal(d, dg.D[iog]), (name, iog)
+        assert do.phylip_text(d, ["%d_%d" % (g.species[p], q) for p, q in og], max_og) == dg.phylip[iog], (name, iog)

@@ -65,6 +65,27 @@ def test_live_reference_equals_oracle_and_goldens(name):
                     assert g.fits[p, j, 0] == pars[0] and g.fits[p, j, 1] == pars[1]
 
 
+@pytest.mark.parametrize("name,double", [("AddTwoSpecies", True), ("FromTrees", True), ("removeFirst", True), ("FromTrees", False)])
+def test_live_reference_dendroblast_equals_oracle_and_goldens(name, double):
+    """the reference's own worker / completion / Phylip writer (orthologues.py:264-291, 396-431) on the orthogroups
+    of the committed goldens == oracle/dendroblast_oracle.py (bit for bit) == the goldens."""
+    from oracle import dendroblast_oracle as do
+    from tests.helpers import DendroGolden
+    sub, golden = FIXTURES[name]
+    wd = os.path.join(REF_TESTS, sub)
+    g, dg = Golden(golden), DendroGolden(golden)
+    ids = [[(g.species[p], q) for p, q in og] for og in dg.ogs]
+    ref = rh.run_reference_dendroblast(wd, ids, q_double_blast=double)
+    M = do.og_matrices(g.n_seqs, g.hit_text, dg.ogs, q_double_blast=double)
+    for iog, og in enumerate(ids):
+        assert np.array_equal(M[iog], ref["M"][iog]), iog
+        d, max_og = do.complete(M[iog])
+        assert np.array_equal(d, ref["D"][iog]), iog
+        assert do.phylip_text(d, ["%d_%d" % x for x in og], max_og) == ref["phylip"][iog], iog
+        if double:
+            assert np.array_equal(dg.M[iog], ref["M"][iog]) and np.array_equal(dg.D[iog], ref["D"][iog]) and dg.phylip[iog] == ref["phylip"][iog]
+
+
 @pytest.mark.parametrize("name", ["AddTwoSpecies", "removeMiddle", "Issue83"])
 def test_live_reference_equals_oracle_with_v2_scores(name):
     wd = os.path.join(REF_TESTS, FIXTURES[name][0])
