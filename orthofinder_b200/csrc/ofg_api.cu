@@ -1418,6 +1418,7 @@ int ofg_add_hits_gz(ofg_ctx* c, int p, int j, const void* host_ptr, size_t nbyte
         GzMember m;
         m.in_off = (u64)cbase + ds; m.in_len = end - ds - 8; m.out_off = raw_total; m.file = pi; m.pad = 0;
         m.out_len = (u64)d[end - 4] | ((u64)d[end - 3] << 8) | ((u64)d[end - 2] << 16) | ((u64)d[end - 1] << 24);
+        if (m.in_len >= 0xffffff00ull) return fail(c, OFG_ERR_UNSUPPORTED, "Blast file of pair (%d,%d): a gzip member of 4 GiB or more", p, j);
         raw_total += m.out_len;
         ms.push_back(m);
         o = end;

@@ -16,6 +16,8 @@ typedef uint32_t u32;
 #define __shared__ static
 #define __launch_bounds__(x)
 static inline void __syncwarp() {}
+static inline void __syncwarp(unsigned) {}
+static inline int __any_sync(unsigned, int p) { return p; }
 static inline u32 lane_id() { return 0; }
 static inline u32 __brev(u32 x) { u32 r = 0; for (int i = 0; i < 32; i++) if (x & (1u << i)) r |= 1u << (31 - i); return r; }
 static inline u32 __funnelshift_r(u32 lo, u32 hi, int sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
