@@ -113,6 +113,8 @@ int ofg_hits_text_copy(ofg_ctx* ctx, int p, int j, void* host_dst, size_t cap);
  * "sel_capacity_frac_inv" (selection capacity = records/this, default 4), "reserve_text_bytes" (size the text arena
  * once), "reserve_gz_bytes" (the same for the compressed arena of ofg_add_hits_gz), "wave_species" (RAW + NORM run over this many query species at a time out of one set of scratch buffers -
  * the reference's "one query species per task", gathering.py:484-485; 0 = the whole partition at once),
+ * "rowsort_short" (-1 = decide per wave from the text bytes per row (default), 0 = never, 1 = always: rows of at most 16 records are
+ * sorted by half a warp each),
  * "length_sort_radix" (0/1: build the length bins with the segmented LSD radix sort only - the fallback of the bucket path),
  * "async" (0/1: ofg_build only enqueues; counts, errors and sizes are read back by ofg_sync or by the first accessor),
  * "scores_v2" (0/1): the `--scores-v2` variant of the path - NormalisedBitScore (gathering.py:157-174)

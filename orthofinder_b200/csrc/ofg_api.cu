@@ -94,6 +94,7 @@ struct ofg_ctx {
     int64_t sel_frac_inv = 4;
     bool homology = false;      // option homology_graph: `--c-homologs` (gathering.py:51-73, 520-521) instead of the connect / RBH graph
     bool keep_self = false;     // option keep_self_hits: qExcludeSelfHits=False of GetBLAST6Scores (DendroBLAST, orthologues.py:272-274); RAW stage only
+    int rowsort_short = -1;     // option rowsort_short: -1 = by the wave's text bytes per row, 0 = never, 1 = always use the half-warp sort for rows <= 16 records
     bool radix_only = false;    // option length_sort_radix: always take the LSD radix path (the fallback of the bucket path)
     int64_t fallback_waves = 0; // waves of the last build that took the radix path
     int wave_species = 0;       // option wave_species: query species per wave (0: the whole partition in one wave)
@@ -549,7 +550,14 @@ int wave_raw(ofg_ctx* c, int wi)
     r.key = c->key.as<u32>(); r.slot0 = rs; r.keyval = nullptr; r.key_sentinel = 1u << (c->key_bits - 1);
     r.long_rows = c->long_rows.as<u32>(); r.n_long = (u32*)(small_ptr(c) + 1); r.pair_nnz = pair_nnz_ptr(c);
     r.scratch_cols = c->coo_col.as<u32>(); r.scratch_vals = c->coo_val.as<double>();
+    // rows of a few records (jobs with a handful of hits per query and target species) go through the half-warp kernel first
+    const bool short_rows = c->rowsort_short >= 0 ? c->rowsort_short != 0 : (nr > 0 && (double)w.text_bytes / 60.0 / (double)nr < 32.0);
+    r.short_max = short_rows ? ROWSORT_SHORT : 0;
     if (nr > 0) {
+        if (short_rows) {
+            rowsort_short_kernel<<<grid_for(c, nr, 64, 8), 256, 0, c->stream>>>(r);
+            CKL("rowsort_short_kernel");
+        }
         rowsort_kernel<<<grid_for(c, nr, ROWSORT_WARPS, 16), ROWSORT_WARPS * 32, 0, c->stream>>>(r);
         CKL("rowsort_kernel");
         rowsort_long_kernel<<<c->n_sm * 2, 256, 0, c->stream>>>(r);
@@ -1068,7 +1076,7 @@ int stage_homology(ofg_ctx* c)
 }
 
 const char* const STAGE_OF_KERNEL[][2] = {
-    {"inflate_kernel", "0"}, {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_long_kernel", "1"},
+    {"inflate_kernel", "0"}, {"parse_kernel", "0"}, {"scatter_rows_kernel", "1"}, {"rowsort_kernel", "1"}, {"rowsort_short_kernel", "1"}, {"rowsort_long_kernel", "1"},
     {"wave_layout_kernel", "2"}, {"rs_desc_kernel", "2"}, {"radix_hist_kernel", "2"}, {"radix_scatter_kernel", "2"},
     {"bk_hist_kernel", "2"}, {"bk_scan_kernel", "2"}, {"bk_route_kernel", "2"}, {"bk_gather_kernel", "2"}, {"bk_split_kernel", "2"}, {"bk_binhist_kernel", "2"}, {"bk_thr_kernel", "3"}, {"bk_cand_kernel", "3"},
     {"bin_tasks_kernel", "3"}, {"bin_cut_kernel", "3"}, {"bin_select_kernel", "3"}, {"pair_sel_off_kernel", "4"}, {"fit_kernel", "4"},
@@ -1328,6 +1336,7 @@ int ofg_set_option(ofg_ctx* c, const char* name, int64_t value)
     else if (!strcmp(name, "async")) c->async = value != 0;
     else if (!strcmp(name, "length_sort_radix")) c->radix_only = value != 0;
     else if (!strcmp(name, "keep_self_hits")) { c->keep_self = value != 0; c->stage_done = 0; }
+    else if (!strcmp(name, "rowsort_short")) c->rowsort_short = (int)value;
     else if (!strcmp(name, "homology_graph")) { c->homology = value != 0; c->stage_done = std::min(c->stage_done, (int)OFG_STAGE_NORM); }
     else if (!strcmp(name, "reserve_text_bytes")) { cudaSetDevice(c->device); return text_reserve(c, value); }
     else if (!strcmp(name, "reserve_gz_bytes")) { cudaSetDevice(c->device); CK(c->gz_comp.ensure((size_t)value + 64)); }

@@ -182,6 +182,7 @@ struct RowSortArgs {
     u64* pair_nnz;             // [P]
     u32* scratch_cols;         // long-row scratch (same indexing as cols)
     double* scratch_vals;
+    int short_max;             // rows of at most this many records were sorted by rowsort_short_kernel (0: none)
 };
 
 __device__ __forceinline__ bool rs_before(u32 cj, double vj, int j, u32 ck, double vk, int k)
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
         nx_pair = pair;
         nx_lj = p_lj;
         nx_Lq = a.lengths[p_li + (row - p_rb)];
-        if (nx_n <= 64) {
+        if (nx_n <= 64 && nx_n > a.short_max) {
             if (lane < nx_n) { nx_c0 = a.cols[nx_s0 + lane]; nx_v0 = a.vals[nx_s0 + lane]; }
             if (lane + 32 < nx_n) { nx_c1 = a.cols[nx_s0 + lane + 32]; nx_v1 = a.vals[nx_s0 + lane + 32]; }
         }
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
             fetch_records();
             row -= ROWSORT_WARPS;
         }
+        if (a.short_max > 0 && n <= a.short_max) continue;   // done by rowsort_short_kernel
         if (n == 0) {
             if (lane == 0) a.rowlen[cur_row] = 0;
             continue;
@@ -408,6 +410,124 @@ __global__ void __launch_bounds__(ROWSORT_WARPS * 32, 8) rowsort_kernel(RowSortA
         }
         __syncwarp();
     }
+}
+
+// Short rows (at most ROWSORT_SHORT = 16 records: every row of a job with a handful of hits per query and target species,
+// BASELINE C4) - half a warp per row, two rows per warp, everything in registers: one record per lane, a 16-element bitonic
+// network on packed (column << 4 | input index) words, the scores and length products fetched from the lane that read them.
+// A warp-per-row kernel leaves 3/4 of its lanes idle on such rows (C4: 8.8 records per row).  Launched before rowsort_kernel,
+// which then skips these rows (RowSortArgs.short_max).
+constexpr int ROWSORT_SHORT = 16;
+__global__ void __launch_bounds__(256) rowsort_short_kernel(RowSortArgs a)
+{
+    const int lane = (int)lane_id(), hl = lane & 15, hbase = lane & 16;
+    u32* const key_rel = a.key - *a.slot0;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nr = a.n_rows - a.row_begin;
+    int64_t per_warp = (nr + n_warps - 1) / n_warps;
+    per_warp += per_warp & 1;   // even: the two halves of a warp alternate rows of one contiguous run
+    const int64_t r0 = a.row_begin + wid * per_warp;
+    const int64_t r1 = r0 + per_warp < a.n_rows ? r0 + per_warp : a.n_rows;
+    if (r0 >= r1) return;
+    int pair = upper_bound_dev(a.pair_row_base, a.P + 1, r0) - 1;
+    int64_t pair_end = a.pair_row_base[pair + 1];
+    int64_t p_li = a.pairs[pair].li_off, p_lj = a.pairs[pair].lj_off, p_rb = a.pairs[pair].row_base;
+    unsigned long long acc_nnz = 0;   // stored entries of pair acc_pair not yet added to pair_nnz (first lane of each half)
+    int acc_pair = pair;
+    // software pipeline: extents of the row two steps ahead and records of the row one step ahead are in flight while a row is sorted
+    const int half = hbase >> 4;
+    auto extent = [&](int64_t rb, u32* s0, int* n) {
+        const int64_t r = rb + half;
+        *s0 = 0; *n = ROWSORT_SHORT + 1;
+        if (rb < r1 && r < r1) { *s0 = a.row_start[r]; *n = (int)(a.row_start[r + 1] - *s0); }
+    };
+    u32 nx_k = 0xffffffffu;
+    double nx_v = 0.0, nx_Lq = 0.0;
+    int64_t nx_lj = p_lj;
+    int nx_pair = pair;
+    auto fetch = [&](int64_t rb, u32 s0, int n) {   // records of this half's row of step rb (extents s0, n)
+        const int64_t r = rb + half;
+        nx_k = 0xffffffffu; nx_v = 0.0;
+        if (rb < r1 && r < r1) {
+            if (r >= pair_end) {
+                while (r >= a.pair_row_base[pair + 1]) pair++;
+                pair_end = a.pair_row_base[pair + 1];
+                p_li = a.pairs[pair].li_off; p_lj = a.pairs[pair].lj_off; p_rb = a.pairs[pair].row_base;
+            }
+            if (n <= ROWSORT_SHORT && hl < n) {
+                nx_k = (a.cols[s0 + hl] << 4) | (u32)hl;
+                nx_v = a.vals[s0 + hl];
+                nx_Lq = a.lengths[p_li + (r - p_rb)];
+            }
+        }
+        nx_pair = pair;
+        nx_lj = p_lj;
+    };
+    u32 e1_s0, e2_s0;
+    int e1_n, e2_n;
+    extent(r0, &e1_s0, &e1_n);
+    extent(r0 + 2, &e2_s0, &e2_n);
+    fetch(r0, e1_s0, e1_n);
+    for (int64_t rb = r0; rb < r1; rb += 2) {
+        const int64_t row = rb + half;
+        const bool valid = row < r1;
+        const u32 s0 = e1_s0;
+        const int n = e1_n;
+        u32 k = nx_k;
+        const double v = nx_v;
+        const int cur_pair = nx_pair;
+        // the length of the hit sequence is gathered while the next row is fetched and this one is sorted
+        const double lprod = k != 0xffffffffu ? nx_Lq * a.lengths[nx_lj + (k >> 4)] : 0.0;
+        e1_s0 = e2_s0; e1_n = e2_n;
+        extent(rb + 4, &e2_s0, &e2_n);
+        fetch(rb + 2, e1_s0, e1_n);
+        const bool todo = valid && n <= ROWSORT_SHORT;
+        if (!__any_sync(OFG_FULL, todo)) continue;
+        if (todo && cur_pair != acc_pair) {
+            if (hl == 0 && acc_nnz) atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_nnz[acc_pair]), acc_nnz);
+            acc_nnz = 0;
+            acc_pair = cur_pair;
+        }
+#pragma unroll
+        for (int kk = 2; kk <= 16; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const u32 o = __shfl_xor_sync(OFG_FULL, k, j);
+                const bool lower = (hl & j) == 0, asc = (hl & kk) == 0 || kk == 16;
+                k = (lower == asc) ? min(k, o) : max(k, o);
+            }
+        }
+        // sorted position hl holds k; the score and length product sit in the lane that loaded record (k & 15)
+        const int src = hbase | (int)(k & 15u);
+        double vs = __shfl_sync(OFG_FULL, v, src);
+        const u32 lfs = __shfl_sync(OFG_FULL, (u32)lprod, src);
+        const u32 prev = __shfl_up_sync(OFG_FULL, k, 1);
+        const bool in = k != 0xffffffffu;
+        const bool head = in && (hl == 0 || (prev >> 4) != (k >> 4));
+        const u32 hb = (__ballot_sync(OFG_FULL, head) >> hbase) & 0xffffu;
+        if (__any_sync(OFG_FULL, in && !head)) {
+            // duplicate HSP lines of a column (rare): the first record of the run takes the maximum of the run
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const double ov = __shfl_down_sync(OFG_FULL, vs, d);
+                const u32 ok = __shfl_down_sync(OFG_FULL, k, d);
+                if (hl + d < 16 && ok != 0xffffffffu && (ok >> 4) == (k >> 4) && ov > vs) vs = ov;
+            }
+        }
+        if (todo) {
+            const int outn = __popc(hb);
+            if (head) {
+                const u32 pos = s0 + (u32)(__popc(hb & ((2u << hl) - 1u)) - 1);
+                a.cols[pos] = k >> 4;
+                a.vals[pos] = vs;
+                key_rel[pos] = lfs;
+            }
+            if (hl >= outn && hl < n) key_rel[s0 + hl] = a.key_sentinel;
+            if (hl == 0) { a.rowlen[row] = (u32)outn; acc_nnz += (unsigned long long)outn; }
+        }
+    }
+    if (hl == 0 && acc_nnz) atomicAdd(reinterpret_cast<unsigned long long*>(&a.pair_nnz[acc_pair]), acc_nnz);
 }
 
 // Rows longer than ROWSORT_MAXN: one CTA per row, O(n^2) rank sort through global scratch.  Rare

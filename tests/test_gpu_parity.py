@@ -1172,3 +1172,32 @@ def test_dendroblast_large_orthogroups_equal_oracle(gb):
         assert np.array_equal(np.diag(got), np.diag(m))
         low = d[np.tril_indices(n, -1)]
         assert abs(mx[iog] - max(-9e99, low.max())) <= 1e-12 * abs(mx[iog])
+
+
+@pytest.mark.parametrize("name", ["ref_AddTwoSpecies", "synth_C2_tiny", "synth_C5_small"])
+def test_half_warp_row_sort_gives_the_same_matrices_and_graph(gb, name):
+    """Rows of at most 16 records can be sorted by half a warp each (rowsort_short_kernel, the C4 regime of a few hits per query and
+    target species); rows above that stay with the warp-per-row kernel.  Forced on and off: same raw matrices (max over duplicate
+    HSP lines included), same graph text as the live reference."""
+    g = Golden(name)
+    S = len(g.n_seqs)
+    raw = {}
+    for mode in (1, 0):
+        gb.set_option("rowsort_short", mode)
+        try:
+            _load(gb, g.n_seqs, g.lengths, g.hit_text)
+            gb.build(_lib.STAGE_RAW)
+            raw[mode] = [gb.pair_csr(p, j) for p in range(S) for j in range(S)]
+            gb.build(_lib.STAGE_GRAPH)
+            assert waterfall.graph_header(sum(g.n_seqs)) + gb.graph_text_body().tobytes() + waterfall.GRAPH_FOOTER == g.graph, mode
+            rep = gb.kernel_report()
+            assert ("rowsort_short_kernel" in rep) == bool(mode)
+        finally:
+            gb.set_option("rowsort_short", -1)
+    n_short = 0
+    for a, b in zip(raw[1], raw[0]):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        n_short += int((np.diff(a[0]) <= 16).sum())
+    assert n_short > 0
+    e = wo.get_blast6_scores(g.hit_text(0, 1), g.n_seqs[0], g.n_seqs[1], False)
+    assert np.array_equal(raw[1][1][0], e[0]) and np.array_equal(raw[1][1][1], e[1].astype(np.uint32)) and np.array_equal(raw[1][1][2], e[2])
