@@ -759,7 +759,9 @@ int wave_norm(ofg_ctx* c, int wi)
         sa.rowfac = c->rowfac.as<double>(); sa.colfac = c->colfac.as<double>(); sa.rowmax = c->rowmax.as<double>();
         sa.best = c->best.as<double>();
         sa.row_flagcnt = c->row_flagcnt.as<u32>();
-        scale_bh_kernel<16><<<grid_for(c, nr, 16, 8), 256, 0, c->stream>>>(sa);
+        // lanes per row by the wave's records per row (estimated from its text size: ~60 bytes per hit line)
+        if ((double)w.text_bytes / 60.0 / (double)nr < 14.0) scale_bh_kernel<8><<<grid_for(c, nr, 32, 8), 256, 0, c->stream>>>(sa);
+        else scale_bh_kernel<16><<<grid_for(c, nr, 16, 8), 256, 0, c->stream>>>(sa);
         CKL("scale_bh_kernel");
     }
     return 0;

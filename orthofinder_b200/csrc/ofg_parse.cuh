@@ -281,6 +281,27 @@ __device__ __forceinline__ bool swar_id(const uint8_t* s_text, u32 end, int len,
     *out = v;
     return act && shape && dig;
 }
+// The same for fields of 9..16 bytes ("123_45678": more than 99 species or more than 99 999 sequences per species): the
+// underscore must lie in the last 8 bytes, the bytes in front of that window are only checked for a second underscore.
+// Called from a warp-uniform branch that is not taken while every id of a round fits 8 bytes.
+__device__ __forceinline__ u64 swar_id_long(const uint8_t* s_text, u32 end, int len, bool act)   // (ok << 32) | value
+{
+    act = act && len > 8 && len <= 16;
+    const u32 e = act ? end : 16u;
+    const int l = act ? len : 16;
+    const u64 w = load8_ending_at(s_text, e), w2 = load8_ending_at(s_text, e - 8u);
+    const u64 us = zero_bytes64(w ^ 0x5f5f5f5f5f5f5f5fULL);
+    const u64 um1 = us - 1ULL;
+    const bool one = us != 0 && (us & um1) == 0;
+    const u64 M = ~(us | um1);
+    const bool shape = one && M != 0;
+    const u64 X = (w & M) | (0x3030303030303030ULL & ~M);
+    u32 v;
+    const bool dig = swar_digits8(X, &v);
+    const u64 vm2 = ~0ULL << (8 * (16 - l));                     // the len - 8 bytes in front of the window
+    const bool head_ok = (zero_bytes64(w2 ^ 0x5f5f5f5f5f5f5f5fULL) & vm2) == 0;
+    return ((u64)(act && shape && dig && head_ok) << 32) | (u64)v;
+}
 
 // "<digits>[.<digits>]" of length 1..8 ending at byte `end`, at most 8 digits: exact fp64 value.
 __device__ __forceinline__ bool swar_score(const uint8_t* s_text, u32 end, int len, bool act, double* out)
@@ -361,8 +382,12 @@ __device__ __forceinline__ void ps_round(const ParseArgs& a, PsWarp& sw, const P
     u32 f0 = 0, f1 = 0;
     int tab1, tab2, tab11, lend;
     bool fast = locate_fields_conv(sw, st, nx, has_next && !from_global, &tab1, &tab2, &tab11, &lend);
-    const bool ok0 = swar_id(sw.text, st + (u32)tab1, tab1, fast, &f0);
-    const bool ok1 = swar_id(sw.text, st + (u32)tab2, tab2 - tab1 - 1, fast, &f1);
+    bool ok0 = swar_id(sw.text, st + (u32)tab1, tab1, fast, &f0);
+    bool ok1 = swar_id(sw.text, st + (u32)tab2, tab2 - tab1 - 1, fast, &f1);
+    if (__any_sync(OFG_FULL, fast && (tab1 > 8 || tab2 - tab1 - 1 > 8))) {   // ids of 9..16 characters in this round
+        if (!ok0) { const u64 r = swar_id_long(sw.text, st + (u32)tab1, tab1, fast); if (r >> 32) { ok0 = true; f0 = (u32)r; } }
+        if (!ok1) { const u64 r = swar_id_long(sw.text, st + (u32)tab2, tab2 - tab1 - 1, fast); if (r >> 32) { ok1 = true; f1 = (u32)r; } }
+    }
     const bool ok2 = swar_score(sw.text, st + (u32)lend, lend - tab11 - 1, fast, &score);
     fast = fast && ok0 && ok1 && ok2;
     if (act) {

@@ -1201,3 +1201,34 @@ def test_half_warp_row_sort_gives_the_same_matrices_and_graph(gb, name):
     assert n_short > 0
     e = wo.get_blast6_scores(g.hit_text(0, 1), g.n_seqs[0], g.n_seqs[1], False)
     assert np.array_equal(raw[1][1][0], e[0]) and np.array_equal(raw[1][1][1], e[1].astype(np.uint32)) and np.array_equal(raw[1][1][2], e[2])
+
+
+def test_long_sequence_identifiers_take_the_fast_path_and_parse_like_the_reference(gb):
+    """Ids of 9..16 characters ("123_45678": more than 99 species or more than 99 999 sequences per species) are parsed by the
+    warp-converged path like the short ones; ids with two underscores, 17+ characters or an underscore in front of an 8+ digit number
+    go through the generic parser.  All must give int(field.split('_', 2)[1]) (blast_file_processor.py:71-72)."""
+    rng = np.random.default_rng(11)
+    n_seqs = [150000, 1200]
+    L = [np.clip(np.round(rng.lognormal(5.8, 0.6, n)), 30, 5000) for n in n_seqs]
+    shapes = [b"%d_%d", b"123_%d", b"1234567_%d", b"sp12345678_%d", b"x_%d_7", b"12345678901_%d", b"abcdefghijklmnop_%d", b"9_%d"]
+
+    def text(p, j, n_lines):
+        out = []
+        for _ in range(n_lines):
+            q = int(rng.integers(0, n_seqs[p]))
+            s = int(rng.integers(0, n_seqs[j]))
+            fq = shapes[int(rng.integers(0, len(shapes)))]
+            fs = shapes[int(rng.integers(0, len(shapes)))]
+            fq = fq % ((p, q) if fq == b"%d_%d" else (q,))
+            fs = fs % ((j, s) if fs == b"%d_%d" else (s,))
+            out.append(fq + b"\t" + fs + b"\t50.0\t10\t1\t0\t1\t10\t1\t10\t1e-5\t%.1f\n" % (20 + 300 * rng.random()))
+        return b"".join(out)
+    texts = {(p, j): text(p, j, 4000) for p in range(2) for j in range(2)}
+    _load(gb, n_seqs, L, lambda p, j: texts[(p, j)])
+    gb.build(_lib.STAGE_RAW)
+    for p in range(2):
+        for j in range(2):
+            indptr, cols, vals = gb.pair_csr(p, j)
+            e = wo.get_blast6_scores(texts[(p, j)], n_seqs[p], n_seqs[j], p == j)
+            assert np.array_equal(indptr, e[0]) and np.array_equal(cols, e[1].astype(np.uint32)) and np.array_equal(vals, e[2]), (p, j)
+    assert gb.counts()["lines"] == 16000
