@@ -542,9 +542,26 @@ class GzBytes(bytes):
     """The raw bytes of a .gz hit file (to be inflated on the device)."""
 
 
+def gz_has_size_hints(data):
+    """True if the first gzip member carries its compressed size in a "BC" extra field (bgzip / BGZF, gzip_members): such
+    files split into members without inflating, so the device can inflate them with one warp per member.  A classic
+    single-member file (what DIAMOND's --compress 1 writes) is one warp's work on the device - host zlib is faster there."""
+    if len(data) < 18 or data[0] != 0x1f or data[1] != 0x8b or not (data[3] & 4):
+        return False
+    xlen = data[10] | (data[11] << 8)
+    o, end = 12, min(12 + xlen, len(data))
+    while o + 4 <= end:
+        ln = data[o + 2] | (data[o + 3] << 8)
+        if data[o] == 0x42 and data[o + 1] == 0x43 and ln == 2:
+            return True
+        o += 4 + ln
+    return False
+
+
 def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty, raw_gz=False):
     """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted).
-    raw_gz: hand .gz files over compressed (GzBytes) instead of inflating them with zlib on the host."""
+    raw_gz: hand .gz files over compressed (GzBytes) instead of inflating them with zlib on the host; "auto": only the files
+    whose members carry size hints (gz_has_size_hints), the others are inflated here, in the reader thread."""
     fn = None
     for d in blastDir_list:
         fn = os.path.join(d, "Blast%d_%d.txt" % (iSpecies, jSpecies))
@@ -556,10 +573,11 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty, raw_gz=Fals
         raise FileNotFoundError(fn)
     if os.path.exists(fn + ".gz"):
         with open(fn + ".gz", "rb") as f:
-            if raw_gz:
-                return GzBytes(f.read()), fn
+            raw = f.read()
+            if raw_gz is True or (raw_gz == "auto" and gz_has_size_hints(raw)):
+                return GzBytes(raw), fn
             try:
-                return _gunzip(f.read()), fn
+                return _gunzip(raw), fn
             except (EOFError, zlib.error) as e:
                 e.hit_file = (iSpecies, jSpecies, d)
                 raise
@@ -598,12 +616,15 @@ class WaterfallMethod:
 
     @staticmethod
     def BuildGraph(seqsInfo, blastDir_list, Lengths, qDoubleBlast=True, v2_scores=False, q_allow_empty=False, device=0,
-                   builder=None, n_readers=None, homology=False, device_gunzip=True, stage=None, keep_self_hits=False):
+                   builder=None, n_readers=None, homology=False, device_gunzip="auto", stage=None, keep_self_hits=False):
         """ProcessBlastHits + ConnectCognates for every species (gathering.py:177-196,251-259), up to
         the device-resident graph.  Returns the GraphBuilder holding it.
         homology=True: the `--c-homologs` graph of gathering_version (3, 2) instead (gathering.py:51-73, 520-521).
         stage=_lib.STAGE_RAW with keep_self_hits=True: only the raw matrices of GetBLAST6Scores(qExcludeSelfHits=False), what
-        DendroBLAST reads (orthologues.py:272-274; orthofinder_b200/dendroblast.py)."""
+        DendroBLAST reads (orthologues.py:272-274; orthofinder_b200/dendroblast.py).
+        device_gunzip: "auto" - .gz files whose members carry size hints (bgzip / BGZF layout) are inflated on the device, one
+        warp per member, classic single-member files by zlib in the reader threads (a single member is one warp's work on the
+        device); True - every .gz file goes to the device; False - every .gz file is inflated on the host."""
         stage = _lib.STAGE_GRAPH if stage is None else stage
         gb = builder or GraphBuilder(device)
         sp = list(seqsInfo.speciesToUse)
@@ -619,7 +640,7 @@ class WaterfallMethod:
                 swap = (not qDoubleBlast) and kp > kj  # blast_file_processor.py:41-54
                 cells.append((kj if swap else kp, kp if swap else kj, p, j, swap))
         try:
-            for (_, _, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers, raw_gz=device_gunzip):
+            for (i_open, j_open, p, j, swap), data, fn in read_hit_files(blastDir_list, cells, q_allow_empty, n_readers, raw_gz=device_gunzip):
                 if data is None:
                     continue
                 if isinstance(data, GzBytes):
@@ -634,7 +655,7 @@ class WaterfallMethod:
                         try:
                             data = _gunzip(data)
                         except (EOFError, zlib.error) as e2:
-                            e2.hit_file = (cells[0][0], cells[0][1], blastDir_list[0])
+                            e2.hit_file = (i_open, j_open, os.path.dirname(fn) + "/")
                             raise
                 gb.add_hits(p, j, data, swap_cols=swap)
         except (EOFError, zlib.error) as e:
@@ -719,7 +740,7 @@ def GetGraphFilename(wd_current, i_unassigned=None, fileIdentifierString="OrthoF
 
 
 def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empty=None, device=0, blastDir_list=None,
-                       v2_scores=False, i_unassigned=None, wd_current=None, n_readers=None):
+                       v2_scores=False, i_unassigned=None, wd_current=None, n_readers=None, device_gunzip="auto"):
     """The part of gathering.DoOrthogroups between :476 and :512 for a `-b <dir> -og` run: reads SpeciesIDs.txt /
     Species*.fa from workingDir and Blast*_*.txt[.gz] from blastDir_list (default [workingDir]; the first directory
     holding a file wins, files.py:313-322) and writes the graph file.
@@ -739,7 +760,7 @@ def DoOrthogroupsGraph(workingDir, graphFN=None, qDoubleBlast=True, q_allow_empt
     if q_allow_empty is None:
         q_allow_empty = q_unassigned   # gathering.py:492 passes q_unassigned as q_allow_empty
     gb = WaterfallMethod.BuildGraph(si, dirs, L, qDoubleBlast=qDoubleBlast, v2_scores=v2_scores, q_allow_empty=q_allow_empty,
-                                    device=device, n_readers=n_readers)
+                                    device=device, n_readers=n_readers, device_gunzip=device_gunzip)
     if graphFN is None:
         graphFN = GetGraphFilename(wd_current or workingDir, i_unassigned)
     WaterfallMethod.WriteGraphParallel(gb, si, graphFN)

@@ -1025,9 +1025,14 @@ def test_working_directory_with_compressed_hit_files_inflated_on_the_device(tmp_
             z = gzip.compress(data[:len(data) // 2], 1) + gzip.compress(data[len(data) // 2:], 1)
         open(wd + fn + ".gz", "wb").write(z)
         os.remove(wd + fn)
-    graph_fn, gb2, si = waterfall.DoOrthogroupsGraph(wd, graphFN=wd + "OrthoFinder_graph.txt")
-    assert open(graph_fn, "rb").read() == g.graph
-    gb2.close()
+    for mode in ("auto", True):   # auto: hinted members on the device, single-member files by zlib in the reader threads
+        graph_fn, gb2, si = waterfall.DoOrthogroupsGraph(wd, graphFN=wd + "OrthoFinder_graph.txt", device_gunzip=mode)
+        assert open(graph_fn, "rb").read() == g.graph
+        on_device = "inflate_kernel" in gb2.kernel_report()
+        assert on_device == (layout == "bgzf" or (mode is True and layout == "single")), (layout, mode)
+        gb2.close()
+    z = open(wd + "Blast0_0.txt.gz", "rb").read()
+    assert waterfall.gz_has_size_hints(z) == (layout == "bgzf")
 
 
 def _write_wd_plain(g, wd):

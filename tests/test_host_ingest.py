@@ -71,3 +71,22 @@ def test_truncated_gzip_raises_like_gzip_open(tmp_path):
     assert ei.value.hit_file[:2] == (0, 1) and 0 < len(ei.value.partial) < len(data)
     with pytest.raises(EOFError):
         list(w.read_hit_files([d], [(0, 1), (0, 1)], n_readers=2))
+
+
+def test_size_hint_detection_of_gzip_layouts():
+    """BuildGraph(device_gunzip="auto") sends a .gz file to the device only if its members can be located from their headers
+    (bgzip / BGZF "BC" extra field); everything else is inflated by zlib in the reader threads."""
+    import gzip
+    from orthofinder_b200 import waterfall
+    data = b"0_0\t1_1\t1\t1\t1\t1\t1\t1\t1\t1\t1e-5\t50\n" * 5000
+    assert waterfall.gz_has_size_hints(waterfall.gzip_members(data, chunk=30000))
+    assert not waterfall.gz_has_size_hints(gzip.compress(data, 1))
+    assert not waterfall.gz_has_size_hints(b"")
+    assert not waterfall.gz_has_size_hints(data)
+    # another extra subfield in front of the size hint, and an extra field without one
+    hinted = bytearray(waterfall.gzip_members(data[:100]))
+    other = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x0c\x00XY\x02\x00\x00\x00" + bytes(hinted[12:18]) + bytes(hinted[18:])
+    assert waterfall.gz_has_size_hints(other)
+    nohint = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00XY\x02\x00\x00\x00" + bytes(hinted[18:])
+    assert not waterfall.gz_has_size_hints(nohint)
+    assert gzip.decompress(waterfall.gzip_members(data, chunk=30000)) == data
