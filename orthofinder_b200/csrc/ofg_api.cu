@@ -689,7 +689,7 @@ int wave_norm(ofg_ctx* c, int wi)
             CKL("bk_binhist_kernel");
             bk_thr_kernel<<<grid_for(c, max_tasks, 8, 8), 256, 0, c->stream>>>(kc);
             CKL("bk_thr_kernel");
-            bk_cand_kernel<<<grid_for(c, max_tiles, 1, 4), 512, 0, c->stream>>>(k, kc);
+            bk_cand_kernel<<<grid_for(c, max_tiles, 1, 3), 512, 0, c->stream>>>(k, kc);
             CKL("bk_cand_kernel");
             BinArgs bu = b;
             bu.n_tasks_dev = n_tasks_nw_ptr(c); bu.key = nullptr; bu.val = nullptr; bu.rec = c->bk_rec.as<uint4>();

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) bk_thr_kernel(BkCandArgs c)
 }
 
 // ---- 7: the candidates of every bin, appended (in arbitrary order) to the bin's slot range
-__global__ void __launch_bounds__(512) bk_cand_kernel(BkArgs a, BkCandArgs c)
+__global__ void __launch_bounds__(512, 3) bk_cand_kernel(BkArgs a, BkCandArgs c)
 {
     const int64_t n_tiles = *a.n_tiles_nw;
     const int64_t voff = (int64_t)*a.slot0;
