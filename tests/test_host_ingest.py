@@ -90,3 +90,24 @@ def test_size_hint_detection_of_gzip_layouts():
     nohint = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00XY\x02\x00\x00\x00" + bytes(hinted[18:])
     assert not waterfall.gz_has_size_hints(nohint)
     assert gzip.decompress(waterfall.gzip_members(data, chunk=30000)) == data
+
+
+def test_phylip_writer_matches_the_reference_bytes():
+    """dendroblast.phylip_text (host formatting of orthologues.py:413-431 WritePhylipMatrix) on the live reference's completed
+    matrices: -inf -> 1.1 * max_og, values in (0, 1e-6) -> 1e-6, "%.6f", zero diagonal, no "-0"."""
+    import numpy as np
+    from orthofinder_b200 import dendroblast
+    from tests.helpers import Golden, DendroGolden
+    for name in ("ref_AddTwoSpecies", "synth_C5_small"):
+        g, dg = Golden(name), DendroGolden(name)
+        n_inf = 0
+        for iog, og in enumerate(dg.ogs):
+            d = dg.D[iog]
+            low = d[np.tril_indices(d.shape[0], -1)]
+            max_og = max(-9e99, low.max())
+            names = ["%d_%d" % (g.species[p], q) for p, q in og]
+            assert dendroblast.phylip_text(d, names, max_og) == dg.phylip[iog], (name, iog)
+            n_inf += int(np.isinf(d).sum())
+        assert name != "synth_C5_small" or n_inf > 0
+    tiny = np.array([[0.5, 2e-7, -0.0], [2e-7, 0.1, -np.inf], [-0.0, -np.inf, 0.3]])
+    assert dendroblast.phylip_text(tiny, ["a", "b", "c"], 2.0) == b"3\na 0.000000 0.000001 0.000000\nb 0.000001 0.000000 2.200000\nc 0.000000 2.200000 0.000000\n"
