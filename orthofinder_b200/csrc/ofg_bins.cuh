@@ -232,23 +232,26 @@ __global__ void __launch_bounds__(512) bk_gather_kernel(BkArgs a)
 }
 
 // ---- 4: the word at every boundary rank; one warp per boundary bucket
-constexpr int BKS_WARPS = 2;   // 2 x 16 KB of words + the select histograms: static shared memory
+constexpr int BKS_WARPS = 8;
+constexpr int BKS_STAGE = 512;   // words of a boundary bucket staged in shared memory (larger buckets, up to BK_CAP, are selected from global memory)
 __global__ void __launch_bounds__(BKS_WARPS * 32) bk_split_kernel(BkArgs a)
 {
-    __shared__ u64 s_bits_all[BKS_WARPS][BK_CAP];
+    __shared__ u64 s_bits_all[BKS_WARPS][BKS_STAGE];
     __shared__ u32 s_hist_all[BKS_WARPS][256];
     const int w = threadIdx.x >> 5, lane = lane_id();
-    u64* s_bits = s_bits_all[w];
+    u64* s_stage = s_bits_all[w];
     u32* s_hist = s_hist_all[w];
     const u32 n_bb = *a.n_bb;
     const int64_t n_warps = (int64_t)gridDim.x * BKS_WARPS;
     for (int64_t i = (int64_t)blockIdx.x * BKS_WARPS + w; i < (int64_t)n_bb; i += n_warps) {
         const BbDesc d = a.bb[i];
         const int n = (int)d.cnt;
+        const bool staged = n <= BKS_STAGE;
+        const u64* s_bits = staged ? s_stage : a.list + d.off;
         u64 vmin = ~0ULL, vmax = 0ULL;
         for (int k = lane; k < n; k += 32) {
             const u64 v = a.list[d.off + k];
-            s_bits[k] = v;
+            if (staged) s_stage[k] = v;
             vmin = v < vmin ? v : vmin;
             vmax = v > vmax ? v : vmax;
         }

@@ -891,6 +891,22 @@ def test_degenerate_lengths_route_to_the_radix_path(gb):
         _check_against_oracle(gb, [G] * S, L, procs=1)
 
 
+def test_boundary_buckets_of_several_hundred_hits_stay_on_the_bucket_path(gb):
+    """Sixteen distinct protein lengths: ~136 distinct length products per pair, i.e. boundary buckets of 350 to ~1400 hits - below the fallback limit (2048) but above what bk_split_kernel stages in shared memory (512 words), so the
+    split words are selected straight from global memory.  No radix fallback, fits bit-equal to the oracle."""
+    S, G = 3, 3000
+    P = synth.params(seed=77, hq=30)
+    rng = np.random.default_rng(77)
+    lens = np.array([90., 113., 131., 157., 181., 211., 263., 311., 383., 457., 563., 701., 907., 1009., 1201., 1499.])
+    L = [rng.choice(lens, G) for _ in range(S)]
+    gb.set_species([G] * S, L)
+    gb.synth_hits(P, list(range(S)))
+    gb.build()
+    assert gb.stat("radix_fallback_waves") == 0
+    _, n_fit = _check_against_oracle(gb, [G] * S, L, procs=2)
+    assert n_fit == S * S
+
+
 def test_bucket_path_on_a_mid_size_job_with_small_and_large_bins(gb):
     """Pairs of very different sizes in one job (bins of 20, 200 and 1000 hits, pairs below 100 hits taken whole, an empty
     pair): 6 species with 40 ... 3000 genes, against the oracle."""
