@@ -206,3 +206,56 @@ def run_reference_dendroblast(wd, ogs, q_double_blast=True):
             phy.append(f.read())
     shutil.rmtree(out, ignore_errors=True)
     return dict(M=M, D=D, phylip=phy, seqsInfo=si)
+
+
+# ---------------------------------------------------------------- the consumer: the bundled mcl binary
+MCL_BINARY = os.path.join(REFERENCE_ROOT, "scripts_of", "bin", "mcl")
+
+
+def read_mcl_binary_matrix(path):
+    """A matrix written by the binary with --write-binary (canonical domains): (colptr i64, rows i32, vals f32)."""
+    import numpy as np
+    b = open(path, "rb").read()
+    nc, nr, fl = np.frombuffer(b[4:28], dtype="<i8")
+    assert fl == 3, "non-canonical domains"
+    offs = np.frombuffer(b[28:28 + 8 * (nc + 1)], dtype="<i8")
+    base = 28 + 8 * (nc + 1)
+    rec = np.dtype([("i", "<i4"), ("v", "<f4")])
+    colptr = np.zeros(nc + 1, np.int64)
+    parts = []
+    for c in range(nc):
+        o = base + int(offs[c])
+        n = int(np.frombuffer(b[o:o + 8], dtype="<i8")[0])
+        parts.append(np.frombuffer(b[o + 24:o + 24 + 8 * n], dtype=rec))
+        colptr[c + 1] = colptr[c] + n
+    a = np.concatenate(parts) if parts else np.zeros(0, rec)
+    return colptr, a["i"].astype(np.int32), a["v"].astype(np.float32)
+
+
+def run_mcl_binary(graph_text, inflation, workdir, dump_iterands=False, extra=(), threads=1):
+    """Runs the reference's bundled mcl exactly as RunMCL does (scripts_of/mcl.py:214-218: `mcl graph -I <inflation>
+    -o clusters -te <n> -V all`) on `graph_text`; returns dict(clusters_text, iterands=[(colptr, rows, vals), ...] incl.
+    the start matrix when dump_iterands, expanded=(...) when extra holds -write-expanded)."""
+    import glob
+    import subprocess
+    os.makedirs(workdir, exist_ok=True)
+    for f in glob.glob(os.path.join(workdir, "ite-*.D")):
+        os.remove(f)
+    g = os.path.join(workdir, "graph.txt")
+    with open(g, "wb") as fh:
+        fh.write(graph_text if isinstance(graph_text, bytes) else graph_text.encode())
+    cmd = [MCL_BINARY, "graph.txt", "-I", str(inflation), "-o", "clusters.txt", "-te", str(threads), "-V", "all"]
+    if dump_iterands:
+        cmd += ["--write-binary", "-dump", "ite", "-dump-stem", "D", "-dump-interval", "0:100000"]
+    cmd += list(extra)
+    subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = {"clusters_text": open(os.path.join(workdir, "clusters.txt")).read()}
+    if dump_iterands:
+        k, its = 0, []
+        while os.path.exists(os.path.join(workdir, "ite-%d.D" % k)):
+            its.append(read_mcl_binary_matrix(os.path.join(workdir, "ite-%d.D" % k)))
+            k += 1
+        out["iterands"] = its
+    if "-write-expanded" in extra:
+        out["expanded"] = read_mcl_binary_matrix(os.path.join(workdir, extra[list(extra).index("-write-expanded") + 1]))
+    return out

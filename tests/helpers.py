@@ -100,3 +100,115 @@ def graph_text_diff(a, b):
         else:
             dec_diff += sum(w1 != w2 for (_, w1), (_, w2) in zip(e1, e2))
     return edge_diff, dec_diff
+
+
+def mcl_graph_text(n, cols):
+    """MCL 'matrix' text exactly as WriteGraphParallel / WriteGraph_perSpecies lay it out (gathering.py:39-48, :279-280)."""
+    out = ["(mclheader\nmcltype matrix\ndimensions %dx%d\n)\n" % (n, n), "\n(mclmatrix\nbegin\n\n"]
+    for i in range(n):
+        out.append("%d    " % i + "".join("%d:%.3f " % (j, w) for j, w in sorted(cols[i].items())) + "$\n")
+    out.append(")\n")
+    return "".join(out).encode()
+
+
+def mcl_synthetic_graph(kind):
+    """Seeded graphs for the MCL step beyond what the golden datasets exercise.
+    'family': one gene family of 1 250 genes with ~28 hits each (columns of the expansion pass the selection number
+    1 100 and the recovery number 1 400 of mcl's default scheme; the dense product walk), 60 four-gene cliques, genes
+    without edges.  'ties': exactly symmetric structures (a gene between two equal triangles / two equal stars, cycles and
+    paths with equal weights, weights that print as 0.000) - overlap cut, attractor systems of several genes."""
+    rng = np.random.default_rng(20261020)
+    if kind == "family":
+        n, fam = 1600, 1250
+        cols = [dict() for _ in range(n)]
+        for i in range(fam):
+            for j in rng.choice(fam, 28, replace=False):
+                if i != j:
+                    w = float(rng.uniform(0.05, 2.5))
+                    cols[i][int(j)] = w
+                    if rng.random() < 0.9:
+                        cols[int(j)][i] = w * float(rng.uniform(0.8, 1.2))
+        for i in range(fam, fam + 240, 4):
+            for a in range(i, i + 4):
+                for b in range(i, i + 4):
+                    if a != b:
+                        cols[a][b] = float(rng.uniform(0.3, 2.0))
+        return mcl_graph_text(n, cols)
+    if kind == "ties":
+        cols, base = [], 0
+
+        def block(k):
+            nonlocal base
+            cols.extend(dict() for _ in range(k))
+            base += k
+            return base - k
+
+        def add(a, b, w):
+            cols[a][b] = w
+            cols[b][a] = w
+        for rep in range(6):
+            o = block(7)                       # gene o+3 between two equal triangles
+            for tri in ((0, 1, 2), (4, 5, 6)):
+                for a in tri:
+                    for b in tri:
+                        if a < b:
+                            add(o + a, o + b, 1.0)
+            for k in (0, 1, 2, 4, 5, 6):
+                add(o + 3, o + k, 0.2 + 0.1 * rep)
+            o = block(10)                      # gene o+3 between two equal stars (hubs o+5 and o+1), o+4 isolated
+            for leaf in (0, 6, 7):
+                add(o + 5, o + leaf, 1.0)
+            for leaf in (2, 8, 9):
+                add(o + 1, o + leaf, 1.0)
+            add(o + 3, o + 5, 0.3)
+            add(o + 3, o + 1, 0.3)
+            o = block(5 + rep)                 # cycle with equal weights
+            for a in range(5 + rep):
+                add(o + a, o + (a + 1) % (5 + rep), 0.75)
+            o = block(4 + rep)                 # path with equal weights
+            for a in range(3 + rep):
+                add(o + a, o + a + 1, 1.5)
+            o = block(3)                       # an edge that prints as 0.000 (dropped when mcl reads it) and a one-way edge
+            cols[o][o + 1] = 0.0004
+            cols[o + 1][o + 2] = 0.8
+        block(3)
+        return mcl_graph_text(base, cols)
+    raise KeyError(kind)
+
+
+def matrix_digest(colptr, rows, vals):
+    """SHA-256 over a column-compressed float matrix (int64 pointers, int32 rows, float32 bit patterns)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(colptr, np.int64).tobytes())
+    h.update(np.ascontiguousarray(rows, np.int32).tobytes())
+    h.update(np.ascontiguousarray(vals, np.float32).tobytes())
+    return h.hexdigest()
+
+
+class MclGolden:
+    """What the reference's bundled mcl binary produced for one golden graph (tools/make_golden_mcl.py)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, "mcl_%s.npz" % name))
+        self.inflations = [float(x) for x in z["inflations"]]
+        self._z = z
+
+    def _tag(self, inflation):
+        return "I%s" % str(float(inflation)).replace(".", "_")
+
+    def clusters_body(self, inflation):
+        return zlib.decompress(self._z[self._tag(inflation) + "_clusters_z"].tobytes()).decode()
+
+    def iterations(self, inflation):
+        return int(self._z[self._tag(inflation) + "_iterations"])
+
+    def digests(self, inflation):
+        return [str(x) for x in self._z[self._tag(inflation) + "_sha256"]], [int(x) for x in self._z[self._tag(inflation) + "_nnz"]]
+
+
+MCL_GOLDENS = REF_GOLDENS + SYNTH_GOLDENS + ["synth_family", "synth_ties"]
+
+
+def mcl_golden_graph(name):
+    return mcl_synthetic_graph(name[len("synth_"):]) if name in ("synth_family", "synth_ties") else Golden(name).graph
