@@ -222,6 +222,51 @@ int ofg_graph_csr_copy(ofg_ctx* ctx, int64_t* row_ids, int64_t* indptr, int32_t*
 int ofg_graph_text_size(ofg_ctx* ctx, size_t* nbytes);
 int ofg_graph_text_copy(ofg_ctx* ctx, void* host_dst, size_t cap);
 
+/* Device pointers of the finished graph of a context that owns every species (single GPU): row_off[g] = first edge of
+ * gene g (n_rows entries; the end of the last row is nnz), global column indices, fp64 weights.  Owned by ctx, valid
+ * until the next build or ofg_destroy; everything enqueued on the context's stream has completed on return.  This is
+ * what ofg_mcl_set_graph_dev takes, so the graph never leaves the device between WriteGraphParallel's replacement and
+ * RunMCL's (gathering.py:512 -> :517). */
+int ofg_graph_dev(ofg_ctx* ctx, int64_t* n_rows, int64_t* nnz, const uint64_t** row_off_dev, const int32_t** indices_dev,
+                  const double** weights_dev);
+
+/* ---- MCL on the device ------------------------------------------------------------------
+ * Replaces the external process of MCL.RunMCL (scripts_of/mcl.py:214-218: `mcl graphFilename -I inflation -o
+ * clustersFilename -te nProcesses -V all`, bundled binary scripts_of/bin/mcl = mcl 14-137 with its default resource
+ * scheme: prune 10000, select 1100, recover 1400, recover percentage 90).  The result is the body of the clusters file
+ * the binary writes - what GetPredictedOGs (mcl.py:36-63) and ConvertSingleIDsToIDPair (mcl.py:93-125) read - and the
+ * per-gene cluster index.  One handle per GPU; calls on one handle are not thread-safe.  Every entry point returns
+ * OFG_OK or a negative OFG_ERR_* code, message via ofg_mcl_last_error. */
+typedef struct ofg_mcl ofg_mcl;
+int ofg_mcl_create(ofg_mcl** out, int device);
+void ofg_mcl_destroy(ofg_mcl* m);
+const char* ofg_mcl_last_error(ofg_mcl* m);
+/* the binary's -P, -S, -R, -pct (percent), -sparse and -L options; defaults = the binary's */
+int ofg_mcl_set_params(ofg_mcl* m, int prune_number, int select_number, int recover_number, double recover_pct, int sparse_overhead,
+                       int max_iterations);
+/* scratch budgets per batch of columns: slots of global-memory hash tables (12 bytes each), stage entries (8 bytes each) */
+int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries);
+/* the graph as the binary reads it from a file: column c = line c of the graph file, rows ascending, the float values
+ * of the printed weights (host arrays; entries that read as 0 and loops are dropped like the binary does) */
+int ofg_mcl_set_graph_host(ofg_mcl* m, int64_t n, const int64_t* colptr, const int32_t* rows, const float* vals);
+/* the graph of ofg_graph_dev, on the same device: weights go through "%.3f" -> strtod -> float on the device, exactly the
+ * values the binary would have read from OrthoFinder_graph.txt */
+int ofg_mcl_set_graph_dev(ofg_mcl* m, int64_t n, const uint64_t* row_off_dev, int64_t nnz, const int32_t* indices_dev,
+                          const double* weights_dev);
+/* the whole process: expansion / inflation until the chaos falls below 1e-4, then the clusters */
+int ofg_mcl_run(ofg_mcl* m, double inflation);
+/* one iteration / the clusters of the current iterand (parity tests against the binary's -dump ite files) */
+int ofg_mcl_step(ofg_mcl* m, double inflation, double* chaos);
+int ofg_mcl_interpret(ofg_mcl* m);
+int ofg_mcl_iterand_copy(ofg_mcl* m, int64_t* colptr, int32_t* rows, float* vals);   /* nnz from ofg_mcl_result */
+/* any pointer may be NULL; n_clusters / n_overlap are -1 before the first clustering; ms = device time of the last run */
+int ofg_mcl_result(ofg_mcl* m, int64_t* iterations, int64_t* n_clusters, int64_t* n_overlap, double* last_chaos, int64_t* nnz, float* ms,
+                   int64_t* n_launches);
+/* labels[g] = index of gene g's cluster in the order of the clusters file (size descending, then smallest member) */
+int ofg_mcl_labels(ofg_mcl* m, int32_t* labels, int64_t n);
+/* the clusters file from "(mclheader" on, byte for byte what the binary writes after its "# cline:" comment line */
+int ofg_mcl_clusters_text(ofg_mcl* m, char* buf, size_t cap, size_t* need);
+
 /* Kernel timing of the last ofg_build (CUDA events on the library's stream), milliseconds per group:
  * 0 parse, 1 rows (bucket + row sort), 2 length sort, 3 select, 4 fit, 5 scale+BH, 6 thresholds,
  * 7 connect, 8 emit, 9 total.  n_launches = kernels launched by the last build. */

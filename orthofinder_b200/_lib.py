@@ -20,7 +20,9 @@ SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "of
            "ofg_pair_fit", "ofg_graph_csr_size", "ofg_graph_csr_copy", "ofg_graph_text_size", "ofg_graph_text_copy",
            "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_sync", "ofg_get_stat", "ofg_dendro_matrices", "ofg_wait_for", "ofg_export_flags_peer",
            "ofg_import_flags_peer", "ofg_device_alloc", "ofg_device_free", "ofg_ipc_get_handle", "ofg_ipc_open_handle",
-           "ofg_ipc_close_handle", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
+           "ofg_ipc_close_handle", "ofg_graph_dev", "ofg_mcl_create", "ofg_mcl_destroy", "ofg_mcl_last_error", "ofg_mcl_set_params",
+           "ofg_mcl_set_budgets", "ofg_mcl_set_graph_host", "ofg_mcl_set_graph_dev", "ofg_mcl_run", "ofg_mcl_step", "ofg_mcl_interpret",
+           "ofg_mcl_iterand_copy", "ofg_mcl_result", "ofg_mcl_labels", "ofg_mcl_clusters_text", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
 _lib = None
 
@@ -40,6 +42,10 @@ def load():
     lib.ofg_stream.argtypes = [ctypes.c_void_p]
     lib.ofg_destroy.restype = None
     lib.ofg_destroy.argtypes = [ctypes.c_void_p]
+    lib.ofg_mcl_last_error.restype = ctypes.c_char_p
+    lib.ofg_mcl_last_error.argtypes = [ctypes.c_void_p]
+    lib.ofg_mcl_destroy.restype = None
+    lib.ofg_mcl_destroy.argtypes = [ctypes.c_void_p]
     vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t
     sigs = {
         "ofg_create": [ctypes.POINTER(vp), i32],
@@ -79,6 +85,20 @@ def load():
         "ofg_graph_text_copy": [vp, vp, sz],
         "ofg_last_timing": [vp, vp, ctypes.POINTER(i64)],
         "ofg_kernel_report": [vp, ctypes.c_char_p, sz],
+        "ofg_graph_dev": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
+        "ofg_mcl_create": [ctypes.POINTER(vp), i32],
+        "ofg_mcl_set_params": [vp, i32, i32, i32, ctypes.c_double, i32, i32],
+        "ofg_mcl_set_budgets": [vp, i64, i64],
+        "ofg_mcl_set_graph_host": [vp, i64, vp, vp, vp],
+        "ofg_mcl_set_graph_dev": [vp, i64, vp, i64, vp, vp],
+        "ofg_mcl_run": [vp, ctypes.c_double],
+        "ofg_mcl_step": [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)],
+        "ofg_mcl_interpret": [vp],
+        "ofg_mcl_iterand_copy": [vp, vp, vp, vp],
+        "ofg_mcl_result": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
+                           ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i64)],
+        "ofg_mcl_labels": [vp, vp, i64],
+        "ofg_mcl_clusters_text": [vp, vp, sz, ctypes.POINTER(sz)],
         "ofg_test_log10": [vp, vp, vp, i64],
         "ofg_test_format": [vp, vp, vp, i64],
         "ofg_test_parse_score": [vp, ctypes.c_char_p, i64, vp, vp, i64],

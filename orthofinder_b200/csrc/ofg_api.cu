@@ -2083,6 +2083,23 @@ int ofg_graph_csr_copy(ofg_ctx* c, int64_t* row_ids, int64_t* indptr, int32_t* i
     return OFG_OK;
 }
 
+int ofg_graph_dev(ofg_ctx* c, int64_t* n_rows, int64_t* nnz, const uint64_t** row_off_dev, const int32_t** indices_dev,
+                  const double** weights_dev)
+{
+    if (!c) return OFG_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (int rc_ = sync_results(c)) return rc_;
+    if (c->stage_done < OFG_STAGE_GRAPH) return fail(c, OFG_ERR_ARG, "graph not built yet");
+    if (c->n_owned_genes != c->N) return fail(c, OFG_ERR_ARG, "the device graph of a partitioned context holds only its own rows");
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_rows) *n_rows = c->n_owned_genes;
+    if (nnz) *nnz = c->tot_edges;
+    if (row_off_dev) *row_off_dev = (const uint64_t*)c->cnt_off.p;
+    if (indices_dev) *indices_dev = c->out_indices.as<int32_t>();
+    if (weights_dev) *weights_dev = c->out_data.as<double>();
+    return OFG_OK;
+}
+
 int ofg_graph_text_size(ofg_ctx* c, size_t* nbytes)
 {
     if (!c || !nbytes) return OFG_ERR_ARG;

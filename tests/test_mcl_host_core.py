@@ -1,0 +1,96 @@
+"""CPU: the MCL engine of libofg (ofg_mcl_driver.h + the per-column functions of ofg_mcl_core.h that the CUDA kernels
+run) compiled for the host and walked phase by phase (libofg_hostcheck.so) - against what the reference's bundled mcl
+binary produced (tests/golden/mcl_*.npz): every iterand bit for bit, the clusters file body byte for byte.  The host build
+uses glibc's pow like the binary; on the device CUDA's pow may differ in the last place (tests/test_zz_mcl_gpu.py)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import MCL_GOLDENS, MclGolden, matrix_digest, mcl_golden_graph
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "orthofinder_b200")
+
+
+def _lib():
+    L = ctypes.CDLL(os.path.join(PKG, "libofg_hostcheck.so"))
+    L.ofg_hostcheck_mcl_new.restype = ctypes.c_void_p
+    L.ofg_hostcheck_mcl_free.argtypes = [ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_params.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                           ctypes.c_long, ctypes.c_long]
+    L.ofg_hostcheck_mcl_start.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_step.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_nnz.restype = ctypes.c_long
+    L.ofg_hostcheck_mcl_nnz.argtypes = [ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_get.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_interpret.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.ofg_hostcheck_mcl_text.restype = ctypes.c_long
+    L.ofg_hostcheck_mcl_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+    return L
+
+
+class HostEngine:
+    def __init__(self, graph_text, P=10000, S=1100, R=1400, pct=0.9, overhead=10, table_budget=0, stage_budget=0):
+        from orthofinder_b200 import mcl as pm
+        self.L = _lib()
+        self.n, cp, ri, v = pm.read_graph_text(graph_text)
+        self.h = self.L.ofg_hostcheck_mcl_new()
+        self.L.ofg_hostcheck_mcl_params(self.h, P, S, R, pct, overhead, table_budget, stage_budget)
+        assert self.L.ofg_hostcheck_mcl_start(self.h, self.n, cp.ctypes.data, ri.ctypes.data, v.ctypes.data) == 0
+
+    def step(self, inflation):
+        ch = ctypes.c_double(0)
+        assert self.L.ofg_hostcheck_mcl_step(self.h, float(inflation), ctypes.byref(ch)) == 0
+        return ch.value
+
+    def matrix(self):
+        nnz = self.L.ofg_hostcheck_mcl_nnz(self.h)
+        cp, ri, v = np.empty(self.n + 1, np.int64), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+        assert self.L.ofg_hostcheck_mcl_get(self.h, cp.ctypes.data, ri.ctypes.data, v.ctypes.data) == 0
+        return cp, ri, v
+
+    def clusters_text(self):
+        lab = np.empty(self.n, np.int32)
+        nc, ov = ctypes.c_long(0), ctypes.c_long(0)
+        assert self.L.ofg_hostcheck_mcl_interpret(self.h, lab.ctypes.data, ctypes.byref(nc), ctypes.byref(ov)) == 0
+        size = self.L.ofg_hostcheck_mcl_text(self.h, None, 0)
+        buf = ctypes.create_string_buffer(size)
+        self.L.ofg_hostcheck_mcl_text(self.h, buf, size)
+        return buf.raw.decode(), lab, nc.value, ov.value
+
+    def close(self):
+        self.L.ofg_hostcheck_mcl_free(self.h)
+
+
+def _run_against_golden(name, inflation, **kw):
+    g = MclGolden(name)
+    sha, nnz = g.digests(inflation)
+    e = HostEngine(mcl_golden_graph(name), **kw)
+    assert matrix_digest(*e.matrix()) == sha[0]
+    k = 0
+    while True:
+        chaos = e.step(inflation)
+        k += 1
+        m = e.matrix()
+        assert len(m[1]) == nnz[k], (k, len(m[1]), nnz[k])
+        assert matrix_digest(*m) == sha[k], "iterand %d differs" % k
+        if chaos < 1e-4:
+            break
+    assert k == g.iterations(inflation)
+    text, lab, nc, ov = e.clusters_text()
+    assert text == g.clusters_body(inflation)
+    e.close()
+
+
+@pytest.mark.parametrize("name,inflation", [("ref_AddTwoSpecies", 1.2), ("ref_FromTrees", 1.5), ("ref_removeFirst", 3.0),
+                                            ("synth_ties", 1.2), ("synth_ties", 1.5), ("synth_ties", 3.0), ("synth_C5_small", 1.5)])
+def test_engine_on_the_host_reproduces_the_binary(name, inflation):
+    _run_against_golden(name, inflation)
+
+
+def test_engine_with_many_small_batches_and_global_tables():
+    """Budgets of a few thousand entries cut every iteration into dozens of batches; C2_tiny's columns of up to 2 400 entries
+    and the 1 250-gene family need hash tables in 'global' memory and lists longer than the shared-memory list."""
+    _run_against_golden("synth_C2_tiny", 3.0, table_budget=20000, stage_budget=30000)
+    _run_against_golden("synth_family", 3.0, table_budget=9000, stage_budget=5000)
