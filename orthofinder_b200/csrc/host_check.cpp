@@ -81,7 +81,7 @@ struct MclHostBackend {
     }
     bool inflate(const MclInflateArgs& a, int64_t ncols)
     {
-        static MclColShared sh;
+        static MclRedShared sh;
         for (int64_t b = 0; b < ncols; b++) mcl_inflate_column(sh, a, a.c0 + b);
         return true;
     }
@@ -124,3 +124,5 @@ long ofg_hostcheck_mcl_text(void* h, char* buf, long cap)
     return (long)t.size();
 }
 }
+
+extern "C" int ofg_hostcheck_mcl_weight(double w, float* out) { return mcl_weight_as_read(w, out) ? 1 : 0; }

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(MCL_NT) mcl_expand_kernel(MclExpandArgs a)
 }
 __global__ void __launch_bounds__(MCL_NT) mcl_inflate_kernel(MclInflateArgs a)
 {
-    __shared__ MclColShared sh;
+    __shared__ MclRedShared sh;
     mcl_inflate_column(sh, a, a.c0 + (int64_t)blockIdx.x);
 }
 __global__ void __launch_bounds__(256) mcl_dag_kernel(MclDagArgs a)
@@ -72,38 +72,13 @@ template <typename T> __global__ void __launch_bounds__(1024) mcl_scan_kernel(co
     for (int64_t i = b; i < e; i++) { const int64_t x = (int64_t)in[i]; out[i] = s; s += x; }
 }
 
-// graph of a built context -> the values the binary would read from OrthoFinder_graph.txt: "%.3f" of the weight
-// (WriteGraph_perSpecies, gathering.py:44), strtod, float.  X = round-half-even(w * 1000) on the exact binary value.
-__device__ __forceinline__ bool mcl_fixed3(double v, unsigned long long* X)
-{
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    if (bits >> 63) return false;
-    const int eb = (int)((bits >> 52) & 0x7ff);
-    if (eb == 0x7ff) return false;
-    unsigned long long mant = bits & 0x000fffffffffffffULL;
-    int e;
-    if (eb == 0) e = -1074; else { mant |= 0x0010000000000000ULL; e = eb - 1075; }
-    const unsigned long long P = mant * 1000ULL;
-    if (e >= 0) {
-        if (e >= 64 || (e > 0 && (P >> (64 - e)) != 0)) return false;
-        *X = P << e;
-        return true;
-    }
-    const int sh = -e;
-    if (sh >= 64) { *X = 0; return true; }
-    unsigned long long q = P >> sh;
-    const unsigned long long rem = P & ((1ULL << sh) - 1ULL), half = 1ULL << (sh - 1);
-    if (rem > half || (rem == half && (q & 1ULL))) q++;
-    *X = q;
-    return true;
-}
-
+// graph of a built context -> the values the binary would read from OrthoFinder_graph.txt (mcl_weight_as_read)
 __global__ void __launch_bounds__(256) mcl_weights_kernel(const double* w, float* out, int64_t nnz, int* bad)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long X = 0;
-        if (!mcl_fixed3(w[i], &X) || X >= (1ULL << 53)) { *bad = 1; X = 0; }
-        out[i] = mcl_value_of_thousandths(X);
+        float f = 0.0f;
+        if (!mcl_weight_as_read(w[i], &f)) *bad = 1;
+        out[i] = f;
     }
 }
 

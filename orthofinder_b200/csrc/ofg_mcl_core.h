@@ -116,9 +116,37 @@ MCL_HD void mcl_start_fill(const MclStartArgs& a, int64_t c)
     for (int64_t p = b; p < o; p++) a.out_v[p] = MCL_D2F(MCL_DDIV((double)a.out_v[p], s));
 }
 
-// the value mcl stores for a weight that WriteGraph_perSpecies printed with "%.3f" (gathering.py:44): strtod of the
-// decimal string, then float.  X = the exact thousandths (ofg_fixed3 of the emit kernel).
-MCL_HD float mcl_value_of_thousandths(unsigned long long X) { return MCL_D2F(MCL_DDIV((double)X, 1000.0)); }
+// The value mcl stores for a weight that WriteGraph_perSpecies printed with "%.3f" (gathering.py:44): strtod of the decimal
+// string, then float.  X = round-half-even(w * 1000) on the exact binary value of w (what glibc's printf prints); X / 1000 in
+// double is the correctly rounded value of that decimal.  false: negative, not finite or too large.
+MCL_HD bool mcl_weight_as_read(double w, float* out)
+{
+    const mcl_u64 bits = mcl_double_bits(w);
+    *out = 0.0f;
+    if (bits >> 63) return (bits << 1) == 0;          // -0.0 prints as "-0.000" and reads as 0
+    const int eb = (int)((bits >> 52) & 0x7ff);
+    if (eb == 0x7ff) return false;
+    mcl_u64 mant = bits & 0x000fffffffffffffULL;
+    int e;
+    if (eb == 0) e = -1074; else { mant |= 0x0010000000000000ULL; e = eb - 1075; }
+    const mcl_u64 P = mant * 1000ULL;                 // < 2^63
+    mcl_u64 X;
+    if (e >= 0) {
+        if (e >= 11 || (e > 0 && (P >> (64 - e)) != 0)) return false;
+        X = P << e;
+    } else {
+        const int sh = -e;
+        if (sh >= 64) X = 0;
+        else {
+            X = P >> sh;
+            const mcl_u64 rem = P & ((1ULL << sh) - 1ULL), half = 1ULL << (sh - 1);
+            if (rem > half || (rem == half && (X & 1ULL))) X++;
+        }
+    }
+    if (X >= (1ULL << 53)) return false;
+    *out = MCL_D2F(MCL_DDIV((double)X, 1000.0));
+    return true;
+}
 
 // ---------------------------------------------------------------------------------------------- plan of one iteration
 struct MclPlanArgs {
@@ -165,6 +193,7 @@ struct MclExpandArgs {
     mcl_u64* stage;             // per column: list scratch, then the kept entries (row << 32 | float bits)
     int32_t* cnt;               // kept entries per column
     mcl_u64* chaos_bits;        // max over columns (bits of a non-negative double)
+    int32_t* err;               // set when a column's table overflowed (inconsistent plan)
     double cut;                 // 0.99999 / P
     int S, R;
     double pct;
@@ -187,6 +216,18 @@ struct MclColShared {
     int32_t tot_i;                // sum
     float tot_f;                  // min
     int32_t sel_bin, sel_above;
+    double seq_sum;
+};
+
+// the reduction scratch alone (inflation needs nothing else)
+struct MclRedShared {
+    double red_a[MCL_NT], red_b[MCL_NT], red_c[MCL_NT];
+    double red2_a[16], red2_b[16], red2_c[16];
+    int32_t red_i[MCL_NT], red2_i[16];
+    float red_f[MCL_NT], red2_f[16];
+    double tot_a, tot_b, tot_c;
+    int32_t tot_i;
+    float tot_f;
     double seq_sum;
 };
 
@@ -302,12 +343,14 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
                 const int32_t r = a.ri[q];
                 const float w = a.v[q];
                 uint32_t h = mcl_hash(r) & mask;
-                for (;;) {
+                int probes = 0;
+                for (; probes <= tcap; probes++) {
                     const int32_t old = MCL_ATOMIC_CAS_I32(&keys[h], -1, r);
                     if (old == -1) { acc[h] = 0.0; break; }
                     if (old == r) break;
                     h = (h + 1u) & mask;
                 }
+                if (probes > tcap) { *a.err = 1; continue; }     // cannot happen with a consistent plan: never spin on the GPU
                 const double pr = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
                 acc[h] = MCL_DADD(acc[h], pr);
             }

@@ -95,7 +95,7 @@ public:
         launches += 3;
         h_table.resize((size_t)n + 1); h_stage.resize((size_t)n + 1);
         if (!be.d2h(h_table.data(), table_off, (size_t)(n + 1) * 8) || !be.d2h(h_stage.data(), stage_off, (size_t)(n + 1) * 8)) return fail();
-        if (!be.memset(chaos_bits, 0, 8)) return fail();
+        if (!be.memset(chaos_bits, 0, 16)) return fail();
         int64_t base = 0;
         for (int64_t c0 = 0; c0 < n;) {
             int64_t c1 = c0 + 1;
@@ -120,7 +120,7 @@ public:
             MclExpandArgs e{};
             e.n = n; e.cp = cur.cp; e.ri = cur.ri; e.v = cur.v; e.c0 = c0;
             e.table_off = table_off; e.stage_off = stage_off; e.tcap = tcap; e.dense = dense;
-            e.gkeys = gkeys; e.gacc = gacc; e.stage = stage; e.cnt = cnt; e.chaos_bits = chaos_bits;
+            e.gkeys = gkeys; e.gacc = gacc; e.stage = stage; e.cnt = cnt; e.chaos_bits = chaos_bits; e.err = (int32_t*)(chaos_bits + 1);
             e.cut = par.P ? 0.99999 / (double)par.P : 0.0; e.S = par.S; e.R = par.R; e.pct = par.pct;
             if (!be.expand(e, c1 - c0)) return fail();
             if (!be.scan_i32(cnt + c0, nxt.cp + c0, c1 - c0, base)) return fail();
@@ -138,10 +138,11 @@ public:
         }
         nxt.nnz = base;
         std::swap(cur, nxt);
-        mcl_u64 bits = 0;
-        if (!be.d2h(&bits, chaos_bits, 8)) return fail();
+        mcl_u64 back[2] = {0, 0};
+        if (!be.d2h(back, chaos_bits, 16)) return fail();
+        if (back[1]) { err = "hash table of a column overflowed (inconsistent plan)"; return false; }
         double ch;
-        memcpy(&ch, &bits, 8);
+        memcpy(&ch, &back[0], 8);
         last_chaos = ch;
         chaos_log.push_back(ch);
         iterations++;
@@ -254,7 +255,7 @@ private:
         bool ok = be.alloc((void**)&cur.cp, c * 8) && be.alloc((void**)&nxt.cp, c * 8) && be.alloc((void**)&tcap, c * 4) &&
                   be.alloc((void**)&dense, c) && be.alloc((void**)&need, c * 8) && be.alloc((void**)&stg, c * 8) &&
                   be.alloc((void**)&table_off, c * 8) && be.alloc((void**)&stage_off, c * 8) && be.alloc((void**)&cnt, c * 4) &&
-                  be.alloc((void**)&chaos_bits, 8) && be.alloc((void**)&attr, c) && be.alloc((void**)&sys, c * 4) &&
+                  be.alloc((void**)&chaos_bits, 16) && be.alloc((void**)&attr, c) && be.alloc((void**)&sys, c * 4) &&
                   be.alloc((void**)&second, c * 4) && be.alloc((void**)&changed, 4);
         return ok ? true : fail();
     }

@@ -80,9 +80,9 @@ class DeviceMCL:
         """The finished graph of a waterfall.GraphBuilder, taken from device memory (same GPU)."""
         n, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
         off, idx, w = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        rc = self._L.ofg_graph_dev(builder._h, ctypes.byref(n), ctypes.byref(nnz), ctypes.byref(off), ctypes.byref(idx), ctypes.byref(w))
+        rc = self._L.ofg_graph_dev(builder.h, ctypes.byref(n), ctypes.byref(nnz), ctypes.byref(off), ctypes.byref(idx), ctypes.byref(w))
         if rc != _lib.OFG_OK:
-            msg = self._L.ofg_last_error(builder._h)
+            msg = self._L.ofg_last_error(builder.h)
             raise RuntimeError("%s: %s" % (_lib.ERR_NAMES.get(rc, rc), msg.decode() if msg else ""))
         self._ck(self._L.ofg_mcl_set_graph_dev(self._h, n.value, off, nnz.value, idx, w))
         self.n = int(n.value)

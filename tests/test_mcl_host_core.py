@@ -94,3 +94,18 @@ def test_engine_with_many_small_batches_and_global_tables():
     and the 1 250-gene family need hash tables in 'global' memory and lists longer than the shared-memory list."""
     _run_against_golden("synth_C2_tiny", 3.0, table_budget=20000, stage_budget=30000)
     _run_against_golden("synth_family", 3.0, table_budget=9000, stage_budget=5000)
+
+
+def test_weight_as_the_binary_reads_it_from_the_graph_file():
+    """"%.3f" -> strtod -> float, for the device path that never writes the file."""
+    L = _lib()
+    L.ofg_hostcheck_mcl_weight.argtypes = [ctypes.c_double, ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(0, 4, 20000), rng.uniform(0, 3000, 5000), 10.0 ** rng.uniform(-9, 12.9, 5000),
+                         (rng.integers(0, 4000, 5000) + 0.5) / 1000.0, [0.0, 0.0004, 0.0005, 0.0015, 0.0025, 9.0e12]])
+    out = ctypes.c_float(0)
+    for x in xs:
+        assert L.ofg_hostcheck_mcl_weight(float(x), ctypes.byref(out)) == 1, x
+        assert out.value == float(np.float32(float("%.3f" % x))), x
+    for bad in (-1.0, float("inf"), float("nan"), 1e13, 1e19):      # beyond 2^53 thousandths: rejected, never approximated
+        assert L.ofg_hostcheck_mcl_weight(bad, ctypes.byref(out)) == 0
