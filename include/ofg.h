@@ -244,8 +244,10 @@ const char* ofg_mcl_last_error(ofg_mcl* m);
 /* the binary's -P, -S, -R, -pct (percent), -sparse and -L options; defaults = the binary's */
 int ofg_mcl_set_params(ofg_mcl* m, int prune_number, int select_number, int recover_number, double recover_pct, int sparse_overhead,
                        int max_iterations);
-/* scratch budgets per batch of columns: slots of global-memory hash tables (12 bytes each), stage entries (8 bytes each) */
-int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries);
+/* scratch budgets per batch of columns: slots of global-memory hash tables / row-indexed accumulators (12 bytes each), stage
+ * entries (8 bytes each); direct_factor: a column that may touch n / direct_factor rows or more accumulates in a row-indexed
+ * array instead of a hash table (default 4; 0 = never).  Results do not depend on any of the three. */
+int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries, int direct_factor);
 /* the graph as the binary reads it from a file: column c = line c of the graph file, rows ascending, the float values
  * of the printed weights (host arrays; entries that read as 0 and loops are dropped like the binary does) */
 int ofg_mcl_set_graph_host(ofg_mcl* m, int64_t n, const int64_t* colptr, const int32_t* rows, const float* vals);

@@ -88,7 +88,7 @@ def load():
         "ofg_graph_dev": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)],
         "ofg_mcl_create": [ctypes.POINTER(vp), i32],
         "ofg_mcl_set_params": [vp, i32, i32, i32, ctypes.c_double, i32, i32],
-        "ofg_mcl_set_budgets": [vp, i64, i64],
+        "ofg_mcl_set_budgets": [vp, i64, i64, i32],
         "ofg_mcl_set_graph_host": [vp, i64, vp, vp, vp],
         "ofg_mcl_set_graph_dev": [vp, i64, vp, i64, vp, vp],
         "ofg_mcl_run": [vp, ctypes.c_double],

@@ -96,12 +96,13 @@ extern "C" {
 
 void* ofg_hostcheck_mcl_new() { return new HostMcl(); }
 void ofg_hostcheck_mcl_free(void* h) { delete (HostMcl*)h; }
-int ofg_hostcheck_mcl_params(void* h, int P, int S, int R, double pct, int overhead, long table_budget, long stage_budget)
+int ofg_hostcheck_mcl_params(void* h, int P, int S, int R, double pct, int overhead, long table_budget, long stage_budget, int direct_factor)
 {
     HostMcl* m = (HostMcl*)h;
     m->par.P = P; m->par.S = S; m->par.R = R; m->par.pct = pct; m->par.overhead = overhead;
     if (table_budget > 0) m->par.table_budget = table_budget;
     if (stage_budget > 0) m->par.stage_budget = stage_budget;
+    if (direct_factor >= 0) m->par.direct_factor = direct_factor;
     return 0;
 }
 int ofg_hostcheck_mcl_start(void* h, long n, const int64_t* cp, const int32_t* ri, const float* v) { return ((HostMcl*)h)->start(n, cp, ri, v) ? 0 : -1; }

@@ -215,11 +215,12 @@ int ofg_mcl_set_params(ofg_mcl* m, int prune_number, int select_number, int reco
     return OFG_OK;
 }
 
-int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries)
+int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries, int direct_factor)
 {
-    if (!m || table_slots < 1 || stage_entries < 1) return OFG_ERR_ARG;
+    if (!m || table_slots < 1 || stage_entries < 1 || direct_factor < 0) return OFG_ERR_ARG;
     m->eng.par.table_budget = table_slots;
     m->eng.par.stage_budget = stage_entries;
+    m->eng.par.direct_factor = direct_factor;
     return OFG_OK;
 }
 

@@ -12,7 +12,8 @@
 //               accumulated in double; the product is float*float rounded to float for columns with
 //               summands * overhead >= n (the binary's dense walk), the exact double product otherwise.
 //               One CTA per column: a hash table (shared memory up to 2 048 slots, global memory beyond) keyed by
-//               row; source entries are taken one at a time (barrier in between), the 256 threads spread over the
+//               row - or, for a column that may touch a quarter of all rows, one accumulator per row (no probing, and
+//               the result is collected in row order without a sort); source entries are taken one at a time (barrier in between), the 256 threads spread over the
 //               rows of M[:,k] - distinct rows, so every accumulator sees its addends in source order.
 //   pruning     val >= 0.99999/P; recovery / selection with "the K largest, ties kept" by a radix select on the float
 //               bits; chaos on what is left; val / (double sum) - the sum of floats >= 1e-8 that add up to < 2 is exact in
@@ -34,6 +35,8 @@ typedef unsigned long long mcl_u64;
 constexpr int MCL_NT = 256;            // threads per CTA (the radix-select histogram relies on 256)
 constexpr int MCL_SMEM_SLOTS = 2048;   // hash slots kept in shared memory
 constexpr int MCL_SMEM_LIST = 1024;    // list entries kept in shared memory (= MCL_SMEM_SLOTS / 2)
+constexpr int MCL_DIRECT_FACTOR = 4;   // columns that may touch n / 4 rows or more accumulate in a row-indexed array
+constexpr int MCL_RUN = 16;            // rows per thread and step when such an array is collected
 
 #if defined(__CUDA_ARCH__)
 #define MCL_PHASE(t) for (int t = (int)threadIdx.x, mcl_once_ = 1; mcl_once_; mcl_once_ = 0, __syncthreads())
@@ -154,7 +157,8 @@ struct MclPlanArgs {
     const int64_t* cp;
     const int32_t* ri;
     int overhead;
-    int32_t* tcap;     // hash capacity of the column (power of two)
+    int direct_factor; // columns that may touch n / direct_factor rows or more use row-indexed accumulators (0: never)
+    int32_t* tcap;     // hash capacity of the column (power of two); 0: row-indexed accumulators (n of them)
     uint8_t* dense;    // 1: products rounded to float (summands * overhead >= n)
     int64_t* need;     // slots the column needs in the GLOBAL table area (0: its table fits shared memory)
     int64_t* stg;      // entries the column needs in the stage area
@@ -169,8 +173,14 @@ MCL_HD void mcl_plan_column(const MclPlanArgs& a, int64_t c)
     if (bound < 1) bound = 1;
     int64_t cap = 64;
     while (cap < 2 * bound) cap <<= 1;
-    a.tcap[c] = (int32_t)cap;
     const bool in_smem = cap <= MCL_SMEM_SLOTS;
+    if (!in_smem && a.direct_factor > 0 && bound * (int64_t)a.direct_factor >= a.n) {      // a large share of all rows: one accumulator per row, no hashing, no sort
+        a.tcap[c] = 0;
+        a.need[c] = a.n;
+        a.stg[c] = bound;
+        return;
+    }
+    a.tcap[c] = (int32_t)cap;
     a.need[c] = in_smem ? 0 : cap;
     int64_t lst = 1;
     while (lst < bound) lst <<= 1;          // the sorting network pads the list to a power of two
@@ -321,7 +331,8 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
 {
     const int64_t p0 = a.cp[c], p1 = a.cp[c + 1];
     const int tcap = a.tcap[c];
-    const bool in_smem = tcap <= MCL_SMEM_SLOTS;
+    const bool direct = tcap == 0;                 // row-indexed accumulators in the global table area
+    const bool in_smem = !direct && tcap <= MCL_SMEM_SLOTS;
     int32_t* keys = in_smem ? sh.keys : a.gkeys + (a.table_off[c] - a.table_off[a.c0]);
     double* acc = in_smem ? sh.acc : a.gacc + (a.table_off[c] - a.table_off[a.c0]);
     mcl_u64* stage = a.stage + (a.stage_off[c] - a.stage_off[a.c0]);
@@ -342,6 +353,12 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
             for (int64_t q = q0 + t; q < q1; q += MCL_NT) {
                 const int32_t r = a.ri[q];
                 const float w = a.v[q];
+                if (direct) {                       // rows of one source column are distinct: no two threads meet
+                    if (keys[r] == -1) { keys[r] = r; acc[r] = 0.0; }
+                    const double prd = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
+                    acc[r] = MCL_DADD(acc[r], prd);
+                    continue;
+                }
                 uint32_t h = mcl_hash(r) & mask;
                 int probes = 0;
                 for (; probes <= tcap; probes++) {
@@ -356,8 +373,27 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
             }
         }
     }
-    // 3. list of the occupied slots: (row << 32) | slot
     int nt = 0;
+    if (direct) {
+        // 3'. the touched rows in row order, with their values: the list is sorted as it is written
+        for (int64_t base = 0; base < a.n; base += (int64_t)MCL_RUN * MCL_NT) {
+            MCL_PHASE(t) {
+                const int64_t lo = base + (int64_t)t * MCL_RUN;
+                int k = 0;
+                for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++) k += keys[i] != -1;
+                sh.scan[t] = k;
+            }
+            mcl_block_scan(sh);
+            MCL_PHASE(t) {
+                const int64_t lo = base + (int64_t)t * MCL_RUN;
+                int o = nt + sh.scan[t];
+                for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++)
+                    if (keys[i] != -1) list[o++] = mcl_pack((int32_t)i, MCL_D2F(acc[i]));
+            }
+            nt += sh.scan_total;
+        }
+    } else {
+    // 3. list of the occupied slots: (row << 32) | slot
     for (int base = 0; base < tcap; base += MCL_NT) {
         MCL_PHASE(t) { sh.scan[t] = (base + t < tcap && keys[base + t] != -1) ? 1 : 0; }
         mcl_block_scan(sh);
@@ -392,6 +428,7 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
             list[i] = (e & 0xffffffff00000000ull) | (mcl_u64)mcl_float_bits(MCL_D2F(acc[(uint32_t)e]));
         }
     }
+    }   // hashed accumulators
     // 6. pruning rule
     MCL_PHASE(t) {
         double ma = 0.0, mp = 0.0;

@@ -24,8 +24,9 @@ struct MclParams {
     int overhead = 10;                     // -sparse
     int max_iter = 10000;                  // -L
     double chaos_limit = 1e-4;
-    int64_t table_budget = (int64_t)1 << 26;   // slots of global hash tables per batch (12 bytes each)
+    int64_t table_budget = (int64_t)1 << 28;   // slots of global hash tables / row-indexed accumulators per batch (12 bytes each)
     int64_t stage_budget = (int64_t)1 << 27;   // stage entries per batch (8 bytes each)
+    int direct_factor = MCL_DIRECT_FACTOR;     // see MclPlanArgs
 };
 
 template <class B> class MclEngine {
@@ -88,7 +89,7 @@ public:
     bool step(double inflation, double* chaos_out)
     {
         MclPlanArgs pl{};
-        pl.n = n; pl.cp = cur.cp; pl.ri = cur.ri; pl.overhead = par.overhead;
+        pl.n = n; pl.cp = cur.cp; pl.ri = cur.ri; pl.overhead = par.overhead; pl.direct_factor = par.direct_factor;
         pl.tcap = tcap; pl.dense = dense; pl.need = need; pl.stg = stg;
         if (!be.plan(pl)) return fail();
         if (!be.scan_i64(need, table_off, n, 0) || !be.scan_i64(stg, stage_off, n, 0)) return fail();

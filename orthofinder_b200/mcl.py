@@ -66,8 +66,8 @@ class DeviceMCL:
     def set_params(self, prune_number=10000, select_number=1100, recover_number=1400, recover_pct=90.0, sparse_overhead=10, max_iterations=10000):
         self._ck(self._L.ofg_mcl_set_params(self._h, prune_number, select_number, recover_number, float(recover_pct), sparse_overhead, max_iterations))
 
-    def set_budgets(self, table_slots, stage_entries):
-        self._ck(self._L.ofg_mcl_set_budgets(self._h, int(table_slots), int(stage_entries)))
+    def set_budgets(self, table_slots=1 << 28, stage_entries=1 << 27, direct_factor=4):
+        self._ck(self._L.ofg_mcl_set_budgets(self._h, int(table_slots), int(stage_entries), int(direct_factor)))
 
     def set_graph(self, n, colptr, rows, vals):
         colptr = np.ascontiguousarray(colptr, np.int64)

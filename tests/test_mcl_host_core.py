@@ -18,7 +18,7 @@ def _lib():
     L.ofg_hostcheck_mcl_new.restype = ctypes.c_void_p
     L.ofg_hostcheck_mcl_free.argtypes = [ctypes.c_void_p]
     L.ofg_hostcheck_mcl_params.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
-                                           ctypes.c_long, ctypes.c_long]
+                                           ctypes.c_long, ctypes.c_long, ctypes.c_int]
     L.ofg_hostcheck_mcl_start.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.ofg_hostcheck_mcl_step.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
     L.ofg_hostcheck_mcl_nnz.restype = ctypes.c_long
@@ -31,12 +31,12 @@ def _lib():
 
 
 class HostEngine:
-    def __init__(self, graph_text, P=10000, S=1100, R=1400, pct=0.9, overhead=10, table_budget=0, stage_budget=0):
+    def __init__(self, graph_text, P=10000, S=1100, R=1400, pct=0.9, overhead=10, table_budget=0, stage_budget=0, direct_factor=-1):
         from orthofinder_b200 import mcl as pm
         self.L = _lib()
         self.n, cp, ri, v = pm.read_graph_text(graph_text)
         self.h = self.L.ofg_hostcheck_mcl_new()
-        self.L.ofg_hostcheck_mcl_params(self.h, P, S, R, pct, overhead, table_budget, stage_budget)
+        self.L.ofg_hostcheck_mcl_params(self.h, P, S, R, pct, overhead, table_budget, stage_budget, direct_factor)
         assert self.L.ofg_hostcheck_mcl_start(self.h, self.n, cp.ctypes.data, ri.ctypes.data, v.ctypes.data) == 0
 
     def step(self, inflation):
@@ -92,8 +92,16 @@ def test_engine_on_the_host_reproduces_the_binary(name, inflation):
 def test_engine_with_many_small_batches_and_global_tables():
     """Budgets of a few thousand entries cut every iteration into dozens of batches; C2_tiny's columns of up to 2 400 entries
     and the 1 250-gene family need hash tables in 'global' memory and lists longer than the shared-memory list."""
-    _run_against_golden("synth_C2_tiny", 3.0, table_budget=20000, stage_budget=30000)
-    _run_against_golden("synth_family", 3.0, table_budget=9000, stage_budget=5000)
+    _run_against_golden("synth_C2_tiny", 3.0, table_budget=20000, stage_budget=30000, direct_factor=0)
+    _run_against_golden("synth_family", 3.0, table_budget=9000, stage_budget=5000, direct_factor=0)
+
+
+def test_engine_with_row_indexed_accumulators():
+    """Columns that may touch a large share of the rows skip the hash table and the sort (default: a quarter; here also
+    every column whose table would not fit shared memory)."""
+    _run_against_golden("synth_C2_tiny", 3.0)
+    _run_against_golden("synth_family", 3.0, table_budget=9000, stage_budget=5000, direct_factor=1000000)
+    _run_against_golden("synth_C5_small", 3.0, direct_factor=1000000)
 
 
 def test_weight_as_the_binary_reads_it_from_the_graph_file():

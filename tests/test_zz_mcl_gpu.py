@@ -69,9 +69,11 @@ def test_family_graph_reaches_selection_and_recovery():
     _stepwise("synth_family", 3.0)
 
 
-def test_small_batches_and_default_batches_agree():
-    _stepwise("synth_C2_tiny", 3.0, table_slots=20000, stage_entries=30000)
-    _stepwise("synth_family", 3.0, table_slots=9000, stage_entries=5000)
+def test_small_batches_hash_tables_in_global_memory_and_row_indexed_accumulators_agree():
+    _stepwise("synth_C2_tiny", 3.0, table_slots=20000, stage_entries=30000, direct_factor=0)      # hash tables only
+    _stepwise("synth_family", 3.0, table_slots=9000, stage_entries=5000, direct_factor=0)
+    _stepwise("synth_family", 3.0, table_slots=9000, stage_entries=5000, direct_factor=1000000)   # row-indexed wherever shared memory is too small
+    _stepwise("synth_C5_small", 1.5, direct_factor=1000000)
 
 
 @pytest.mark.parametrize("name", MCL_GOLDENS)
