@@ -76,7 +76,9 @@ struct MclHostBackend {
     bool expand(const MclExpandArgs& a, int64_t ncols)
     {
         static MclColShared sh;
-        for (int64_t b = 0; b < ncols; b++) mcl_expand_column(sh, a, a.c0 + b);
+        static MclColSharedLite lite;
+        for (int64_t b = 0; b < ncols; b++) mcl_expand_column_hashed(sh, a, a.c0 + b);
+        for (int64_t b = 0; b < ncols; b++) mcl_expand_column_direct(lite, a, a.c0 + b);
         return true;
     }
     bool inflate(const MclInflateArgs& a, int64_t ncols)

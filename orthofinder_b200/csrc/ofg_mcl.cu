@@ -30,7 +30,12 @@ __global__ void __launch_bounds__(256) mcl_plan_kernel(MclPlanArgs a)
 __global__ void __launch_bounds__(MCL_NT) mcl_expand_kernel(MclExpandArgs a)
 {
     __shared__ MclColShared sh;
-    mcl_expand_column(sh, a, a.c0 + (int64_t)blockIdx.x);
+    mcl_expand_column_hashed(sh, a, a.c0 + (int64_t)blockIdx.x);
+}
+__global__ void __launch_bounds__(MCL_NT) mcl_expand_direct_kernel(MclExpandArgs a)
+{
+    __shared__ MclColSharedLite sh;
+    mcl_expand_column_direct(sh, a, a.c0 + (int64_t)blockIdx.x);
 }
 __global__ void __launch_bounds__(MCL_NT) mcl_inflate_kernel(MclInflateArgs a)
 {
@@ -133,8 +138,10 @@ struct CudaBackend {
     }
     bool expand(const MclExpandArgs& a, int64_t ncols)
     {
-        mcl_expand_kernel<<<(unsigned)ncols, MCL_NT, 0, stream>>>(a);
-        return launched("mcl_expand_kernel");
+        mcl_expand_kernel<<<(unsigned)ncols, MCL_NT, 0, stream>>>(a);               // columns with hashed accumulators
+        if (!launched("mcl_expand_kernel")) return false;
+        mcl_expand_direct_kernel<<<(unsigned)ncols, MCL_NT, 0, stream>>>(a);        // columns with row-indexed accumulators
+        return launched("mcl_expand_direct_kernel");
     }
     bool inflate(const MclInflateArgs& a, int64_t ncols)
     {

@@ -241,6 +241,24 @@ struct MclRedShared {
     double seq_sum;
 };
 
+// the same without the hash table and the list (columns with row-indexed accumulators)
+struct MclColSharedLite {
+    mcl_u64 tmp64[MCL_NT];
+    int32_t scan[MCL_NT];
+    int32_t scan2[16];
+    double red_a[MCL_NT], red_b[MCL_NT], red_c[MCL_NT];
+    double red2_a[16], red2_b[16], red2_c[16];
+    int32_t red_i[MCL_NT], red2_i[16];
+    float red_f[MCL_NT], red2_f[16];
+    uint32_t hist[256];
+    int32_t scan_total;
+    double tot_a, tot_b, tot_c;
+    int32_t tot_i;
+    float tot_f;
+    int32_t sel_bin, sel_above;
+    double seq_sum;
+};
+
 // exclusive scan of sh.scan[0..256), total in sh.scan_total
 template <class SH> MCL_HD void mcl_block_scan(SH& sh)
 {
@@ -327,108 +345,9 @@ template <class SH> MCL_HD float mcl_kth_largest(SH& sh, const mcl_u64* list, in
     return mcl_bits_float(prefix);
 }
 
-template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a, int64_t c)
+// steps 6-8 on the expanded column: `list` holds nt entries (row << 32 | float bits) in row order
+template <class SH> MCL_HD void mcl_prune_column(SH& sh, const MclExpandArgs& a, int64_t c, mcl_u64* list, int nt, mcl_u64* stage)
 {
-    const int64_t p0 = a.cp[c], p1 = a.cp[c + 1];
-    const int tcap = a.tcap[c];
-    const bool direct = tcap == 0;                 // row-indexed accumulators in the global table area
-    const bool in_smem = !direct && tcap <= MCL_SMEM_SLOTS;
-    int32_t* keys = in_smem ? sh.keys : a.gkeys + (a.table_off[c] - a.table_off[a.c0]);
-    double* acc = in_smem ? sh.acc : a.gacc + (a.table_off[c] - a.table_off[a.c0]);
-    mcl_u64* stage = a.stage + (a.stage_off[c] - a.stage_off[a.c0]);
-    mcl_u64* list = in_smem ? sh.list : stage;
-    const uint32_t mask = (uint32_t)tcap - 1u;
-    const bool dense = a.dense[c] != 0;
-
-    // 1. empty table (the global tables were preset by the host)
-    if (in_smem) {
-        MCL_PHASE(t) { for (int i = t; i < tcap; i += MCL_NT) keys[i] = -1; }
-    }
-    // 2. accumulate: one source entry at a time, its column spread over the threads
-    for (int64_t p = p0; p < p1; p++) {
-        const int32_t k = a.ri[p];
-        const float f = a.v[p];
-        const int64_t q0 = a.cp[k], q1 = a.cp[k + 1];
-        MCL_PHASE(t) {
-            for (int64_t q = q0 + t; q < q1; q += MCL_NT) {
-                const int32_t r = a.ri[q];
-                const float w = a.v[q];
-                if (direct) {                       // rows of one source column are distinct: no two threads meet
-                    if (keys[r] == -1) { keys[r] = r; acc[r] = 0.0; }
-                    const double prd = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
-                    acc[r] = MCL_DADD(acc[r], prd);
-                    continue;
-                }
-                uint32_t h = mcl_hash(r) & mask;
-                int probes = 0;
-                for (; probes <= tcap; probes++) {
-                    const int32_t old = MCL_ATOMIC_CAS_I32(&keys[h], -1, r);
-                    if (old == -1) { acc[h] = 0.0; break; }
-                    if (old == r) break;
-                    h = (h + 1u) & mask;
-                }
-                if (probes > tcap) { *a.err = 1; continue; }     // cannot happen with a consistent plan: never spin on the GPU
-                const double pr = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
-                acc[h] = MCL_DADD(acc[h], pr);
-            }
-        }
-    }
-    int nt = 0;
-    if (direct) {
-        // 3'. the touched rows in row order, with their values: the list is sorted as it is written
-        for (int64_t base = 0; base < a.n; base += (int64_t)MCL_RUN * MCL_NT) {
-            MCL_PHASE(t) {
-                const int64_t lo = base + (int64_t)t * MCL_RUN;
-                int k = 0;
-                for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++) k += keys[i] != -1;
-                sh.scan[t] = k;
-            }
-            mcl_block_scan(sh);
-            MCL_PHASE(t) {
-                const int64_t lo = base + (int64_t)t * MCL_RUN;
-                int o = nt + sh.scan[t];
-                for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++)
-                    if (keys[i] != -1) list[o++] = mcl_pack((int32_t)i, MCL_D2F(acc[i]));
-            }
-            nt += sh.scan_total;
-        }
-    } else {
-    // 3. list of the occupied slots: (row << 32) | slot
-    for (int base = 0; base < tcap; base += MCL_NT) {
-        MCL_PHASE(t) { sh.scan[t] = (base + t < tcap && keys[base + t] != -1) ? 1 : 0; }
-        mcl_block_scan(sh);
-        MCL_PHASE(t) {
-            if (base + t < tcap && keys[base + t] != -1)
-                list[nt + sh.scan[t]] = ((mcl_u64)(uint32_t)keys[base + t] << 32) | (mcl_u64)(uint32_t)(base + t);
-        }
-        nt += sh.scan_total;
-    }
-    // 4. rows ascending: bitonic network over the list padded to a power of two
-    int m = 1;
-    while (m < nt) m <<= 1;
-    MCL_PHASE(t) { for (int i = nt + t; i < m; i += MCL_NT) list[i] = ~0ull; }
-    for (int k2 = 2; k2 <= m; k2 <<= 1) {
-        for (int j = k2 >> 1; j > 0; j >>= 1) {
-            MCL_PHASE(t) {
-                for (int i = t; i < m; i += MCL_NT) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const mcl_u64 x = list[i], y = list[l];
-                        const bool up = (i & k2) == 0;
-                        if ((x > y) == up) { list[i] = y; list[l] = x; }
-                    }
-                }
-            }
-        }
-    }
-    // 5. values: (row << 32) | bits of (float) sum
-    MCL_PHASE(t) {
-        for (int i = t; i < nt; i += MCL_NT) {
-            const mcl_u64 e = list[i];
-            list[i] = (e & 0xffffffff00000000ull) | (mcl_u64)mcl_float_bits(MCL_D2F(acc[(uint32_t)e]));
-        }
-    }
-    }   // hashed accumulators
     // 6. pruning rule
     MCL_PHASE(t) {
         double ma = 0.0, mp = 0.0;
@@ -527,6 +446,154 @@ template <class SH> MCL_HD void mcl_expand_column(SH& sh, const MclExpandArgs& a
         outn += sh.scan_total;
     }
     MCL_PHASE(t) { if (t == 0) a.cnt[c] = outn; }
+}
+
+// expansion of a column with hashed accumulators (shared memory up to MCL_SMEM_SLOTS slots, else the global table area)
+template <class SH> MCL_HD void mcl_expand_column_hashed(SH& sh, const MclExpandArgs& a, int64_t c)
+{
+    const int tcap = a.tcap[c];
+    if (tcap == 0) return;                         // a column of the row-indexed kernel (CTA-uniform: before any barrier)
+    const int64_t p0 = a.cp[c], p1 = a.cp[c + 1];
+    const bool in_smem = tcap <= MCL_SMEM_SLOTS;
+    int32_t* keys = in_smem ? sh.keys : a.gkeys + (a.table_off[c] - a.table_off[a.c0]);
+    double* acc = in_smem ? sh.acc : a.gacc + (a.table_off[c] - a.table_off[a.c0]);
+    mcl_u64* stage = a.stage + (a.stage_off[c] - a.stage_off[a.c0]);
+    mcl_u64* list = in_smem ? sh.list : stage;
+    const uint32_t mask = (uint32_t)tcap - 1u;
+    const bool dense = a.dense[c] != 0;
+
+    // 1. empty table (the global tables were preset by the host)
+    if (in_smem) {
+        MCL_PHASE(t) { for (int i = t; i < tcap; i += MCL_NT) keys[i] = -1; }
+    }
+    // 2. accumulate: one source entry at a time, its column spread over the threads
+    for (int64_t p = p0; p < p1; p++) {
+        const int32_t k = a.ri[p];
+        const float f = a.v[p];
+        const int64_t q0 = a.cp[k], q1 = a.cp[k + 1];
+        MCL_PHASE(t) {
+            for (int64_t q = q0 + t; q < q1; q += MCL_NT) {
+                const int32_t r = a.ri[q];
+                const float w = a.v[q];
+                uint32_t h = mcl_hash(r) & mask;
+                int probes = 0;
+                for (; probes <= tcap; probes++) {
+                    const int32_t old = MCL_ATOMIC_CAS_I32(&keys[h], -1, r);
+                    if (old == -1) { acc[h] = 0.0; break; }
+                    if (old == r) break;
+                    h = (h + 1u) & mask;
+                }
+                if (probes > tcap) { *a.err = 1; continue; }     // cannot happen with a consistent plan: never spin on the GPU
+                const double pr = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
+                acc[h] = MCL_DADD(acc[h], pr);
+            }
+        }
+    }
+    // 3. list of the occupied slots: (row << 32) | slot
+    int nt = 0;
+    for (int base = 0; base < tcap; base += MCL_NT) {
+        MCL_PHASE(t) { sh.scan[t] = (base + t < tcap && keys[base + t] != -1) ? 1 : 0; }
+        mcl_block_scan(sh);
+        MCL_PHASE(t) {
+            if (base + t < tcap && keys[base + t] != -1)
+                list[nt + sh.scan[t]] = ((mcl_u64)(uint32_t)keys[base + t] << 32) | (mcl_u64)(uint32_t)(base + t);
+        }
+        nt += sh.scan_total;
+    }
+    // 4. rows ascending: bitonic network over the list padded to a power of two
+    int m = 1;
+    while (m < nt) m <<= 1;
+    MCL_PHASE(t) { for (int i = nt + t; i < m; i += MCL_NT) list[i] = ~0ull; }
+    for (int k2 = 2; k2 <= m; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            MCL_PHASE(t) {
+                for (int i = t; i < m; i += MCL_NT) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const mcl_u64 x = list[i], y = list[l];
+                        const bool up = (i & k2) == 0;
+                        if ((x > y) == up) { list[i] = y; list[l] = x; }
+                    }
+                }
+            }
+        }
+    }
+    // 5. values: (row << 32) | bits of (float) sum
+    MCL_PHASE(t) {
+        for (int i = t; i < nt; i += MCL_NT) {
+            const mcl_u64 e = list[i];
+            list[i] = (e & 0xffffffff00000000ull) | (mcl_u64)mcl_float_bits(MCL_D2F(acc[(uint32_t)e]));
+        }
+    }
+    mcl_prune_column(sh, a, c, list, nt, stage);
+}
+
+// expansion of a column that may touch a large share of the rows: one accumulator per row in the global table area (no
+// probing), four source rows in flight per thread, the result collected in row order (no sort)
+template <class SH> MCL_HD void mcl_expand_column_direct(SH& sh, const MclExpandArgs& a, int64_t c)
+{
+    if (a.tcap[c] != 0) return;                    // a column of the hashed kernel (CTA-uniform: before any barrier)
+    const int64_t p0 = a.cp[c], p1 = a.cp[c + 1];
+    int32_t* keys = a.gkeys + (a.table_off[c] - a.table_off[a.c0]);      // -1: row not touched yet
+    double* acc = a.gacc + (a.table_off[c] - a.table_off[a.c0]);
+    mcl_u64* stage = a.stage + (a.stage_off[c] - a.stage_off[a.c0]);
+    mcl_u64* list = stage;
+    const bool dense = a.dense[c] != 0;
+    for (int64_t p = p0; p < p1; p++) {
+        const int32_t k = a.ri[p];
+        const float f = a.v[p];
+        const int64_t q0 = a.cp[k], q1 = a.cp[k + 1];
+        MCL_PHASE(t) {
+            for (int64_t q = q0 + t; q < q1; q += 4 * (int64_t)MCL_NT) {     // rows of one source column are distinct: no two meet
+                int32_t r[4], kk[4];
+                double pr[4], av[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; j++) {
+                    const int64_t qq = q + (int64_t)j * MCL_NT;
+                    r[j] = -1;
+                    if (qq < q1) {
+                        r[j] = a.ri[qq];
+                        const float w = a.v[qq];
+                        pr[j] = dense ? (double)MCL_FMUL(f, w) : MCL_DMUL((double)f, (double)w);
+                    }
+                }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; j++)
+                    if (r[j] >= 0) { kk[j] = keys[r[j]]; av[j] = kk[j] == -1 ? 0.0 : acc[r[j]]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = 0; j < 4; j++)
+                    if (r[j] >= 0) {
+                        acc[r[j]] = MCL_DADD(av[j], pr[j]);
+                        if (kk[j] == -1) keys[r[j]] = r[j];
+                    }
+            }
+        }
+    }
+    // the touched rows in row order, with their values: the list is sorted as it is written
+    int nt = 0;
+    for (int64_t base = 0; base < a.n; base += (int64_t)MCL_RUN * MCL_NT) {
+        MCL_PHASE(t) {
+            const int64_t lo = base + (int64_t)t * MCL_RUN;
+            int k = 0;
+            for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++) k += keys[i] != -1;
+            sh.scan[t] = k;
+        }
+        mcl_block_scan(sh);
+        MCL_PHASE(t) {
+            const int64_t lo = base + (int64_t)t * MCL_RUN;
+            int o = nt + sh.scan[t];
+            for (int64_t i = lo; i < lo + MCL_RUN && i < a.n; i++)
+                if (keys[i] != -1) list[o++] = mcl_pack((int32_t)i, MCL_D2F(acc[i]));
+        }
+        nt += sh.scan_total;
+    }
+    mcl_prune_column(sh, a, c, list, nt, stage);
 }
 
 // ---------------------------------------------------------------------------------------------- inflation + packing

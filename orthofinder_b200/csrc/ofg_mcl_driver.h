@@ -125,7 +125,7 @@ public:
             e.cut = par.P ? 0.99999 / (double)par.P : 0.0; e.S = par.S; e.R = par.R; e.pct = par.pct;
             if (!be.expand(e, c1 - c0)) return fail();
             if (!be.scan_i32(cnt + c0, nxt.cp + c0, c1 - c0, base)) return fail();
-            launches += 2;
+            launches += 3;
             int64_t nb = 0;
             if (!be.d2h(&nb, nxt.cp + c1, 8)) return fail();
             if (!reserve(nxt, nb, true, base)) return false;
