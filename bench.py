@@ -412,6 +412,15 @@ def run_ours(args):
         out["path_roofline"] = {"B_alg_bytes_per_line": T + 124, "achieved_GBps_per_gpu": value / world * (T + 124) / 1e9,
                                 "frac_of_measured_peak": value / world * (T + 124) / 1e9 / peak,
                                 "frac_of_8TBps": value / world * (T + 124) / 8e12}
+    # ---- the consumer: MCL on the graph that sits in device memory; not part of the headline metric
+    if args.mcl > 0 and rank == 0 and world == 1:
+        try:
+            from orthofinder_b200 import mcl as pm
+            r = pm.MCL.RunMCLOnBuilder(gb, None, args.mcl)
+            r.pop("labels", None)
+            out["mcl"] = dict(r, inflation=args.mcl, genes=S * G, edges=c["edges"], unit="ms (device time of the whole process, CUDA events)")
+        except Exception as e:
+            out["mcl"] = {"error": "%s: %s" % (type(e).__name__, e)}
     # ---- e2e through the host API with pinned host buffers
     if not args.no_e2e:
         try:
@@ -685,6 +694,8 @@ def main():
                     help="what the pinned host buffers of the e2e leg hold: the .gz files (inflated on the device) or plain text")
     ap.add_argument("--e2e-host-gb", type=float, default=110.0, help="N > 1: host memory all ranks together may pin for the e2e leg")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mcl", type=float, default=0.0, metavar="INFLATION",
+                    help="N = 1: after the timed loop, cluster the device-resident graph with MCL on the device (SURVEY N3) and add an `mcl` block")
     ap.add_argument("--cpu-species", type=int, default=4, help="species in the cpu_baseline sample")
     ap.add_argument("--ref-species", type=int, default=8, help="species in the reference-arm sample")
     args = ap.parse_args()
