@@ -117,3 +117,39 @@ def test_weight_as_the_binary_reads_it_from_the_graph_file():
         assert out.value == float(np.float32(float("%.3f" % x))), x
     for bad in (-1.0, float("inf"), float("nan"), 1e13, 1e19):      # beyond 2^53 thousandths: rejected, never approximated
         assert L.ofg_hostcheck_mcl_weight(bad, ctypes.byref(out)) == 0
+
+
+@pytest.mark.reference
+def test_clusters_file_is_read_by_the_live_reference_like_the_binarys(tmp_path):
+    """The file MCL.RunMCL writes (own `# cline:` comment + the body) through the reference's own readers: GetPredictedOGs
+    (mcl.py:36-63) and ConvertSingleIDsToIDPair (mcl.py:93-125) give what they give for the binary's file."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("live reference not present (GPU box)")
+    from orthofinder_b200 import mcl as pm
+    from tests.helpers import Golden
+    gathering, util, files = rh._import_reference_real()[:3]
+    import scripts_of.mcl as ref_mcl
+    name = "ref_AddTwoSpecies"
+    graph = mcl_golden_graph(name)
+    ref = rh.run_mcl_binary(graph, 1.2, str(tmp_path / "bin"))
+    e = HostEngine(graph)
+    while e.step(1.2) >= 1e-4:
+        pass
+    text, lab, nc, ov = e.clusters_text()
+    e.close()
+    mine = str(tmp_path / "clusters_mine.txt")
+    pm._write_clusters(mine, text, 1.2)
+    theirs = str(tmp_path / "bin" / "clusters.txt")
+    assert ref_mcl.GetPredictedOGs(mine) == ref_mcl.GetPredictedOGs(theirs)
+    assert pm.GetPredictedOGs(mine) == ref_mcl.GetPredictedOGs(theirs)
+    g = Golden(name)
+    starts = np.concatenate(([0], np.cumsum(g.n_seqs)[:-1]))
+    seqsInfo = util.SequencesInfo(nSeqs=sum(g.n_seqs), nSpecies=len(g.n_seqs), speciesToUse=list(g.species), seqStartingIndices=[int(x) for x in starts],
+                                  nSeqsPerSpecies={sp: n for sp, n in zip(g.species, g.n_seqs)})
+    outs = []
+    for fn in (mine, theirs):
+        out = fn + ".pairs"
+        ref_mcl.ConvertSingleIDsToIDPair(seqsInfo, fn, out)
+        outs.append(open(out).read().split("\n", 1)[1])        # without the first line (the command-line comment)
+    assert outs[0] == outs[1]
