@@ -14,8 +14,11 @@ CUDA is first touched inside BuildGraph, i.e. after the ParallelTaskManager sing
 from . import waterfall
 
 
-def patch_gathering(gathering, device=0, build_graph=None, write_graph=None):
-    """build_graph / write_graph default to waterfall.WaterfallMethod.BuildGraph / WriteGraphParallel (tests pass stubs)."""
+def patch_gathering(gathering, device=0, build_graph=None, write_graph=None, mcl_on_device=False, run_mcl_on_builder=None):
+    """build_graph / write_graph default to waterfall.WaterfallMethod.BuildGraph / WriteGraphParallel (tests pass stubs).
+    mcl_on_device: cluster the graph that is still in the builder's device memory (orthofinder_b200.mcl.MCL.RunMCLOnBuilder,
+    INTEGRATION.md section 7) instead of starting the reference's external `mcl` process on the graph file (mcl.py:214-218);
+    the graph file is written all the same and the clusters file has the binary's body."""
     files, util, mcl = gathering.files, gathering.util, gathering.mcl
     build_graph = build_graph or waterfall.WaterfallMethod.BuildGraph
     write_graph = write_graph or waterfall.WaterfallMethod.WriteGraphParallel
@@ -42,12 +45,20 @@ def patch_gathering(gathering, device=0, build_graph=None, write_graph=None):
         if not homology:
             util.PrintTime("Connected putative homologues")                  # :511
         graphFilename = write_graph(gb, seqsInfo, files.FileHandler.GetGraphFilename(i_unassigned))   # :512, files.py:324-327
+        clustersFilename, clustersFilename_pairs = files.FileHandler.CreateUnusedClustersFN(
+            "_I%0.1f" % options.mclInflation, i_unassigned)                  # :515-516
+        if mcl_on_device:
+            if run_mcl_on_builder is None:
+                from . import mcl as device_mcl
+                device_mcl.MCL.RunMCLOnBuilder(gb, clustersFilename, options.mclInflation, device=device)
+            else:
+                run_mcl_on_builder(gb, clustersFilename, options.mclInflation)
+            util.PrintTime("Ran MCL")                                        # mcl.py:218
         if hasattr(gb, "close"):
             gb.close()
-        # unchanged from here on (gathering.py:514-527)
-        clustersFilename, clustersFilename_pairs = files.FileHandler.CreateUnusedClustersFN(
-            "_I%0.1f" % options.mclInflation, i_unassigned)
-        mcl.MCL.RunMCL(graphFilename, clustersFilename, options.nProcessAlg, options.mclInflation)
+        # unchanged from here on (gathering.py:517-527)
+        if not mcl_on_device:
+            mcl.MCL.RunMCL(graphFilename, clustersFilename, options.nProcessAlg, options.mclInflation)
         mcl.ConvertSingleIDsToIDPair(seqsInfo, clustersFilename, clustersFilename_pairs, q_unassigned)
         if not q_unassigned:
             gathering.post_clustering_orthogroups(clustersFilename_pairs, speciesInfoObj, seqsInfo, speciesNamesDict, options, speciesXML)

@@ -162,3 +162,33 @@ def test_patched_DoOrthogroups_plumbing(tmp_path, i_unassigned, double, v2, vers
         assert calls["graphFN"] == out + "OrthoFinder_unassigned_clade_3_graph.txt" == waterfall.GetGraphFilename(out, 3)
         assert all(c[0] != "post" for c in mcl_calls)                              # gathering.py:525
     assert mcl_calls[0][0] == calls["graphFN"] and mcl_calls[0][3] == 1.2           # mcl.MCL.RunMCL(graphFilename, ..., inflation)
+
+
+def test_patched_DoOrthogroups_can_cluster_on_the_device(tmp_path):
+    """mcl_on_device=True: the builder goes to RunMCLOnBuilder with the clusters filename of FileHandler.CreateUnusedClustersFN and
+    the inflation; the reference's external mcl process is not started; ConvertSingleIDsToIDPair gets the same clusters file."""
+    gathering, util, files, matrices = rh._import_reference_real()
+    from orthofinder_b200 import integration
+    wd = os.path.join(REF_TESTS, FIXTURES["FromTrees"][0])
+    sp, n_all, _ = util.GetSpeciesToUse(wd + "SpeciesIDs.txt")
+    si = util.GetSeqsInfo([wd], sp, n_all)
+    out = str(tmp_path) + "/"
+    fh = files.FileHandler
+    saved = (fh.wd_base, fh.wd_current)
+    fh.wd_base, fh.wd_current = [wd], out
+    builder, calls = object(), []
+    saved_mcl = (gathering.mcl.MCL.RunMCL, gathering.mcl.ConvertSingleIDsToIDPair, gathering.post_clustering_orthogroups)
+    gathering.mcl.MCL.RunMCL = staticmethod(lambda *a: calls.append(("binary",) + a))
+    gathering.mcl.ConvertSingleIDsToIDPair = lambda *a, **k: calls.append(("convert",) + a)
+    gathering.post_clustering_orthogroups = lambda *a, **k: calls.append(("post",))
+    try:
+        integration.patch_gathering(gathering, build_graph=lambda *a, **k: builder, write_graph=lambda gb, s_, fn: fn, mcl_on_device=True,
+                                    run_mcl_on_builder=lambda gb, fn, infl: calls.append(("device", gb, fn, infl)))
+        gathering.DoOrthogroups(_Options(qDoubleBlast=True, v2_scores=False, gathering_version=(1, 0)), None, si, {}, None, None)
+    finally:
+        integration.unpatch_gathering(gathering)
+        gathering.mcl.MCL.RunMCL, gathering.mcl.ConvertSingleIDsToIDPair, gathering.post_clustering_orthogroups = saved_mcl
+        fh.wd_base, fh.wd_current = saved
+    assert [c[0] for c in calls] == ["device", "convert", "post"]
+    assert calls[0][1] is builder and calls[0][3] == 1.2 and calls[0][2].startswith(out + "clusters_OrthoFinder_I1.2")
+    assert calls[1][2] == calls[0][2]                # ConvertSingleIDsToIDPair(seqsInfo, clustersFilename, ...)
