@@ -251,6 +251,9 @@ int ofg_mcl_set_budgets(ofg_mcl* m, int64_t table_slots, int64_t stage_entries, 
 /* the graph as the binary reads it from a file: column c = line c of the graph file, rows ascending, the float values
  * of the printed weights (host arrays; entries that read as 0 and loops are dropped like the binary does) */
 int ofg_mcl_set_graph_host(ofg_mcl* m, int64_t n, const int64_t* colptr, const int32_t* rows, const float* vals);
+/* the same from the bytes of the graph FILE (what RunMCL's graphFilename holds): parsed on the host like the binary reads it
+ * (strtod, then float); OFG_ERR_PARSE with the reason for anything that is not a square MCL matrix with ascending ids */
+int ofg_mcl_set_graph_text(ofg_mcl* m, const char* text, size_t nbytes);
 /* the graph of ofg_graph_dev, on the same device: weights go through "%.3f" -> strtod -> float on the device, exactly the
  * values the binary would have read from OrthoFinder_graph.txt */
 int ofg_mcl_set_graph_dev(ofg_mcl* m, int64_t n, const uint64_t* row_off_dev, int64_t nnz, const int32_t* indices_dev,

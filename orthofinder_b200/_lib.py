@@ -21,7 +21,7 @@ SYMBOLS = ["ofg_create", "ofg_destroy", "ofg_last_error", "ofg_set_species", "of
            "ofg_last_timing", "ofg_kernel_report", "ofg_stream", "ofg_sync", "ofg_get_stat", "ofg_dendro_matrices", "ofg_wait_for", "ofg_export_flags_peer",
            "ofg_import_flags_peer", "ofg_device_alloc", "ofg_device_free", "ofg_ipc_get_handle", "ofg_ipc_open_handle",
            "ofg_ipc_close_handle", "ofg_graph_dev", "ofg_mcl_create", "ofg_mcl_destroy", "ofg_mcl_last_error", "ofg_mcl_set_params",
-           "ofg_mcl_set_budgets", "ofg_mcl_set_graph_host", "ofg_mcl_set_graph_dev", "ofg_mcl_run", "ofg_mcl_step", "ofg_mcl_interpret",
+           "ofg_mcl_set_budgets", "ofg_mcl_set_graph_host", "ofg_mcl_set_graph_text", "ofg_mcl_set_graph_dev", "ofg_mcl_run", "ofg_mcl_step", "ofg_mcl_interpret",
            "ofg_mcl_iterand_copy", "ofg_mcl_result", "ofg_mcl_labels", "ofg_mcl_clusters_text", "ofg_test_log10", "ofg_test_format", "ofg_test_parse_score", "ofg_test_lmfit"]
 
 _lib = None
@@ -90,6 +90,7 @@ def load():
         "ofg_mcl_set_params": [vp, i32, i32, i32, ctypes.c_double, i32, i32],
         "ofg_mcl_set_budgets": [vp, i64, i64, i32],
         "ofg_mcl_set_graph_host": [vp, i64, vp, vp, vp],
+        "ofg_mcl_set_graph_text": [vp, ctypes.c_char_p, sz],
         "ofg_mcl_set_graph_dev": [vp, i64, vp, i64, vp, vp],
         "ofg_mcl_run": [vp, ctypes.c_double],
         "ofg_mcl_step": [vp, ctypes.c_double, ctypes.POINTER(ctypes.c_double)],

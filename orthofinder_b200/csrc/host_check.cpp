@@ -1,6 +1,7 @@
 // CPU build of the host/device-shared pieces of libofg (fit core, record parser, synthetic
 // generator) so their control flow can be checked without a GPU.  Test helper only: the product
 // never loads this library.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "ofg_fit_core.h"
@@ -129,3 +130,17 @@ long ofg_hostcheck_mcl_text(void* h, char* buf, long cap)
 }
 
 extern "C" int ofg_hostcheck_mcl_weight(double w, float* out) { return mcl_weight_as_read(w, out) ? 1 : 0; }
+// parses a graph file's text like ofg_mcl_set_graph_text; arrays are returned through the caller's buffers when they are large enough
+extern "C" long ofg_hostcheck_mcl_parse(const char* text, long nbytes, long* n, int64_t* cp, long cp_cap, int32_t* ri, float* v, long e_cap, char* err, long err_cap)
+{
+    std::vector<int64_t> c; std::vector<int32_t> r; std::vector<float> w;
+    int64_t nn = 0;
+    const std::string msg = mcl_parse_graph_text(text, (size_t)nbytes, &nn, c, r, w);
+    if (!msg.empty()) { snprintf(err, (size_t)err_cap, "%s", msg.c_str()); return -1; }
+    *n = (long)nn;
+    if ((long)c.size() <= cp_cap && (long)r.size() <= e_cap) {
+        memcpy(cp, c.data(), c.size() * 8);
+        if (!r.empty()) { memcpy(ri, r.data(), r.size() * 4); memcpy(v, w.data(), w.size() * 4); }
+    }
+    return (long)r.size();
+}

@@ -260,6 +260,18 @@ int ofg_mcl_set_graph_host(ofg_mcl* m, int64_t n, const int64_t* colptr, const i
     return OFG_OK;
 }
 
+int ofg_mcl_set_graph_text(ofg_mcl* m, const char* text, size_t nbytes)
+{
+    if (!m || !text) return OFG_ERR_ARG;
+    std::vector<int64_t> cp;
+    std::vector<int32_t> ri;
+    std::vector<float> v;
+    int64_t n = 0;
+    const std::string msg = mcl_parse_graph_text(text, nbytes, &n, cp, ri, v);
+    if (!msg.empty()) return mcl_fail(m, OFG_ERR_PARSE, "graph file: " + msg);
+    return ofg_mcl_set_graph_host(m, n, cp.data(), ri.data(), v.data());
+}
+
 int ofg_mcl_set_graph_dev(ofg_mcl* m, int64_t n, const uint64_t* row_off_dev, int64_t nnz, const int32_t* indices_dev, const double* weights_dev)
 {
     if (!m || n < 1 || n > 0x7ffffff0 || nnz < 0 || !row_off_dev || (nnz && (!indices_dev || !weights_dev))) return OFG_ERR_ARG;

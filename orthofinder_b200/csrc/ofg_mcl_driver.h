@@ -12,6 +12,7 @@
 // Interpretation: dag + attractor flags (thread per column), label rounds until nothing changes, cluster order on the host.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -313,4 +314,70 @@ inline std::string mcl_clusters_text(const std::vector<int32_t>& labels, int64_t
     }
     out += ")\n";
     return out;
+}
+
+// The graph file that WriteGraphParallel writes and the binary reads (MCL "matrix" interchange format: header up to
+// `begin`, then `<column> <row>:<value> ... $` records, `)` at the end; gathering.py:39-48, :279-280) -> column-compressed
+// arrays with the values the binary stores (strtod, then float).  Returns an empty string or the reason for refusing.
+inline std::string mcl_parse_graph_text(const char* text, size_t nbytes, int64_t* n_out, std::vector<int64_t>& cp, std::vector<int32_t>& ri,
+                                        std::vector<float>& v)
+{
+    const char* p = text;
+    const char* end = text + nbytes;
+    auto find = [&](const char* from, const char* word) -> const char* {
+        const size_t L = strlen(word);
+        for (const char* q = from; q + L <= end; q++) if (memcmp(q, word, L) == 0) return q;
+        return nullptr;
+    };
+    const char* dim = find(p, "dimensions");
+    if (!dim) return "no `dimensions` line";
+    dim += 10;
+    char* e = nullptr;
+    std::string head(dim, (size_t)std::min<ptrdiff_t>(end - dim, 64));
+    const long long nr = strtoll(head.c_str(), &e, 10);
+    if (!e || *e != 'x') return "malformed `dimensions` line";
+    const long long nc = strtoll(e + 1, &e, 10);
+    if (nr < 1 || nr != nc || nr > 0x7ffffff0LL) return "the matrix must be square with 1 .. 2^31 - 16 nodes";
+    const char* b = find(dim, "begin");
+    if (!b) return "no `begin`";
+    p = b + 5;
+    const int64_t n = (int64_t)nr;
+    std::vector<int64_t> count((size_t)n, 0);
+    ri.clear(); v.clear();
+    std::vector<int64_t> col_of;      // column of every entry, in file order (columns ascend, so entries are already grouped)
+    int64_t cur = -1, last_col = -1;
+    std::string tok;
+    while (p < end) {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\r' || *p == '\t')) p++;
+        if (p >= end) break;
+        if (*p == ')') break;
+        if (*p == '$') { cur = -1; p++; continue; }
+        const char* q = p;
+        while (q < end && *q != ' ' && *q != '\n' && *q != '\r' && *q != '\t' && *q != '$') q++;
+        tok.assign(p, (size_t)(q - p));
+        p = q;
+        if (cur < 0) {                                   // column id
+            const long long c = strtoll(tok.c_str(), &e, 10);
+            if (*e != 0 || c <= last_col || c >= n) return "column ids must ascend and stay below the dimension";
+            cur = last_col = (int64_t)c;
+            continue;
+        }
+        const size_t colon = tok.find(':');
+        const long long r = strtoll(tok.c_str(), &e, 10);
+        if ((colon == std::string::npos ? *e != 0 : e != tok.c_str() + colon) || r < 0 || r >= n) return "malformed entry `" + tok + "`";
+        double w = 1.0;
+        if (colon != std::string::npos) {
+            w = strtod(tok.c_str() + colon + 1, &e);
+            if (*e != 0 || e == tok.c_str() + colon + 1) return "malformed value in `" + tok + "`";
+        }
+        if (!(w >= 0.0) || w > 3.0e38) return "weights must be finite and non-negative";
+        if (count[(size_t)cur] > 0 && ri.back() >= (int32_t)r) return "rows of a column must ascend";
+        ri.push_back((int32_t)r);
+        v.push_back((float)w);
+        count[(size_t)cur]++;
+    }
+    cp.assign((size_t)n + 1, 0);
+    for (int64_t c = 0; c < n; c++) cp[(size_t)c + 1] = cp[(size_t)c] + count[(size_t)c];
+    *n_out = n;
+    return std::string();
 }

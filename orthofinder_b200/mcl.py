@@ -76,6 +76,13 @@ class DeviceMCL:
         self._ck(self._L.ofg_mcl_set_graph_host(self._h, int(n), colptr.ctypes.data, rows.ctypes.data, vals.ctypes.data))
         self.n = int(n)
 
+    def set_graph_text(self, text):
+        """The bytes of a graph file (parsed by the library on the host)."""
+        text = bytes(text)
+        self._ck(self._L.ofg_mcl_set_graph_text(self._h, text, len(text)))
+        m = re.search(rb"dimensions\s+(\d+)x", text)
+        self.n = int(m.group(1))
+
     def set_graph_from_builder(self, builder):
         """The finished graph of a waterfall.GraphBuilder, taken from device memory (same GPU)."""
         n, nnz = ctypes.c_int64(0), ctypes.c_int64(0)
@@ -152,10 +159,10 @@ class MCL:
         first line, a comment with the command line, differs).  `nProcesses` (the binary's -te) has no meaning here and
         does not change the result there either."""
         with open(graphFilename, "rb") as f:
-            n, colptr, rows, vals = read_graph_text(f.read())
+            text = f.read()
         m = DeviceMCL(device)
         try:
-            m.set_graph(n, colptr, rows, vals)
+            m.set_graph_text(text)
             res = m.run(inflation)
             _write_clusters(clustersFilename, m.clusters_text(), inflation)
         finally:

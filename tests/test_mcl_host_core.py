@@ -153,3 +153,30 @@ def test_clusters_file_is_read_by_the_live_reference_like_the_binarys(tmp_path):
         ref_mcl.ConvertSingleIDsToIDPair(seqsInfo, fn, out)
         outs.append(open(out).read().split("\n", 1)[1])        # without the first line (the command-line comment)
     assert outs[0] == outs[1]
+
+
+def test_graph_file_reader_of_the_library():
+    """mcl_parse_graph_text (ofg_mcl_set_graph_text, what RunMCL uses) == the Python reader, on every golden graph; refusals."""
+    from orthofinder_b200 import mcl as pm
+    L = _lib()
+    L.ofg_hostcheck_mcl_parse.restype = ctypes.c_long
+    L.ofg_hostcheck_mcl_parse.argtypes = [ctypes.c_char_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_long, ctypes.c_char_p, ctypes.c_long]
+    err = ctypes.create_string_buffer(256)
+    for name in MCL_GOLDENS:
+        text = bytes(mcl_golden_graph(name))
+        n, cp, ri, v = pm.read_graph_text(text)
+        n2 = ctypes.c_long(0)
+        cp2, ri2, v2 = np.empty(n + 1, np.int64), np.empty(len(ri) + 1, np.int32), np.empty(len(ri) + 1, np.float32)
+        k = L.ofg_hostcheck_mcl_parse(text, len(text), ctypes.byref(n2), cp2.ctypes.data, n + 1, ri2.ctypes.data, v2.ctypes.data, len(ri) + 1, err, 256)
+        assert k == len(ri) and n2.value == n, (name, err.value)
+        assert np.array_equal(cp2, cp) and np.array_equal(ri2[:k], ri) and np.array_equal(v2[:k].view(np.uint32), v.view(np.uint32)), name
+    head = b"(mclheader\nmcltype matrix\ndimensions 3x3\n)\n(mclmatrix\nbegin\n"
+    good = head + b"0 1:0.5 2:1e-3 $\n1 0:0.5\n   2 $\n)\n"          # continuation line, entry without a value (reads as 1)
+    n2 = ctypes.c_long(0)
+    cp2, ri2, v2 = np.empty(4, np.int64), np.empty(8, np.int32), np.empty(8, np.float32)
+    assert L.ofg_hostcheck_mcl_parse(good, len(good), ctypes.byref(n2), cp2.ctypes.data, 4, ri2.ctypes.data, v2.ctypes.data, 8, err, 256) == 4
+    assert list(cp2) == [0, 2, 4, 4] and list(ri2[:4]) == [1, 2, 0, 2] and list(v2[:4]) == [np.float32(0.5), np.float32(1e-3), np.float32(0.5), 1.0]
+    for bad in (b"nothing", head.replace(b"3x3", b"3x4") + b")\n", head + b"1 0:1 $\n0 1:1 $\n)\n", head + b"0 2:1 1:1 $\n)\n",
+                head + b"0 7:1 $\n)\n", head + b"0 1:abc $\n)\n", head + b"0 1:-2 $\n)\n"):
+        assert L.ofg_hostcheck_mcl_parse(bad, len(bad), ctypes.byref(n2), cp2.ctypes.data, 4, ri2.ctypes.data, v2.ctypes.data, 8, err, 256) == -1, bad
