@@ -180,3 +180,76 @@ def test_graph_file_reader_of_the_library():
     for bad in (b"nothing", head.replace(b"3x3", b"3x4") + b")\n", head + b"1 0:1 $\n0 1:1 $\n)\n", head + b"0 2:1 1:1 $\n)\n",
                 head + b"0 7:1 $\n)\n", head + b"0 1:abc $\n)\n", head + b"0 1:-2 $\n)\n"):
         assert L.ofg_hostcheck_mcl_parse(bad, len(bad), ctypes.byref(n2), cp2.ctypes.data, 4, ri2.ctypes.data, v2.ctypes.data, 8, err, 256) == -1, bad
+
+
+def _clique_graph(n, n_cliques, seed):
+    """Disjoint cliques on random members of 0..n-1 (all other nodes without edges): cluster lines with members of 1 to
+    len(str(n)) digits, to exercise the line wrapping of the clusters file."""
+    from tests.helpers import mcl_graph_text
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n)
+    cols = [dict() for _ in range(n)]
+    pos = 0
+    for _ in range(n_cliques):
+        size = int(rng.integers(15, 60))
+        members = [int(x) for x in perm[pos:pos + size]]
+        pos += size
+        for a in members:
+            cols[a] = {b: 1.0 for b in members if b != a}
+    return mcl_graph_text(n, cols)
+
+
+@pytest.mark.parametrize("n,n_cliques", [(9, 1), (700, 8), (12000, 60), (120000, 150)])
+def test_clusters_text_wrapping_for_every_id_width(n, n_cliques):
+    """The C++ writer of the library (mcl_clusters_text) == the oracle's writer (fitted to the binary's files for id widths 1-6)."""
+    from oracle import mcl_oracle as mo
+    graph = _clique_graph(n, n_cliques if n > 9 else 0, 11) if n > 9 else mcl_golden_graph("synth_ties")
+    e = HostEngine(graph)
+    while e.step(2.0) >= 1e-4:
+        pass
+    text, lab, nc, ov = e.clusters_text()
+    e.close()
+    assert text == mo.clusters_text_body(lab, e.n)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("n,n_cliques", [(700, 8), (12000, 60), (120000, 150)])
+def test_clusters_text_wrapping_against_the_binary(tmp_path, n, n_cliques):
+    from oracle import mcl_oracle as mo, ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("live reference not present (GPU box)")
+    graph = _clique_graph(n, n_cliques, 11)
+    ref = rh.run_mcl_binary(graph, 2.0, str(tmp_path), threads=4)
+    e = HostEngine(graph)
+    while e.step(2.0) >= 1e-4:
+        pass
+    text, lab, nc, ov = e.clusters_text()
+    e.close()
+    assert text == mo.clusters_body_of_file(ref["clusters_text"])
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name,variant,inflation", [("ref_AddTwoSpecies", "graph_v2", 1.5), ("ref_FromTrees", "graph_hom", 1.2),
+                                                    ("synth_C5_small", "graph_v2", 2.0), ("ref_removeFirst", "graph_hom", 4.0)])
+def test_other_graphs_of_the_path_against_the_binary(tmp_path, name, variant, inflation):
+    """The --scores-v2 and --c-homologs graphs (all weights 1.000 / 2.000 there: ties everywhere) through the binary, the oracle and
+    the host-walked engine: iterands bit for bit, clusters file byte for byte."""
+    from oracle import mcl_oracle as mo, ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("live reference not present (GPU box)")
+    from tests.helpers import Golden
+    graph = getattr(Golden(name), variant)
+    ref = rh.run_mcl_binary(graph, inflation, str(tmp_path), dump_iterands=True)
+    e = HostEngine(graph)
+    pr = mo.Process(*mo.parse_graph_text(graph))
+    assert matrix_digest(*e.matrix()) == matrix_digest(*ref["iterands"][0]) == matrix_digest(*pr.matrix(0))
+    for k in range(1, len(ref["iterands"])):
+        ch = e.step(inflation)
+        ch2 = pr.step(inflation)
+        want = matrix_digest(*ref["iterands"][k])
+        assert matrix_digest(*e.matrix()) == want and matrix_digest(*pr.matrix(0)) == want, k
+        assert (ch < 1e-4) == (k == len(ref["iterands"]) - 1) == (ch2 < 1e-4), (k, ch, ch2)
+    text = e.clusters_text()[0]
+    e.close()
+    assert text == mo.clusters_body_of_file(ref["clusters_text"])
+    assert mo.clusters_text_body(pr.interpret(0)[1], pr.n) == text
