@@ -558,6 +558,29 @@ def gz_has_size_hints(data):
     return False
 
 
+def csv_unquote(data):
+    """The reference reads hit files through csv.reader(delimiter='\\t') with the default dialect (blast_file_processor.py:65-66): a
+    field that starts with '"' is quoted - '""' inside it is one quote, tabs and line breaks inside it belong to the field.  No search
+    program writes such files and the device parser refuses a quote (OFG_LINE_QUOTE), so a file that contains one is rewritten HERE,
+    by the csv module itself, into the plain rows it yields; the device then parses those.  Tabs and line breaks inside a field become
+    spaces (int() / float() strip them like any other white space, blast_file_processor.py:72-79), a quote that is left inside a field
+    becomes an apostrophe (either makes an id or a score unreadable, :74-82; the other columns are not read); a row without fields is a blank line
+    (skipped, :68-69).  Text mode of open() / gzip.open('rt') means universal newlines, reproduced first."""
+    import csv
+    import io
+    text = bytes(data).decode("utf-8", errors="surrogateescape").replace("\r\n", "\n").replace("\r", "\n")
+    rows = []
+    for row in csv.reader(io.StringIO(text, newline=""), delimiter="\t"):
+        if row:
+            rows.append("\t".join(f.replace("\t", " ").replace("\n", " ").replace('"', "'") for f in row))
+    return ("\n".join(rows) + "\n").encode("utf-8", errors="surrogateescape") if rows else b""
+
+
+def _plain_rows(data):
+    """Host-side bytes of a hit file as the device takes them: files with csv quoting are rewritten (csv_unquote)."""
+    return csv_unquote(data) if b'"' in data else data
+
+
 def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty, raw_gz=False):
     """File lookup of blast_file_processor.py:59-65 (first directory holding the file wins, .gz accepted).
     raw_gz: hand .gz files over compressed (GzBytes) instead of inflating them with zlib on the host; "auto": only the files
@@ -577,12 +600,12 @@ def _read_hit_file(blastDir_list, iSpecies, jSpecies, q_allow_empty, raw_gz=Fals
             if raw_gz is True or (raw_gz == "auto" and gz_has_size_hints(raw)):
                 return GzBytes(raw), fn
             try:
-                return _gunzip(raw), fn
+                return _plain_rows(_gunzip(raw)), fn
             except (EOFError, zlib.error) as e:
                 e.hit_file = (iSpecies, jSpecies, d)
                 raise
     with open(fn, "rb") as f:
-        return f.read(), fn
+        return _plain_rows(f.read()), fn
 
 
 def read_hit_files(blastDir_list, requests, q_allow_empty=False, n_readers=None, window=None, raw_gz=False):
@@ -653,7 +676,7 @@ class WaterfallMethod:
                         if e.code != _lib.ERR_UNSUPPORTED:
                             raise
                         try:
-                            data = _gunzip(data)
+                            data = _plain_rows(_gunzip(data))
                         except (EOFError, zlib.error) as e2:
                             e2.hit_file = (i_open, j_open, os.path.dirname(fn) + "/")
                             raise

@@ -212,3 +212,28 @@ MCL_GOLDENS = REF_GOLDENS + SYNTH_GOLDENS + ["synth_family", "synth_ties"]
 
 def mcl_golden_graph(name):
     return mcl_synthetic_graph(name[len("synth_"):]) if name in ("synth_family", "synth_ties") else Golden(name).graph
+
+
+def csv_quote_hit_text(text, seed=3):
+    """Rewrites plain hit rows with csv quoting that csv.reader(delimiter='\\t') undoes (blast_file_processor.py:65-66): quoted ids and
+    scores, an ignored column holding a tab, a line break or a doubled quote inside quotes, \\r\\n line ends.  Same rows after parsing."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k, line in enumerate(bytes(text).split(b"\n")):
+        if not line:
+            continue
+        f = line.split(b"\t")
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            f[0] = b'"' + f[0] + b'"'
+        elif kind == 1:
+            f[1] = b'"' + f[1] + b'"'
+            f[11] = b'"' + f[11] + b'"'
+        elif kind == 2:
+            f[4] = b'"a\tb"'                     # a tab inside an ignored column
+        elif kind == 3:
+            f[5] = b'"x""y"'                     # doubled quote
+        elif kind == 4:
+            f[6] = b'"two\nlines"'               # a line break inside an ignored column
+        out.append(b"\t".join(f) + (b"\r\n" if k % 3 == 0 else b"\n"))
+    return b"".join(out)

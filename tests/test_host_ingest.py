@@ -111,3 +111,90 @@ def test_phylip_writer_matches_the_reference_bytes():
         assert name != "synth_C5_small" or n_inf > 0
     tiny = np.array([[0.5, 2e-7, -0.0], [2e-7, 0.1, -np.inf], [-0.0, -np.inf, 0.3]])
     assert dendroblast.phylip_text(tiny, ["a", "b", "c"], 2.0) == b"3\na 0.000000 0.000001 0.000000\nb 0.000001 0.000000 2.200000\nc 0.000000 2.200000 0.000000\n"
+
+
+def test_csv_quoted_files_become_the_rows_the_csv_module_yields(tmp_path):
+    """Files with csv quoting (accepted by the reference's csv.reader, refused by the device parser) are rewritten by the reader
+    threads: the oracle's matrices of the rewritten text == those of the original rows; unquoted files pass through untouched."""
+    import numpy as np
+    from oracle import waterfall_oracle as wo
+    from tests.helpers import Golden, csv_quote_hit_text
+    g = Golden("ref_removeFirst")
+    d = str(tmp_path) + "/"
+    S = len(g.n_seqs)
+    for (p, j), t in g.texts.items():
+        with open(d + "Blast%d_%d.txt" % (p, j), "wb") as f:
+            f.write(csv_quote_hit_text(t, seed=p * S + j) if (p + j) % 2 == 0 else t)
+    for (p, j, *_), data, fn in w.read_hit_files([d], [(p, j) for p in range(S) for j in range(S)], n_readers=3):
+        if (p + j) % 2:
+            assert data == g.texts[(p, j)]
+            continue
+        assert b'"' not in data and b"x'y" in data              # the literal quote of the doubled-quote column (nobody reads it) is gone
+        a = wo.get_blast6_scores(g.texts[(p, j)], g.n_seqs[p], g.n_seqs[j], p == j)
+        b = wo.get_blast6_scores(data, g.n_seqs[p], g.n_seqs[j], p == j)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert w.csv_unquote(b'"0_1"\t"0_2"\t' + b"\t".join([b"1"] * 9) + b'\t" 57.5"\r\n\r\n') == b"0_1\t0_2\t" + b"\t".join([b"1"] * 9) + b"\t 57.5\n"
+
+
+@pytest.mark.reference
+def test_csv_quoted_file_through_the_live_reference(tmp_path):
+    """The reference's own GetBLAST6Scores on the quoted file == on the original file (so rewriting the rows is the right thing)."""
+    import numpy as np
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("live reference not present (GPU box)")
+    from tests.helpers import Golden, csv_quote_hit_text
+    gathering, util, files, matrices = rh._import_reference_real()
+    from scripts_of import blast_file_processor as bfp
+    g = Golden("ref_removeFirst")
+    S = len(g.n_seqs)
+    starts = np.concatenate(([0], np.cumsum(g.n_seqs)[:-1]))
+    si = util.SequencesInfo(nSeqs=sum(g.n_seqs), nSpecies=S, speciesToUse=list(range(S)), seqStartingIndices=[int(x) for x in starts],
+                            nSeqsPerSpecies={k: n for k, n in enumerate(g.n_seqs)})
+    plain, quoted = str(tmp_path / "plain") + "/", str(tmp_path / "quoted") + "/"
+    os.makedirs(plain), os.makedirs(quoted)
+    for (p, j) in ((0, 1), (1, 1)):
+        with open(plain + "Blast%d_%d.txt" % (p, j), "wb") as f:
+            f.write(g.texts[(p, j)])
+        with open(quoted + "Blast%d_%d.txt" % (p, j), "wb") as f:
+            f.write(csv_quote_hit_text(g.texts[(p, j)], seed=7))
+        A = bfp.GetBLAST6Scores(si, [plain], p, j)
+        B = bfp.GetBLAST6Scores(si, [quoted], p, j)
+        assert (A != B).nnz == 0 and A.nnz > 0
+        mine = w.csv_unquote(open(quoted + "Blast%d_%d.txt" % (p, j), "rb").read())
+        with open(quoted + "Blast%d_%d.txt" % (p, j), "wb") as f:
+            f.write(mine)
+        assert (bfp.GetBLAST6Scores(si, [quoted], p, j) != A).nnz == 0
+
+
+def test_quoted_working_directory_gives_the_reference_graph_through_the_oracle(tmp_path):
+    """The host half of tests/test_zz_quoted_gpu.py on the CPU: what the reader threads hand to the device for a working directory
+    with quoted (and quoted + gzip-compressed) hit files parses - by the oracle - into the live reference's graph."""
+    from oracle import waterfall_oracle as wo
+    from orthofinder_b200 import synth
+    from tests.helpers import Golden, csv_quote_hit_text
+    wd = str(tmp_path) + "/"
+    synth.write_working_directory(wd, "C2_tiny")
+    g = Golden("synth_C2_tiny")
+    for k, fn in enumerate(sorted(f for f in os.listdir(wd) if f.startswith("Blast") and f.endswith(".txt"))):
+        if k % 3 == 2:
+            continue
+        with open(wd + fn, "rb") as f:
+            data = csv_quote_hit_text(f.read(), seed=k)
+        if k % 3 == 0:
+            with open(wd + fn, "wb") as f:
+                f.write(data)
+        else:
+            with open(wd + fn + ".gz", "wb") as f:
+                f.write(gzip.compress(data, 1))
+            os.remove(wd + fn)
+    S = len(g.n_seqs)
+    texts = {}
+    n_rewritten = 0
+    for (p, j), data, fn in w.read_hit_files([wd], [(p, j) for p in range(S) for j in range(S)], n_readers=4, raw_gz="auto"):
+        assert not isinstance(data, w.GzBytes) and b'"' not in data
+        n_rewritten += b"x'y" in data
+        texts[(p, j)] = data
+    assert n_rewritten >= S * S // 2
+    ref = wo.waterfall(g.n_seqs, g.lengths, lambda p, j: texts[(p, j)])
+    assert wo.graph_text(ref["indptr"], ref["indices"], ref["data"], sum(g.n_seqs)) == g.graph
