@@ -20,7 +20,8 @@
  *   dag            per column keep val >= bar, bar = 0.999 self + 0.001 max if self < max, else self / 1.01;
  *   clusters       nodes with a loop in the dag are attractors, connected attractors form a system, every node joins
  *                  the systems it reaches; a node reaching several stays in the first (systems in order of their smallest
- *                  attractor); output order: size descending, then smallest member.
+ *                  attractor); nodes that reach no system form one cluster together; output order: size descending, then
+ *                  smallest member.
  */
 #include <math.h>
 #include <stdint.h>
@@ -296,10 +297,13 @@ int mclo_interpret(void *hh, int which, int32_t *label, int32_t *overlap)
             }
         }
     }
-    int nov = 0;
+    int nov = 0, garbage = -1;
     for (int i = 0; i < n; i++) {
         if (second[i] >= 0) nov++;
-        if (sys[i] < 0) sys[i] = i;          /* reaches nothing: a cluster of its own */
+        if (sys[i] < 0) {                    /* reaches no attractor system: the binary collects these nodes in ONE cluster */
+            if (garbage < 0) garbage = i;    /* ("added <k> garbage entries"); its id = its smallest member, never an attractor */
+            sys[i] = garbage;
+        }
     }
     *overlap = nov;
     /* output order: size descending, then smallest member */

@@ -13,6 +13,7 @@ The fp64 B / BH / connect pickles are read back before deletion so that weights 
 at 1e-9 instead of the file's %.3f.
 """
 import os
+import re
 import sys
 import io
 import pickle
@@ -232,7 +233,7 @@ def read_mcl_binary_matrix(path):
     return colptr, a["i"].astype(np.int32), a["v"].astype(np.float32)
 
 
-def run_mcl_binary(graph_text, inflation, workdir, dump_iterands=False, extra=(), threads=1):
+def run_mcl_binary(graph_text, inflation, workdir, dump_iterands=False, extra=(), threads=1, log=False):
     """Runs the reference's bundled mcl exactly as RunMCL does (scripts_of/mcl.py:214-218: `mcl graph -I <inflation>
     -o clusters -te <n> -V all`) on `graph_text`; returns dict(clusters_text, iterands=[(colptr, rows, vals), ...] incl.
     the start matrix when dump_iterands, expanded=(...) when extra holds -write-expanded)."""
@@ -244,12 +245,17 @@ def run_mcl_binary(graph_text, inflation, workdir, dump_iterands=False, extra=()
     g = os.path.join(workdir, "graph.txt")
     with open(g, "wb") as fh:
         fh.write(graph_text if isinstance(graph_text, bytes) else graph_text.encode())
-    cmd = [MCL_BINARY, "graph.txt", "-I", str(inflation), "-o", "clusters.txt", "-te", str(threads), "-V", "all"]
+    cmd = [MCL_BINARY, "graph.txt", "-I", str(inflation), "-o", "clusters.txt", "-te", str(threads), "-v" if log else "-V", "all"]
     if dump_iterands:
         cmd += ["--write-binary", "-dump", "ite", "-dump-stem", "D", "-dump-interval", "0:100000"]
     cmd += list(extra)
-    subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    done = subprocess.run(cmd, cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE if log else subprocess.DEVNULL)
     out = {"clusters_text": open(os.path.join(workdir, "clusters.txt")).read()}
+    if log:
+        # per iteration: (chaos, clusters of the interim dag, nodes in overlap) from the binary's progress table (-v all)
+        rows = [ln.split() for ln in done.stderr.decode(errors="replace").splitlines() if re.match(r"^\s+\d+\s+\d+\.\d+\s", ln)]
+        out["log"] = [(float(r[1]), int(r[10]), int(r[11]), int(r[13][4:]) if len(r) > 13 and r[13].startswith("[!m=") else 0) for r in rows]
+        # (chaos, clusters, nodes in overlap, nodes in no cluster - printed as a trailing "[!m=.. e=..]")
     if dump_iterands:
         k, its = 0, []
         while os.path.exists(os.path.join(workdir, "ite-%d.D" % k)):

@@ -188,9 +188,13 @@ public:
         std::vector<int32_t> hs((size_t)n), h2((size_t)n);
         if (n && (!be.d2h(hs.data(), sys, (size_t)n * 4) || !be.d2h(h2.data(), second, (size_t)n * 4))) return fail();
         n_overlap = 0;
+        int32_t garbage = -1;
         for (int64_t i = 0; i < n; i++) {
             if (h2[(size_t)i] != MCL_NONE) n_overlap++;
-            if (hs[(size_t)i] == MCL_NONE) hs[(size_t)i] = (int32_t)i;      // reaches nothing: a cluster of its own
+            if (hs[(size_t)i] == MCL_NONE) {     // reaches no attractor system: the binary puts all such nodes into ONE cluster
+                if (garbage < 0) garbage = (int32_t)i;   // ("added <k> garbage entries"); id = its smallest member, never an attractor
+                hs[(size_t)i] = garbage;
+            }
         }
         // output order of the binary: size descending, then smallest member
         std::vector<int32_t> size((size_t)n, 0), first((size_t)n, -1);

@@ -253,3 +253,21 @@ def test_other_graphs_of_the_path_against_the_binary(tmp_path, name, variant, in
     e.close()
     assert text == mo.clusters_body_of_file(ref["clusters_text"])
     assert mo.clusters_text_body(pr.interpret(0)[1], pr.n) == text
+
+
+def test_unconverged_iterand_engine_and_oracle_agree():
+    """After 10 of 17 iterations synth_ties still has nodes in overlap and nine nodes without an attractor (one shared cluster):
+    the engine's dag / label rounds / cluster order give the oracle's clusters."""
+    from oracle import mcl_oracle as mo
+    graph = mcl_golden_graph("synth_ties")
+    e = HostEngine(graph)
+    pr = mo.Process(*mo.parse_graph_text(graph))
+    for _ in range(10):
+        e.step(1.5)
+        pr.step(1.5)
+    text, lab, nc, ov = e.clusters_text()
+    nc2, lab2, ov2 = pr.interpret(0)
+    e.close()
+    assert (nc, ov) == (nc2, ov2) and ov > 0
+    assert np.array_equal(lab, lab2) and text == mo.clusters_text_body(lab2, pr.n)
+    assert 9 in np.bincount(lab).tolist()
