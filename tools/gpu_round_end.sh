@@ -14,3 +14,5 @@ print("roofline", d["roofline"]); print("cpu", d["cpu_baseline"]); print("clocks
 r=json.loads(open("gpurun_out/bench_reference.json").read().strip().splitlines()[-1]); print("reference arm %.4e %s" % (r["value"], r["config"]["workload"]))
 PY
 bash tools/gpu_final.sh
+# MCL on the device: whole process on a device-resident graph
+timeout 300 python tools/mcl_timing.py 1.2 C2_small > gpurun_out/mcl_timing.jsonl 2> gpurun_out/mcl_timing.err; echo "mcl timing exit $?"; cat gpurun_out/mcl_timing.jsonl
