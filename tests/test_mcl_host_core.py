@@ -271,3 +271,55 @@ def test_unconverged_iterand_engine_and_oracle_agree():
     assert (nc, ov) == (nc2, ov2) and ov > 0
     assert np.array_equal(lab, lab2) and text == mo.clusters_text_body(lab2, pr.n)
     assert 9 in np.bincount(lab).tolist()
+
+
+def _random_graph(rng):
+    """2-70 nodes, four weight styles (continuous, a few equal values, values that print as 0.000 or with large integer parts,
+    heavy-tailed), loops in the input, one-way and unequal two-way edges, isolated nodes."""
+    from tests.helpers import mcl_graph_text
+    n = int(rng.integers(2, 70))
+    cols = [dict() for _ in range(n)]
+    kind = int(rng.integers(0, 4))
+    dens = float(rng.choice([0.03, 0.1, 0.3, 0.8]))
+    for i in range(n):
+        for j in range(n):
+            if rng.random() < dens and (i != j or rng.random() < 0.2):
+                if kind == 0:
+                    w = float(rng.uniform(0.001, 3))
+                elif kind == 1:
+                    w = float(rng.choice([0.5, 1.0, 1.0, 2.0]))
+                elif kind == 2:
+                    w = float(rng.choice([0.0004, 0.001, 0.25, 1.5, 12.345, 250.0]))
+                else:
+                    w = round(float(rng.lognormal(0, 1.5)), 3)
+                cols[i][j] = w
+                if rng.random() < 0.7:
+                    cols[j][i] = w if rng.random() < 0.6 else w * float(rng.uniform(0.5, 1.5))
+    return n, mcl_graph_text(n, cols)
+
+
+@pytest.mark.reference
+def test_random_graphs_against_the_binary(tmp_path):
+    """120 random graphs at random inflations through the binary, the oracle and the host-walked engine: every iterand bit for
+    bit, the same last iteration, the clusters file byte for byte (550 more were run by hand in the build container)."""
+    from oracle import mcl_oracle as mo, ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("live reference not present (GPU box)")
+    rng = np.random.default_rng(77)
+    for trial in range(120):
+        n, graph = _random_graph(rng)
+        inflation = float(rng.choice([1.2, 1.5, 2.0, 3.3, 5.0]))
+        ref = rh.run_mcl_binary(graph, inflation, str(tmp_path / "w"), dump_iterands=True)
+        its = ref["iterands"]
+        pr = mo.Process(*mo.parse_graph_text(graph))
+        e = HostEngine(graph)
+        assert matrix_digest(*pr.matrix(0)) == matrix_digest(*e.matrix()) == matrix_digest(*its[0]), trial
+        for k in range(1, len(its)):
+            ch, ch2 = pr.step(inflation), e.step(inflation)
+            want = matrix_digest(*its[k])
+            assert matrix_digest(*pr.matrix(0)) == want and matrix_digest(*e.matrix()) == want, (trial, k)
+            assert (ch < 1e-4) == (ch2 < 1e-4) == (k == len(its) - 1), (trial, k, ch, ch2)
+        body = mo.clusters_body_of_file(ref["clusters_text"])
+        assert mo.clusters_text_body(pr.interpret(0)[1], n) == body, trial
+        assert e.clusters_text()[0] == body, trial
+        e.close()
