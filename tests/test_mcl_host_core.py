@@ -323,3 +323,24 @@ def test_random_graphs_against_the_binary(tmp_path):
         assert mo.clusters_text_body(pr.interpret(0)[1], n) == body, trial
         assert e.clusters_text()[0] == body, trial
         e.close()
+
+
+@pytest.mark.parametrize("P,S,R,pct", [(200, 10, 15, 90), (100, 8, 20, 95), (50, 20, 5, 90), (20, 3, 8, 99), (10000, 4, 4, 50), (40, 6, 12, 97)])
+def test_engine_pruning_branches_equal_the_oracle(P, S, R, pct):
+    """Small prune / select / recover numbers (the binary's -P -S -R -pct; ofg_mcl_set_params) make every branch of the pruning rule
+    and the radix select fire on a fixture-sized graph: the engine's iterands and clusters == the oracle's, which
+    tests/test_mcl_oracle.py pins against the binary for the same settings."""
+    from oracle import mcl_oracle as mo
+    graph = mcl_golden_graph("ref_AddTwoSpecies")
+    kw = dict(P=P, S=S, R=R, pct=pct / 100.0)
+    e = HostEngine(graph, **kw)
+    pr = mo.Process(*mo.parse_graph_text(graph))
+    for k in range(1, 200):
+        ch, ch2 = pr.step(1.2, **kw), e.step(1.2)
+        assert matrix_digest(*e.matrix()) == matrix_digest(*pr.matrix(0)), k
+        assert (ch < 1e-4) == (ch2 < 1e-4)
+        if ch < 1e-4:
+            break
+    text = e.clusters_text()[0]
+    e.close()
+    assert text == mo.clusters_text_body(pr.interpret(0)[1], pr.n)
