@@ -10,11 +10,7 @@ import pytest
 from orthofinder_b200 import synth, waterfall
 from tests.helpers import Golden, csv_quote_hit_text
 
-# Written after the GPU budget of round 2 was spent: this test has NOT run on a GPU yet.  Its host half (the bytes the reader
-# threads hand to the device parse into the reference's graph) is checked on the CPU by
-# tests/test_host_ingest.py::test_quoted_working_directory_gives_the_reference_graph_through_the_oracle; the device half is the plain-text
-# path every other test uses.  xfail(strict=False) keeps an unverified test from masking the verified suite (`-x`): a pass shows as XPASS.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a GPU (round-2 GPU budget spent); host half verified on the CPU")]
+pytestmark = pytest.mark.gpu
 
 
 def test_working_directory_with_csv_quoted_hit_files(tmp_path):
